@@ -1,0 +1,495 @@
+// Attention kernels of the generation path (flash-style, online softmax, nothing T x T is ever materialised):
+//   * attn_varlen: packed variable-length sequences (cu_seqlens), bidirectional (ESM-2 encoder, hd = 64) or causal with
+//     grouped-query heads (Llama-3 prefill, hd = 128). Padded batches are the same kernel: the host passes the valid
+//     spans, so pad rows cost no FLOPs and can never be attended to (key-padding mask of fair-esm / HF's 4-D mask).
+//   * attn_decode_paged: one new token per sequence against the paged KV cache, the 4 query heads of a KV group share
+//     each K/V panel, warps split the context and merge their (max, sum, acc) triples through shared memory.
+// Round-1 implementation uses mma.sync m16n8k16 bf16 tiles fed by cp.async + ldmatrix; both kernels are HBM/L2 friendly
+// (every K/V byte is read once per (sequence, kv head) q-tile). A tcgen05/TMEM variant is the planned successor for the
+// long-protein encoder case where attention FLOPs stop being negligible.
+//
+// Replaces: fair-esm MultiheadAttention bmm/softmax/bmm (reached from cstp_v3/modelling.py:48) and HF Llama
+// sdpa/eager attention + DynamicCache (reached from language_model/opus_llama.py:127-132).
+#include "common.h"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace opus {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- primitives
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => zero-fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Tile of ROWS x D bf16 in shared memory, stored as D/64 panels of [ROWS][64] with the 16-byte chunks of every
+// 128-byte row XOR-swizzled by (row & 7): conflict-free for both cp.async stores and ldmatrix loads.
+template <int ROWS>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+  return (uint32_t)((chunk >> 3) * (ROWS * 128) + row * 128 + (((chunk & 7) ^ (row & 7)) << 4));
+}
+
+// ---------------------------------------------------------------------------------------------- varlen / prefill
+constexpr int BM = 128;  // query rows per CTA (8 warps x 16)
+constexpr int BN = 64;   // keys per pipeline step
+constexpr int ATT_THREADS = 256;
+
+struct AttnParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* k;
+  const __nv_bfloat16* v;
+  __nv_bfloat16* o;
+  const int* cu_seqlens;
+  int ldq, ldk, ldv, ldo;  // row strides (elements)
+  int n_q_heads, group;    // group = q heads per kv head
+  float scale_log2;        // softmax scale * log2(e)
+};
+
+template <int D, int ROWS>
+__device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_bfloat16* g, int ld, int row0, int len,
+                                                int tid) {
+  constexpr int CH = D / 8;  // 16-byte chunks per row
+  for (int i = tid; i < ROWS * CH; i += ATT_THREADS) {
+    const int r = i / CH, c = i - r * CH;
+    const int gr = row0 + r;
+    const bool valid = gr < len;
+    const __nv_bfloat16* src = g + (size_t)(valid ? gr : 0) * ld + c * 8;
+    cp_async16(smem_base + tile_off<ROWS>(r, c), src, valid);
+  }
+}
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_varlen_kernel(const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int Q_BYTES = BM * D * 2, KV_BYTES = BN * D * 2;
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + Q_BYTES;             // 2 stages
+  const uint32_t sV = sK + 2 * KV_BYTES;        // 2 stages
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int seq_start = p.cu_seqlens[b];
+  const int len = p.cu_seqlens[b + 1] - seq_start;
+  const int mblk = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
+  const int q0 = mblk * BM;
+  if (q0 >= len) return;
+  const int kvh = h / p.group;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+
+  const __nv_bfloat16* gq = p.q + (size_t)seq_start * p.ldq + (size_t)h * D;
+  const __nv_bfloat16* gk = p.k + (size_t)seq_start * p.ldk + (size_t)kvh * D;
+  const __nv_bfloat16* gv = p.v + (size_t)seq_start * p.ldv + (size_t)kvh * D;
+
+  const int kv_end = CAUSAL ? min(len, q0 + BM) : len;
+  const int n_blocks = (kv_end + BN - 1) / BN;
+
+  load_tile_async<D, BM>(sQ, gq, p.ldq, q0, len, tid);
+  load_tile_async<D, BN>(sK, gk, p.ldk, 0, len, tid);
+  load_tile_async<D, BN>(sV, gv, p.ldv, 0, len, tid);
+  cp_async_commit();
+
+  uint32_t qf[D / 16][4];
+  float o_acc[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+
+  const int qrow_lo = q0 + warp * 16 + g;  // sequence-relative query index of this thread's first row (second: +8)
+
+  for (int j = 0; j < n_blocks; ++j) {
+    const int st = j & 1;
+    if (j + 1 < n_blocks) {
+      load_tile_async<D, BN>(sK + (st ^ 1) * KV_BYTES, gk, p.ldk, (j + 1) * BN, len, tid);
+      load_tile_async<D, BN>(sV + (st ^ 1) * KV_BYTES, gv, p.ldv, (j + 1) * BN, len, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+
+    if (j == 0) {
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const int row = warp * 16 + (lane & 15);
+        const int chunk = kk * 2 + (lane >> 4);
+        ldsm_x4(sQ + tile_off<BM>(row, chunk), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+      }
+    }
+
+    // warps whose 16 query rows are all above this key block (causal) or beyond the sequence have nothing to do
+    const int k0 = j * BN;
+    const bool warp_active = (q0 + warp * 16 < len) && (!CAUSAL || k0 <= q0 + warp * 16 + 15);
+    if (warp_active) {
+      float s[BN / 8][4];
+#pragma unroll
+      for (int i = 0; i < BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+      const uint32_t kb = sK + st * KV_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+#pragma unroll
+        for (int nb2 = 0; nb2 < BN / 16; ++nb2) {
+          uint32_t b0, b1, b2, b3;
+          const int n = nb2 * 16 + (lane & 7) + ((lane >> 4) << 3);
+          const int chunk = kk * 2 + ((lane >> 3) & 1);
+          ldsm_x4(kb + tile_off<BN>(n, chunk), b0, b1, b2, b3);
+          mma_bf16_16816(s[2 * nb2], qf[kk], b0, b1);
+          mma_bf16_16816(s[2 * nb2 + 1], qf[kk], b2, b3);
+        }
+      }
+      // mask + running max
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = k0 + nb * 8 + t4 * 2 + (e & 1);
+          const int qr = qrow_lo + ((e >> 1) << 3);
+          const bool ok = key < len && (!CAUSAL || key <= qr);
+          const float val = ok ? s[nb][e] * p.scale_log2 : -INFINITY;
+          s[nb][e] = val;
+          mx[e >> 1] = fmaxf(mx[e >> 1], val);
+        }
+      }
+      float corr[2], m_use[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);
+        m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;  // fully masked row so far: avoid (-inf) - (-inf)
+        corr[r] = exp2f(m_run[r] - m_use[r]);           // m_run = -inf -> 0
+        m_run[r] = m_new;
+        l_run[r] *= corr[r];
+      }
+      float ls[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nb = 0; nb < BN / 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = exp2f(s[nb][e] - m_use[e >> 1]);
+          s[nb][e] = pv;
+          ls[e >> 1] += pv;
+        }
+      }
+      l_run[0] += ls[0];
+      l_run[1] += ls[1];
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+        o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+      }
+      const uint32_t vb = sV + st * KV_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < BN / 16; ++kk) {
+        uint32_t a[4];
+        a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+        a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+        a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+        for (int db2 = 0; db2 < D / 16; ++db2) {
+          uint32_t b0, b1, b2, b3;
+          const int key = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+          const int chunk = db2 * 2 + (lane >> 4);
+          ldsm_x4_t(vb + tile_off<BN>(key, chunk), b0, b1, b2, b3);
+          mma_bf16_16816(o_acc[2 * db2], a, b0, b1);
+          mma_bf16_16816(o_acc[2 * db2 + 1], a, b2, b3);
+        }
+      }
+    }
+    __syncthreads();  // everyone done with stage `st` before it is refilled
+  }
+
+  // finalise: divide by the row sums (quad-reduced) and store bf16
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qr = qrow_lo + r * 8;
+    if (qr < len) {
+      const float inv = l_run[r] > 0.f ? 1.0f / l_run[r] : 0.f;
+      __nv_bfloat16* dst = p.o + (size_t)(seq_start + qr) * p.ldo + (size_t)h * D;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        const uint32_t w = pack_bf16x2(o_acc[i][2 * r] * inv, o_acc[i][2 * r + 1] * inv);
+        *reinterpret_cast<uint32_t*>(dst + i * 8 + t4 * 2) = w;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- paged decode
+constexpr int DEC_WARPS = 4;
+constexpr int DEC_BS = 16;   // tokens per KV block (cache page)
+constexpr int DEC_D = 128;   // head dim
+constexpr int DEC_PANEL = DEC_BS * DEC_D * 2;  // 4 KB
+
+struct DecodeParams {
+  const __nv_bfloat16* q;  // [B, ldq], head h at column h*128 (already rotated)
+  int ldq;
+  const __nv_bfloat16* kcache;  // [blocks][n_kv_heads][16][128]
+  const __nv_bfloat16* vcache;
+  const int* block_table;  // [B, max_blocks]
+  int max_blocks;
+  const int* ctx_len;  // [B] number of valid cached tokens (including the one just appended)
+  __nv_bfloat16* o;    // [B, ldo]
+  int ldo;
+  int n_kv_heads, group;
+  float scale_log2;
+};
+
+__device__ __forceinline__ void load_panel_async(uint32_t smem_base, const __nv_bfloat16* panel, int lane) {
+  // 4 KB contiguous panel = 256 chunks of 16 B; row = chunk / 16 (256-byte rows), c = chunk % 16
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int id = i * 32 + lane;
+    cp_async16(smem_base + tile_off<DEC_BS>(id >> 4, id & 15), reinterpret_cast<const uint8_t*>(panel) + id * 16, true);
+  }
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const DecodeParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // per warp: 2 stages x (K panel + V panel) = 16 KB; then the merge area
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int kvh = blockIdx.x, b = blockIdx.y;
+  const int ctx = p.ctx_len[b];
+  const int n_blocks = (ctx + DEC_BS - 1) / DEC_BS;
+  const uint32_t s_warp = smem_u32(smem) + warp * (4 * DEC_PANEL);
+  float* s_merge = reinterpret_cast<float*>(smem + DEC_WARPS * 4 * DEC_PANEL);  // [warps][GROUP][128+2]
+
+  // Q fragments: rows 0..GROUP-1 of the m16 tile are the query heads of this KV group, the rest are zero
+  uint32_t qf[DEC_D / 16][4];
+  {
+    const __nv_bfloat16* qrow = p.q + (size_t)b * p.ldq + (size_t)(kvh * GROUP + g) * DEC_D;
+#pragma unroll
+    for (int kk = 0; kk < DEC_D / 16; ++kk) {
+      qf[kk][0] = (g < GROUP) ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + t4 * 2) : 0u;
+      qf[kk][1] = 0u;
+      qf[kk][2] = (g < GROUP) ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + 8 + t4 * 2) : 0u;
+      qf[kk][3] = 0u;
+    }
+  }
+  float o_acc[DEC_D / 8][4];
+#pragma unroll
+  for (int i = 0; i < DEC_D / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+  float m_run = -INFINITY, l_run = 0.f;
+
+  const int* bt = p.block_table + (size_t)b * p.max_blocks;
+  auto panel_ptr = [&](const __nv_bfloat16* cache, int blk_idx) {
+    return cache + ((size_t)bt[blk_idx] * p.n_kv_heads + kvh) * (DEC_BS * DEC_D);
+  };
+
+  int it = 0;
+  if (warp < n_blocks) {
+    load_panel_async(s_warp, panel_ptr(p.kcache, warp), lane);
+    load_panel_async(s_warp + DEC_PANEL, panel_ptr(p.vcache, warp), lane);
+  }
+  cp_async_commit();
+  for (int blk = warp; blk < n_blocks; blk += DEC_WARPS, ++it) {
+    const int st = it & 1;
+    const int nxt = blk + DEC_WARPS;
+    if (nxt < n_blocks) {
+      load_panel_async(s_warp + (st ^ 1) * 2 * DEC_PANEL, panel_ptr(p.kcache, nxt), lane);
+      load_panel_async(s_warp + (st ^ 1) * 2 * DEC_PANEL + DEC_PANEL, panel_ptr(p.vcache, nxt), lane);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint32_t kb = s_warp + st * 2 * DEC_PANEL, vb = kb + DEC_PANEL;
+
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int kk = 0; kk < DEC_D / 16; ++kk) {
+      uint32_t b0, b1, b2, b3;
+      const int n = (lane & 7) + ((lane >> 4) << 3);
+      const int chunk = kk * 2 + ((lane >> 3) & 1);
+      ldsm_x4(kb + tile_off<DEC_BS>(n, chunk), b0, b1, b2, b3);
+      mma_bf16_16816(s[0], qf[kk], b0, b1);
+      mma_bf16_16816(s[1], qf[kk], b2, b3);
+    }
+    // rows g (valid if g < GROUP); elements e=0,1 of each n-block
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = blk * DEC_BS + nb * 8 + t4 * 2 + e;
+        const float val = key < ctx ? s[nb][e] * p.scale_log2 : -INFINITY;
+        s[nb][e] = val;
+        mx = fmaxf(mx, val);
+      }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(m_run, mx);
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+    const float corr = exp2f(m_run - m_use);
+    m_run = m_new;
+    float ls = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float pv = exp2f(s[nb][e] - m_use);
+        s[nb][e] = pv;
+        ls += pv;
+      }
+    }
+    l_run = l_run * corr + ls;
+#pragma unroll
+    for (int i = 0; i < DEC_D / 8; ++i) { o_acc[i][0] *= corr; o_acc[i][1] *= corr; }
+    uint32_t a[4];
+    a[0] = pack_bf16x2(s[0][0], s[0][1]);
+    a[1] = 0u;
+    a[2] = pack_bf16x2(s[1][0], s[1][1]);
+    a[3] = 0u;
+#pragma unroll
+    for (int db2 = 0; db2 < DEC_D / 16; ++db2) {
+      uint32_t b0, b1, b2, b3;
+      const int key = (lane & 7) + (((lane >> 3) & 1) << 3);
+      const int chunk = db2 * 2 + (lane >> 4);
+      ldsm_x4_t(vb + tile_off<DEC_BS>(key, chunk), b0, b1, b2, b3);
+      mma_bf16_16816(o_acc[2 * db2], a, b0, b1);
+      mma_bf16_16816(o_acc[2 * db2 + 1], a, b2, b3);
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+
+  // merge the per-warp partial softmax states
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  constexpr int MS = DEC_D + 2;
+  if (g < GROUP) {
+    float* dst = s_merge + ((size_t)warp * GROUP + g) * MS;
+#pragma unroll
+    for (int i = 0; i < DEC_D / 8; ++i) {
+      dst[i * 8 + t4 * 2] = o_acc[i][0];
+      dst[i * 8 + t4 * 2 + 1] = o_acc[i][1];
+    }
+    if (t4 == 0) { dst[DEC_D] = m_run; dst[DEC_D + 1] = l_run; }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < GROUP * DEC_D; idx += DEC_WARPS * 32) {
+    const int hh = idx / DEC_D, c = idx - hh * DEC_D;
+    float mmax = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) mmax = fmaxf(mmax, s_merge[((size_t)w * GROUP + hh) * MS + DEC_D]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < DEC_WARPS; ++w) {
+      const float* src = s_merge + ((size_t)w * GROUP + hh) * MS;
+      const float mw = src[DEC_D];
+      const float sc = (mw == -INFINITY) ? 0.f : exp2f(mw - mmax);
+      num += src[c] * sc;
+      den += src[DEC_D + 1] * sc;
+    }
+    p.o[(size_t)b * p.ldo + (size_t)(kvh * GROUP + hh) * DEC_D + c] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+  }
+}
+
+template <int D, bool CAUSAL>
+int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st) {
+  constexpr int SMEM = BM * D * 2 + 4 * BN * D * 2;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(attn_varlen_kernel<D, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+        cudaSuccess)
+      return OPUS_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid((max_len + BM - 1) / BM, p.n_q_heads, n_seqs);
+  attn_varlen_kernel<D, CAUSAL><<<grid, ATT_THREADS, SMEM, st>>>(p);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
+}
+
+}  // namespace
+
+int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int max_len, int n_q_heads,
+                int n_kv_heads, int head_dim, int causal, float scale, cudaStream_t st) {
+  if (n_seqs == 0 || max_len == 0) return OPUS_OK;
+  if (n_kv_heads <= 0 || n_q_heads % n_kv_heads) return OPUS_ERR_ARG;
+  if ((ldq | ldk | ldv) % 8 || ldo % 2) return OPUS_ERR_ARG;
+  AttnParams p;
+  p.q = q; p.k = k; p.v = v; p.o = o;
+  p.cu_seqlens = cu_seqlens;
+  p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+  p.n_q_heads = n_q_heads;
+  p.group = n_q_heads / n_kv_heads;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  if (head_dim == 64 && !causal) return launch_varlen<64, false>(p, n_seqs, max_len, st);
+  if (head_dim == 64 && causal) return launch_varlen<64, true>(p, n_seqs, max_len, st);
+  if (head_dim == 128 && !causal) return launch_varlen<128, false>(p, n_seqs, max_len, st);
+  if (head_dim == 128 && causal) return launch_varlen<128, true>(p, n_seqs, max_len, st);
+  return OPUS_ERR_ARG;
+}
+
+int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
+                      const int* block_table, int max_blocks, const int* ctx_len, __nv_bfloat16* o, int ldo,
+                      int n_seqs, int n_q_heads, int n_kv_heads, int head_dim, int block_size, float scale,
+                      cudaStream_t st) {
+  if (n_seqs == 0) return OPUS_OK;
+  if (head_dim != DEC_D || block_size != DEC_BS || n_kv_heads <= 0 || n_q_heads % n_kv_heads) return OPUS_ERR_ARG;
+  const int group = n_q_heads / n_kv_heads;
+  DecodeParams p;
+  p.q = q; p.ldq = ldq;
+  p.kcache = kcache; p.vcache = vcache;
+  p.block_table = block_table; p.max_blocks = max_blocks;
+  p.ctx_len = ctx_len;
+  p.o = o; p.ldo = ldo;
+  p.n_kv_heads = n_kv_heads; p.group = group;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(n_kv_heads, n_seqs);
+  const int smem = DEC_WARPS * 4 * DEC_PANEL + DEC_WARPS * 8 * (DEC_D + 2) * 4;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(attn_decode_paged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_paged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_paged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(attn_decode_paged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  switch (group) {
+    case 1: attn_decode_paged_kernel<1><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
+    case 2: attn_decode_paged_kernel<2><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
+    case 4: attn_decode_paged_kernel<4><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
+    case 8: attn_decode_paged_kernel<8><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
+    default: return OPUS_ERR_ARG;
+  }
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
+}
+
+}  // namespace opus

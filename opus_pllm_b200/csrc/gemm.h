@@ -1,0 +1,64 @@
+// Internal (C++) interface of the tcgen05 GEMM; the C-ABI wrapper is opus_gemm_bf16 in capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/opus_b200.h"
+
+namespace opus {
+
+enum EpiMode : int {
+  EPI_BF16 = OPUS_EPI_BF16,                // out bf16 = acc (+ bias)
+  EPI_BF16_GELU = OPUS_EPI_BF16_GELU,      // out bf16 = gelu_erf(acc + bias)
+  EPI_RES_F32 = OPUS_EPI_RES_F32,          // out f32  = residual_f32 + acc (+ bias)
+  EPI_RES_BF16 = OPUS_EPI_RES_BF16,        // out bf16 = bf16(residual_bf16 + bf16(acc (+ bias)))
+  EPI_SWIGLU = OPUS_EPI_SWIGLU,            // interleaved (gate, up) features -> out bf16 = silu(gate) * up, half width
+  EPI_PARTIAL_F32 = OPUS_EPI_PARTIAL_F32,  // split-K partial sums: out f32 [split][rows][ldo]
+  EPI_F32 = OPUS_EPI_F32,                  // out f32 = acc (+ bias)   (transposed form only)
+};
+
+// Device-visible parameter block.
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, k_blocks;
+  int split_k;
+  int transposed;
+  int epi;
+  int group_m;
+  void* out;
+  int ldo;
+  const float* bias;
+  const void* residual;
+  int ldr;
+  uint64_t hint_a, hint_b;
+};
+
+// D[M,N] = A[M,K] * B[N,K]^T, both operands bf16 row-major with K contiguous.
+//  transposed == 0: out[m*ldo + n], bias[n]; A = activations, B = weights.
+//  transposed == 1: out[n*ldo + m], bias[m]; A = weights (M = output features), B = activations (N = batch rows).
+//  split_k > 1 requires EPI_PARTIAL_F32; partial s of element (r, c) [r = batch/activation row, c = feature] is at
+//  out[(s*rows + r)*ldo + c].
+struct GemmArgs {
+  const void* A;
+  int lda;
+  const void* B;
+  int ldb;
+  int M, N, K;
+  int transposed;
+  int epi;
+  void* out;
+  int ldo;
+  const float* bias;
+  const void* residual;
+  int ldr;
+  int split_k;  // 0/1 = none
+  int block_n;  // 0 = auto
+};
+
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+int gemm_pick_bn(int N, int transposed);
+int gemm_pick_split_k(int M, int N, int K, int bn);
+size_t gemm_workspace_bytes(int M, int N, int split_k);
+
+}  // namespace opus

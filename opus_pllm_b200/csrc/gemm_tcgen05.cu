@@ -1,0 +1,468 @@
+// bf16 GEMM on the 5th-gen tensor cores:  D[M,N] = epilogue( A[M,K] * B[N,K]^T ),  fp32 accumulate in TMEM.
+//
+//   * operands are K-major (row-major [rows, K]) bf16 in global memory, moved by TMA (SWIZZLE_128B, 64-wide K boxes)
+//     into a multi-stage shared-memory ring;
+//   * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16) into one of two TMEM accumulator buffers;
+//   * four epilogue warps drain the other accumulator with tcgen05.ld and apply the fused epilogue
+//     (bias / erf-GELU / residual / SwiGLU / split-K partial), so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * persistent CTAs (one per SM) walk a grouped-M raster of (m, n, k-split) work items.
+//
+// "Transposed" mode is the swap-AB form used by decode and the projectors: the WEIGHT matrix is the A operand
+// (128 output features per tile) and the small batch is the B operand (BN = 32..256 rows), and the epilogue stores
+// D^T so the result is again [batch, features] row-major. That keeps M = 128 UMMA tiles full at batch <= 256 while
+// the kernel is purely weight-streaming (HBM-bound).
+//
+// Replaces, on the reference's path, every nn.Linear executed by cuBLAS: fair-esm q/k/v/out/fc1/fc2
+// (cstp_v3/modelling.py:48), CSTP projection (modelling.py:396-400), switch projector (protein_mlp/builder.py:21-24),
+// and HF Llama q/k/v/o/gate/up/down/lm_head (reached through language_model/opus_llama.py:82-93).
+#include "common.h"
+#include "gemm.h"
+#include "ptx.cuh"
+
+#include <cuda.h>
+#include <mutex>
+
+namespace opus {
+
+namespace {
+
+constexpr int BM = 128;       // UMMA M (rows of A per tile) == TMEM lanes
+constexpr int BK = 64;        // K elements per stage = one 128-byte swizzle atom of bf16
+constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
+constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int NUM_EPI_THREADS = 128;
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGE_A = BM * BK * 2;
+  static constexpr int STAGE_B = BN * BK * 2;
+  static constexpr int STAGE = STAGE_A + STAGE_B;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int m, n, kb_begin, kb_end, split;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
+  TileCoord c;
+  const int mn = t / p.split_k;
+  c.split = t - mn * p.split_k;
+  const int per_group = p.group_m * p.num_n_tiles;
+  const int g = mn / per_group;
+  const int r = mn - g * per_group;
+  const int first_m = g * p.group_m;
+  const int gsz = min(p.num_m_tiles - first_m, p.group_m);
+  c.m = first_m + r % gsz;
+  c.n = r / gsz;
+  c.kb_begin = (int)(((long long)c.split * p.k_blocks) / p.split_k);
+  c.kb_end = (int)(((long long)(c.split + 1) * p.k_blocks) / p.split_k);
+  return c;
+}
+
+// ---- epilogue for one 32-column chunk held by one thread (= one accumulator row) ----
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]);
+  q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]);
+  q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dst) = q;
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int row, int col0,
+                                               int split) {
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+
+  if (!p.transposed) {
+    // element (row, col0+i) -> out[row*ldo + col0+i]; bias indexed by column
+    const bool row_ok = row < p.M;
+    if (p.epi == EPI_PARTIAL_F32) {
+      if (row_ok) {
+        float* dst = reinterpret_cast<float*>(p.out) + ((size_t)split * p.M + row) * p.ldo + col0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          if (col0 + g * 4 + 4 <= p.N) *reinterpret_cast<float4*>(dst + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+      return;
+    }
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (col0 + g * 4 + 4 <= p.N) {
+          const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + g * 4);
+          v[g * 4] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+        }
+      }
+    }
+    if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU) {
+      if (p.epi == EPI_BF16_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      }
+      if (row_ok) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (col0 + g * 8 + 8 <= p.N) store_bf16x8(dst + g * 8, v + g * 8);
+      }
+    } else if (p.epi == EPI_RES_F32) {
+      // out_f32 = residual_f32 + (acc + bias)   (fp32 residual stream of the encoder; in-place allowed)
+      if (row_ok) {
+        const float* res = reinterpret_cast<const float*>(p.residual) + (size_t)row * p.ldr + col0;
+        float* dst = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (col0 + g * 4 + 4 <= p.N) {
+            const float4 q = *reinterpret_cast<const float4*>(res + g * 4);
+            *reinterpret_cast<float4*>(dst + g * 4) =
+                make_float4(q.x + v[g * 4], q.y + v[g * 4 + 1], q.z + v[g * 4 + 2], q.w + v[g * 4 + 3]);
+          }
+        }
+      }
+    } else if (p.epi == EPI_RES_BF16) {
+      // out = bf16( residual + bf16(acc) )  -- mirrors `residual + self.o_proj(x)` in bf16 (HF modeling_llama.py)
+      if (row_ok) {
+        const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldr + col0;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (col0 + g * 8 + 8 <= p.N) {
+            const uint4 q = *reinterpret_cast<const uint4*>(res + g * 8);
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&q);
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 rf = __bfloat1622float2(rb[j]);
+              o[2 * j] = rf.x + bf16_round(v[g * 8 + 2 * j]);
+              o[2 * j + 1] = rf.y + bf16_round(v[g * 8 + 2 * j + 1]);
+            }
+            store_bf16x8(dst + g * 8, o);
+          }
+        }
+      }
+    } else if (p.epi == EPI_SWIGLU) {
+      // columns (2j, 2j+1) = (gate_j, up_j) -> out[row, j] = bf16( bf16(silu(bf16 gate)) * bf16 up )
+      if (row_ok) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float g = bf16_round(v[2 * j]);
+          const float u = bf16_round(v[2 * j + 1]);
+          o[j] = bf16_round(silu_f(g)) * u;
+        }
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + (col0 >> 1);
+        if (col0 + 16 <= p.N) store_bf16x8(dst, o);
+        if (col0 + 32 <= p.N) store_bf16x8(dst + 8, o + 8);
+      }
+    }
+    return;
+  }
+
+  // ---- transposed (swap-AB): accumulator row = output feature `row`, column = batch row n -> out[n*ldo + row] ----
+  const bool row_ok = row < p.M;
+  if (p.epi == EPI_PARTIAL_F32) {
+    float* base = reinterpret_cast<float*>(p.out) + (size_t)split * p.N * p.ldo;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int n = col0 + i;
+      if (row_ok && n < p.N) base[(size_t)n * p.ldo + row] = v[i];
+    }
+    return;
+  }
+  if (p.epi == EPI_SWIGLU) {
+    // rows (2j, 2j+1) = (gate_j, up_j) live in adjacent lanes
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float other = __shfl_down_sync(0xffffffffu, v[i], 1);
+      const int n = col0 + i;
+      if (((row & 1) == 0) && row + 1 < p.M && n < p.N) {
+        const float g = bf16_round(v[i]);
+        const float u = bf16_round(other);
+        reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + (row >> 1)] =
+            __float2bfloat16_rn(bf16_round(silu_f(g)) * u);
+      }
+    }
+    return;
+  }
+  const float b = (p.bias != nullptr && row_ok) ? p.bias[row] : 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int n = col0 + i;
+    if (!(row_ok && n < p.N)) continue;
+    float x = v[i] + b;
+    if (p.epi == EPI_BF16) {
+      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + row] = __float2bfloat16_rn(x);
+    } else if (p.epi == EPI_BF16_GELU) {
+      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + row] = __float2bfloat16_rn(gelu_erf(x));
+    } else if (p.epi == EPI_RES_F32) {
+      const float rres = reinterpret_cast<const float*>(p.residual)[(size_t)n * p.ldr + row];
+      reinterpret_cast<float*>(p.out)[(size_t)n * p.ldo + row] = rres + x;
+    } else if (p.epi == EPI_RES_BF16) {
+      const float rres = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)n * p.ldr + row]);
+      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + row] = __float2bfloat16_rn(rres + bf16_round(x));
+    } else if (p.epi == EPI_F32) {
+      reinterpret_cast<float*>(p.out)[(size_t)n * p.ldo + row] = x;
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte aligned bases
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * C::STAGES;     // [2]       MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * C::STAGES + 2;  // [2]     epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], NUM_EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE;
+          uint8_t* sb = sa + C::STAGE_A;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
+          tma_load_2d_hint(sa, &tmap_a, &full_bar[stage], kb * BK, tc.m * BM, p.hint_a);
+          tma_load_2d_hint(sb, &tmap_b, &full_bar[stage], kb * BK, tc.n * BN, p.hint_b);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+          const uint64_t da = umma_smem_desc_sw128(sa);
+          const uint64_t db = umma_smem_desc_sw128(sa + C::STAGE_A);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (= 16 bf16) along K inside the swizzle atom: +2 in 16-byte address units
+            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = tc.m * BM + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = tc.n * BN + c * 32;
+        if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// [rows, cols] bf16 row-major, row stride ld elements; box = box_rows x 64 columns, 128-byte swizzle.
+int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return OPUS_ERR_DRIVER;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? OPUS_OK : OPUS_ERR_TMAP;
+}
+
+template <int BN>
+int launch(const GemmParams& p, const void* A, int lda, const void* B, int ldb, int grid, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
+        cudaSuccess)
+      return OPUS_ERR_CUDA;
+    configured = true;
+  }
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, A, p.M, p.K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN);
+  if (rc) return rc;
+  gemm_bf16_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM, stream>>>(ta, tb, p);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+}  // namespace
+
+int gemm_pick_bn(int N, int transposed) {
+  if (transposed) {
+    if (N <= 32) return 32;
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    return 256;
+  }
+  return (N % 256 == 0 || N > 1024) ? 256 : (N >= 128 ? 128 : 64);
+}
+
+int gemm_pick_split_k(int M, int N, int K, int bn) {
+  const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+  const int kb = (K + BK - 1) / BK;
+  const int sms = num_sms();
+  if (tiles >= sms / 2) return 1;
+  int s = sms / tiles;  // fill the machine once
+  if (s > kb / 4) s = kb / 4;  // keep >= 4 k-blocks (256 of K) per split
+  if (s > 16) s = 16;
+  return s < 1 ? 1 : s;
+}
+
+size_t gemm_workspace_bytes(int M, int N, int split_k) { return (size_t)split_k * M * N * sizeof(float); }
+
+// D = epi(A * B^T). See gemm.h for the contract.
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return OPUS_ERR_ARG;
+  if ((a.lda % 8) || (a.ldb % 8) || (a.K % 8)) return OPUS_ERR_ARG;  // TMA: 16-byte aligned rows
+  if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return OPUS_ERR_ARG;
+  if (!a.transposed && (a.N % 8)) return OPUS_ERR_ARG;
+  if (a.epi == EPI_SWIGLU && ((a.transposed ? a.M : a.N) % 16)) return OPUS_ERR_ARG;
+  if ((a.epi == EPI_RES_F32 || a.epi == EPI_RES_BF16) && a.residual == nullptr) return OPUS_ERR_ARG;
+  if (a.epi == EPI_F32 && !a.transposed) return OPUS_ERR_ARG;
+
+  const int bn = a.block_n > 0 ? a.block_n : gemm_pick_bn(a.N, a.transposed);
+  GemmParams p{};
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.num_m_tiles = (a.M + BM - 1) / BM;
+  p.num_n_tiles = (a.N + bn - 1) / bn;
+  p.k_blocks = (a.K + BK - 1) / BK;
+  p.split_k = a.split_k > 0 ? a.split_k : 1;
+  if (p.split_k > p.k_blocks) p.split_k = p.k_blocks;
+  if (p.split_k > 1 && a.epi != EPI_PARTIAL_F32) return OPUS_ERR_ARG;
+  p.transposed = a.transposed;
+  p.epi = a.epi;
+  p.out = a.out; p.ldo = a.ldo;
+  p.bias = a.bias;
+  p.residual = a.residual; p.ldr = a.ldr;
+  p.group_m = a.transposed ? p.num_m_tiles : 16;
+  if (p.group_m > p.num_m_tiles) p.group_m = p.num_m_tiles;
+  // weights are streamed once in the swap-AB form; activations are re-read by every tile
+  p.hint_a = a.transposed ? kCacheEvictFirst : kCacheEvictNormal;
+  p.hint_b = a.transposed ? kCacheEvictLast : kCacheEvictNormal;
+
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  switch (bn) {
+    case 32: return launch<32>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
+    case 64: return launch<64>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
+    case 128: return launch<128>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
+    case 256: return launch<256>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
+    default: return OPUS_ERR_ARG;
+  }
+}
+
+}  // namespace opus

@@ -1,0 +1,53 @@
+// Internal C++ declarations of the bandwidth and attention kernels (launchers). The C-ABI wrappers live in capi.cu.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/opus_b200.h"
+
+namespace opus {
+
+// ---- bandwidth.cu ----
+int esm_embed(const int* tok, const float* scale, const float* table, float* x, int n_tok, int dim, cudaStream_t st);
+int layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows, int cols,
+                       float eps, cudaStream_t st);
+// y = w * rmsnorm(h), h = x (or bf16(sum of n_partial fp32 partials)) (+ residual); h optionally written to h_out;
+// y == nullptr skips the normalisation (pure reduce + residual).
+int rmsnorm_bf16(const __nv_bfloat16* x, const float* partial, int n_partial, const __nv_bfloat16* residual,
+                 __nv_bfloat16* h_out, const __nv_bfloat16* w, __nv_bfloat16* y, int rows, int cols, float eps,
+                 cudaStream_t st);
+int splitk_reduce_bf16(const float* partial, int n_partial, const float* bias, __nv_bfloat16* out, int rows, int cols,
+                       int ldo, int gelu, cudaStream_t st);
+int rope_esm(__nv_bfloat16* qkv, const int* pos, const float* cos_t, const float* sin_t, int n_tok, int n_heads,
+             int head_dim, int ld, float q_scale, cudaStream_t st);
+int rope_llama_kvappend(__nv_bfloat16* qkv, const float* partial, int n_partial, const int* pos, const int* slot,
+                        const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t, __nv_bfloat16* kcache,
+                        __nv_bfloat16* vcache, int n_tok, int n_q_heads, int n_kv_heads, int head_dim, int ld,
+                        int block_size, cudaStream_t st);
+int final_ln_meanpool(const float* x, const int* cu_seqlens, const float* gamma, const float* beta, float* pooled,
+                      __nv_bfloat16* pooled_l2, float* hidden_out, int n_seqs, int dim, float eps, cudaStream_t st);
+int l2norm_f32_bf16(const float* x, __nv_bfloat16* y, int rows, int dim, cudaStream_t st);
+int splice_gather(const int* src, const __nv_bfloat16* embed, const __nv_bfloat16* soft, __nv_bfloat16* out, int n_rows,
+                  int dim, cudaStream_t st);
+int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* finished, const int* eos_ids, int n_eos,
+               int pad_id, int* next_tok, int* out_ids, int out_ld, int step, int* n_unfinished, cudaStream_t st,
+               const int* step_ptr = nullptr);
+int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, int n_rows, int dim, cudaStream_t st);
+int decode_advance(int* ctx_len, int* pos, int* slot, const int* block_table, int max_blocks, int block_size, int n,
+                   cudaStream_t st, int* step = nullptr);
+int lora_merge(__nv_bfloat16* W, const __nv_bfloat16* A, const __nv_bfloat16* B, int out_f, int in_f, int r, float scale,
+               cudaStream_t st);
+
+// ---- attention.cu ----
+int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int max_len, int n_q_heads,
+                int n_kv_heads, int head_dim, int causal, float scale, cudaStream_t st);
+int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
+                      const int* block_table, int max_blocks, const int* ctx_len, __nv_bfloat16* o, int ldo,
+                      int n_seqs, int n_q_heads, int n_kv_heads, int head_dim, int block_size, float scale,
+                      cudaStream_t st);
+
+}  // namespace opus

@@ -1,0 +1,293 @@
+// Host-side orchestration of the three composite forwards (ESM-2 encoder, projectors, Llama prefill / decode) on top of
+// the kernels in gemm_tcgen05.cu / bandwidth.cu / attention.cu. Pure launch sequencing: no allocation, no sync.
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.h"
+#include "gemm.h"
+#include "kernels.h"
+#include "models.h"
+
+namespace opus {
+
+#define OPUS_TRY(expr)                                   \
+  do {                                                   \
+    const int _rc = (expr);                              \
+    if (_rc != OPUS_OK) return fail(_rc, #expr);         \
+  } while (0)
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+// activations [rows, K] x weight [N, K]^T -> out, choosing the weight-streaming (swap-AB) form for small `rows`.
+int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* out, int ldo, const float* bias,
+           const void* residual, int ldr, float* ws, size_t ws_bytes, cudaStream_t st) {
+  GemmArgs a{};
+  a.K = K;
+  a.epi = epi;
+  a.out = out; a.ldo = ldo;
+  a.bias = bias;
+  a.residual = residual; a.ldr = ldr;
+  if (rows <= 256) {
+    a.transposed = 1;
+    a.A = w; a.lda = K; a.M = N;
+    a.B = x; a.ldb = K; a.N = rows;
+  } else {
+    a.transposed = 0;
+    a.A = x; a.lda = K; a.M = rows;
+    a.B = w; a.ldb = K; a.N = N;
+  }
+  (void)ws; (void)ws_bytes;
+  return gemm_bf16(a, st);
+}
+
+// swap-AB GEMM with split-K partials into `partial` ([s][rows][N] fp32). Returns the split count via *splits.
+int linear_splitk(const void* x, int rows, const void* w, int N, int K, float* partial, size_t partial_bytes,
+                  int* splits, cudaStream_t st) {
+  const int bn = gemm_pick_bn(rows, 1);
+  int s = gemm_pick_split_k(N, rows, K, bn);
+  while (s > 1 && gemm_workspace_bytes(rows, N, s) > partial_bytes) --s;
+  if (gemm_workspace_bytes(rows, N, s) > partial_bytes) return OPUS_ERR_ARG;
+  GemmArgs a{};
+  a.transposed = 1;
+  a.A = w; a.lda = K; a.M = N;
+  a.B = x; a.ldb = K; a.N = rows;
+  a.K = K;
+  a.epi = EPI_PARTIAL_F32;
+  a.out = partial; a.ldo = N;
+  a.split_k = s;
+  *splits = s;
+  return gemm_bf16(a, st);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ ESM-2
+int esm2_forward(const opus_esm2_model* m, const opus_esm2_workspace* ws, const int* tokens, const float* tok_scale,
+                 const int* pos, const int* cu_seqlens, int n_seqs, int n_tok, int max_len, float* pooled,
+                 void* pooled_l2, float* hidden_out, cudaStream_t st) {
+  if (!m || !ws || !m->layers) return fail(OPUS_ERR_ARG, "esm2_forward: null model/workspace");
+  if (n_tok <= 0 || n_seqs <= 0) return OPUS_OK;
+  const int d = m->dim, hd = d / m->n_heads, ffn = m->ffn_dim;
+  if (hd != 64) return fail(OPUS_ERR_ARG, "esm2_forward: head_dim must be 64");
+  OPUS_TRY(esm_embed(tokens, tok_scale, m->embed, ws->x, n_tok, d, st));
+  bf16* xn = static_cast<bf16*>(ws->xn);
+  bf16* qkv = static_cast<bf16*>(ws->qkv);
+  bf16* attn = static_cast<bf16*>(ws->attn);
+  bf16* ffb = static_cast<bf16*>(ws->ffn);
+  for (int l = 0; l < m->n_layers; ++l) {
+    const opus_esm2_layer& L = m->layers[l];
+    OPUS_TRY(layernorm_f32_bf16(ws->x, L.ln1_g, L.ln1_b, xn, n_tok, d, m->ln_eps, st));
+    OPUS_TRY(linear(xn, n_tok, L.wqkv, 3 * d, d, EPI_BF16, qkv, 3 * d, L.bqkv, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(rope_esm(qkv, pos, m->rope_cos, m->rope_sin, n_tok, m->n_heads, hd, 3 * d, 0.125f, st));
+    OPUS_TRY(attn_varlen(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu_seqlens, n_seqs, max_len,
+                         m->n_heads, m->n_heads, hd, 0, 1.0f, st));
+    OPUS_TRY(linear(attn, n_tok, L.wo, d, d, EPI_RES_F32, ws->x, d, L.bo, ws->x, d, nullptr, 0, st));
+    OPUS_TRY(layernorm_f32_bf16(ws->x, L.ln2_g, L.ln2_b, xn, n_tok, d, m->ln_eps, st));
+    OPUS_TRY(linear(xn, n_tok, L.w1, ffn, d, EPI_BF16_GELU, ffb, ffn, L.b1, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(linear(ffb, n_tok, L.w2, d, ffn, EPI_RES_F32, ws->x, d, L.b2, ws->x, d, nullptr, 0, st));
+  }
+  OPUS_TRY(final_ln_meanpool(ws->x, cu_seqlens, m->lnf_g, m->lnf_b, pooled, static_cast<bf16*>(pooled_l2), hidden_out,
+                             n_seqs, d, m->ln_eps, st));
+  return OPUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ projectors
+int projector_forward(const opus_projector_model* m, const void* x_l2, int n, void* cstp_out, void* h0, void* out,
+                      float* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!m) return fail(OPUS_ERR_ARG, "projector_forward: null model");
+  if (n <= 0) return OPUS_OK;
+  const void* cur = x_l2;
+  int cur_dim = m->in_dim;
+  if (m->w_cstp != nullptr) {
+    OPUS_TRY(linear(cur, n, m->w_cstp, m->cstp_dim, cur_dim, EPI_BF16, cstp_out, m->cstp_dim, m->b_cstp, nullptr, 0, ws,
+                    ws_bytes, st));
+    cur = cstp_out;
+    cur_dim = m->cstp_dim;
+  }
+  if (m->w2 == nullptr) {  // 'linear' projector type
+    OPUS_TRY(linear(cur, n, m->w0, m->hidden_dim, cur_dim, EPI_BF16, out, m->hidden_dim, m->b0, nullptr, 0, ws,
+                    ws_bytes, st));
+    return OPUS_OK;
+  }
+  OPUS_TRY(linear(cur, n, m->w0, m->hidden_dim, cur_dim, EPI_BF16_GELU, h0, m->hidden_dim, m->b0, nullptr, 0, ws,
+                  ws_bytes, st));
+  OPUS_TRY(linear(h0, n, m->w2, m->hidden_dim, m->hidden_dim, EPI_BF16, out, m->hidden_dim, m->b2, nullptr, 0, ws,
+                  ws_bytes, st));
+  return OPUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Llama prefill
+int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
+                  const void* embeds, const int* pos, const int* slot, const int* cu_seqlens, const int* last_rows,
+                  int n_seqs, int n_tok, int max_len, cudaStream_t st) {
+  if (!m || !kv || !ws || !m->layers) return fail(OPUS_ERR_ARG, "llama_prefill: null argument");
+  if (n_tok <= 0 || n_seqs <= 0) return OPUS_OK;
+  const int d = m->dim, hd = m->head_dim, Hq = m->n_q_heads, Hkv = m->n_kv_heads, ffn = m->ffn_dim;
+  const int qkv_n = (Hq + 2 * Hkv) * hd;
+  if (hd != 128) return fail(OPUS_ERR_ARG, "llama_prefill: head_dim must be 128");
+  bf16* h = static_cast<bf16*>(ws->h);
+  bf16* xn = static_cast<bf16*>(ws->xn);
+  bf16* qkv = static_cast<bf16*>(ws->qkv);
+  bf16* attn = static_cast<bf16*>(ws->attn);
+  bf16* act = static_cast<bf16*>(ws->act);
+  if (embeds != ws->h) {
+    if (cudaMemcpyAsync(h, embeds, (size_t)n_tok * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(OPUS_ERR_CUDA, "llama_prefill: copy embeds");
+    note_launch();
+  }
+  const size_t layer_stride = (size_t)kv->num_blocks * Hkv * kv->block_size * hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  for (int l = 0; l < m->n_layers; ++l) {
+    const opus_llama_layer& L = m->layers[l];
+    bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
+    bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
+    OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(L.ln1_w), xn, n_tok, d, m->rms_eps,
+                          st));
+    OPUS_TRY(linear(xn, n_tok, L.wqkv, qkv_n, d, EPI_BF16, qkv, qkv_n, nullptr, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(rope_llama_kvappend(qkv, nullptr, 0, pos, slot, static_cast<const bf16*>(m->rope_cos),
+                                 static_cast<const bf16*>(m->rope_sin), kc, vc, n_tok, Hq, Hkv, hd, qkv_n,
+                                 kv->block_size, st));
+    OPUS_TRY(attn_varlen(qkv, qkv_n, qkv + Hq * hd, qkv_n, qkv + (Hq + Hkv) * hd, qkv_n, attn, Hq * hd, cu_seqlens,
+                         n_seqs, max_len, Hq, Hkv, hd, 1, scale, st));
+    OPUS_TRY(linear(attn, n_tok, L.wo, d, Hq * hd, EPI_RES_BF16, h, d, nullptr, h, d, nullptr, 0, st));
+    OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(L.ln2_w), xn, n_tok, d, m->rms_eps,
+                          st));
+    OPUS_TRY(linear(xn, n_tok, L.wgu, 2 * ffn, d, EPI_SWIGLU, act, ffn, nullptr, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(linear(act, n_tok, L.wdown, d, ffn, EPI_RES_BF16, h, d, nullptr, h, d, nullptr, 0, st));
+  }
+  // last token of every sequence -> final norm -> lm_head
+  bf16* last_h = static_cast<bf16*>(ws->last_h);
+  OPUS_TRY(embed_gather(last_rows, h, last_h, n_seqs, d, st));
+  OPUS_TRY(rmsnorm_bf16(last_h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(m->norm_w), last_h, n_seqs, d,
+                        m->rms_eps, st));
+  OPUS_TRY(linear(last_h, n_seqs, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr,
+                  0, st));
+  return OPUS_OK;
+}
+
+int llama_select(const opus_llama_model* m, const opus_llama_workspace* ws, const opus_decode_state* s, int n_seqs,
+                 cudaStream_t st) {
+  return argmax_eos(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->finished, s->eos_ids, s->n_eos,
+                    s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1, s->n_unfinished, st, s->step);
+}
+
+// ------------------------------------------------------------------------------------------------ Llama decode step
+int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
+                      const opus_decode_state* s, int B, cudaStream_t st) {
+  if (!m || !kv || !ws || !s) return fail(OPUS_ERR_ARG, "llama_decode_step: null argument");
+  if (B <= 0) return OPUS_OK;
+  const int d = m->dim, hd = m->head_dim, Hq = m->n_q_heads, Hkv = m->n_kv_heads, ffn = m->ffn_dim;
+  const int qkv_n = (Hq + 2 * Hkv) * hd;
+  bf16* h = static_cast<bf16*>(ws->h);
+  bf16* xn = static_cast<bf16*>(ws->xn);
+  bf16* qkv = static_cast<bf16*>(ws->qkv);
+  bf16* attn = static_cast<bf16*>(ws->attn);
+  bf16* act = static_cast<bf16*>(ws->act);
+  const size_t layer_stride = (size_t)kv->num_blocks * Hkv * kv->block_size * hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+
+  OPUS_TRY(decode_advance(s->ctx_len, s->pos, s->slot, s->block_table, s->max_blocks, kv->block_size, B, st, s->step));
+  OPUS_TRY(embed_gather(s->next_tok, static_cast<const bf16*>(m->embed), h, B, d, st));
+  OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(m->layers[0].ln1_w), xn, B, d,
+                        m->rms_eps, st));
+  for (int l = 0; l < m->n_layers; ++l) {
+    const opus_llama_layer& L = m->layers[l];
+    bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
+    bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
+    int sp = 1;
+    OPUS_TRY(linear_splitk(xn, B, L.wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st));
+    OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
+                                 static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n, kv->block_size,
+                                 st));
+    OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv,
+                               hd, kv->block_size, scale, st));
+    OPUS_TRY(linear_splitk(attn, B, L.wo, d, Hq * hd, ws->partial, ws->partial_bytes, &sp, st));
+    OPUS_TRY(rmsnorm_bf16(nullptr, ws->partial, sp, h, h, static_cast<const bf16*>(L.ln2_w), xn, B, d, m->rms_eps, st));
+    OPUS_TRY(linear(xn, B, L.wgu, 2 * ffn, d, EPI_SWIGLU, act, ffn, nullptr, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(linear_splitk(act, B, L.wdown, d, ffn, ws->partial, ws->partial_bytes, &sp, st));
+    const bf16* next_w = static_cast<const bf16*>(l + 1 < m->n_layers ? m->layers[l + 1].ln1_w : m->norm_w);
+    OPUS_TRY(rmsnorm_bf16(nullptr, ws->partial, sp, h, h, next_w, xn, B, d, m->rms_eps, st));
+  }
+  OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st));
+  OPUS_TRY(llama_select(m, ws, s, B, st));
+  return OPUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decode loop + graph
+namespace {
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+using GraphKey = std::tuple<const void*, const void*, const void*, const void*, int>;
+std::map<GraphKey, GraphEntry> g_graphs;
+std::mutex g_graph_mu;
+}  // namespace
+
+int release_graphs() {
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  for (auto& kv : g_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  g_graphs.clear();
+  return OPUS_OK;
+}
+
+int llama_decode_loop(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
+                      const opus_decode_state* s, int B, int n_steps, int check_every, int use_graph,
+                      cudaStream_t st) {
+  if (n_steps <= 0) return 0;
+  GraphEntry entry;
+  if (use_graph) {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    const GraphKey key{m->lm_head, ws->h, s->out_ids, kv->k, B};
+    auto it = g_graphs.find(key);
+    if (it == g_graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      const long long before = launch_count(false);
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        return fail(OPUS_ERR_CUDA, "decode_loop: begin capture");
+      const int rc = llama_decode_step(m, kv, ws, s, B, st);
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc != OPUS_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      if (ce != cudaSuccess || graph == nullptr) return fail(OPUS_ERR_CUDA, "decode_loop: end capture");
+      GraphEntry e;
+      e.launches = launch_count(false) - before;
+      note_launch(-e.launches);  // capture did not execute anything
+      if (cudaGraphInstantiate(&e.exec, graph, 0) != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return fail(OPUS_ERR_CUDA, "decode_loop: instantiate");
+      }
+      cudaGraphDestroy(graph);
+      it = g_graphs.emplace(key, e).first;
+    }
+    entry = it->second;
+  }
+  int done = 0;
+  for (int i = 0; i < n_steps; ++i) {
+    if (use_graph) {
+      if (cudaGraphLaunch(entry.exec, st) != cudaSuccess) return fail(OPUS_ERR_CUDA, "decode_loop: graph launch");
+      note_launch(entry.launches);
+    } else {
+      const int rc = llama_decode_step(m, kv, ws, s, B, st);
+      if (rc != OPUS_OK) return rc;
+    }
+    ++done;
+    if (check_every > 0 && (done % check_every) == 0 && i + 1 < n_steps) {
+      int left = 1;
+      if (cudaMemcpyAsync(&left, s->n_unfinished, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess)
+        return fail(OPUS_ERR_CUDA, "decode_loop: read n_unfinished");
+      if (left <= 0) break;
+    }
+  }
+  return done;
+}
+
+}  // namespace opus

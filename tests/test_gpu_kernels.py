@@ -1,0 +1,358 @@
+"""GPU parity tests of every kernel behind the C ABI against the oracle (oracle/ops_ref.py), same seeded inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ops_ref as R  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from opus_pllm_b200 import ops as o
+    o.device_check()
+    return o
+
+
+def _randn(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _close_bf16(got: torch.Tensor, want_f32: torch.Tensor, ulps: float = 1.0, atol: float = 1e-3):
+    """bf16 result vs fp32 oracle: within `ulps` bf16 ulps (2^-8 relative) + atol (accumulation-order noise)."""
+    got = got.float()
+    err = (got - want_f32).abs()
+    tol = atol + ulps * (2.0 ** -8) * want_f32.abs()
+    bad = err > tol
+    assert not bad.any(), (
+        f"{int(bad.sum())}/{bad.numel()} elements off; max err {float(err.max()):.4g} at "
+        f"{tuple(int(i) for i in torch.nonzero(bad)[0])}; got {float(got[bad][0]):.6g} want {float(want_f32[bad][0]):.6g}")
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [
+    # rows, N, K
+    (128, 256, 64),
+    (256, 512, 128),
+    (300, 1280, 1280),     # M tail, encoder out-proj shape
+    (1000, 3840, 1280),    # encoder qkv
+    (516, 5120, 1280),
+    (384, 1280, 5120),
+    (520, 6144, 4096),     # llama qkv (prefill)
+    (130, 128, 4096),      # small N tile
+]
+
+
+@pytest.mark.parametrize("rows,N,K", GEMM_SHAPES)
+def test_gemm_plain_and_bias(ops, rows, N, K):
+    from opus_pllm_b200._lib import EPI_BF16
+    x = _randn((rows, K), 1)
+    w = _randn((N, K), 2, scale=K ** -0.5)
+    bias = _randn((N,), 3, dtype=torch.float32)
+    want = R.linear_ref(x, w, bias)
+    got = ops.gemm(x, w, epilogue=EPI_BF16, bias=bias, transposed=False)
+    _close_bf16(got, want)
+    got_nb = ops.gemm(x, w, epilogue=EPI_BF16, transposed=False)
+    _close_bf16(got_nb, R.linear_ref(x, w))
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_block_n_variants(ops, bn):
+    from opus_pllm_b200._lib import EPI_BF16
+    x = _randn((400, 1024), 4)
+    w = _randn((768, 1024), 5, scale=1 / 32)
+    got = ops.gemm(x, w, epilogue=EPI_BF16, transposed=False, block_n=bn)
+    _close_bf16(got, R.linear_ref(x, w))
+
+
+def test_gemm_gelu(ops):
+    from opus_pllm_b200._lib import EPI_BF16_GELU
+    x = _randn((260, 1280), 6)
+    w = _randn((5120, 1280), 7, scale=1280 ** -0.5)
+    b = _randn((5120,), 8, dtype=torch.float32)
+    got = ops.gemm(x, w, epilogue=EPI_BF16_GELU, bias=b, transposed=False)
+    _close_bf16(got, R.gelu_erf(R.linear_ref(x, w, b)))
+
+
+def test_gemm_residual_f32_inplace(ops):
+    from opus_pllm_b200._lib import EPI_RES_F32
+    x = _randn((300, 5120), 9)
+    w = _randn((1280, 5120), 10, scale=5120 ** -0.5)
+    b = _randn((1280,), 11, dtype=torch.float32)
+    res = _randn((300, 1280), 12, dtype=torch.float32)
+    want = res + R.linear_ref(x, w, b)
+    out = res.clone()
+    ops.gemm(x, w, epilogue=EPI_RES_F32, bias=b, residual=out, out=out, transposed=False)
+    assert torch.allclose(out, want, rtol=1e-4, atol=2e-3), float((out - want).abs().max())
+
+
+def test_gemm_residual_bf16(ops):
+    from opus_pllm_b200._lib import EPI_RES_BF16
+    x = _randn((257, 4096), 13)
+    w = _randn((4096, 4096), 14, scale=1 / 64)
+    res = _randn((257, 4096), 15)
+    want = R.bf16r(res.float() + R.bf16r(R.linear_ref(x, w)))
+    got = ops.gemm(x, w, epilogue=EPI_RES_BF16, residual=res, transposed=False)
+    _close_bf16(got, want, ulps=2.0, atol=2e-2)
+
+
+def test_gemm_swiglu(ops):
+    from opus_pllm_b200._lib import EPI_SWIGLU
+    x = _randn((300, 1024), 16)
+    w = _randn((2 * 1536, 1024), 17, scale=1 / 32)
+    want = R.swiglu_interleaved_ref(R.linear_ref(x, w))
+    got = ops.gemm(x, w, epilogue=EPI_SWIGLU, transposed=False)
+    assert got.shape == (300, 1536)
+    _close_bf16(got, want, ulps=3.0, atol=2e-2)
+
+
+@pytest.mark.parametrize("rows", [1, 8, 33, 64, 100, 256])
+def test_gemm_transposed_weight_streaming(ops, rows):
+    from opus_pllm_b200._lib import EPI_BF16, EPI_BF16_GELU
+    x = _randn((rows, 2048), 18)
+    w = _randn((1000 + 24, 2048), 19, scale=2048 ** -0.5)  # 1024 features
+    b = _randn((1024,), 20, dtype=torch.float32)
+    got = ops.gemm(x, w, epilogue=EPI_BF16, bias=b, transposed=True)
+    _close_bf16(got, R.linear_ref(x, w, b))
+    got = ops.gemm(x, w, epilogue=EPI_BF16_GELU, bias=b, transposed=True)
+    _close_bf16(got, R.gelu_erf(R.linear_ref(x, w, b)))
+
+
+def test_gemm_transposed_swiglu_and_residual(ops):
+    from opus_pllm_b200._lib import EPI_SWIGLU, EPI_RES_BF16
+    x = _randn((64, 1024), 21)
+    w = _randn((2 * 1024, 1024), 22, scale=1 / 32)
+    got = ops.gemm(x, w, epilogue=EPI_SWIGLU, transposed=True)
+    _close_bf16(got, R.swiglu_interleaved_ref(R.linear_ref(x, w)), ulps=3.0, atol=2e-2)
+    res = _randn((64, 2048), 23)
+    got = ops.gemm(x, w, epilogue=EPI_RES_BF16, residual=res, transposed=True)
+    _close_bf16(got, R.bf16r(res.float() + R.bf16r(R.linear_ref(x, w))), ulps=2.0, atol=2e-2)
+
+
+@pytest.mark.parametrize("transposed,rows", [(True, 64), (False, 300)])
+def test_gemm_split_k_partials(ops, transposed, rows):
+    from opus_pllm_b200._lib import EPI_PARTIAL_F32
+    x = _randn((rows, 4096), 24)
+    w = _randn((512, 4096), 25, scale=1 / 64)
+    part = ops.gemm(x, w, epilogue=EPI_PARTIAL_F32, transposed=transposed, split_k=4)
+    assert part.shape == (4, rows, 512)
+    want = R.linear_ref(x, w)
+    assert torch.allclose(part.sum(0), want, rtol=1e-4, atol=2e-3), float((part.sum(0) - want).abs().max())
+    red = ops.splitk_reduce(part)
+    _close_bf16(red, want)
+
+
+def test_gemm_linearity_full_size(ops):
+    """size-independent property at a BASELINE-sized weight: f(x1 + x2) == f(x1) + f(x2) up to bf16 rounding."""
+    from opus_pllm_b200._lib import EPI_F32
+    w = _randn((28672, 4096), 26, scale=1 / 64)
+    x1 = _randn((64, 4096), 27)
+    x2 = _randn((64, 4096), 28)
+    xs = (x1.float() + x2.float()).to(torch.bfloat16)
+    f = lambda x: ops.gemm(x, w, epilogue=EPI_F32, transposed=True)  # noqa: E731
+    lhs = f(xs)
+    rhs = f(x1) + f(x2)
+    # xs is rounded to bf16, so allow the corresponding perturbation
+    assert torch.allclose(lhs, rhs, rtol=0, atol=0.15), float((lhs - rhs).abs().max())
+    want = R.linear_ref(x1, w)
+    assert torch.allclose(f(x1), want, rtol=1e-4, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------------ norms
+def test_layernorm(ops):
+    x = _randn((1000, 1280), 30, scale=3.0, dtype=torch.float32) + 0.5
+    g = _randn((1280,), 31, dtype=torch.float32)
+    b = _randn((1280,), 32, dtype=torch.float32)
+    _close_bf16(ops.layernorm(x, g, b, 1e-5), R.layernorm_ref(x, g, b, 1e-5), ulps=1.0, atol=1e-4)
+
+
+def test_rmsnorm_exact(ops):
+    x = _randn((777, 4096), 33, scale=2.0)
+    w = _randn((4096,), 34)
+    got = ops.rmsnorm(x, w, 1e-5)
+    want = R.rmsnorm_ref(x, w, 1e-5)
+    # same rounding points as HF -> allow only rare 1-ulp flips from reduction order
+    diff = (got.float() - want).abs() > (2.0 ** -7) * want.abs() + 1e-6
+    assert diff.float().mean() < 1e-3, float(diff.float().mean())
+
+
+def test_rmsnorm_residual_partials(ops):
+    part = _randn((3, 64, 4096), 35, dtype=torch.float32)
+    res = _randn((64, 4096), 36)
+    w = _randn((4096,), 37)
+    h_out = torch.empty_like(res)
+    y = ops.rmsnorm(None, w, 1e-5, partial=part, residual=res, h_out=h_out)
+    h_want = R.bf16r(res.float() + R.bf16r(part.sum(0)))
+    _close_bf16(h_out, h_want, ulps=1.0, atol=1e-6)
+    y_want = R.rmsnorm_ref(h_out, w, 1e-5)
+    diff = (y.float() - y_want).abs() > (2.0 ** -7) * y_want.abs() + 1e-6
+    assert diff.float().mean() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ embeddings / rope
+def test_esm_embed(ops):
+    table = _randn((33, 1280), 40, dtype=torch.float32)
+    tok = torch.randint(0, 33, (500,), dtype=torch.int32).cuda()
+    scale = torch.full((500,), 0.88, dtype=torch.float32).cuda()
+    scale[7] = 0.0
+    got = ops.esm_embed(tok, scale, table)
+    want = table[tok.long()] * scale[:, None]
+    assert torch.equal(got, want)
+
+
+def test_rope_esm(ops):
+    T, H, D = 300, 20, 64
+    qkv = _randn((T, 3 * H * D), 41)
+    pos = torch.arange(T, dtype=torch.int32).cuda()
+    pos[100:] -= 100  # two packed sequences
+    cos, sin = R.esm_rope_tables(512, D, "cuda")
+    want_q = R.rope_half_ref((qkv[:, : H * D].float() * 0.125).view(T, H, D).transpose(0, 1), cos[pos.long()],
+                             sin[pos.long()]).transpose(0, 1).reshape(T, H * D)
+    want_k = R.rope_half_ref(qkv[:, H * D: 2 * H * D].float().view(T, H, D).transpose(0, 1), cos[pos.long()],
+                             sin[pos.long()]).transpose(0, 1).reshape(T, H * D)
+    v_before = qkv[:, 2 * H * D:].clone()
+    ops.rope_esm_(qkv, pos, cos.contiguous(), sin.contiguous(), H, D, 0.125)
+    _close_bf16(qkv[:, : H * D], want_q, ulps=1.0, atol=1e-6)
+    _close_bf16(qkv[:, H * D: 2 * H * D], want_k, ulps=1.0, atol=1e-6)
+    assert torch.equal(qkv[:, 2 * H * D:], v_before)
+
+
+def test_rope_llama_kvappend_bit_exact(ops):
+    T, Hq, Hkv, D, BS = 200, 32, 8, 128, 16
+    qkv = _randn((T, (Hq + 2 * Hkv) * D), 42)
+    orig = qkv.clone()
+    pos = torch.cat([torch.arange(120), torch.arange(80)]).to(torch.int32).cuda()
+    nblk = 32
+    perm = torch.randperm(nblk)[: (T + BS - 1) // BS]
+    slot = (perm[torch.arange(T) // BS] * BS + torch.arange(T) % BS).to(torch.int32).cuda()
+    slot[5] = -1
+    cos, sin = R.llama_rope_tables(256, D, device="cuda")
+    kc = torch.zeros((nblk, Hkv, BS, D), dtype=torch.bfloat16, device="cuda")
+    vc = torch.zeros_like(kc)
+    ops.rope_llama_kvappend_(qkv, pos, slot, cos, sin, kc, vc, Hq, Hkv, D, BS)
+    q_want = R.llama_rope_bf16_ref(orig[:, : Hq * D].view(T, Hq, D), cos[pos.long()], sin[pos.long()])
+    k_want = R.llama_rope_bf16_ref(orig[:, Hq * D: (Hq + Hkv) * D].view(T, Hkv, D), cos[pos.long()], sin[pos.long()])
+    v_want = orig[:, (Hq + Hkv) * D:].view(T, Hkv, D)
+    assert torch.equal(qkv[:, : Hq * D].view(T, Hq, D), q_want)
+    assert torch.equal(qkv[:, Hq * D: (Hq + Hkv) * D].view(T, Hkv, D), k_want)
+    for t in (0, 5, 17, 199):
+        s = int(slot[t])
+        if s < 0:
+            continue
+        assert torch.equal(kc[s // BS, :, s % BS, :], k_want[t])
+        assert torch.equal(vc[s // BS, :, s % BS, :], v_want[t])
+    written = (kc.abs().sum((1, 3)) > 0).sum()
+    assert int(written) == T - 1
+
+
+def test_final_ln_meanpool(ops):
+    lens = [258, 3, 40, 130]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    x = _randn((sum(lens), 1280), 43, scale=2.0, dtype=torch.float32)
+    g = _randn((1280,), 44, dtype=torch.float32)
+    b = _randn((1280,), 45, dtype=torch.float32)
+    pooled, pooled_l2, hidden = ops.final_ln_meanpool(x, cu, g, b, 1e-5, want_hidden=True)
+    h_want = R.layernorm_ref(x, g, b)
+    assert torch.allclose(hidden, h_want, rtol=1e-4, atol=1e-4)
+    p_want = R.meanpool_ref(h_want, cu.tolist())
+    assert torch.allclose(pooled, p_want, rtol=1e-4, atol=1e-4), float((pooled - p_want).abs().max())
+    l2_want = torch.nn.functional.normalize(p_want, dim=-1)
+    _close_bf16(pooled_l2, l2_want, ulps=1.0, atol=1e-5)
+
+
+def test_splice_gather(ops):
+    embed = _randn((1000, 4096), 46)
+    soft = _randn((16, 4096), 47)
+    src = torch.tensor([5, 7, -1, -2, -16, 999, -(2 ** 31), 0], dtype=torch.int32).cuda()
+    out = ops.splice_gather(src, embed, soft)
+    assert torch.equal(out[0], embed[5]) and torch.equal(out[1], embed[7])
+    assert torch.equal(out[2], soft[0]) and torch.equal(out[3], soft[1]) and torch.equal(out[4], soft[15])
+    assert torch.equal(out[5], embed[999]) and bool((out[6] == 0).all()) and torch.equal(out[7], embed[0])
+
+
+def test_argmax_eos(ops):
+    B, V = 9, 128256
+    logits = _randn((B, V), 48)
+    logits[0, 77] = 100.0
+    logits[0, 5000] = 100.0      # tie -> lowest index
+    logits[1, V - 1] = 200.0     # last column
+    logits[2, 128001] = 300.0    # EOS
+    logits[3, 42] = 50.0
+    finished = torch.zeros(B, dtype=torch.int32).cuda()
+    finished[3] = 1
+    eos = torch.tensor([128001, 128009], dtype=torch.int32).cuda()
+    nxt = torch.zeros(B, dtype=torch.int32).cuda()
+    out_ids = torch.full((B, 4), -7, dtype=torch.int32).cuda()
+    n_unf = torch.tensor([B - 1], dtype=torch.int32).cuda()
+    want_tok, want_fin = R.greedy_select_ref(logits, finished, [128001, 128009], 128001)
+    ops.argmax_eos(logits, finished, eos, 128001, nxt, out_ids, 2, n_unf)
+    assert torch.equal(nxt.long(), want_tok) and int(nxt[0]) == 77 and int(nxt[3]) == 128001
+    assert torch.equal(out_ids[:, 2].long(), want_tok) and bool((out_ids[:, [0, 1, 3]] == -7).all())
+    assert torch.equal(finished.bool(), want_fin)
+    assert int(n_unf) == B - 2
+
+
+def test_lora_merge(ops):
+    W = _randn((512, 256), 49, scale=0.05)
+    A = _randn((16, 256), 50, scale=0.02)
+    Bm = _randn((512, 16), 51, scale=0.02)
+    want = R.bf16r(W.float() + 2.0 * (Bm.float() @ A.float()))
+    ops.lora_merge_(W, A, Bm, 2.0)
+    _close_bf16(W, want, ulps=1.0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("lens", [[258, 258], [1, 64, 65, 127, 128, 129, 300], [700]])
+def test_attn_encoder_varlen(ops, lens):
+    H, D = 20, 64
+    T = sum(lens)
+    qkv = _randn((T, 3 * H * D), 60)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    q, k, v = qkv[:, : H * D], qkv[:, H * D: 2 * H * D], qkv[:, 2 * H * D:]
+    got = ops.attn_varlen(q, k, v, cu, max(lens), H, H, D, False, 0.125)
+    for b in range(len(lens)):
+        s, e = int(cu[b]), int(cu[b + 1])
+        want = R.attention_ref(q[s:e].view(-1, H, D), k[s:e].view(-1, H, D), v[s:e].view(-1, H, D), False, 0.125)
+        _close_bf16(got[s:e].view(-1, H, D), want, ulps=2.0, atol=8e-3)
+
+
+@pytest.mark.parametrize("lens", [[512, 512], [1, 17, 128, 200, 333], [515]])
+def test_attn_prefill_causal_gqa(ops, lens):
+    Hq, Hkv, D = 32, 8, 128
+    T = sum(lens)
+    qkv = _randn((T, (Hq + 2 * Hkv) * D), 61)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    q, k, v = qkv[:, : Hq * D], qkv[:, Hq * D: (Hq + Hkv) * D], qkv[:, (Hq + Hkv) * D:]
+    sc = 1 / math.sqrt(D)
+    got = ops.attn_varlen(q, k, v, cu, max(lens), Hq, Hkv, D, True, sc)
+    for b in range(len(lens)):
+        s, e = int(cu[b]), int(cu[b + 1])
+        want = R.attention_ref(q[s:e].view(-1, Hq, D), k[s:e].view(-1, Hkv, D), v[s:e].view(-1, Hkv, D), True, sc)
+        _close_bf16(got[s:e].view(-1, Hq, D), want, ulps=2.0, atol=8e-3)
+
+
+@pytest.mark.parametrize("ctxs", [[1, 16, 17, 528, 100, 33], [544] * 8])
+def test_attn_decode_paged(ops, ctxs):
+    Hq, Hkv, D, BS = 32, 8, 128, 16
+    B = len(ctxs)
+    max_blocks = (max(ctxs) + BS - 1) // BS
+    nblk = B * max_blocks + 3
+    g = torch.Generator().manual_seed(62)
+    perm = torch.randperm(nblk, generator=g)
+    bt = perm[: B * max_blocks].view(B, max_blocks).to(torch.int32).cuda()
+    kc = _randn((nblk, Hkv, BS, D), 63)
+    vc = _randn((nblk, Hkv, BS, D), 64)
+    q = _randn((B, Hq * D), 65)
+    ctx = torch.tensor(ctxs, dtype=torch.int32).cuda()
+    sc = 1 / math.sqrt(D)
+    got = ops.attn_decode_paged(q, kc, vc, bt, ctx, Hq, Hkv, D, sc, BS)
+    for b in range(B):
+        n = ctxs[b]
+        blocks = bt[b, : (n + BS - 1) // BS].long()
+        kk = kc[blocks].permute(0, 2, 1, 3).reshape(-1, Hkv, D)[:n]
+        vv = vc[blocks].permute(0, 2, 1, 3).reshape(-1, Hkv, D)[:n]
+        want = R.attention_ref(q[b].view(1, Hq, D), kk, vv, False, sc)
+        _close_bf16(got[b].view(1, Hq, D), want, ulps=2.0, atol=8e-3)
