@@ -1,0 +1,243 @@
+"""Llama-3 prefill + greedy decode over a paged KV cache, driven through the C ABI.
+
+Stands in for what `OpusLlamaForCausalLM.generate` delegates to HF (`LlamaForCausalLM.forward` + `GenerationMixin`,
+multi_modality_v1/model/language_model/opus_llama.py:127-132): prefill over the spliced prompt embeddings, then a
+greedy loop that is one CUDA-graph replay per token with argmax / EOS bookkeeping on the device.
+Weights use HF state-dict names; LoRA adapters are merged at load (model/builder.py:107-109).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+
+BLOCK = 16  # tokens per KV-cache page
+
+
+class BlockAllocator:
+    """Free-list page allocator for the paged KV cache (pages are recycled between generate() calls)."""
+
+    def __init__(self, num_blocks: int):
+        self.num_blocks = num_blocks
+        self.free = list(range(num_blocks - 1, -1, -1))
+
+    def alloc(self, n: int) -> list[int]:
+        if n > len(self.free):
+            raise L.OpusError(f"KV cache exhausted: need {n} pages, {len(self.free)} free")
+        out = self.free[-n:][::-1]
+        del self.free[-n:]
+        return out
+
+    def release(self, blocks):
+        self.free.extend(reversed(list(blocks)))
+
+
+class B200Llama:
+    def __init__(self, weights: dict, n_layers: int, dim: int, n_q_heads: int, n_kv_heads: int, head_dim: int,
+                 ffn_dim: int, vocab: int, rms_eps: float = 1e-5, rope_theta: float = 500000.0, device="cuda",
+                 max_positions: int = 8192, lora: dict | None = None, lora_alpha: float = 32.0, lora_r: int = 16):
+        L.load()
+        self.device = torch.device(device)
+        self.n_layers, self.dim, self.Hq, self.Hkv, self.hd = n_layers, dim, n_q_heads, n_kv_heads, head_dim
+        self.ffn, self.vocab, self.rms_eps, self.rope_theta = ffn_dim, vocab, rms_eps, rope_theta
+        self.qkv_n = (n_q_heads + 2 * n_kv_heads) * head_dim
+        b16 = lambda t: t.detach().to(self.device, torch.bfloat16).contiguous()  # noqa: E731
+
+        def merged(key: str) -> torch.Tensor:
+            W = b16(weights[key + ".weight"])
+            if lora is not None and key + ".lora_A.weight" in lora:
+                if W.data_ptr() == weights[key + ".weight"].data_ptr():
+                    W = W.clone()
+                ops.lora_merge_(W, b16(lora[key + ".lora_A.weight"]), b16(lora[key + ".lora_B.weight"]),
+                                lora_alpha / lora_r)
+            return W
+
+        self.embed = b16(weights["model.embed_tokens.weight"])
+        self._keep = []
+        layers = (L.LlamaLayer * n_layers)()
+        for i in range(n_layers):
+            p = f"model.layers.{i}."
+            q, k, v = (merged(p + f"self_attn.{n}") for n in ("q_proj", "k_proj", "v_proj"))
+            g, u = merged(p + "mlp.gate_proj"), merged(p + "mlp.up_proj")
+            t = dict(ln1_w=b16(weights[p + "input_layernorm.weight"]),
+                     wqkv=torch.cat([q, k, v], 0).contiguous(),
+                     wo=merged(p + "self_attn.o_proj"),
+                     ln2_w=b16(weights[p + "post_attention_layernorm.weight"]),
+                     # rows interleaved (gate_0, up_0, gate_1, up_1, ...) so SwiGLU lives in the GEMM epilogue
+                     wgu=torch.stack([g, u], 1).reshape(2 * ffn_dim, dim).contiguous(),
+                     wdown=merged(p + "mlp.down_proj"))
+            del q, k, v, g, u
+            self._keep.append(t)
+            for kk, vv in t.items():
+                setattr(layers[i], kk, vv.data_ptr())
+        self._layers = layers
+        self.norm_w = b16(weights["model.norm.weight"])
+        self.lm_head = b16(weights["lm_head.weight"])
+        self._build_rope(max_positions)
+        self._cache = None
+        self._alloc = None
+        self._ws_rows = 0
+        self._ws_seqs = 0
+
+    # HF LlamaRotaryEmbedding (default rope): fp32 angles, cos/sin cast to the activation dtype (bf16)
+    def _build_rope(self, max_pos: int):
+        hd = self.hd
+        inv_freq = 1.0 / (self.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+        fr = torch.outer(torch.arange(max_pos, dtype=torch.float32), inv_freq)
+        emb = torch.cat([fr, fr], -1)
+        self.rope_cos = emb.cos().to(torch.bfloat16).to(self.device).contiguous()
+        self.rope_sin = emb.sin().to(torch.bfloat16).to(self.device).contiguous()
+        self.max_positions = max_pos
+        m = L.LlamaModel()
+        m.n_layers, m.dim, m.n_q_heads, m.n_kv_heads, m.head_dim = self.n_layers, self.dim, self.Hq, self.Hkv, self.hd
+        m.ffn_dim, m.vocab, m.rope_max_pos, m.rms_eps = self.ffn, self.vocab, max_pos, self.rms_eps
+        m.embed = self.embed.data_ptr()
+        m.layers = C.cast(self._layers, C.POINTER(L.LlamaLayer))
+        m.norm_w, m.lm_head = self.norm_w.data_ptr(), self.lm_head.data_ptr()
+        m.rope_cos, m.rope_sin = self.rope_cos.data_ptr(), self.rope_sin.data_ptr()
+        self._model = m
+        L.load().opus_release_graphs()
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def _ensure_cache(self, need_blocks: int):
+        if self._cache is None or self._cache_blocks < need_blocks:
+            L.load().opus_release_graphs()
+            self._cache = None
+            nb = max(need_blocks, 64)
+            shape = (self.n_layers, nb, self.Hkv, BLOCK, self.hd)
+            self._k = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
+            self._v = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
+            kv = L.KvCache()
+            kv.k, kv.v, kv.num_blocks, kv.block_size = self._k.data_ptr(), self._v.data_ptr(), nb, BLOCK
+            self._cache, self._cache_blocks = kv, nb
+            self._alloc = BlockAllocator(nb)
+        return self._cache
+
+    def _ensure_ws(self, rows: int, n_seqs: int):
+        if rows > self._ws_rows or n_seqs > self._ws_seqs:
+            L.load().opus_release_graphs()
+            rows = max(rows, self._ws_rows, 256)
+            n_seqs = max(n_seqs, self._ws_seqs, 8)
+            dev, bf = self.device, torch.bfloat16
+            part_bytes = 16 * n_seqs * max(self.qkv_n, self.dim) * 4
+            b = dict(h=torch.empty((rows, self.dim), dtype=bf, device=dev),
+                     xn=torch.empty((rows, self.dim), dtype=bf, device=dev),
+                     qkv=torch.empty((rows, self.qkv_n), dtype=bf, device=dev),
+                     attn=torch.empty((rows, self.Hq * self.hd), dtype=bf, device=dev),
+                     act=torch.empty((rows, self.ffn), dtype=bf, device=dev),
+                     partial=torch.empty((part_bytes // 4,), dtype=torch.float32, device=dev),
+                     last_h=torch.empty((n_seqs, self.dim), dtype=bf, device=dev),
+                     logits=torch.empty((n_seqs, self.vocab), dtype=bf, device=dev))
+            ws = L.LlamaWorkspace()
+            for k, v in b.items():
+                setattr(ws, k, v.data_ptr())
+            ws.partial_bytes = part_bytes
+            self._ws, self._ws_bufs, self._ws_rows, self._ws_seqs = ws, b, rows, n_seqs
+        return self._ws
+
+    def _upload(self, arr: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def prefill(self, embeds: torch.Tensor, cu_seqlens: np.ndarray, max_new_tokens: int):
+        """embeds bf16 [n_tok, dim] packed; returns a dict holding the decode state (logits of the last prompt token of
+        every sequence are in state['logits'])."""
+        cu = np.asarray(cu_seqlens, dtype=np.int32)
+        n_seqs, n_tok = len(cu) - 1, int(cu[-1])
+        lens = np.diff(cu)
+        max_len = int(lens.max())
+        total = max_len + max_new_tokens
+        if total > self.max_positions:
+            self._build_rope(1 << (total - 1).bit_length())
+        max_blocks = (total + BLOCK - 1) // BLOCK
+        kv = self._ensure_cache(n_seqs * max_blocks)
+        ws = self._ensure_ws(max(n_tok, n_seqs), n_seqs)
+        blocks = self._alloc.alloc(n_seqs * max_blocks)
+        bt = np.asarray(blocks, dtype=np.int32).reshape(n_seqs, max_blocks)
+        seq_of = np.repeat(np.arange(n_seqs, dtype=np.int32), lens)
+        pos = (np.arange(n_tok, dtype=np.int32) - cu[:-1][seq_of]).astype(np.int32)
+        slot = (bt[seq_of, pos // BLOCK] * BLOCK + pos % BLOCK).astype(np.int32)
+        last_rows = (cu[1:] - 1).astype(np.int32)
+        d = dict(pos=self._upload(pos), slot=self._upload(slot), cu=self._upload(cu), last=self._upload(last_rows),
+                 bt=self._upload(bt), ctx=self._upload(lens.astype(np.int32)))
+        embeds = embeds.contiguous()
+        assert embeds.dtype == torch.bfloat16 and embeds.shape == (n_tok, self.dim)
+        rc = L.load().opus_llama_prefill(C.byref(self._model), C.byref(kv), C.byref(ws), embeds.data_ptr(),
+                                         d["pos"].data_ptr(), d["slot"].data_ptr(), d["cu"].data_ptr(),
+                                         d["last"].data_ptr(), n_seqs, n_tok, max_len,
+                                         torch.cuda.current_stream().cuda_stream)
+        L.check(rc, "opus_llama_prefill")
+        d.update(n_seqs=n_seqs, max_blocks=max_blocks, blocks=blocks, logits=self._ws_bufs["logits"][:n_seqs],
+                 embeds=embeds)
+        return d
+
+    def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int):
+        n, dev = st["n_seqs"], self.device
+        key = (n, max_new_tokens, tuple(eos_ids), pad_id)
+        cached = getattr(self, "_state_cache", None)
+        if cached is None or cached[0] != key:
+            i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
+            bufs = dict(next_tok=i32(n), ctx_len=i32(n), pos=i32(n), slot=i32(n), block_table=i32(n, st["max_blocks"]),
+                        finished=i32(n), n_unfinished=i32(1), step=i32(1), out_ids=i32(n, max_new_tokens),
+                        eos=torch.tensor(list(eos_ids) or [-1], dtype=torch.int32, device=dev))
+            self._state_cache = (key, bufs)
+            L.load().opus_release_graphs()
+        bufs = self._state_cache[1]
+        if bufs["block_table"].shape != st["bt"].shape:
+            bufs["block_table"] = torch.zeros_like(st["bt"])
+            L.load().opus_release_graphs()
+        bufs["block_table"].copy_(st["bt"])
+        bufs["ctx_len"].copy_(st["ctx"])
+        bufs["finished"].zero_()
+        bufs["step"].zero_()
+        bufs["n_unfinished"].fill_(n)
+        bufs["out_ids"].fill_(pad_id)
+        s = L.DecodeState()
+        for k in ("next_tok", "ctx_len", "pos", "slot", "block_table", "finished", "n_unfinished", "step", "out_ids"):
+            setattr(s, k, bufs[k].data_ptr())
+        s.max_blocks, s.out_ld = st["max_blocks"], max_new_tokens
+        s.eos_ids, s.n_eos, s.pad_id = bufs["eos"].data_ptr(), len(eos_ids), pad_id
+        return s, bufs
+
+    @torch.no_grad()
+    def generate_packed(self, embeds: torch.Tensor, cu_seqlens, max_new_tokens: int, eos_ids=(), pad_id: int = 0,
+                        use_graph: bool = True, check_every: int = 16, return_prefill_logits: bool = False):
+        """Greedy generation from packed prompt embeddings. Returns int64 [n_seqs, n_new] (new tokens only; finished
+        rows padded with pad_id; trimmed at the step where every row had finished, like HF)."""
+        lib = L.load()
+        st = self.prefill(embeds, cu_seqlens, max_new_tokens)
+        try:
+            s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id)
+            stream = torch.cuda.current_stream().cuda_stream
+            prefill_logits = st["logits"].clone() if return_prefill_logits else None
+            L.check(lib.opus_llama_select(C.byref(self._model), C.byref(self._ws), C.byref(s), st["n_seqs"], stream),
+                    "opus_llama_select")
+            if max_new_tokens > 1:
+                rc = lib.opus_llama_decode_loop(C.byref(self._model), C.byref(self._cache), C.byref(self._ws),
+                                                C.byref(s), st["n_seqs"], max_new_tokens - 1,
+                                                check_every if len(eos_ids) else 0, int(use_graph), stream)
+                L.check(rc, "opus_llama_decode_loop")
+            out = bufs["out_ids"].to(torch.int64)
+        finally:
+            self._alloc.release(st["blocks"])
+        if len(eos_ids):
+            out = _trim_like_hf(out, eos_ids)
+        return (out, prefill_logits) if return_prefill_logits else out
+
+
+def _trim_like_hf(out: torch.Tensor, eos_ids) -> torch.Tensor:
+    """HF stops at the first step where every row has emitted an EOS; later columns do not exist in its output."""
+    is_eos = torch.zeros_like(out, dtype=torch.bool)
+    for e in eos_ids:
+        is_eos |= out == e
+    has = is_eos.any(1)
+    if not bool(has.all()):
+        return out
+    first = is_eos.float().argmax(1)
+    return out[:, : int(first.max()) + 1]

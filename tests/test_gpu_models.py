@@ -1,0 +1,288 @@
+"""GPU parity of the composite forwards (encoder, projectors, splice, prefill logits, greedy decode) vs the oracle.
+
+Tolerances (north star: "within a stated bf16 tolerance, max-abs and cosine"):
+  * encoder pooled embedding  : cosine >= 0.9995, max-abs <= 3e-2 (values are post-LayerNorm, O(1))
+  * projector soft tokens     : cosine >= 0.999
+  * prefill last-token logits : cosine >= 0.999 vs the fp32 oracle, max-abs <= 6 % of the logit std
+  * greedy decode             : token-identical over 32 new tokens on >= 99 % of prompts (peaked-logit weights)
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import esm2_ref, llama_ref, mm_ref  # noqa: E402
+from opus_pllm_b200 import synth  # noqa: E402
+
+
+def _cos(a, b):
+    a, b = a.float().flatten(), b.float().flatten()
+    return float(torch.dot(a, b) / (a.norm() * b.norm()))
+
+
+def _dev(d, dtype=None):
+    return {k: (v.cuda() if dtype is None else v.cuda().to(dtype)) for k, v in d.items()}
+
+
+# ------------------------------------------------------------------------------------------------ encoder
+@pytest.mark.parametrize("n_layers,dim,heads,ffn,lens", [
+    (2, 128, 2, 512, [5, 1, 40, 130, 258]),
+    (3, 1280, 20, 5120, [256, 17, 300]),
+])
+def test_encoder_vs_oracle(n_layers, dim, heads, ffn, lens):
+    from opus_pllm_b200.encoder import B200ProteinEncoder
+    w = synth.esm2_weights(n_layers, dim, ffn)
+    seqs = [s[:n] for s, n in zip(synth.proteins(len(lens), max(lens)), lens)]
+    seqs[1] = seqs[1][:-1] + "X" if len(seqs[1]) > 0 else seqs[1]  # a non-standard residue goes through the LUT
+    enc = B200ProteinEncoder(w, n_layers, dim, heads, ffn)
+    pooled, pooled_l2, hidden, pk = enc.encode(seqs, want_hidden=True)
+    wd = _dev(w)
+    want = esm2_ref.get_protein_seq_embeddings(wd, seqs, n_layers, heads)            # fp32 truth
+    want_ac = esm2_ref.get_protein_seq_embeddings(wd, seqs, n_layers, heads, torch.bfloat16)  # reference-style autocast
+    assert torch.equal(torch.from_numpy(pk.tokens).long(),
+                       torch.cat([esm2_ref.tokenize([s])[0] for s in seqs]))
+    # the oracle's own bf16-autocast run bounds what "bf16 tolerance" means for this depth
+    noise = float((want_ac - want).abs().max())
+    err = float((pooled - want).abs().max())
+    assert _cos(pooled, want) >= 0.9995, _cos(pooled, want)
+    assert err <= max(3e-2, 3 * noise), (err, noise)
+    for b in range(len(seqs)):
+        assert _cos(pooled[b], want[b]) >= 0.9995
+    l2 = torch.nn.functional.normalize(want, dim=-1)
+    assert _cos(pooled_l2, l2) >= 0.9995
+    assert enc.get_protein_seq_embeddings(seqs).dtype == torch.float32
+
+
+def test_encoder_padded_equals_varlen():
+    """key-padding mask semantics: a sequence's embedding does not depend on what it is batched with."""
+    from opus_pllm_b200.encoder import B200ProteinEncoder
+    w = synth.esm2_weights(2, 128, 512)
+    enc = B200ProteinEncoder(w, 2, 128, 2, 512)
+    seqs = synth.proteins(6, 10, 200, seed=7)
+    together = enc.get_protein_seq_embeddings(seqs)
+    alone = torch.cat([enc.get_protein_seq_embeddings([s]) for s in seqs])
+    assert torch.allclose(together, alone, rtol=0, atol=2e-3), float((together - alone).abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ projectors
+def test_projectors_vs_oracle():
+    from opus_pllm_b200.projector import B200ProteinProjector, B200SwitchProjector, FusedProjectors
+    from opus_pllm_b200 import ops
+    H = 256
+    pw = synth.projector_weights(1280, 5120, 8 * H)
+    x = synth.weight((12, 1280), "pooled", 1.0).cuda()
+    pp = B200ProteinProjector(pw["protein_projection.linear.weight"], pw["protein_projection.linear.bias"])
+    sw = B200SwitchProjector(5120, 8 * H).load_state_dict(pw)
+    pwd = _dev(pw)
+    c_want = mm_ref.protein_forward(x, pwd["protein_projection.linear.weight"], pwd["protein_projection.linear.bias"])
+    c_got = pp.protein_forward(x)
+    assert c_got.shape == (12, 5120) and _cos(c_got, c_want) >= 0.9995
+    s_want = mm_ref.switch_projector(c_want, pwd, H)
+    s_got = sw(c_got).reshape(12, 8, H)
+    assert _cos(s_got, s_want) >= 0.999, _cos(s_got, s_want)
+    fused = FusedProjectors(pp, sw)(ops.l2norm(x)).reshape(12, 8, H)
+    assert torch.equal(fused, s_got)
+    # 'linear' projector type and identity CSTP projector
+    lin = B200SwitchProjector(1280, 8 * H, "linear").load_state_dict(
+        {"weight": pw["0.weight"][:, :1280].contiguous(), "bias": pw["0.bias"]})
+    l_want = torch.nn.functional.linear(x, pwd["0.weight"][:, :1280], pwd["0.bias"])
+    assert _cos(lin(x.to(torch.bfloat16)), l_want) >= 0.999
+
+
+# ------------------------------------------------------------------------------------------------ splice
+def test_splice_vs_oracle_and_left_padding():
+    from opus_pllm_b200.model import build_from_state_dicts
+    cfg = dict(n_layers=1, dim=256, n_q_heads=2, n_kv_heads=1, head_dim=128, ffn_dim=512, vocab=512)
+    lw = synth.llama_weights(cfg["n_layers"], cfg["dim"], 2, 1, 128, 512, 512)
+    esm_cfg = dict(n_layers=1, dim=128, n_heads=2, ffn_dim=256)
+    ew = synth.esm2_weights(1, 128, 256)
+    sw = synth.projector_weights(128, 128, 8 * 256)
+    model = build_from_state_dicts(lw, cfg, ew, esm_cfg, None,
+                                   {k: v for k, v in sw.items() if k[0] in "02"}, eos_token_id=[3])
+    ids = torch.tensor([[7, 7, 5, -200, 9, 10, 11],
+                        [7, 7, 7, 7, 20, 21, 22],      # no sentinel: consumes a protein slot
+                        [7, 30, -200, 31, -200, 32, 33]]).cuda()
+    mask = ids != 7
+    seqs = synth.proteins(4, 12, 30, seed=3)
+    soft = model._soft_tokens(seqs, None)
+    out = model.prepare_inputs_labels_for_multimodal(ids, None, mask, None, None, seqs, inference_mode=True)
+    assert out[0] is None and out[1] is None and out[5] is None
+    want_e, want_m, want_p, lens = mm_ref.splice(ids, mask, soft.float(), model.llama.embed.float(), True)
+    assert lens == [12, 3, 20]
+    assert torch.equal(out[4].float(), want_e) and torch.equal(out[2].bool(), want_m)
+    # right padding + position ids + labels (training-side contract, opus_arch.py:259-269)
+    labels = torch.where(ids == -200, torch.full_like(ids, -100), ids)
+    pos_in = torch.arange(ids.shape[1]).cuda()
+    out_r = model.prepare_inputs_labels_for_multimodal(ids, pos_in, mask, None, labels, seqs, inference_mode=False)
+    want_e, want_m, want_p, _ = mm_ref.splice(ids, mask, soft.float(), model.llama.embed.float(), False)
+    assert torch.equal(out_r[4].float(), want_e) and torch.equal(out_r[1], want_p)
+    assert out_r[5].shape == want_m.shape and out_r[5][0].tolist()[:12] == [5] + [-100] * 8 + [9, 10, 11]
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, seqs, inputs_embeds=out[4])
+    with pytest.raises(NotImplementedError):
+        model.encode_seq2embedding([1, 2, 3])
+
+
+# ------------------------------------------------------------------------------------------------ llama
+SMALL = dict(n_layers=2, dim=512, n_q_heads=4, n_kv_heads=2, head_dim=128, ffn_dim=1024, vocab=2048)
+
+
+def _oracle_cfg(c):
+    return llama_ref.LlamaCfg(n_layers=c["n_layers"], dim=c["dim"], n_q_heads=c["n_q_heads"],
+                              n_kv_heads=c["n_kv_heads"], head_dim=c["head_dim"], ffn_dim=c["ffn_dim"],
+                              vocab=c["vocab"])
+
+
+def _padded(embeds_packed, cu, dim):
+    lens = np.diff(cu)
+    B, Lm = len(lens), int(lens.max())
+    e = torch.zeros(B, Lm, dim, dtype=embeds_packed.dtype, device=embeds_packed.device)
+    m = torch.zeros(B, Lm, dtype=torch.bool, device=embeds_packed.device)
+    for b in range(B):
+        e[b, Lm - lens[b]:] = embeds_packed[cu[b]: cu[b + 1]]
+        m[b, Lm - lens[b]:] = True
+    return e, m
+
+
+@pytest.mark.parametrize("cfg,lens", [(SMALL, [40, 7, 129, 64]),
+                                      (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
+                                            ffn_dim=14336, vocab=8192), [300, 33])])
+def test_prefill_logits_vs_oracle(cfg, lens):
+    from opus_pllm_b200.llama import B200Llama
+    w = synth.llama_weights(seed=1, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    emb = synth.weight((int(cu[-1]), cfg["dim"]), "prompt_embeds", 0.02).cuda().to(torch.bfloat16)
+    st = model.prefill(emb, cu, 4)
+    got = st["logits"].float().clone()
+    model._alloc.release(st["blocks"])
+    e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+    pos = (m_pad.long().cumsum(-1) - 1).masked_fill(~m_pad, 1)
+    ocfg = _oracle_cfg(cfg)
+    want32, _ = llama_ref.llama_forward(_dev(w, torch.float32), ocfg, e_pad.float(), m_pad, pos)
+    want16, _ = llama_ref.llama_forward(_dev(w, torch.bfloat16), ocfg, e_pad, m_pad, pos)
+    sigma = float(want32.std())
+    noise = float((want16 - want32).abs().max())          # the reference bf16 path's own distance from fp32
+    err = float((got - want32).abs().max())
+    assert _cos(got, want32) >= 0.999, _cos(got, want32)
+    assert err <= max(0.06 * sigma, 2.0 * noise), (err, sigma, noise)
+    for b in range(len(lens)):
+        assert _cos(got[b], want32[b]) >= 0.999
+
+
+def test_greedy_decode_token_parity_peaked():
+    """>= 99 % of prompts token-identical over 32 new tokens (north star), peaked-logit synthetic weights."""
+    from opus_pllm_b200.llama import B200Llama
+    cfg = SMALL
+    w = synth.llama_weights(seed=2, peaked=True, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [30 + (i * 7) % 50 for i in range(32)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(5))
+    emb = w["model.embed_tokens.weight"][tok].cuda().to(torch.bfloat16)
+    got = model.generate_packed(emb, cu, 32)
+    got_nograph = model.generate_packed(emb, cu, 32, use_graph=False)
+    assert torch.equal(got, got_nograph)
+    e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+    want = llama_ref.greedy_generate(_dev(w, torch.bfloat16), _oracle_cfg(cfg), e_pad, m_pad, 32)
+    same = (got.cpu() == want.cpu()).all(1).float().mean()
+    assert got.shape == (32, 32) and float(same) >= 0.99, float(same)
+    assert len(torch.unique(got)) > 32  # not a degenerate constant stream
+
+
+def test_greedy_decode_default_init_margin_aware():
+    """HF-init statistics: random logits have tiny top-1 margins, so token identity is fragile by construction
+    (SURVEY.md §7); every disagreement must be explained by a near-tie in the oracle's own logits."""
+    from opus_pllm_b200.llama import B200Llama
+    cfg = SMALL
+    w = synth.llama_weights(seed=3, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [20 + i for i in range(16)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    emb = synth.weight((int(cu[-1]), cfg["dim"]), "e", 0.02).cuda().to(torch.bfloat16)
+    got, logits = model.generate_packed(emb, cu, 8, return_prefill_logits=True)
+    e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+    want, wl = llama_ref.greedy_generate(_dev(w, torch.float32), _oracle_cfg(cfg), e_pad.float(), m_pad, 8,
+                                         return_logits=True)
+    first = got[:, 0].cpu() == want[:, 0].cpu()
+    top2 = wl[:, 0].topk(2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1]).cpu()
+    assert bool((first | (margin < 0.05 * float(wl[:, 0].std()))).all())
+    assert _cos(logits, wl[:, 0]) >= 0.999
+
+
+def test_eos_and_pad_semantics():
+    from opus_pllm_b200.llama import B200Llama
+    cfg = SMALL
+    w = synth.llama_weights(seed=2, peaked=True, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [12, 20, 9, 15]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(6))
+    emb = w["model.embed_tokens.weight"][tok].cuda().to(torch.bfloat16)
+    free = model.generate_packed(emb, cu, 12)
+    eos = [int(free[0, 3]), int(free[1, 6])]            # make rows 0 and 1 stop early
+    got = model.generate_packed(emb, cu, 12, eos_ids=eos, pad_id=eos[0], check_every=2)
+    e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+    want = llama_ref.greedy_generate(_dev(w, torch.bfloat16), _oracle_cfg(cfg), e_pad, m_pad, 12, eos_ids=eos,
+                                     pad_id=eos[0])
+    assert got.shape == want.shape and torch.equal(got.cpu(), want.cpu())
+
+
+def test_lora_merge_at_load():
+    from opus_pllm_b200.llama import B200Llama
+    cfg = SMALL
+    kw = {k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()}
+    w = synth.llama_weights(seed=4, device="cuda", **kw)
+    lora = synth.lora_adapters(w, cfg["n_layers"], r=16, device="cuda")
+    model = B200Llama(w, lora=lora, lora_alpha=32.0, lora_r=16, **cfg)
+    wm = dict(w)
+    for key in [k[: -len(".lora_A.weight")] for k in lora if k.endswith(".lora_A.weight")]:
+        wm[key + ".weight"] = llama_ref.lora_merge_ref(w[key + ".weight"], lora[key + ".lora_A.weight"],
+                                                       lora[key + ".lora_B.weight"], 32.0, 16)
+    lens = [33, 21]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    emb = synth.weight((int(cu[-1]), cfg["dim"]), "e2", 0.02).cuda().to(torch.bfloat16)
+    st = model.prefill(emb, cu, 2)
+    got = st["logits"].float().clone()
+    model._alloc.release(st["blocks"])
+    e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+    pos = (m_pad.long().cumsum(-1) - 1).masked_fill(~m_pad, 1)
+    want, _ = llama_ref.llama_forward(_dev(wm, torch.float32), _oracle_cfg(cfg), e_pad.float(), m_pad, pos)
+    base, _ = llama_ref.llama_forward(_dev(w, torch.float32), _oracle_cfg(cfg), e_pad.float(), m_pad, pos)
+    assert _cos(got, want) >= 0.999 and _cos(got, want) > _cos(got, base)
+
+
+# ------------------------------------------------------------------------------------------------ whole path
+def test_generate_end_to_end_vs_oracle_pipeline():
+    """proteins + prompts with -200 sentinels -> tokens, through the reference-shaped generate() call."""
+    from opus_pllm_b200.model import build_from_state_dicts
+    cfg = SMALL
+    kw = {k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()}
+    lw = synth.llama_weights(seed=2, peaked=True, device="cuda", **kw)
+    esm_cfg = dict(n_layers=2, dim=128, n_heads=2, ffn_dim=512)
+    ew = synth.esm2_weights(2, 128, 512)
+    pw = synth.projector_weights(128, 256, 8 * cfg["dim"])
+    model = build_from_state_dicts(lw, cfg, ew, esm_cfg, pw, pw)
+    B = 8
+    seqs = synth.proteins(B, 20, 90, seed=11)
+    prompts = synth.prompt_ids(B, 48, vocab=cfg["vocab"], ragged=5, sentinel_at=10)
+    L = max(p.numel() for p in prompts)
+    pad = 1
+    ids = torch.stack([torch.cat([torch.full((L - p.numel(),), pad), p]) for p in prompts]).cuda()
+    mask = ids != pad
+    got = model.generate(ids, seqs, attention_mask=mask, pad_token_id=pad, do_sample=False, temperature=0,
+                         top_p=0.7, num_beams=1, max_new_tokens=32, use_cache=True)
+    assert got.dtype == torch.int64 and got.shape == (B, 32)
+    # oracle pipeline on the same weights
+    pooled = esm2_ref.get_protein_seq_embeddings(_dev(ew), seqs, 2, 2)
+    pwd = _dev(pw)
+    c = mm_ref.protein_forward(pooled, pwd["protein_projection.linear.weight"], pwd["protein_projection.linear.bias"])
+    soft = mm_ref.switch_projector(c, pwd, cfg["dim"])
+    emb, m, _, _ = mm_ref.splice(ids, mask, soft.to(torch.bfloat16), lw["model.embed_tokens.weight"].cuda().bfloat16())
+    want = llama_ref.greedy_generate(_dev(lw, torch.bfloat16), _oracle_cfg(cfg), emb, m, 32)
+    same = (got.cpu() == want.cpu()).all(1).float().mean()
+    assert float(same) >= 0.99, float(same)
