@@ -248,10 +248,16 @@ int llama_decode_loop(const opus_llama_model* m, const opus_kv_cache* kv, const 
     if (it == g_graphs.end()) {
       cudaGraph_t graph = nullptr;
       const long long before = launch_count(false);
-      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+      // The caller's stream may be the legacy default stream, which cannot be captured: record the step on a private
+      // non-blocking stream (nothing executes during capture) and replay the instantiated graph on the caller's stream.
+      static cudaStream_t cap_stream = nullptr;
+      if (cap_stream == nullptr &&
+          cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(OPUS_ERR_CUDA, "decode_loop: create capture stream");
+      if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
         return fail(OPUS_ERR_CUDA, "decode_loop: begin capture");
-      const int rc = llama_decode_step(m, kv, ws, s, B, st);
-      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      const int rc = llama_decode_step(m, kv, ws, s, B, cap_stream);
+      const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
       if (rc != OPUS_OK) {
         if (graph) cudaGraphDestroy(graph);
         return rc;

@@ -141,7 +141,9 @@ class B200ProteinEncoder:
         pk = packed if packed is not None else PackedTokens(seqs)
         if pk.max_len > self.max_positions:
             self._build_rope(1 << (pk.max_len - 1).bit_length())
-        tok, pos, scale, cu = (self._upload(a) for a in (pk.tokens, pk.pos, pk.scale, pk.cu))
+        if getattr(pk, "device_arrays", None) is None:
+            pk.device_arrays = tuple(self._upload(a) for a in (pk.tokens, pk.pos, pk.scale, pk.cu))
+        tok, pos, scale, cu = pk.device_arrays
         ws = self._workspace(pk.n_tok)
         pooled = torch.empty((pk.n_seqs, self.dim), dtype=torch.float32, device=self.device)
         pooled_l2 = torch.empty((pk.n_seqs, self.dim), dtype=torch.bfloat16, device=self.device)
@@ -152,7 +154,9 @@ class B200ProteinEncoder:
                                             pooled.data_ptr(), pooled_l2.data_ptr(), _ptr(hidden),
                                             torch.cuda.current_stream().cuda_stream)
         L.check(rc, "opus_esm2_forward")
-        self._last_inputs = (tok, pos, scale, cu)  # keep alive until the stream has consumed them
+        if packed is None:
+            self._last_inputs = pk.device_arrays  # keep alive until the stream has consumed them
+            pk.device_arrays = None
         return pooled, pooled_l2, hidden, pk
 
     def get_protein_seq_embeddings(self, data: list[str]) -> torch.Tensor:

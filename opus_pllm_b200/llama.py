@@ -144,10 +144,9 @@ class B200Llama:
         return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().to(self.device, non_blocking=True)
 
     # ------------------------------------------------------------------------------------------ forward
-    @torch.no_grad()
-    def prefill(self, embeds: torch.Tensor, cu_seqlens: np.ndarray, max_new_tokens: int):
-        """embeds bf16 [n_tok, dim] packed; returns a dict holding the decode state (logits of the last prompt token of
-        every sequence are in state['logits'])."""
+    def make_plan(self, cu_seqlens, max_new_tokens: int) -> dict:
+        """Host-side planning for one batch: KV pages, slot mapping and positions, uploaded once (pinned -> device).
+        The plan owns its KV pages until `release_plan`."""
         cu = np.asarray(cu_seqlens, dtype=np.int32)
         n_seqs, n_tok = len(cu) - 1, int(cu[-1])
         lens = np.diff(cu)
@@ -156,25 +155,38 @@ class B200Llama:
         if total > self.max_positions:
             self._build_rope(1 << (total - 1).bit_length())
         max_blocks = (total + BLOCK - 1) // BLOCK
-        kv = self._ensure_cache(n_seqs * max_blocks)
-        ws = self._ensure_ws(max(n_tok, n_seqs), n_seqs)
+        self._ensure_cache(n_seqs * max_blocks)
+        self._ensure_ws(max(n_tok, n_seqs), n_seqs)
         blocks = self._alloc.alloc(n_seqs * max_blocks)
         bt = np.asarray(blocks, dtype=np.int32).reshape(n_seqs, max_blocks)
         seq_of = np.repeat(np.arange(n_seqs, dtype=np.int32), lens)
         pos = (np.arange(n_tok, dtype=np.int32) - cu[:-1][seq_of]).astype(np.int32)
         slot = (bt[seq_of, pos // BLOCK] * BLOCK + pos % BLOCK).astype(np.int32)
         last_rows = (cu[1:] - 1).astype(np.int32)
-        d = dict(pos=self._upload(pos), slot=self._upload(slot), cu=self._upload(cu), last=self._upload(last_rows),
-                 bt=self._upload(bt), ctx=self._upload(lens.astype(np.int32)))
+        return dict(pos=self._upload(pos), slot=self._upload(slot), cu=self._upload(cu), last=self._upload(last_rows),
+                    bt=self._upload(bt), ctx=self._upload(lens.astype(np.int32)), n_seqs=n_seqs, n_tok=n_tok,
+                    max_len=max_len, max_blocks=max_blocks, blocks=blocks, max_new=max_new_tokens)
+
+    def release_plan(self, plan: dict):
+        if plan.get("blocks") is not None:
+            self._alloc.release(plan["blocks"])
+            plan["blocks"] = None
+
+    @torch.no_grad()
+    def prefill(self, embeds: torch.Tensor, cu_seqlens=None, max_new_tokens: int = 1, plan: dict | None = None):
+        """embeds bf16 [n_tok, dim] packed. Runs the prompt through all layers, fills the paged cache, leaves the logits
+        of the last prompt token of every sequence in plan['logits']."""
+        d = plan if plan is not None else self.make_plan(cu_seqlens, max_new_tokens)
+        n_seqs, n_tok = d["n_seqs"], d["n_tok"]
         embeds = embeds.contiguous()
         assert embeds.dtype == torch.bfloat16 and embeds.shape == (n_tok, self.dim)
-        rc = L.load().opus_llama_prefill(C.byref(self._model), C.byref(kv), C.byref(ws), embeds.data_ptr(),
-                                         d["pos"].data_ptr(), d["slot"].data_ptr(), d["cu"].data_ptr(),
-                                         d["last"].data_ptr(), n_seqs, n_tok, max_len,
+        rc = L.load().opus_llama_prefill(C.byref(self._model), C.byref(self._cache), C.byref(self._ws),
+                                         embeds.data_ptr(), d["pos"].data_ptr(), d["slot"].data_ptr(),
+                                         d["cu"].data_ptr(), d["last"].data_ptr(), n_seqs, n_tok, d["max_len"],
                                          torch.cuda.current_stream().cuda_stream)
         L.check(rc, "opus_llama_prefill")
-        d.update(n_seqs=n_seqs, max_blocks=max_blocks, blocks=blocks, logits=self._ws_bufs["logits"][:n_seqs],
-                 embeds=embeds)
+        d["logits"] = self._ws_bufs["logits"][:n_seqs]
+        d["embeds"] = embeds
         return d
 
     def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int):
@@ -207,11 +219,13 @@ class B200Llama:
 
     @torch.no_grad()
     def generate_packed(self, embeds: torch.Tensor, cu_seqlens, max_new_tokens: int, eos_ids=(), pad_id: int = 0,
-                        use_graph: bool = True, check_every: int = 16, return_prefill_logits: bool = False):
+                        use_graph: bool = True, check_every: int = 16, return_prefill_logits: bool = False,
+                        plan: dict | None = None):
         """Greedy generation from packed prompt embeddings. Returns int64 [n_seqs, n_new] (new tokens only; finished
         rows padded with pad_id; trimmed at the step where every row had finished, like HF)."""
         lib = L.load()
-        st = self.prefill(embeds, cu_seqlens, max_new_tokens)
+        own_plan = plan is None
+        st = self.prefill(embeds, cu_seqlens, max_new_tokens, plan=plan)
         try:
             s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id)
             stream = torch.cuda.current_stream().cuda_stream
@@ -225,7 +239,8 @@ class B200Llama:
                 L.check(rc, "opus_llama_decode_loop")
             out = bufs["out_ids"].to(torch.int64)
         finally:
-            self._alloc.release(st["blocks"])
+            if own_plan:
+                self.release_plan(st)
         if len(eos_ids):
             out = _trim_like_hf(out, eos_ids)
         return (out, prefill_logits) if return_prefill_logits else out

@@ -158,7 +158,7 @@ def test_prefill_logits_vs_oracle(cfg, lens):
     emb = synth.weight((int(cu[-1]), cfg["dim"]), "prompt_embeds", 0.02).cuda().to(torch.bfloat16)
     st = model.prefill(emb, cu, 4)
     got = st["logits"].float().clone()
-    model._alloc.release(st["blocks"])
+    model.release_plan(st)
     e_pad, m_pad = _padded(emb, cu, cfg["dim"])
     pos = (m_pad.long().cumsum(-1) - 1).masked_fill(~m_pad, 1)
     ocfg = _oracle_cfg(cfg)
@@ -248,7 +248,7 @@ def test_lora_merge_at_load():
     emb = synth.weight((int(cu[-1]), cfg["dim"]), "e2", 0.02).cuda().to(torch.bfloat16)
     st = model.prefill(emb, cu, 2)
     got = st["logits"].float().clone()
-    model._alloc.release(st["blocks"])
+    model.release_plan(st)
     e_pad, m_pad = _padded(emb, cu, cfg["dim"])
     pos = (m_pad.long().cumsum(-1) - 1).masked_fill(~m_pad, 1)
     want, _ = llama_ref.llama_forward(_dev(wm, torch.float32), _oracle_cfg(cfg), e_pad.float(), m_pad, pos)
