@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — OPUS-PLLM protein-conditioned generation hot path on B200 (contract: see the task statement / DESIGN.md §5).
+
+One "step" = one pass of the whole hot path over one batch of synthetic prompts:
+    ESM-2-650M encoder -> mean-pool/L2 -> CSTP + switch projector -> soft-token splice -> Llama-3-8B(+LoRA merged)
+    prefill -> greedy decode.
+Default workload = BASELINE.json configs[1] ("c2"): 64 prompts/GPU, protein length 256, spliced prompt length 512,
+32 new tokens. metric = generated tokens/s over the whole job (all ranks), weak scaling (fixed work per GPU).
+
+  value : device-timed, inputs (token ids, splice map, KV plan) already resident in HBM
+  e2e   : same metric through the reference-shaped public call model.generate(input_ids, seqs, ...) with HOST inputs
+          (pinned ids + python strings) and a device->host read of the generated ids inside the timed region
+  roofline     : the dominant kernel (prefill tcgen05 GEMM), timed live with CUDA events, vs MEASURED_PEAKS.json
+  cpu_baseline : the oracle (reference path restated, oracle/) on this box's host cores, bounded sample, rank 0, N=1
+
+`--impl reference` times the reference's own CPU implementation of the path (the oracle port: the reference is pure
+Python over torch / fair-esm / transformers and fair-esm is not installable offline) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (prompts per GPU, protein length, spliced prompt length, new tokens)
+    "c2": dict(batch=64, protein_len=256, prompt_len=512, new_tokens=32,
+               desc="OPUS-PLLM-Llama3-8B random-init, subcellular-localization prompts, bs 64, seq 512, 32 new tokens"),
+    "c3": dict(batch=256, protein_len=256, prompt_len=128, new_tokens=128,
+               desc="Llama3-8B+LoRA GO-term generation shard, bs 256/GPU, prompt 128, 128 new tokens"),
+    "tiny": dict(batch=8, protein_len=64, prompt_len=64, new_tokens=8, desc="tiny smoke workload (not a bench line)"),
+}
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained",
+                    d["bf16_tflops"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out = ""
+        sm, mx, power, reasons = [], [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            # samples under load = the upper half of the power draw distribution
+            thr = statistics.median(power) if power else 0
+            load = [s for s, p in zip(sm, power) if p >= thr] or sm
+            self.result = {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                           "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_runner(sd, wl, torch):
+    """Returns (run_once() -> generated tokens, sample description, cores). Full-size weights, bounded sample."""
+    import psutil
+    from oracle import esm2_ref, llama_ref, mm_ref
+    from opus_pllm_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lcfg, ecfg = sd["llama_cfg"], sd["esm_cfg"]
+    avail_gb = psutil.virtual_memory().available / 2 ** 30
+    per_layer_gb = 4 * (lcfg["dim"] * (lcfg["n_q_heads"] + 2 * lcfg["n_kv_heads"]) * lcfg["head_dim"] +
+                        lcfg["dim"] * lcfg["n_q_heads"] * lcfg["head_dim"] + 3 * lcfg["dim"] * lcfg["ffn_dim"]) / 2 ** 30
+    fixed_gb = 4 * (2 * lcfg["vocab"] * lcfg["dim"]) / 2 ** 30 + 8.0
+    n_layers = int(max(1, min(lcfg["n_layers"], (avail_gb * 0.6 - fixed_gb) // per_layer_gb)))
+    keep = lambda k: (not k.startswith("model.layers.")) or int(k.split(".")[2]) < n_layers  # noqa: E731
+    lw = {k: v.detach().to("cpu", torch.float32) for k, v in sd["llama"].items() if keep(k)}
+    if sd.get("lora"):
+        for k in [k[: -len(".lora_A.weight")] for k in sd["lora"] if k.endswith(".lora_A.weight") and keep(k)]:
+            lw[k + ".weight"] = llama_ref.lora_merge_ref(lw[k + ".weight"], sd["lora"][k + ".lora_A.weight"].float().cpu(),
+                                                         sd["lora"][k + ".lora_B.weight"].float().cpu(), 32.0, 16)
+    ew = {k: v.detach().to("cpu", torch.float32) for k, v in sd["esm"].items()}
+    pw = {k: v.detach().to("cpu", torch.float32) for k, v in sd["proj"].items()}
+    ocfg = llama_ref.LlamaCfg(n_layers=n_layers, dim=lcfg["dim"], n_q_heads=lcfg["n_q_heads"],
+                              n_kv_heads=lcfg["n_kv_heads"], head_dim=lcfg["head_dim"], ffn_dim=lcfg["ffn_dim"],
+                              vocab=lcfg["vocab"])
+    B, T, new = 2, min(128, wl["prompt_len"]), min(8, wl["new_tokens"])
+    seqs = synth.proteins(B, wl["protein_len"])
+    prompts = synth.prompt_ids(B, T - 7, vocab=lcfg["vocab"])
+    ids = torch.stack(prompts)
+
+    def run_once():
+        with torch.no_grad():
+            pooled = esm2_ref.get_protein_seq_embeddings(ew, seqs, ecfg["n_layers"], ecfg["n_heads"])
+            c = mm_ref.protein_forward(pooled, pw["protein_projection.linear.weight"],
+                                       pw["protein_projection.linear.bias"])
+            soft = mm_ref.switch_projector(c, pw, lcfg["dim"])
+            emb, mask, _, _ = mm_ref.splice(ids, None, soft, lw["model.embed_tokens.weight"])
+            out = llama_ref.greedy_generate(lw, ocfg, emb, mask, new)
+        return int(out.numel())
+
+    layers_note = "" if n_layers == lcfg["n_layers"] else f", Llama depth cut to {n_layers}/{lcfg['n_layers']} layers (host RAM)"
+    sample = (f"oracle port of the reference path, fp32, {cores} threads: {B} prompts x (protein {wl['protein_len']} aa, "
+              f"prompt {T} tokens, {new} new tokens), full-width ESM-2-650M + projectors + Llama-3-8B{layers_note}")
+    return run_once, sample, cores
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", default="full", choices=["full", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    import torch
+    from opus_pllm_b200 import presets, synth
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        dev = f"cuda:{local_rank}" if torch.cuda.is_available() else "cpu"   # GPU only used to hash the weights faster
+        sd = presets.synthetic_state_dicts(args.size, dev, with_lora=True)
+        run_once, sample, cores = cpu_reference_runner(sd, wl, torch)
+        del sd
+        for _ in range(args.warmup):
+            run_once()
+        t0 = time.perf_counter()
+        toks = 0
+        for _ in range(args.steps):
+            toks += run_once()
+        dt = time.perf_counter() - t0
+        v = toks / dt
+        print(json.dumps({
+            "impl": "reference", "metric": "generated tokens/s (whole job)", "value": v, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from opus_pllm_b200 import ops
+    ops.device_check()
+    peaks = _peaks()
+
+    model, sd = presets.build_synthetic_model(args.size, dev, with_lora=True, keep_state=True)
+    lcfg = sd["llama_cfg"]
+    if args.no_cpu_baseline or rank != 0 or world != 1:
+        sd = None
+    torch.cuda.empty_cache()
+
+    B, new = wl["batch"], wl["new_tokens"]
+    seqs = synth.proteins(B, wl["protein_len"], seed=1234 + rank)
+    prompts = synth.prompt_ids(B, wl["prompt_len"] - 7, vocab=lcfg["vocab"], seed=1234 + rank)
+    ids_host = torch.stack(prompts).pin_memory()                    # [B, L] int64, one -200 sentinel per row
+    use_graph = not args.no_graph
+
+    # device-resident inputs for `value`
+    pk = model.protein_encoder.tokenize(seqs)
+    pk.device_arrays = tuple(ops.h2d(a, dev) for a in (pk.tokens, pk.pos, pk.scale, pk.cu))
+    plan_sp = model._plan(ids_host, None, B)
+    src_d = ops.h2d(plan_sp.src, dev)
+    plan = model.llama.make_plan(plan_sp.cu, new)
+    fused = None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    gathered = torch.empty((world * B, new), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step_device(record=False):
+        if record: ev[0].record()
+        _, pooled_l2, _, _ = model.protein_encoder.encode(None, packed=pk)
+        if record: ev[1].record()
+        soft = model._fused(pooled_l2) if model._fused is not None else None
+        if soft is None:
+            soft = model._soft_tokens(seqs, None)
+        embeds = ops.splice_gather(src_d, model.llama.embed, soft.reshape(-1, lcfg["dim"]))
+        if record: ev[2].record()
+        st = model.llama.prefill(embeds, plan=plan)
+        if record: ev[3].record()
+        out = model.llama.generate_from_prefill(st, new, use_graph=use_graph)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        if record: ev[4].record()
+        return out
+
+    def step_e2e():
+        out = model.generate(ids_host, seqs, attention_mask=None, pad_token_id=128001, do_sample=False,
+                             temperature=0, top_p=0.7, num_beams=1, max_new_tokens=new, use_cache=True,
+                             use_graph=use_graph)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        return ops.d2h(out)
+
+    model._soft_tokens(seqs[:2], None)  # builds the fused projector object
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        sync_all()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(warmup):
+        step_device()
+    ops.launch_count(reset=True)
+    with ClockSampler(local_rank) as clk:
+        ms = timed(step_device, args.steps)
+    launches = ops.launch_count(reset=True)
+    tokens_per_step = world * B * new
+    value = tokens_per_step * args.steps / (ms / 1e3)
+
+    # phase breakdown of one more step (events inside the step; same stream)
+    sync_all(); step_device(record=True); sync_all()
+    phases = {"encoder_ms": ev[0].elapsed_time(ev[1]), "projector_splice_ms": ev[1].elapsed_time(ev[2]),
+              "prefill_ms": ev[2].elapsed_time(ev[3]), "decode_ms": ev[3].elapsed_time(ev[4])}
+
+    # e2e: host inputs, H2D + D2H inside the timed region
+    for _ in range(2):
+        step_e2e()
+    ops.XFER["h2d_bytes"] = ops.XFER["d2h_bytes"] = 0
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = {"value": tokens_per_step * args.steps / (ms_e2e / 1e3), "unit": "tokens/s",
+           "h2d_bytes_per_step": ops.XFER["h2d_bytes"] // args.steps,
+           "d2h_bytes_per_step": ops.XFER["d2h_bytes"] // args.steps, "ms_per_step": ms_e2e / args.steps}
+
+    # dominant kernel: the prefill tcgen05 GEMM (4 launches per layer at M = B*prompt_len), timed in isolation
+    from opus_pllm_b200 import _lib as L
+    M = B * wl["prompt_len"]
+    d, f, qn = lcfg["dim"], lcfg["ffn_dim"], (lcfg["n_q_heads"] + 2 * lcfg["n_kv_heads"]) * lcfg["head_dim"]
+    layer0 = model.llama._keep[0]
+    bufs = model.llama._ws_bufs
+    shapes = [("qkv", bufs["xn"][:M], layer0["wqkv"], L.EPI_BF16, None, bufs["qkv"][:M]),
+              ("o_proj", bufs["attn"][:M], layer0["wo"], L.EPI_RES_BF16, bufs["h"][:M], bufs["h"][:M]),
+              ("gate_up", bufs["xn"][:M], layer0["wgu"], L.EPI_SWIGLU, None, bufs["act"][:M]),
+              ("down", bufs["act"][:M], layer0["wdown"], L.EPI_RES_BF16, bufs["h"][:M], bufs["h"][:M])]
+    for t in (bufs["xn"], bufs["attn"], bufs["act"], bufs["h"]):
+        t[:M].normal_(0, 0.05)
+    flops_total, ms_total, per_shape = 0.0, 0.0, {}
+    for name, x, w, epi, res, out in shapes:
+        run = lambda: ops.gemm(x, w, epilogue=epi, residual=res, out=out, transposed=False)  # noqa: E731
+        for _ in range(3):
+            run()
+        reps = 5
+        t = timed(lambda: run(), reps) / reps
+        fl = 2.0 * M * w.shape[0] * w.shape[1]
+        per_shape[name] = {"ms": t, "tflops": fl / t / 1e9}
+        flops_total += fl; ms_total += t
+    achieved = flops_total / ms_total / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("gemm_prefill_dram_bytes_per_launch")
+    roofline = {"kernel": "gemm_bf16_tcgen05_kernel<256> (prefill linears, M=%d)" % M, "bound": "tensor",
+                "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
+                "traffic": traffic, "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
+                "per_shape": per_shape}
+    # decode step vs HBM roofline (SURVEY.md §8d bytes): weights once per step + KV read + KV write
+    steps_dec = max(new - 1, 1)
+    ctx_mean = wl["prompt_len"] + (new + 1) / 2.0
+    dec_bytes = 15009316864 * (lcfg["n_layers"] / 32.0 if args.size == "full" else 0) + 131072.0 * B * ctx_mean + 131072.0 * B
+    dec_ms = phases["decode_ms"] / steps_dec
+    roofline_decode = {"bound": "hbm", "achieved": dec_bytes / dec_ms / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
+                       "frac": dec_bytes / dec_ms / 1e6 / peaks["hbm"], "ms_per_decode_step": dec_ms,
+                       "bytes_per_step": dec_bytes}
+    pre_flops = (2.0 * M * 6979321856 + 2.0 * B * 4096 * 128256 + 2.0 * 4096 * 32 * B * wl["prompt_len"] ** 2) if args.size == "full" else 0
+    roofline_prefill = {"bound": "tensor", "achieved": pre_flops / phases["prefill_ms"] / 1e9, "peak": peaks["tf_sustained"],
+                        "unit": "TFLOP/s", "frac": pre_flops / phases["prefill_ms"] / 1e9 / peaks["tf_sustained"]}
+    n_res = pk.n_residues
+    enc_flops = 2.0 * pk.n_tok * 648806400 + 4.0 * 1280 * 33 * float((pk.cu[1:] - pk.cu[:-1]).astype("float64").__pow__(2).sum())
+    encoder = {"residues_per_s": world * n_res / (phases["encoder_ms"] / 1e3),
+               "tflops": (enc_flops / phases["encoder_ms"] / 1e9) if args.size == "full" else None,
+               "frac_of_sustained_peak": (enc_flops / phases["encoder_ms"] / 1e9 / peaks["tf_sustained"]) if args.size == "full" else None}
+
+    cpu_baseline = None
+    if sd is not None:
+        run_once, sample, cores = cpu_reference_runner(sd, wl, torch)
+        del sd
+        run_once()
+        t0 = time.perf_counter()
+        toks = run_once()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": toks / dt, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample,
+                        "seconds": dt}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "generated tokens/s (whole job)", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}", "prompts_per_gpu": B,
+                       "protein_len": wl["protein_len"], "prompt_len": wl["prompt_len"], "new_tokens": new,
+                       "weights": "random-init (hash-seeded) ESM-2-650M + CSTP/switch projectors + Llama-3-8B, LoRA r=16 merged at load",
+                       "parallelism": f"dp{world} (replica per GPU, one NCCL all-gather of generated ids per step)",
+                       "l2": "inputs larger than L2 (15 GB of weights streamed per decode step, 126 MB L2)",
+                       "cuda_graph_decode": use_graph},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.result, "roofline": roofline,
+            "roofline_decode": roofline_decode, "roofline_prefill": roofline_prefill, "encoder": encoder,
+            "phases_ms": phases, "cpu_baseline": cpu_baseline}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -133,7 +133,8 @@ class B200ProteinEncoder:
         return PackedTokens(seqs)
 
     def _upload(self, arr: np.ndarray) -> torch.Tensor:
-        return torch.from_numpy(arr).pin_memory().to(self.device, non_blocking=True)
+        from .ops import h2d
+        return h2d(arr, self.device)
 
     @torch.no_grad()
     def encode(self, seqs: list[str], want_hidden: bool = False, packed: PackedTokens | None = None):

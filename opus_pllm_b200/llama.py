@@ -141,7 +141,7 @@ class B200Llama:
         return self._ws
 
     def _upload(self, arr: np.ndarray) -> torch.Tensor:
-        return torch.from_numpy(np.ascontiguousarray(arr)).pin_memory().to(self.device, non_blocking=True)
+        return ops.h2d(arr, self.device)
 
     # ------------------------------------------------------------------------------------------ forward
     def make_plan(self, cu_seqlens, max_new_tokens: int) -> dict:
@@ -223,27 +223,34 @@ class B200Llama:
                         plan: dict | None = None):
         """Greedy generation from packed prompt embeddings. Returns int64 [n_seqs, n_new] (new tokens only; finished
         rows padded with pad_id; trimmed at the step where every row had finished, like HF)."""
-        lib = L.load()
         own_plan = plan is None
         st = self.prefill(embeds, cu_seqlens, max_new_tokens, plan=plan)
         try:
-            s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id)
-            stream = torch.cuda.current_stream().cuda_stream
             prefill_logits = st["logits"].clone() if return_prefill_logits else None
-            L.check(lib.opus_llama_select(C.byref(self._model), C.byref(self._ws), C.byref(s), st["n_seqs"], stream),
-                    "opus_llama_select")
-            if max_new_tokens > 1:
-                rc = lib.opus_llama_decode_loop(C.byref(self._model), C.byref(self._cache), C.byref(self._ws),
-                                                C.byref(s), st["n_seqs"], max_new_tokens - 1,
-                                                check_every if len(eos_ids) else 0, int(use_graph), stream)
-                L.check(rc, "opus_llama_decode_loop")
-            out = bufs["out_ids"].to(torch.int64)
+            out = self.generate_from_prefill(st, max_new_tokens, eos_ids, pad_id, use_graph, check_every)
         finally:
             if own_plan:
                 self.release_plan(st)
+        return (out, prefill_logits) if return_prefill_logits else out
+
+    @torch.no_grad()
+    def generate_from_prefill(self, st: dict, max_new_tokens: int, eos_ids=(), pad_id: int = 0,
+                              use_graph: bool = True, check_every: int = 16) -> torch.Tensor:
+        """Select the first token from the prefill logits, then run the greedy decode loop (CUDA-graph replays)."""
+        lib = L.load()
+        s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id)
+        stream = torch.cuda.current_stream().cuda_stream
+        L.check(lib.opus_llama_select(C.byref(self._model), C.byref(self._ws), C.byref(s), st["n_seqs"], stream),
+                "opus_llama_select")
+        if max_new_tokens > 1:
+            rc = lib.opus_llama_decode_loop(C.byref(self._model), C.byref(self._cache), C.byref(self._ws),
+                                            C.byref(s), st["n_seqs"], max_new_tokens - 1,
+                                            check_every if len(eos_ids) else 0, int(use_graph), stream)
+            L.check(rc, "opus_llama_decode_loop")
+        out = bufs["out_ids"].to(torch.int64)
         if len(eos_ids):
             out = _trim_like_hf(out, eos_ids)
-        return (out, prefill_logits) if return_prefill_logits else out
+        return out
 
 
 def _trim_like_hf(out: torch.Tensor, eos_ids) -> torch.Tensor:

@@ -146,8 +146,8 @@ class B200OpusLlama:
         return emb
 
     def _plan(self, input_ids, attention_mask, n_seq):
-        ids = input_ids.detach().cpu().numpy()
-        mask = None if attention_mask is None else attention_mask.detach().bool().cpu().numpy()
+        ids = ops.d2h(input_ids.detach()).numpy()
+        mask = None if attention_mask is None else ops.d2h(attention_mask.detach().bool()).numpy()
         return SplicePlan(ids, mask, self.n_soft, n_seq, self.config.tokenizer_model_max_length)
 
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
@@ -222,7 +222,7 @@ class B200OpusLlama:
             mask = None if attention_mask is None else attention_mask.detach().bool().cpu().numpy()
             plan = SplicePlan(np.where(ids == DEFAULT_SEQ_TOKEN_INDEX, 0, ids), mask, self.n_soft, 1 << 30)
             soft2d = torch.zeros((1, self.llama.dim), dtype=torch.bfloat16, device=self.device)
-        src_d = torch.from_numpy(plan.src).pin_memory().to(self.device, non_blocking=True)
+        src_d = ops.h2d(plan.src, self.device)
         embeds = ops.splice_gather(src_d, self.llama.embed, soft2d)
         return self.llama.generate_packed(embeds, plan.cu, max_new, eos_ids=eos_ids, pad_id=int(pad_id),
                                           use_graph=use_graph, return_prefill_logits=return_logits)

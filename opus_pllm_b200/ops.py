@@ -29,6 +29,25 @@ def _chk(t: torch.Tensor, dtype, name: str, contiguous: bool = True):
     return t
 
 
+XFER = {"h2d_bytes": 0, "d2h_bytes": 0}  # host<->device traffic issued by the package (bench.py reports it)
+
+
+def h2d(arr, device) -> torch.Tensor:
+    """numpy array / CPU tensor -> device tensor through pinned memory, asynchronous on the current stream."""
+    import numpy as np
+    t = torch.from_numpy(np.ascontiguousarray(arr)) if not isinstance(arr, torch.Tensor) else arr.contiguous()
+    XFER["h2d_bytes"] += t.numel() * t.element_size()
+    if not t.is_pinned():
+        t = t.pin_memory()
+    return t.to(device, non_blocking=True)
+
+
+def d2h(t: torch.Tensor) -> torch.Tensor:
+    if t.is_cuda:
+        XFER["d2h_bytes"] += t.numel() * t.element_size()
+    return t.cpu()
+
+
 def device_check():
     L.check(L.load().opus_device_check(), "opus_device_check")
 
