@@ -105,17 +105,26 @@ class B200Llama:
 
     # ------------------------------------------------------------------------------------------ buffers
     def _ensure_cache(self, need_blocks: int):
-        if self._cache is None or self._cache_blocks < need_blocks:
+        """Make sure `need_blocks` pages are FREE. Growing re-allocates the (zero-initialised) cache: page ids held by
+        live plans stay valid, their contents do not survive — plans are re-prefilled before every decode."""
+        free = len(self._alloc.free) if self._alloc is not None else 0
+        if self._cache is None or free < need_blocks:
             L.load().opus_release_graphs()
+            old = self._cache_blocks if self._cache is not None else 0
+            nb = max(old + need_blocks - free, 64)
             self._cache = None
-            nb = max(need_blocks, 64)
+            self._k = self._v = None
             shape = (self.n_layers, nb, self.Hkv, BLOCK, self.hd)
             self._k = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
             self._v = torch.zeros(shape, dtype=torch.bfloat16, device=self.device)
             kv = L.KvCache()
             kv.k, kv.v, kv.num_blocks, kv.block_size = self._k.data_ptr(), self._v.data_ptr(), nb, BLOCK
             self._cache, self._cache_blocks = kv, nb
-            self._alloc = BlockAllocator(nb)
+            if self._alloc is None:
+                self._alloc = BlockAllocator(nb)
+            else:
+                self._alloc.free[:0] = list(range(nb - 1, old - 1, -1))
+                self._alloc.num_blocks = nb
         return self._cache
 
     def _ensure_ws(self, rows: int, n_seqs: int):
