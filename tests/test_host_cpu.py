@@ -1,0 +1,168 @@
+"""CPU tests (no GPU) of the host logic, the C ABI surface and the data-parallel plumbing (gloo, world_size 2)."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from opus_pllm_b200 import synth
+from oracle import esm2_ref, mm_ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_shared_library_exports_every_declared_symbol():
+    from opus_pllm_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "opus_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*|long long)\s+(opus_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 25
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.opus_abi_version() == 1
+    assert isinstance(lib.opus_last_error(), bytes)
+
+
+def test_no_cpu_fallback_ops_fail_loudly_without_cuda():
+    from opus_pllm_b200 import _lib, ops
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    with pytest.raises(_lib.OpusError):
+        ops.gemm(x, x)
+    with pytest.raises(_lib.OpusError):
+        ops.layernorm(torch.zeros(4, 64), torch.ones(64), torch.zeros(64))
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.OpusError):
+            ops.device_check()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "opus_pllm_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+# ------------------------------------------------------------------------------------------------ tokeniser
+def test_packed_tokens_match_batch_converter_semantics():
+    from opus_pllm_b200.encoder import PackedTokens
+    seqs = ["MKTAYIAKQR", "A", "", "XBUZO.-", "acd"]
+    pk = PackedTokens(seqs)
+    want = esm2_ref.tokenize(seqs)
+    lens = [len(s) + 2 for s in seqs]
+    assert pk.cu.tolist() == [0] + np.cumsum(lens).tolist() and pk.max_len == max(lens) and pk.n_residues == 21
+    for i, n in enumerate(lens):
+        assert pk.tokens[pk.cu[i]: pk.cu[i + 1]].tolist() == want[i, :n].tolist()
+        assert pk.pos[pk.cu[i]: pk.cu[i + 1]].tolist() == list(range(n))
+    assert np.allclose(pk.scale, 0.88)
+
+
+# ------------------------------------------------------------------------------------------------ splice plan
+@pytest.mark.parametrize("seed", range(5))
+def test_splice_plan_matches_oracle(seed):
+    from opus_pllm_b200.model import SplicePlan
+    rng = np.random.default_rng(seed)
+    B, L, H, n_soft = 6, 14, 8, 8
+    ids = rng.integers(2, 50, size=(B, L)).astype(np.int64)
+    mask = np.ones((B, L), dtype=bool)
+    for b in range(B):
+        pad = rng.integers(0, 6)
+        mask[b, :pad] = False
+        for _ in range(rng.integers(0, 3)):
+            ids[b, rng.integers(pad, L)] = -200
+    n_slots = int(sum(max(1, int((ids[b][mask[b]] == -200).sum())) for b in range(B)))
+    embed = torch.randn(50, H)
+    soft = torch.randn(n_slots, n_soft, H)
+    plan = SplicePlan(ids, mask, n_soft, n_slots)
+    table = torch.cat([embed, soft.reshape(-1, H)])
+    idx = torch.from_numpy(np.where(plan.src >= 0, plan.src, 50 + (-plan.src - 1)))
+    packed = table[idx]
+    for left in (True, False):
+        e, m, p, lens = mm_ref.splice(torch.from_numpy(ids), torch.from_numpy(mask), soft, embed, left)
+        assert lens == plan.lens.tolist()
+        src, pm = plan.padded_src(left)
+        assert np.array_equal(pm, m.numpy())
+        for b in range(B):
+            assert torch.equal(e[b][m[b]], packed[plan.cu[b]: plan.cu[b + 1]])
+    assert plan.n_seq_used == n_slots
+    with pytest.raises(IndexError):
+        SplicePlan(np.array([[-200, -200]]), None, n_soft, 1)
+
+
+def test_splice_plan_truncation():
+    from opus_pllm_b200.model import SplicePlan
+    plan = SplicePlan(np.array([[5, -200, 6, 7]]), None, 8, 1, max_length=6)
+    assert plan.lens.tolist() == [6] and plan.src.tolist() == [5, -1, -2, -3, -4, -5]
+
+
+# ------------------------------------------------------------------------------------------------ small host helpers
+def test_block_allocator_and_trim():
+    from opus_pllm_b200.llama import BlockAllocator, _trim_like_hf
+    from opus_pllm_b200._lib import OpusError
+    a = BlockAllocator(8)
+    x = a.alloc(3)
+    y = a.alloc(5)
+    assert sorted(x + y) == list(range(8))
+    with pytest.raises(OpusError):
+        a.alloc(1)
+    a.release(x)
+    assert sorted(a.alloc(3)) == sorted(x)
+    out = torch.tensor([[4, 9, 9, 9], [4, 5, 9, 9]])
+    assert _trim_like_hf(out, [9]).shape == (2, 3)
+    assert _trim_like_hf(torch.tensor([[4, 9, 9], [4, 5, 6]]), [9]).shape == (2, 3)
+
+
+def test_synth_is_deterministic_known_answers():
+    a = synth.hash_uniform((4,), "x", 3)
+    b = synth.hash_uniform((2, 2), "x", 3).flatten()
+    assert torch.equal(a, b)
+    assert [round(float(v), 6) for v in synth.hash_uniform((1000, 1000), "x", 3)[0, :3]] == [-0.351248, -0.427369,
+                                                                                            -0.160979]
+    assert synth.proteins(2, 5)[0] == synth.proteins(1, 5)[0] and set(synth.proteins(1, 50)[0]) <= set(synth.AMINO)
+    p = synth.prompt_ids(3, 20, vocab=1000)
+    assert all(int((x == -200).sum()) == 1 for x in p)
+
+
+# ------------------------------------------------------------------------------------------------ data parallel
+def test_shard_bounds_match_accelerate_semantics():
+    from opus_pllm_b200.dp import shard_bounds, split_between_processes
+    items = list(range(10))
+    got = [split_between_processes(items, r, 4) for r in range(4)]
+    assert got == [[0, 1, 2], [3, 4, 5], [6, 7], [8, 9]]
+    assert [shard_bounds(3, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 3), (3, 3)]
+
+
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from opus_pllm_b200.dp import gather_token_ids, split_between_processes
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    prompts = list(range(7))
+    mine = split_between_processes(prompts)
+    ids = torch.tensor([[p * 10 + t for t in range(3 + rank)] for p in mine], dtype=torch.int64)
+    out = gather_token_ids(ids, pad_id=-1)
+    q.put((rank, out.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_gather_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [[p * 10 + t for t in range(3)] + [-1] for p in range(4)] + [[p * 10 + t for t in range(4)] for p in range(4, 7)]
+    assert res[0] == want and res[1] == want
