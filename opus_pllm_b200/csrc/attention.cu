@@ -12,6 +12,7 @@
 // sdpa/eager attention + DynamicCache (reached from language_model/opus_llama.py:127-132).
 #include "common.h"
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace opus {
@@ -83,6 +84,8 @@ __device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_b
 
 template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_varlen_kernel(const AttnParams p) {
+  grid_dep_launch();
+  grid_dep_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int Q_BYTES = BM * D * 2, KV_BYTES = BN * D * 2;
   const uint32_t sQ = smem_u32(smem);
@@ -277,6 +280,8 @@ __device__ __forceinline__ void load_panel_async(uint32_t smem_base, const __nv_
 
 template <int GROUP>
 __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const DecodeParams p) {
+  grid_dep_launch();
+  grid_dep_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   // per warp: 2 stages x (K panel + V panel) = 16 KB; then the merge area
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -429,7 +434,7 @@ int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st)
     configured = true;
   }
   dim3 grid((max_len + BM - 1) / BM, p.n_q_heads, n_seqs);
-  attn_varlen_kernel<D, CAUSAL><<<grid, ATT_THREADS, SMEM, st>>>(p);
+  launch_pdl(attn_varlen_kernel<D, CAUSAL>, dim3(grid), dim3(ATT_THREADS), SMEM, st, p);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -482,10 +487,10 @@ int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcac
     configured = true;
   }
   switch (group) {
-    case 1: attn_decode_paged_kernel<1><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
-    case 2: attn_decode_paged_kernel<2><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
-    case 4: attn_decode_paged_kernel<4><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
-    case 8: attn_decode_paged_kernel<8><<<grid, DEC_WARPS * 32, smem, st>>>(p); break;
+    case 1: launch_pdl(attn_decode_paged_kernel<1>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    case 2: launch_pdl(attn_decode_paged_kernel<2>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    case 4: launch_pdl(attn_decode_paged_kernel<4>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    case 8: launch_pdl(attn_decode_paged_kernel<8>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
     default: return OPUS_ERR_ARG;
   }
   note_launch();

@@ -4,6 +4,7 @@
 // All are coalesced 128-bit accesses with warp-shuffle reductions; none of them is reshaped into a GEMM.
 #include "common.h"
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace opus {
@@ -38,6 +39,8 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
 // ------------------------------------------------------------------------------------------------
 __global__ void esm_embed_kernel(const int* __restrict__ tok, const float* __restrict__ scale,
                                  const float* __restrict__ table, float* __restrict__ x, int n_tok, int dim) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= n_tok) return;
   const int lane = threadIdx.x & 31;
@@ -58,6 +61,8 @@ template <int MAX_V4>  // float4 chunks per lane
 __global__ void layernorm_f32_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows,
                                           int cols, float eps) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -103,25 +108,30 @@ __global__ void layernorm_f32_bf16_kernel(const float* __restrict__ x, const flo
 // ------------------------------------------------------------------------------------------------
 // L1: RMSNorm (HF LlamaRMSNorm, modeling_llama.py:62-67): y = w * bf16(x * rsqrt(mean(x^2) + eps)), fp32 inside.
 // Optional fused residual add (h = bf16(x + r) written back, then normalised) and optional split-K reduction of fp32
-// partial sums:  x_eff = bf16(residual + bf16(sum_s partial[s] (+bias)))   -- the decode o_proj / down_proj tail.
-// One warp per row; cols % 256 == 0 (8 bf16 per lane per step).
+// partial sums:  x_eff = bf16(residual + bf16(sum_s partial[s]))   -- the decode o_proj / down_proj tail.
+// TPR threads cooperate on one row (RPC rows per CTA): TPR = 128 for prefill-sized inputs (many rows, few registers,
+// high occupancy), TPR = 512 for decode-sized inputs (few rows: all partial-sum loads of a row are issued at once).
 // ------------------------------------------------------------------------------------------------
-template <int MAX_V8>
-__global__ void rmsnorm_bf16_kernel(const __nv_bfloat16* x,                     // [rows, cols] or nullptr if partials
-                                    const float* __restrict__ partial, int n_partial,  // [n_partial][rows][cols]
-                                    const __nv_bfloat16* residual,              // nullable (may alias h_out)
-                                    __nv_bfloat16* h_out,                       // nullable: x (+ residual) written back
-                                    const __nv_bfloat16* __restrict__ w, __nv_bfloat16* y, int rows,
-                                    int cols, float eps) {
-  const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  float v[MAX_V8][8];
+template <int TPR, int RPC, int MAXC>
+__global__ void __launch_bounds__(TPR* RPC)
+rmsnorm_bf16_kernel(const __nv_bfloat16* x,                            // [rows, cols] or nullptr if partials
+                    const float* __restrict__ partial, int n_partial,  // [n_partial][rows][cols]
+                    const __nv_bfloat16* residual,                     // nullable (may alias h_out)
+                    __nv_bfloat16* h_out,                              // nullable: x (+ residual) written back
+                    const __nv_bfloat16* __restrict__ w, __nv_bfloat16* y, int rows, int cols, float eps) {
+  grid_dep_launch();
+  grid_dep_wait();
+  constexpr int WPR = TPR / 32;  // warps per row
+  __shared__ float red[RPC][WPR];
+  const int r_in = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  const int row = blockIdx.x * RPC + r_in;
+  const bool row_ok = row < rows;
+  float v[MAXC][8];
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_V8; ++i) {
-    const int c = (i * 32 + lane) * 8;
-    if (c < cols) {
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = (i * TPR + t) * 8;
+    if (row_ok && c < cols) {
       const size_t off = (size_t)row * cols + c;
       if (partial != nullptr) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -148,11 +158,17 @@ __global__ void rmsnorm_bf16_kernel(const __nv_bfloat16* x,                     
     }
   }
   if (y == nullptr) return;
-  const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[r_in][t >> 5] = sq;
+  __syncthreads();
+  float tot = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAX_V8; ++i) {
-    const int c = (i * 32 + lane) * 8;
-    if (c < cols) {
+  for (int i = 0; i < WPR; ++i) tot += red[r_in][i];
+  const float rstd = rsqrtf(tot / cols + eps);
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = (i * TPR + t) * 8;
+    if (row_ok && c < cols) {
       float wv[8], o[8];
       bf16x8_to_float(*reinterpret_cast<const uint4*>(w + c), wv);
 #pragma unroll
@@ -168,6 +184,8 @@ __global__ void rmsnorm_bf16_kernel(const __nv_bfloat16* x,                     
 __global__ void splitk_reduce_bf16_kernel(const float* __restrict__ partial, int n_partial,
                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                                           size_t rows, int cols, int ldo, int gelu) {
+  grid_dep_launch();
+  grid_dep_wait();
   const size_t total = rows * (size_t)cols / 4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t e = i * 4;
@@ -199,6 +217,8 @@ __global__ void splitk_reduce_bf16_kernel(const float* __restrict__ partial, int
 __global__ void rope_esm_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ pos,
                                 const float* __restrict__ cos_t, const float* __restrict__ sin_t, int n_tok,
                                 int n_heads, int head_dim, int ld, float q_scale) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int half = head_dim / 2;
   const int per_head = half / 4;                 // threads per head
   const int per_tok = 2 * n_heads * per_head;    // q heads then k heads
@@ -253,6 +273,8 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
                                            const __nv_bfloat16* __restrict__ sin_t, __nv_bfloat16* __restrict__ kcache,
                                            __nv_bfloat16* __restrict__ vcache, int n_tok, int n_q_heads,
                                            int n_kv_heads, int head_dim, int ld, int block_size) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int half = head_dim / 2;
   const int per_head = half / 4;  // threads per head (each: 4 pairs)
   const int heads_total = n_q_heads + 2 * n_kv_heads;
@@ -340,6 +362,8 @@ __global__ void final_ln_meanpool_kernel(const float* __restrict__ x, const int*
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* __restrict__ pooled, __nv_bfloat16* __restrict__ pooled_l2_bf16,
                                          float* __restrict__ hidden_out, int dim, float eps) {
+  grid_dep_launch();
+  grid_dep_wait();
   extern __shared__ float red[];  // [nwarps][dim]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -416,6 +440,8 @@ __global__ void final_ln_meanpool_kernel(const float* __restrict__ x, const int*
 
 // P1 alone: rows fp32 -> L2-normalised bf16 (pre-computed-embedding path, opus_arch.py:151-161).
 __global__ void l2norm_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int rows, int dim) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -432,6 +458,8 @@ __global__ void l2norm_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat1
 __global__ void splice_gather_kernel(const int* __restrict__ src, const __nv_bfloat16* __restrict__ embed,
                                      const __nv_bfloat16* __restrict__ soft, __nv_bfloat16* __restrict__ out,
                                      int n_rows, int dim) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -455,6 +483,8 @@ __global__ void argmax_eos_kernel(const __nv_bfloat16* __restrict__ logits, int 
                                   int* __restrict__ finished, const int* __restrict__ eos_ids, int n_eos, int pad_id,
                                   int* __restrict__ next_tok, int* __restrict__ out_ids, int out_ld, int step_imm,
                                   const int* __restrict__ step_ptr, int* __restrict__ n_unfinished) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int b = blockIdx.x;
   const __nv_bfloat16* row = logits + (size_t)b * ld;
   float best = -INFINITY;
@@ -509,6 +539,8 @@ __global__ void argmax_eos_kernel(const __nv_bfloat16* __restrict__ logits, int 
 // decode input: x[b,:] = table[tok[b],:]; also advances positions / cache slots for the step (one launch per step).
 __global__ void embed_gather_kernel(const int* __restrict__ tok, const __nv_bfloat16* __restrict__ table,
                                     __nv_bfloat16* __restrict__ x, int n_rows, int dim) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -521,6 +553,8 @@ __global__ void embed_gather_kernel(const int* __restrict__ tok, const __nv_bflo
 __global__ void decode_advance_kernel(int* __restrict__ ctx_len, int* __restrict__ pos, int* __restrict__ slot,
                                       const int* __restrict__ block_table, int max_blocks, int block_size, int n,
                                       int* __restrict__ step) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0 && step != nullptr) *step += 1;
   if (b >= n) return;
@@ -534,6 +568,8 @@ __global__ void decode_advance_kernel(int* __restrict__ ctx_len, int* __restrict
 // W [out, in], A [r, in], B [out, r].  One-off at load time; r is small (<= 64) so a direct kernel is enough.
 __global__ void lora_merge_kernel(__nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ A,
                                   const __nv_bfloat16* __restrict__ Bm, int out_f, int in_f, int r, float scale) {
+  grid_dep_launch();
+  grid_dep_wait();
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (idx >= (size_t)out_f * in_f) return;
   const int o = (int)(idx / in_f), i = (int)(idx - (size_t)o * in_f);
@@ -553,7 +589,7 @@ inline int ok() {
 int esm_embed(const int* tok, const float* scale, const float* table, float* x, int n_tok, int dim, cudaStream_t st) {
   if (dim % 4) return OPUS_ERR_ARG;
   if (n_tok == 0) return OPUS_OK;
-  esm_embed_kernel<<<cdiv(n_tok, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(tok, scale, table, x, n_tok, dim);
+  launch_pdl(esm_embed_kernel, dim3(cdiv(n_tok, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, tok, scale, table, x, n_tok, dim);
   return ok();
 }
 
@@ -562,25 +598,30 @@ int layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, __
   if (cols % 4 || cols > 128 * 16) return OPUS_ERR_ARG;
   if (rows == 0) return OPUS_OK;
   const int grid = cdiv(rows, WARPS_PER_BLOCK), blk = WARPS_PER_BLOCK * 32;
-  if (cols <= 128 * 4) layernorm_f32_bf16_kernel<4><<<grid, blk, 0, st>>>(x, gamma, beta, y, rows, cols, eps);
-  else if (cols <= 128 * 10) layernorm_f32_bf16_kernel<10><<<grid, blk, 0, st>>>(x, gamma, beta, y, rows, cols, eps);
-  else layernorm_f32_bf16_kernel<16><<<grid, blk, 0, st>>>(x, gamma, beta, y, rows, cols, eps);
+  if (cols <= 128 * 4) launch_pdl(layernorm_f32_bf16_kernel<4>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
+  else if (cols <= 128 * 10) launch_pdl(layernorm_f32_bf16_kernel<10>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
+  else launch_pdl(layernorm_f32_bf16_kernel<16>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
   return ok();
 }
 
 int rmsnorm_bf16(const __nv_bfloat16* x, const float* partial, int n_partial, const __nv_bfloat16* residual,
                  __nv_bfloat16* h_out, const __nv_bfloat16* w, __nv_bfloat16* y, int rows, int cols, float eps,
                  cudaStream_t st) {
-  if (cols % 8 || cols > 256 * 32) return OPUS_ERR_ARG;
+  if (cols % 8 || cols > 8192) return OPUS_ERR_ARG;
   if ((x == nullptr) == (partial == nullptr)) return OPUS_ERR_ARG;
   if (rows == 0) return OPUS_OK;
-  const int grid = cdiv(rows, WARPS_PER_BLOCK), blk = WARPS_PER_BLOCK * 32;
-  if (cols <= 256 * 8)
-    rmsnorm_bf16_kernel<8><<<grid, blk, 0, st>>>(x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
-  else if (cols <= 256 * 16)
-    rmsnorm_bf16_kernel<16><<<grid, blk, 0, st>>>(x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
-  else
-    rmsnorm_bf16_kernel<32><<<grid, blk, 0, st>>>(x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+  if (rows <= 1024) {  // decode-sized: one 512-thread CTA per row
+    if (cols <= 4096)
+      launch_pdl(rmsnorm_bf16_kernel<512, 1, 1>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+    else
+      launch_pdl(rmsnorm_bf16_kernel<512, 1, 2>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+  } else {             // prefill-sized: 128 threads per row, two rows per CTA
+    const int grid = cdiv(rows, 2);
+    if (cols <= 4096)
+      launch_pdl(rmsnorm_bf16_kernel<128, 2, 4>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+    else
+      launch_pdl(rmsnorm_bf16_kernel<128, 2, 8>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+  }
   return ok();
 }
 
@@ -591,7 +632,7 @@ int splitk_reduce_bf16(const float* partial, int n_partial, const float* bias, _
   const long long total = (long long)rows * cols / 4;
   int grid = cdiv(total, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  splitk_reduce_bf16_kernel<<<grid, 256, 0, st>>>(partial, n_partial, bias, out, (size_t)rows, cols, ldo, gelu);
+  launch_pdl(splitk_reduce_bf16_kernel, dim3(grid), dim3(256), 0, st, partial, n_partial, bias, out, (size_t)rows, cols, ldo, gelu);
   return ok();
 }
 
@@ -600,7 +641,7 @@ int rope_esm(__nv_bfloat16* qkv, const int* pos, const float* cos_t, const float
   if (head_dim % 8 || ld % 4) return OPUS_ERR_ARG;
   if (n_tok == 0) return OPUS_OK;
   const long long total = (long long)n_tok * 2 * n_heads * (head_dim / 8);
-  rope_esm_kernel<<<cdiv(total, 256), 256, 0, st>>>(qkv, pos, cos_t, sin_t, n_tok, n_heads, head_dim, ld, q_scale);
+  launch_pdl(rope_esm_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, pos, cos_t, sin_t, n_tok, n_heads, head_dim, ld, q_scale);
   return ok();
 }
 
@@ -611,7 +652,7 @@ int rope_llama_kvappend(__nv_bfloat16* qkv, const float* partial, int n_partial,
   if (head_dim % 8 || ld % 4) return OPUS_ERR_ARG;
   if (n_tok == 0) return OPUS_OK;
   const long long total = (long long)n_tok * (n_q_heads + 2 * n_kv_heads) * (head_dim / 8);
-  rope_llama_kvappend_kernel<<<cdiv(total, 256), 256, 0, st>>>(qkv, partial, n_partial, pos, slot, cos_t, sin_t, kcache,
+  launch_pdl(rope_llama_kvappend_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, partial, n_partial, pos, slot, cos_t, sin_t, kcache,
                                                               vcache, n_tok, n_q_heads, n_kv_heads, head_dim, ld,
                                                               block_size);
   return ok();
@@ -623,14 +664,14 @@ int final_ln_meanpool(const float* x, const int* cu_seqlens, const float* gamma,
   if (n_seqs == 0) return OPUS_OK;
   const int threads = 256;
   const size_t smem = (size_t)(threads / 32) * dim * sizeof(float);
-  final_ln_meanpool_kernel<10><<<n_seqs, threads, smem, st>>>(x, cu_seqlens, gamma, beta, pooled, pooled_l2, hidden_out,
+  launch_pdl(final_ln_meanpool_kernel<10>, dim3(n_seqs), dim3(threads), smem, st, x, cu_seqlens, gamma, beta, pooled, pooled_l2, hidden_out,
                                                              dim, eps);
   return ok();
 }
 
 int l2norm_f32_bf16(const float* x, __nv_bfloat16* y, int rows, int dim, cudaStream_t st) {
   if (rows == 0) return OPUS_OK;
-  l2norm_f32_bf16_kernel<<<cdiv(rows, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(x, y, rows, dim);
+  launch_pdl(l2norm_f32_bf16_kernel, dim3(cdiv(rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, x, y, rows, dim);
   return ok();
 }
 
@@ -638,7 +679,7 @@ int splice_gather(const int* src, const __nv_bfloat16* embed, const __nv_bfloat1
                   int dim, cudaStream_t st) {
   if (dim % 8) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
-  splice_gather_kernel<<<cdiv(n_rows, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(src, embed, soft, out, n_rows, dim);
+  launch_pdl(splice_gather_kernel, dim3(cdiv(n_rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, src, embed, soft, out, n_rows, dim);
   return ok();
 }
 
@@ -647,7 +688,7 @@ int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* 
                const int* step_ptr) {
   if (ld % 8) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
-  argmax_eos_kernel<<<n_rows, 1024, 0, st>>>(logits, ld, vocab, finished, eos_ids, n_eos, pad_id, next_tok, out_ids,
+  launch_pdl(argmax_eos_kernel, dim3(n_rows), dim3(1024), 0, st, logits, ld, vocab, finished, eos_ids, n_eos, pad_id, next_tok, out_ids,
                                             out_ld, step, step_ptr, n_unfinished);
   return ok();
 }
@@ -655,14 +696,14 @@ int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* 
 int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, int n_rows, int dim, cudaStream_t st) {
   if (dim % 8) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
-  embed_gather_kernel<<<cdiv(n_rows, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(tok, table, x, n_rows, dim);
+  launch_pdl(embed_gather_kernel, dim3(cdiv(n_rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, tok, table, x, n_rows, dim);
   return ok();
 }
 
 int decode_advance(int* ctx_len, int* pos, int* slot, const int* block_table, int max_blocks, int block_size, int n,
                    cudaStream_t st, int* step) {
   if (n == 0) return OPUS_OK;
-  decode_advance_kernel<<<cdiv(n, 128), 128, 0, st>>>(ctx_len, pos, slot, block_table, max_blocks, block_size, n, step);
+  launch_pdl(decode_advance_kernel, dim3(cdiv(n, 128)), dim3(128), 0, st, ctx_len, pos, slot, block_table, max_blocks, block_size, n, step);
   return ok();
 }
 
@@ -670,7 +711,7 @@ int lora_merge(__nv_bfloat16* W, const __nv_bfloat16* A, const __nv_bfloat16* B,
                cudaStream_t st) {
   const long long total = (long long)out_f * in_f;
   if (total == 0) return OPUS_OK;
-  lora_merge_kernel<<<cdiv(total, 256), 256, 0, st>>>(W, A, B, out_f, in_f, r, scale);
+  launch_pdl(lora_merge_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, W, A, B, out_f, in_f, r, scale);
   return ok();
 }
 

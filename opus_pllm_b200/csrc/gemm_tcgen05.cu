@@ -17,6 +17,7 @@
 // and HF Llama q/k/v/o/gate/up/down/lm_head (reached through language_model/opus_llama.py:82-93).
 #include "common.h"
 #include "gemm.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <cuda.h>
@@ -252,14 +253,39 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  grid_dep_launch();  // PDL: the next kernel may be scheduled as soon as every CTA of this grid got here
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // PDL prologue: the WEIGHT operand never depends on the preceding kernel, so the first ring pass of weight
+      // tiles is requested before waiting for it; only the activation operand has to wait. At decode batch sizes this
+      // keeps HBM busy across kernel boundaries.
+      int pre = 0;
+      if ((int)blockIdx.x < num_tiles) {
+        const TileCoord tc = decode_tile(p, blockIdx.x);
+        pre = min(C::STAGES, tc.kb_end - tc.kb_begin);
+        for (int i = 0; i < pre; ++i) {
+          uint8_t* sa = smem + i * C::STAGE;
+          mbar_arrive_expect_tx(&full_bar[i], C::STAGE);
+          if (p.transposed) tma_load_2d_hint(sa, &tmap_a, &full_bar[i], (tc.kb_begin + i) * BK, tc.m * BM, p.hint_a);
+          else tma_load_2d_hint(sa + C::STAGE_A, &tmap_b, &full_bar[i], (tc.kb_begin + i) * BK, tc.n * BN, p.hint_b);
+        }
+        grid_dep_wait();
+        for (int i = 0; i < pre; ++i) {
+          uint8_t* sa = smem + i * C::STAGE;
+          if (p.transposed) tma_load_2d_hint(sa + C::STAGE_A, &tmap_b, &full_bar[i], (tc.kb_begin + i) * BK, tc.n * BN, p.hint_b);
+          else tma_load_2d_hint(sa, &tmap_a, &full_bar[i], (tc.kb_begin + i) * BK, tc.m * BM, p.hint_a);
+        }
+        if (pre == C::STAGES) { stage = 0; phase = 1; } else { stage = pre; }
+      } else {
+        grid_dep_wait();
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t);
-        for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+        for (int kb = tc.kb_begin + (t == (int)blockIdx.x ? pre : 0); kb < tc.kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE;
           uint8_t* sb = sa + C::STAGE_A;
@@ -304,6 +330,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    grid_dep_wait();            // residual / output buffers may still be in use by the preceding kernel
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -383,9 +410,9 @@ int launch(const GemmParams& p, const void* A, int lda, const void* B, int ldb, 
   if (rc) return rc;
   rc = make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN);
   if (rc) return rc;
-  gemm_bf16_tcgen05_kernel<BN><<<grid, NUM_THREADS, C::SMEM, stream>>>(ta, tb, p);
+  const cudaError_t le = launch_pdl(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, p);
   note_launch();
-  return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
 
 int g_num_sms = 0;

@@ -24,6 +24,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------- programmatic dependent launch ----------------------------------
+// wait: blocks until every prerequisite grid has completed and its writes are visible (no-op without PDL).
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// launch_dependents: lets the next kernel in the stream be scheduled once all CTAs of this grid have issued it.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------- mbarrier -------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -59,7 +65,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
       printf("opus_b200: mbarrier wait timed out (block %d, thread %d, parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();
