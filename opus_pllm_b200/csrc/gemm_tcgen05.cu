@@ -253,8 +253,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  grid_dep_launch();  // PDL: the next kernel may be scheduled as soon as every CTA of this grid got here
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -295,6 +293,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      // PDL trigger, issued LATE (all loads of this CTA are in flight): dependents that became resident earlier would
+      // only sit in griddepcontrol.wait next to a long-running GEMM.
+      grid_dep_launch();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
