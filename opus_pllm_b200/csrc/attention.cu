@@ -434,7 +434,7 @@ int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st)
     configured = true;
   }
   dim3 grid((max_len + BM - 1) / BM, p.n_q_heads, n_seqs);
-  launch_pdl(attn_varlen_kernel<D, CAUSAL>, dim3(grid), dim3(ATT_THREADS), SMEM, st, p);
+  launch_pdl(false, attn_varlen_kernel<D, CAUSAL>, dim3(grid), dim3(ATT_THREADS), SMEM, st, p);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -487,10 +487,10 @@ int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcac
     configured = true;
   }
   switch (group) {
-    case 1: launch_pdl(attn_decode_paged_kernel<1>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
-    case 2: launch_pdl(attn_decode_paged_kernel<2>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
-    case 4: launch_pdl(attn_decode_paged_kernel<4>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
-    case 8: launch_pdl(attn_decode_paged_kernel<8>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    case 1: launch_pdl(true, attn_decode_paged_kernel<1>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    case 2: launch_pdl(true, attn_decode_paged_kernel<2>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    case 4: launch_pdl(true, attn_decode_paged_kernel<4>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    case 8: launch_pdl(true, attn_decode_paged_kernel<8>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
     default: return OPUS_ERR_ARG;
   }
   note_launch();

@@ -589,7 +589,7 @@ inline int ok() {
 int esm_embed(const int* tok, const float* scale, const float* table, float* x, int n_tok, int dim, cudaStream_t st) {
   if (dim % 4) return OPUS_ERR_ARG;
   if (n_tok == 0) return OPUS_OK;
-  launch_pdl(esm_embed_kernel, dim3(cdiv(n_tok, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, tok, scale, table, x, n_tok, dim);
+  launch_pdl(n_tok <= 1024, esm_embed_kernel, dim3(cdiv(n_tok, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, tok, scale, table, x, n_tok, dim);
   return ok();
 }
 
@@ -598,9 +598,9 @@ int layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, __
   if (cols % 4 || cols > 128 * 16) return OPUS_ERR_ARG;
   if (rows == 0) return OPUS_OK;
   const int grid = cdiv(rows, WARPS_PER_BLOCK), blk = WARPS_PER_BLOCK * 32;
-  if (cols <= 128 * 4) launch_pdl(layernorm_f32_bf16_kernel<4>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
-  else if (cols <= 128 * 10) launch_pdl(layernorm_f32_bf16_kernel<10>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
-  else launch_pdl(layernorm_f32_bf16_kernel<16>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
+  if (cols <= 128 * 4) launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<4>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
+  else if (cols <= 128 * 10) launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<10>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
+  else launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<16>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
   return ok();
 }
 
@@ -612,15 +612,15 @@ int rmsnorm_bf16(const __nv_bfloat16* x, const float* partial, int n_partial, co
   if (rows == 0) return OPUS_OK;
   if (rows <= 1024) {  // decode-sized: one 512-thread CTA per row
     if (cols <= 4096)
-      launch_pdl(rmsnorm_bf16_kernel<512, 1, 1>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+      launch_pdl(true, rmsnorm_bf16_kernel<512, 1, 1>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
     else
-      launch_pdl(rmsnorm_bf16_kernel<512, 1, 2>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+      launch_pdl(true, rmsnorm_bf16_kernel<512, 1, 2>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
   } else {             // prefill-sized: 128 threads per row, two rows per CTA
     const int grid = cdiv(rows, 2);
     if (cols <= 4096)
-      launch_pdl(rmsnorm_bf16_kernel<128, 2, 4>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+      launch_pdl(false, rmsnorm_bf16_kernel<128, 2, 4>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
     else
-      launch_pdl(rmsnorm_bf16_kernel<128, 2, 8>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+      launch_pdl(false, rmsnorm_bf16_kernel<128, 2, 8>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
   }
   return ok();
 }
@@ -632,7 +632,7 @@ int splitk_reduce_bf16(const float* partial, int n_partial, const float* bias, _
   const long long total = (long long)rows * cols / 4;
   int grid = cdiv(total, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  launch_pdl(splitk_reduce_bf16_kernel, dim3(grid), dim3(256), 0, st, partial, n_partial, bias, out, (size_t)rows, cols, ldo, gelu);
+  launch_pdl(rows <= 1024, splitk_reduce_bf16_kernel, dim3(grid), dim3(256), 0, st, partial, n_partial, bias, out, (size_t)rows, cols, ldo, gelu);
   return ok();
 }
 
@@ -641,7 +641,7 @@ int rope_esm(__nv_bfloat16* qkv, const int* pos, const float* cos_t, const float
   if (head_dim % 8 || ld % 4) return OPUS_ERR_ARG;
   if (n_tok == 0) return OPUS_OK;
   const long long total = (long long)n_tok * 2 * n_heads * (head_dim / 8);
-  launch_pdl(rope_esm_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, pos, cos_t, sin_t, n_tok, n_heads, head_dim, ld, q_scale);
+  launch_pdl(n_tok <= 1024, rope_esm_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, pos, cos_t, sin_t, n_tok, n_heads, head_dim, ld, q_scale);
   return ok();
 }
 
@@ -652,7 +652,7 @@ int rope_llama_kvappend(__nv_bfloat16* qkv, const float* partial, int n_partial,
   if (head_dim % 8 || ld % 4) return OPUS_ERR_ARG;
   if (n_tok == 0) return OPUS_OK;
   const long long total = (long long)n_tok * (n_q_heads + 2 * n_kv_heads) * (head_dim / 8);
-  launch_pdl(rope_llama_kvappend_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, partial, n_partial, pos, slot, cos_t, sin_t, kcache,
+  launch_pdl(n_tok <= 1024, rope_llama_kvappend_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, partial, n_partial, pos, slot, cos_t, sin_t, kcache,
                                                               vcache, n_tok, n_q_heads, n_kv_heads, head_dim, ld,
                                                               block_size);
   return ok();
@@ -664,14 +664,14 @@ int final_ln_meanpool(const float* x, const int* cu_seqlens, const float* gamma,
   if (n_seqs == 0) return OPUS_OK;
   const int threads = 256;
   const size_t smem = (size_t)(threads / 32) * dim * sizeof(float);
-  launch_pdl(final_ln_meanpool_kernel<10>, dim3(n_seqs), dim3(threads), smem, st, x, cu_seqlens, gamma, beta, pooled, pooled_l2, hidden_out,
+  launch_pdl(false, final_ln_meanpool_kernel<10>, dim3(n_seqs), dim3(threads), smem, st, x, cu_seqlens, gamma, beta, pooled, pooled_l2, hidden_out,
                                                              dim, eps);
   return ok();
 }
 
 int l2norm_f32_bf16(const float* x, __nv_bfloat16* y, int rows, int dim, cudaStream_t st) {
   if (rows == 0) return OPUS_OK;
-  launch_pdl(l2norm_f32_bf16_kernel, dim3(cdiv(rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, x, y, rows, dim);
+  launch_pdl(rows <= 1024, l2norm_f32_bf16_kernel, dim3(cdiv(rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, x, y, rows, dim);
   return ok();
 }
 
@@ -679,7 +679,7 @@ int splice_gather(const int* src, const __nv_bfloat16* embed, const __nv_bfloat1
                   int dim, cudaStream_t st) {
   if (dim % 8) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
-  launch_pdl(splice_gather_kernel, dim3(cdiv(n_rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, src, embed, soft, out, n_rows, dim);
+  launch_pdl(n_rows <= 1024, splice_gather_kernel, dim3(cdiv(n_rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, src, embed, soft, out, n_rows, dim);
   return ok();
 }
 
@@ -688,7 +688,7 @@ int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* 
                const int* step_ptr) {
   if (ld % 8) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
-  launch_pdl(argmax_eos_kernel, dim3(n_rows), dim3(1024), 0, st, logits, ld, vocab, finished, eos_ids, n_eos, pad_id, next_tok, out_ids,
+  launch_pdl(true, argmax_eos_kernel, dim3(n_rows), dim3(1024), 0, st, logits, ld, vocab, finished, eos_ids, n_eos, pad_id, next_tok, out_ids,
                                             out_ld, step, step_ptr, n_unfinished);
   return ok();
 }
@@ -696,14 +696,14 @@ int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* 
 int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, int n_rows, int dim, cudaStream_t st) {
   if (dim % 8) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
-  launch_pdl(embed_gather_kernel, dim3(cdiv(n_rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, tok, table, x, n_rows, dim);
+  launch_pdl(n_rows <= 1024, embed_gather_kernel, dim3(cdiv(n_rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, tok, table, x, n_rows, dim);
   return ok();
 }
 
 int decode_advance(int* ctx_len, int* pos, int* slot, const int* block_table, int max_blocks, int block_size, int n,
                    cudaStream_t st, int* step) {
   if (n == 0) return OPUS_OK;
-  launch_pdl(decode_advance_kernel, dim3(cdiv(n, 128)), dim3(128), 0, st, ctx_len, pos, slot, block_table, max_blocks, block_size, n, step);
+  launch_pdl(true, decode_advance_kernel, dim3(cdiv(n, 128)), dim3(128), 0, st, ctx_len, pos, slot, block_table, max_blocks, block_size, n, step);
   return ok();
 }
 
@@ -711,7 +711,7 @@ int lora_merge(__nv_bfloat16* W, const __nv_bfloat16* A, const __nv_bfloat16* B,
                cudaStream_t st) {
   const long long total = (long long)out_f * in_f;
   if (total == 0) return OPUS_OK;
-  launch_pdl(lora_merge_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, W, A, B, out_f, in_f, r, scale);
+  launch_pdl(false, lora_merge_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, W, A, B, out_f, in_f, r, scale);
   return ok();
 }
 

@@ -411,7 +411,7 @@ int launch(const GemmParams& p, const void* A, int lda, const void* B, int ldb, 
   if (rc) return rc;
   rc = make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN);
   if (rc) return rc;
-  const cudaError_t le = launch_pdl(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, p);
+  const cudaError_t le = launch_pdl(p.transposed != 0, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, p);
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
