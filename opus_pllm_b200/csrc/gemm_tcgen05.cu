@@ -21,6 +21,7 @@
 #include "ptx.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace opus {
@@ -476,7 +477,12 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   p.out = a.out; p.ldo = a.ldo;
   p.bias = a.bias;
   p.residual = a.residual; p.ldr = a.ldr;
-  p.group_m = a.transposed ? p.num_m_tiles : 16;
+  static int group_override = -1;
+  if (group_override < 0) {
+    const char* e = std::getenv("OPUS_GEMM_GROUP_M");
+    group_override = e ? atoi(e) : 0;
+  }
+  p.group_m = a.transposed ? p.num_m_tiles : (group_override > 0 ? group_override : 16);
   if (p.group_m > p.num_m_tiles) p.group_m = p.num_m_tiles;
   // weights are streamed once in the swap-AB form; activations are re-read by every tile
   p.hint_a = a.transposed ? kCacheEvictFirst : kCacheEvictNormal;
