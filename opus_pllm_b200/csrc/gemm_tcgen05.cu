@@ -41,8 +41,7 @@ struct Cfg {
   static constexpr int STAGE = STAGE_A + STAGE_B;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int EPI_STAGE_BYTES = 4 * 32 * 33 * 4;  // per-epilogue-warp 32x33 fp32 transposition tiles
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct TileCoord {
@@ -214,63 +213,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   }
 }
 
-// ---- coalesced epilogue for the non-transposed form ----
-// tcgen05.ld hands every thread one accumulator ROW (32 consecutive columns), so direct stores touch 32 different
-// 128-byte lines per instruction (LSU-bound at small K). The chunk is transposed through a padded per-warp shared-memory
-// tile instead: afterwards lane = column, and every global access of the warp is one contiguous row segment.
-constexpr int EPI_LD = 33;  // padded row stride (floats) of the 32x32 staging tile: conflict-free both ways
-
-__device__ __forceinline__ void epilogue_chunk_coalesced(const GemmParams& p, const uint32_t (&r)[32], float* stage,
-                                                         int row0, int col0, int split, int lane) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) stage[lane * EPI_LD + j] = __uint_as_float(r[j]);
-  __syncwarp();
-  const int col = col0 + lane;
-  const bool col_ok = col < p.N;
-  const float bias = (p.bias != nullptr && col_ok && p.epi != EPI_PARTIAL_F32) ? p.bias[col] : 0.0f;
-  const int rows_here = min(32, p.M - row0);
-  if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU) {
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row0 * p.ldo + col;
-    const bool gelu = p.epi == EPI_BF16_GELU;
-    for (int rr = 0; rr < rows_here; ++rr) {
-      float v = stage[rr * EPI_LD + lane] + bias;
-      if (gelu) v = gelu_erf(v);
-      if (col_ok) out[(size_t)rr * p.ldo] = __float2bfloat16_rn(v);
-    }
-  } else if (p.epi == EPI_RES_F32) {
-    const float* res = reinterpret_cast<const float*>(p.residual) + (size_t)row0 * p.ldr + col;
-    float* out = reinterpret_cast<float*>(p.out) + (size_t)row0 * p.ldo + col;
-    for (int rr = 0; rr < rows_here; ++rr) {
-      if (col_ok) out[(size_t)rr * p.ldo] = res[(size_t)rr * p.ldr] + (stage[rr * EPI_LD + lane] + bias);
-    }
-  } else if (p.epi == EPI_RES_BF16) {
-    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row0 * p.ldr + col;
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row0 * p.ldo + col;
-    for (int rr = 0; rr < rows_here; ++rr) {
-      if (col_ok) {
-        const float t = bf16_round(stage[rr * EPI_LD + lane] + bias);
-        out[(size_t)rr * p.ldo] = __float2bfloat16_rn(__bfloat162float(res[(size_t)rr * p.ldr]) + t);
-      }
-    }
-  } else if (p.epi == EPI_SWIGLU) {
-    // columns (2j, 2j+1) = (gate_j, up_j) sit in adjacent lanes; even lanes produce out[row, col/2]
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row0 * p.ldo + (col >> 1);
-    for (int rr = 0; rr < rows_here; ++rr) {
-      const float v = stage[rr * EPI_LD + lane];
-      const float up = __shfl_down_sync(0xffffffffu, v, 1);
-      if (((lane & 1) == 0) && col + 1 < p.N) {
-        const float g = bf16_round(v);
-        out[(size_t)rr * p.ldo] = __float2bfloat16_rn(bf16_round(silu_f(g)) * bf16_round(up));
-      }
-    }
-  } else if (p.epi == EPI_PARTIAL_F32) {
-    float* out = reinterpret_cast<float*>(p.out) + ((size_t)split * p.M + row0) * p.ldo + col;
-    for (int rr = 0; rr < rows_here; ++rr)
-      if (col_ok) out[(size_t)rr * p.ldo] = stage[rr * EPI_LD + lane];
-  }
-  __syncwarp();  // the staging tile is reused by the next chunk
-}
-
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -285,7 +227,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint64_t* acc_full = bars + 2 * C::STAGES;     // [2]       MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * C::STAGES + 2;  // [2]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE + 256);  // [4 warps][32][33]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -406,11 +347,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
         const int col0 = tc.n * BN + c * 32;
-        if (col0 < p.N) {
-          if (p.transposed) epilogue_chunk(p, r, row, col0, tc.split);
-          else epilogue_chunk_coalesced(p, r, epi_stage + (warp - 2) * (32 * EPI_LD), tc.m * BM + quad * 32, col0,
-                                        tc.split, lane);
-        }
+        if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
