@@ -31,8 +31,8 @@ namespace {
 constexpr int BM = 128;       // UMMA M (rows of A per tile) == TMEM lanes
 constexpr int BK = 64;        // K elements per stage = one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
-constexpr int NUM_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int NUM_EPI_THREADS = 128;
+constexpr int NUM_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int NUM_EPI_THREADS = 256;  // two warps per TMEM lane quadrant, each draining every other 32-column chunk
 
 template <int BN>
 struct Cfg {
@@ -117,12 +117,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       if (row_ok) {
         const float* res = reinterpret_cast<const float*>(p.residual) + (size_t)row * p.ldr + col0;
         float* dst = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+        // all residual loads first: `out` may alias `residual` (in-place), so interleaving load/store pairs would
+        // serialise eight L2 round trips per chunk
+        float4 q[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          q[g] = (col0 + g * 4 + 4 <= p.N) ? *reinterpret_cast<const float4*>(res + g * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           if (col0 + g * 4 + 4 <= p.N) {
-            const float4 q = *reinterpret_cast<const float4*>(res + g * 4);
             *reinterpret_cast<float4*>(dst + g * 4) =
-                make_float4(q.x + v[g * 4], q.y + v[g * 4 + 1], q.z + v[g * 4 + 2], q.w + v[g * 4 + 3]);
+                make_float4(q[g].x + v[g * 4], q[g].y + v[g * 4 + 1], q[g].z + v[g * 4 + 2], q[g].w + v[g * 4 + 3]);
           }
         }
       }
@@ -131,10 +136,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       if (row_ok) {
         const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldr + col0;
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+        uint4 qq[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          qq[g] = (col0 + g * 8 + 8 <= p.N) ? *reinterpret_cast<const uint4*>(res + g * 8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (col0 + g * 8 + 8 <= p.N) {
-            const uint4 q = *reinterpret_cast<const uint4*>(res + g * 8);
+            const uint4 q = qq[g];
             const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&q);
             float o[8];
 #pragma unroll
@@ -330,8 +339,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
+    const int chunk0 = (warp - 2) >> 2;  // 0 or 1: the pair of warps of a quadrant interleave the column chunks
     grid_dep_wait();            // residual / output buffers may still be in use by the preceding kernel
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -342,7 +352,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = tc.m * BM + quad * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chunk0; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + c * 32, r);
         tmem_ld_wait();
