@@ -82,9 +82,11 @@ int opus_splitk_reduce_bf16(const float* partial, int n_partial, const float* bi
  * called at cstp_v3/modelling.py:48).  tok: int32 [n_tok]; table fp32 [vocab, dim]; x fp32 [n_tok, dim]. */
 int opus_esm_embed(const int32_t* tok, const float* scale, const float* table, float* x, int n_tok, int dim,
                    void* stream);
-/* y bf16 = LayerNorm(x fp32) * gamma + beta, row-wise (fair-esm pre-LN blocks). */
-int opus_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int cols,
-                            float eps, void* stream);
+/* y bf16 = LayerNorm(x fp32 (+ delta)) * gamma + beta, row-wise (fair-esm pre-LN blocks). If delta (bf16, nullable) is
+ * given, the pending branch output is first folded into the fp32 residual stream in place (x += delta); delta may
+ * alias y. */
+int opus_layernorm_f32_bf16(float* x, const void* delta, const float* gamma, const float* beta, void* y, int rows,
+                            int cols, float eps, void* stream);
 /* HF LlamaRMSNorm with optional fused residual add and split-K reduction:
  *   h = x  or  bf16(sum_s partial[s])      (exactly one of x / partial non-null)
  *   h = bf16(h + residual) if residual;  h_out <- h if h_out;  y <- w * bf16(h * rsqrt(mean(h^2)+eps)) if y. */
@@ -105,10 +107,11 @@ int opus_rope_llama_kvappend_bf16(void* qkv, const float* partial, int n_partial
                                   void* stream);
 /* Final LayerNorm of every residue + mean over residues [1, len-1) of each packed sequence + L2 normalise
  * (cstp_v3/modelling.py:53-55 and F.normalize at :398). pooled fp32 [n_seqs, dim]; pooled_l2 bf16 (nullable);
- * hidden_out fp32 [n_tok, dim] (nullable) receives the per-residue normalised states (representations[33]). */
-int opus_final_ln_meanpool(const float* x, const int32_t* cu_seqlens, const float* gamma, const float* beta,
-                           float* pooled, void* pooled_l2, float* hidden_out, int n_seqs, int dim, float eps,
-                           void* stream);
+ * hidden_out fp32 [n_tok, dim] (nullable) receives the per-residue normalised states (representations[33]);
+ * delta bf16 [n_tok, dim] (nullable) is a pending branch output added to x before the norm. */
+int opus_final_ln_meanpool(const float* x, const void* delta, const int32_t* cu_seqlens, const float* gamma,
+                           const float* beta, float* pooled, void* pooled_l2, float* hidden_out, int n_seqs, int dim,
+                           float eps, void* stream);
 int opus_l2norm_f32_bf16(const float* x, void* y, int rows, int dim, void* stream);
 /* Soft-token splice gather (multi_modality_v1/model/opus_arch.py:176-270): out[i,:] = src[i] >= 0 ? embed[src[i]] :
  * src[i] == INT32_MIN ? 0 : soft[-src[i]-1]. */

@@ -82,12 +82,12 @@ _SIGNATURES = {
     "opus_gemm_suggest_split_k": (c_int, [c_int, c_int, c_int, c_int]),
     "opus_splitk_reduce_bf16": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "opus_esm_embed": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
-    "opus_layernorm_f32_bf16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_float, _P]),
+    "opus_layernorm_f32_bf16": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "opus_rmsnorm_bf16": (c_int, [_P, _P, c_int, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "opus_rope_esm_bf16": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, _P]),
     "opus_rope_llama_kvappend_bf16": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
                                               c_int, c_int, _P]),
-    "opus_final_ln_meanpool": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
+    "opus_final_ln_meanpool": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "opus_l2norm_f32_bf16": (c_int, [_P, _P, c_int, c_int, _P]),
     "opus_splice_gather_bf16": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     "opus_argmax_eos": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),

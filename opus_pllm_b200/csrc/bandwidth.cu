@@ -57,16 +57,19 @@ __global__ void esm_embed_kernel(const int* __restrict__ tok, const float* __res
 // ------------------------------------------------------------------------------------------------
 // E2: LayerNorm over fp32 rows -> bf16 (the GEMM operand).  One warp per row, values kept in registers.
 // ------------------------------------------------------------------------------------------------
+// If `delta` != nullptr the pending bf16 branch output (out_proj / fc2 result) is first folded into the fp32 residual
+// stream: x <- x + delta (written back), then normalised. `delta` may alias `y` (each lane reads its delta elements
+// before it writes the same positions of y).
 template <int MAX_V4>  // float4 chunks per lane
-__global__ void layernorm_f32_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int rows,
+__global__ void layernorm_f32_bf16_kernel(float* x, const __nv_bfloat16* delta, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, __nv_bfloat16* y, int rows,
                                           int cols, float eps) {
   grid_dep_launch();
   grid_dep_wait();
   const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float* src = x + (size_t)row * cols;
+  float* src = x + (size_t)row * cols;
   float4 v[MAX_V4];
   float sum = 0.f;
 #pragma unroll
@@ -74,6 +77,13 @@ __global__ void layernorm_f32_bf16_kernel(const float* __restrict__ x, const flo
     const int c = (i * 32 + lane) * 4;
     if (c < cols) {
       v[i] = ld4(src + c);
+      if (delta != nullptr) {
+        const uint2 dq = *reinterpret_cast<const uint2*>(delta + (size_t)row * cols + c);
+        const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dq);
+        const float2 da = __bfloat1622float2(d2[0]), db = __bfloat1622float2(d2[1]);
+        v[i].x += da.x; v[i].y += da.y; v[i].z += db.x; v[i].w += db.y;
+        *reinterpret_cast<float4*>(src + c) = v[i];
+      }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -112,8 +122,8 @@ __global__ void layernorm_f32_bf16_kernel(const float* __restrict__ x, const flo
 // TPR threads cooperate on one row (RPC rows per CTA): TPR = 128 for prefill-sized inputs (many rows, few registers,
 // high occupancy), TPR = 512 for decode-sized inputs (few rows: all partial-sum loads of a row are issued at once).
 // ------------------------------------------------------------------------------------------------
-template <int TPR, int RPC, int MAXC>
-__global__ void __launch_bounds__(TPR* RPC)
+template <int TPR, int RPC, int MAXC, bool PLAIN>
+__global__ void __launch_bounds__(TPR* RPC, PLAIN ? 5 : 1)
 rmsnorm_bf16_kernel(const __nv_bfloat16* x,                            // [rows, cols] or nullptr if partials
                     const float* __restrict__ partial, int n_partial,  // [n_partial][rows][cols]
                     const __nv_bfloat16* residual,                     // nullable (may alias h_out)
@@ -126,35 +136,58 @@ rmsnorm_bf16_kernel(const __nv_bfloat16* x,                            // [rows,
   const int r_in = threadIdx.x / TPR, t = threadIdx.x % TPR;
   const int row = blockIdx.x * RPC + r_in;
   const bool row_ok = row < rows;
-  float v[MAXC][8];
+  uint4 raw[MAXC];  // the row kept as packed bf16 (h is bf16-exact): 4 registers per 8 elements -> high occupancy
   float sq = 0.f;
+  if constexpr (PLAIN) {
+    // plain norm (no partial sums, no residual): issue every load of the row before consuming any (memory-level parallelism)
 #pragma unroll
-  for (int i = 0; i < MAXC; ++i) {
-    const int c = (i * TPR + t) * 8;
-    if (row_ok && c < cols) {
-      const size_t off = (size_t)row * cols + c;
-      if (partial != nullptr) {
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int s = 0; s < n_partial; ++s) {
-          const float* pp = partial + (size_t)s * rows * cols + off;
-          const float4 a = ld4(pp), b = ld4(pp + 4);
-          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = (i * TPR + t) * 8;
+      raw[i] = (row_ok && c < cols) ? *reinterpret_cast<const uint4*>(x + (size_t)row * cols + c) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = (i * TPR + t) * 8;
+      if (row_ok && c < cols) {
+        float v[8];
+        bf16x8_to_float(raw[i], v);
+        if (h_out != nullptr) *reinterpret_cast<uint4*>(h_out + (size_t)row * cols + c) = raw[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = (i * TPR + t) * 8;
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (row_ok && c < cols) {
+        const size_t off = (size_t)row * cols + c;
+        float v[8];
+        if (partial != nullptr) {
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int s = 0; s < n_partial; ++s) {
+            const float* pp = partial + (size_t)s * rows * cols + off;
+            const float4 a = ld4(pp), b = ld4(pp + 4);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = bf16_round(acc[j]);
+        } else {
+          bf16x8_to_float(*reinterpret_cast<const uint4*>(x + off), v);
         }
+        if (residual != nullptr) {
+          float r[8];
+          bf16x8_to_float(*reinterpret_cast<const uint4*>(residual + off), r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = bf16_round(acc[j]);
-      } else {
-        bf16x8_to_float(*reinterpret_cast<const uint4*>(x + off), v[i]);
+          for (int j = 0; j < 8; ++j) v[j] = bf16_round(v[j] + r[j]);
+        }
+        raw[i] = float_to_bf16x8(v);
+        if (h_out != nullptr) *reinterpret_cast<uint4*>(h_out + off) = raw[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
       }
-      if (residual != nullptr) {
-        float r[8];
-        bf16x8_to_float(*reinterpret_cast<const uint4*>(residual + off), r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = bf16_round(v[i][j] + r[j]);
-      }
-      if (h_out != nullptr) *reinterpret_cast<uint4*>(h_out + off) = float_to_bf16x8(v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sq += v[i][j] * v[i][j];
     }
   }
   if (y == nullptr) return;
@@ -169,10 +202,11 @@ rmsnorm_bf16_kernel(const __nv_bfloat16* x,                            // [rows,
   for (int i = 0; i < MAXC; ++i) {
     const int c = (i * TPR + t) * 8;
     if (row_ok && c < cols) {
-      float wv[8], o[8];
+      float v[8], wv[8], o[8];
+      bf16x8_to_float(raw[i], v);
       bf16x8_to_float(*reinterpret_cast<const uint4*>(w + c), wv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = wv[j] * bf16_round(v[i][j] * rstd);
+      for (int j = 0; j < 8; ++j) o[j] = wv[j] * bf16_round(v[j] * rstd);
       *reinterpret_cast<uint4*>(y + (size_t)row * cols + c) = float_to_bf16x8(o);
     }
   }
@@ -276,7 +310,7 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
   grid_dep_launch();
   grid_dep_wait();
   const int half = head_dim / 2;
-  const int per_head = half / 4;  // threads per head (each: 4 pairs)
+  const int per_head = half / 8;  // threads per head (each: 8 rotation pairs, 16-byte accesses)
   const int heads_total = n_q_heads + 2 * n_kv_heads;
   const int per_tok = heads_total * per_head;
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -284,60 +318,49 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
   const int tok = (int)(idx / per_tok);
   const int r = (int)(idx - (size_t)tok * per_tok);
   const int hsel = r / per_head;
-  const int j0 = (r - hsel * per_head) * 4;
+  const int j0 = (r - hsel * per_head) * 8;
   __nv_bfloat16* base = qkv + (size_t)tok * ld + (size_t)hsel * head_dim;
 
-  float x1[4], x2[4];
+  float x1[8], x2[8];
   if (partial != nullptr) {
     const size_t off = (size_t)tok * ld + (size_t)hsel * head_dim;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = 0; s < n_partial; ++s) {
       const float* pp = partial + (size_t)s * n_tok * ld + off;
-      const float4 t1 = ld4(pp + j0), t2 = ld4(pp + half + j0);
-      a.x += t1.x; a.y += t1.y; a.z += t1.z; a.w += t1.w;
-      b.x += t2.x; b.y += t2.y; b.z += t2.z; b.w += t2.w;
+      const float4 t1 = ld4(pp + j0), t2 = ld4(pp + j0 + 4), t3 = ld4(pp + half + j0), t4 = ld4(pp + half + j0 + 4);
+      a[0] += t1.x; a[1] += t1.y; a[2] += t1.z; a[3] += t1.w; a[4] += t2.x; a[5] += t2.y; a[6] += t2.z; a[7] += t2.w;
+      b[0] += t3.x; b[1] += t3.y; b[2] += t3.z; b[3] += t3.w; b[4] += t4.x; b[5] += t4.y; b[6] += t4.z; b[7] += t4.w;
     }
-    x1[0] = bf16_round(a.x); x1[1] = bf16_round(a.y); x1[2] = bf16_round(a.z); x1[3] = bf16_round(a.w);
-    x2[0] = bf16_round(b.x); x2[1] = bf16_round(b.y); x2[2] = bf16_round(b.z); x2[3] = bf16_round(b.w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x1[i] = bf16_round(a[i]); x2[i] = bf16_round(b[i]); }
   } else {
-    const uint2 lo = *reinterpret_cast<const uint2*>(base + j0);
-    const uint2 hi = *reinterpret_cast<const uint2*>(base + half + j0);
-    const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lo);
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
-    const float2 la = __bfloat1622float2(l2[0]), lb = __bfloat1622float2(l2[1]);
-    const float2 ha = __bfloat1622float2(h2[0]), hb = __bfloat1622float2(h2[1]);
-    x1[0] = la.x; x1[1] = la.y; x1[2] = lb.x; x1[3] = lb.y;
-    x2[0] = ha.x; x2[1] = ha.y; x2[2] = hb.x; x2[3] = hb.y;
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(base + j0), x1);
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(base + half + j0), x2);
   }
 
   const bool is_v = hsel >= n_q_heads + n_kv_heads;
-  float o1[4], o2[4];
+  float o1[8], o2[8];
   if (!is_v) {
     const int p = pos[tok];
-    const uint2 c1 = *reinterpret_cast<const uint2*>(cos_t + (size_t)p * head_dim + j0);
-    const uint2 s1 = *reinterpret_cast<const uint2*>(sin_t + (size_t)p * head_dim + j0);
-    const uint2 c2 = *reinterpret_cast<const uint2*>(cos_t + (size_t)p * head_dim + half + j0);
-    const uint2 s2 = *reinterpret_cast<const uint2*>(sin_t + (size_t)p * head_dim + half + j0);
-    const __nv_bfloat16* c1h = reinterpret_cast<const __nv_bfloat16*>(&c1);
-    const __nv_bfloat16* s1h = reinterpret_cast<const __nv_bfloat16*>(&s1);
-    const __nv_bfloat16* c2h = reinterpret_cast<const __nv_bfloat16*>(&c2);
-    const __nv_bfloat16* s2h = reinterpret_cast<const __nv_bfloat16*>(&s2);
+    float c1[8], s1[8], c2[8], s2[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(cos_t + (size_t)p * head_dim + j0), c1);
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(sin_t + (size_t)p * head_dim + j0), s1);
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(cos_t + (size_t)p * head_dim + half + j0), c2);
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(sin_t + (size_t)p * head_dim + half + j0), s2);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       // first half: x1*cos + (-x2)*sin ; second half: x2*cos + x1*sin ; every op rounds to bf16 like torch
-      o1[i] = bf16_round(bf16_round(x1[i] * __bfloat162float(c1h[i])) + bf16_round(-x2[i] * __bfloat162float(s1h[i])));
-      o2[i] = bf16_round(bf16_round(x2[i] * __bfloat162float(c2h[i])) + bf16_round(x1[i] * __bfloat162float(s2h[i])));
+      o1[i] = bf16_round(bf16_round(x1[i] * c1[i]) + bf16_round(-x2[i] * s1[i]));
+      o2[i] = bf16_round(bf16_round(x2[i] * c2[i]) + bf16_round(x1[i] * s2[i]));
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { o1[i] = x1[i]; o2[i] = x2[i]; }
+    for (int i = 0; i < 8; ++i) { o1[i] = x1[i]; o2[i] = x2[i]; }
   }
-  uint2 w1, w2;
-  w1.x = pack_bf16x2(o1[0], o1[1]); w1.y = pack_bf16x2(o1[2], o1[3]);
-  w2.x = pack_bf16x2(o2[0], o2[1]); w2.y = pack_bf16x2(o2[2], o2[3]);
+  const uint4 w1 = float_to_bf16x8(o1), w2 = float_to_bf16x8(o2);
   if (!is_v || partial != nullptr) {
-    *reinterpret_cast<uint2*>(base + j0) = w1;
-    *reinterpret_cast<uint2*>(base + half + j0) = w2;
+    *reinterpret_cast<uint4*>(base + j0) = w1;
+    *reinterpret_cast<uint4*>(base + half + j0) = w2;
   }
   if (hsel >= n_q_heads && slot != nullptr) {
     const int sl = slot[tok];
@@ -345,8 +368,8 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
       const int kvh = is_v ? hsel - n_q_heads - n_kv_heads : hsel - n_q_heads;
       const int blk = sl / block_size, off = sl - blk * block_size;
       __nv_bfloat16* dst = (is_v ? vcache : kcache) + (((size_t)blk * n_kv_heads + kvh) * block_size + off) * head_dim;
-      *reinterpret_cast<uint2*>(dst + j0) = w1;
-      *reinterpret_cast<uint2*>(dst + half + j0) = w2;
+      *reinterpret_cast<uint4*>(dst + j0) = w1;
+      *reinterpret_cast<uint4*>(dst + half + j0) = w2;
     }
   }
 }
@@ -358,7 +381,8 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
 // Outputs: pooled fp32 [B, dim] (the reference's return value) and l2-normalised bf16 [B, dim] (projector GEMM input).
 // ------------------------------------------------------------------------------------------------
 template <int MAX_V4>
-__global__ void final_ln_meanpool_kernel(const float* __restrict__ x, const int* __restrict__ cu_seqlens,
+__global__ void final_ln_meanpool_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
+                                         const int* __restrict__ cu_seqlens,
                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                          float* __restrict__ pooled, __nv_bfloat16* __restrict__ pooled_l2_bf16,
                                          float* __restrict__ hidden_out, int dim, float eps) {
@@ -380,6 +404,12 @@ __global__ void final_ln_meanpool_kernel(const float* __restrict__ x, const int*
     for (int i = 0; i < MAX_V4; ++i) {
       const int c = (i * 32 + lane) * 4;
       v[i] = (c < dim) ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (delta != nullptr && c < dim) {
+        const uint2 dq = *reinterpret_cast<const uint2*>(delta + (size_t)t * dim + c);
+        const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dq);
+        const float2 da = __bfloat1622float2(d2[0]), db = __bfloat1622float2(d2[1]);
+        v[i].x += da.x; v[i].y += da.y; v[i].z += db.x; v[i].w += db.y;
+      }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
     const float mean = warp_sum(sum) / dim;
@@ -593,14 +623,14 @@ int esm_embed(const int* tok, const float* scale, const float* table, float* x, 
   return ok();
 }
 
-int layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows, int cols,
-                       float eps, cudaStream_t st) {
+int layernorm_f32_bf16(float* x, const __nv_bfloat16* delta, const float* gamma, const float* beta, __nv_bfloat16* y,
+                       int rows, int cols, float eps, cudaStream_t st) {
   if (cols % 4 || cols > 128 * 16) return OPUS_ERR_ARG;
   if (rows == 0) return OPUS_OK;
   const int grid = cdiv(rows, WARPS_PER_BLOCK), blk = WARPS_PER_BLOCK * 32;
-  if (cols <= 128 * 4) launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<4>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
-  else if (cols <= 128 * 10) launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<10>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
-  else launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<16>, dim3(grid), dim3(blk), 0, st, x, gamma, beta, y, rows, cols, eps);
+  if (cols <= 128 * 4) launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<4>, dim3(grid), dim3(blk), 0, st, x, delta, gamma, beta, y, rows, cols, eps);
+  else if (cols <= 128 * 10) launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<10>, dim3(grid), dim3(blk), 0, st, x, delta, gamma, beta, y, rows, cols, eps);
+  else launch_pdl(rows <= 1024, layernorm_f32_bf16_kernel<16>, dim3(grid), dim3(blk), 0, st, x, delta, gamma, beta, y, rows, cols, eps);
   return ok();
 }
 
@@ -610,17 +640,20 @@ int rmsnorm_bf16(const __nv_bfloat16* x, const float* partial, int n_partial, co
   if (cols % 8 || cols > 8192) return OPUS_ERR_ARG;
   if ((x == nullptr) == (partial == nullptr)) return OPUS_ERR_ARG;
   if (rows == 0) return OPUS_OK;
+  const bool plain = partial == nullptr && residual == nullptr;
   if (rows <= 1024) {  // decode-sized: one 512-thread CTA per row
     if (cols <= 4096)
-      launch_pdl(true, rmsnorm_bf16_kernel<512, 1, 1>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+      launch_pdl(true, rmsnorm_bf16_kernel<512, 1, 1, false>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
     else
-      launch_pdl(true, rmsnorm_bf16_kernel<512, 1, 2>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+      launch_pdl(true, rmsnorm_bf16_kernel<512, 1, 2, false>, dim3(rows), dim3(512), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
   } else {             // prefill-sized: 128 threads per row, two rows per CTA
     const int grid = cdiv(rows, 2);
-    if (cols <= 4096)
-      launch_pdl(false, rmsnorm_bf16_kernel<128, 2, 4>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+    if (cols <= 4096 && plain)
+      launch_pdl(false, rmsnorm_bf16_kernel<128, 2, 4, true>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+    else if (cols <= 4096)
+      launch_pdl(false, rmsnorm_bf16_kernel<128, 2, 4, false>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
     else
-      launch_pdl(false, rmsnorm_bf16_kernel<128, 2, 8>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
+      launch_pdl(false, rmsnorm_bf16_kernel<128, 2, 8, false>, dim3(grid), dim3(256), 0, st, x, partial, n_partial, residual, h_out, w, y, rows, cols, eps);
   }
   return ok();
 }
@@ -649,22 +682,23 @@ int rope_llama_kvappend(__nv_bfloat16* qkv, const float* partial, int n_partial,
                         const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t, __nv_bfloat16* kcache,
                         __nv_bfloat16* vcache, int n_tok, int n_q_heads, int n_kv_heads, int head_dim, int ld,
                         int block_size, cudaStream_t st) {
-  if (head_dim % 8 || ld % 4) return OPUS_ERR_ARG;
+  if (head_dim % 16 || ld % 8) return OPUS_ERR_ARG;
   if (n_tok == 0) return OPUS_OK;
-  const long long total = (long long)n_tok * (n_q_heads + 2 * n_kv_heads) * (head_dim / 8);
+  const long long total = (long long)n_tok * (n_q_heads + 2 * n_kv_heads) * (head_dim / 16);
   launch_pdl(n_tok <= 1024, rope_llama_kvappend_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, partial, n_partial, pos, slot, cos_t, sin_t, kcache,
                                                               vcache, n_tok, n_q_heads, n_kv_heads, head_dim, ld,
                                                               block_size);
   return ok();
 }
 
-int final_ln_meanpool(const float* x, const int* cu_seqlens, const float* gamma, const float* beta, float* pooled,
+int final_ln_meanpool(const float* x, const __nv_bfloat16* delta, const int* cu_seqlens, const float* gamma,
+                      const float* beta, float* pooled,
                       __nv_bfloat16* pooled_l2, float* hidden_out, int n_seqs, int dim, float eps, cudaStream_t st) {
   if (dim % 4 || dim > 128 * 10) return OPUS_ERR_ARG;
   if (n_seqs == 0) return OPUS_OK;
   const int threads = 256;
   const size_t smem = (size_t)(threads / 32) * dim * sizeof(float);
-  launch_pdl(false, final_ln_meanpool_kernel<10>, dim3(n_seqs), dim3(threads), smem, st, x, cu_seqlens, gamma, beta, pooled, pooled_l2, hidden_out,
+  launch_pdl(false, final_ln_meanpool_kernel<10>, dim3(n_seqs), dim3(threads), smem, st, x, delta, cu_seqlens, gamma, beta, pooled, pooled_l2, hidden_out,
                                                              dim, eps);
   return ok();
 }

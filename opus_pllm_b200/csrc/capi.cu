@@ -90,9 +90,10 @@ int opus_esm_embed(const int32_t* tok, const float* scale, const float* table, f
   RET(esm_embed(tok, scale, table, x, n_tok, dim, ST(stream)), "opus_esm_embed");
 }
 
-int opus_layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, void* y, int rows, int cols,
-                            float eps, void* stream) {
-  RET(layernorm_f32_bf16(x, gamma, beta, static_cast<bf16*>(y), rows, cols, eps, ST(stream)),
+int opus_layernorm_f32_bf16(float* x, const void* delta, const float* gamma, const float* beta, void* y, int rows,
+                            int cols, float eps, void* stream) {
+  RET(layernorm_f32_bf16(x, static_cast<const bf16*>(delta), gamma, beta, static_cast<bf16*>(y), rows, cols, eps,
+                         ST(stream)),
       "opus_layernorm_f32_bf16");
 }
 
@@ -120,10 +121,10 @@ int opus_rope_llama_kvappend_bf16(void* qkv, const float* partial, int n_partial
       "opus_rope_llama_kvappend_bf16");
 }
 
-int opus_final_ln_meanpool(const float* x, const int32_t* cu_seqlens, const float* gamma, const float* beta,
-                           float* pooled, void* pooled_l2, float* hidden_out, int n_seqs, int dim, float eps,
-                           void* stream) {
-  RET(final_ln_meanpool(x, cu_seqlens, gamma, beta, pooled, static_cast<bf16*>(pooled_l2), hidden_out, n_seqs, dim,
+int opus_final_ln_meanpool(const float* x, const void* delta, const int32_t* cu_seqlens, const float* gamma,
+                           const float* beta, float* pooled, void* pooled_l2, float* hidden_out, int n_seqs, int dim,
+                           float eps, void* stream) {
+  RET(final_ln_meanpool(x, static_cast<const bf16*>(delta), cu_seqlens, gamma, beta, pooled, static_cast<bf16*>(pooled_l2), hidden_out, n_seqs, dim,
                         eps, ST(stream)),
       "opus_final_ln_meanpool");
 }

@@ -12,8 +12,9 @@ namespace opus {
 
 // ---- bandwidth.cu ----
 int esm_embed(const int* tok, const float* scale, const float* table, float* x, int n_tok, int dim, cudaStream_t st);
-int layernorm_f32_bf16(const float* x, const float* gamma, const float* beta, __nv_bfloat16* y, int rows, int cols,
-                       float eps, cudaStream_t st);
+// y = LayerNorm(x (+ delta)); when delta != nullptr x is updated in place (x += delta) — delta may alias y.
+int layernorm_f32_bf16(float* x, const __nv_bfloat16* delta, const float* gamma, const float* beta, __nv_bfloat16* y,
+                       int rows, int cols, float eps, cudaStream_t st);
 // y = w * rmsnorm(h), h = x (or bf16(sum of n_partial fp32 partials)) (+ residual); h optionally written to h_out;
 // y == nullptr skips the normalisation (pure reduce + residual).
 int rmsnorm_bf16(const __nv_bfloat16* x, const float* partial, int n_partial, const __nv_bfloat16* residual,
@@ -27,7 +28,8 @@ int rope_llama_kvappend(__nv_bfloat16* qkv, const float* partial, int n_partial,
                         const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t, __nv_bfloat16* kcache,
                         __nv_bfloat16* vcache, int n_tok, int n_q_heads, int n_kv_heads, int head_dim, int ld,
                         int block_size, cudaStream_t st);
-int final_ln_meanpool(const float* x, const int* cu_seqlens, const float* gamma, const float* beta, float* pooled,
+int final_ln_meanpool(const float* x, const __nv_bfloat16* delta, const int* cu_seqlens, const float* gamma,
+                      const float* beta, float* pooled,
                       __nv_bfloat16* pooled_l2, float* hidden_out, int n_seqs, int dim, float eps, cudaStream_t st);
 int l2norm_f32_bf16(const float* x, __nv_bfloat16* y, int rows, int dim, cudaStream_t st);
 int splice_gather(const int* src, const __nv_bfloat16* embed, const __nv_bfloat16* soft, __nv_bfloat16* out, int n_rows,

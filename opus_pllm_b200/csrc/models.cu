@@ -78,20 +78,26 @@ int esm2_forward(const opus_esm2_model* m, const opus_esm2_workspace* ws, const 
   bf16* qkv = static_cast<bf16*>(ws->qkv);
   bf16* attn = static_cast<bf16*>(ws->attn);
   bf16* ffb = static_cast<bf16*>(ws->ffn);
+  // The fp32 residual stream x is only touched by the LayerNorm kernels: out_proj / fc2 write their bf16 result
+  // ("delta") into the xn buffer (free once the GEMM that read it has run) and the NEXT LayerNorm folds it into x.
+  // That keeps the GEMM epilogues light (bf16 stores, no fp32 read-modify-write with row-per-thread access) and
+  // matches the reference's autocast rounding (half-precision Linear output added to the fp32 stream).
+  const bf16* pending = nullptr;
   for (int l = 0; l < m->n_layers; ++l) {
     const opus_esm2_layer& L = m->layers[l];
-    OPUS_TRY(layernorm_f32_bf16(ws->x, L.ln1_g, L.ln1_b, xn, n_tok, d, m->ln_eps, st));
+    OPUS_TRY(layernorm_f32_bf16(ws->x, pending, L.ln1_g, L.ln1_b, xn, n_tok, d, m->ln_eps, st));
     OPUS_TRY(linear(xn, n_tok, L.wqkv, 3 * d, d, EPI_BF16, qkv, 3 * d, L.bqkv, nullptr, 0, nullptr, 0, st));
     OPUS_TRY(rope_esm(qkv, pos, m->rope_cos, m->rope_sin, n_tok, m->n_heads, hd, 3 * d, 0.125f, st));
     OPUS_TRY(attn_varlen(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu_seqlens, n_seqs, max_len,
                          m->n_heads, m->n_heads, hd, 0, 1.0f, st));
-    OPUS_TRY(linear(attn, n_tok, L.wo, d, d, EPI_RES_F32, ws->x, d, L.bo, ws->x, d, nullptr, 0, st));
-    OPUS_TRY(layernorm_f32_bf16(ws->x, L.ln2_g, L.ln2_b, xn, n_tok, d, m->ln_eps, st));
+    OPUS_TRY(linear(attn, n_tok, L.wo, d, d, EPI_BF16, xn, d, L.bo, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(layernorm_f32_bf16(ws->x, xn, L.ln2_g, L.ln2_b, xn, n_tok, d, m->ln_eps, st));
     OPUS_TRY(linear(xn, n_tok, L.w1, ffn, d, EPI_BF16_GELU, ffb, ffn, L.b1, nullptr, 0, nullptr, 0, st));
-    OPUS_TRY(linear(ffb, n_tok, L.w2, d, ffn, EPI_RES_F32, ws->x, d, L.b2, ws->x, d, nullptr, 0, st));
+    OPUS_TRY(linear(ffb, n_tok, L.w2, d, ffn, EPI_BF16, xn, d, L.b2, nullptr, 0, nullptr, 0, st));
+    pending = xn;
   }
-  OPUS_TRY(final_ln_meanpool(ws->x, cu_seqlens, m->lnf_g, m->lnf_b, pooled, static_cast<bf16*>(pooled_l2), hidden_out,
-                             n_seqs, d, m->ln_eps, st));
+  OPUS_TRY(final_ln_meanpool(ws->x, pending, cu_seqlens, m->lnf_g, m->lnf_b, pooled, static_cast<bf16*>(pooled_l2),
+                             hidden_out, n_seqs, d, m->ln_eps, st));
   return OPUS_OK;
 }
 

@@ -116,10 +116,14 @@ def esm_embed(tok: torch.Tensor, scale: torch.Tensor, table: torch.Tensor) -> to
     return x
 
 
-def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              delta: torch.Tensor | None = None) -> torch.Tensor:
+    """y = LN(x (+ delta)); with delta, x is updated in place (x += delta)."""
     _chk(x, F32, "x"); _chk(gamma, F32, "gamma"); _chk(beta, F32, "beta")
+    if delta is not None:
+        _chk(delta, BF16, "delta")
     y = torch.empty(x.shape, dtype=BF16, device=x.device)
-    L.check(L.load().opus_layernorm_f32_bf16(_p(x), _p(gamma), _p(beta), _p(y), x.shape[0], x.shape[1], eps,
+    L.check(L.load().opus_layernorm_f32_bf16(_p(x), _p(delta), _p(gamma), _p(beta), _p(y), x.shape[0], x.shape[1], eps,
                                              _stream()), "opus_layernorm_f32_bf16")
     return y
 
@@ -160,13 +164,13 @@ def rope_llama_kvappend_(qkv: torch.Tensor, pos: torch.Tensor, slot: torch.Tenso
 
 
 def final_ln_meanpool(x: torch.Tensor, cu_seqlens: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
-                      eps: float = 1e-5, want_hidden: bool = False):
+                      eps: float = 1e-5, want_hidden: bool = False, delta: torch.Tensor | None = None):
     _chk(x, F32, "x"); _chk(cu_seqlens, I32, "cu_seqlens")
     n_seqs, dim = cu_seqlens.numel() - 1, x.shape[1]
     pooled = torch.empty((n_seqs, dim), dtype=F32, device=x.device)
     pooled_l2 = torch.empty((n_seqs, dim), dtype=BF16, device=x.device)
     hidden = torch.empty_like(x) if want_hidden else None
-    L.check(L.load().opus_final_ln_meanpool(_p(x), _p(cu_seqlens), _p(gamma), _p(beta), _p(pooled), _p(pooled_l2),
+    L.check(L.load().opus_final_ln_meanpool(_p(x), _p(delta), _p(cu_seqlens), _p(gamma), _p(beta), _p(pooled), _p(pooled_l2),
                                             _p(hidden), n_seqs, dim, eps, _stream()), "opus_final_ln_meanpool")
     return pooled, pooled_l2, hidden
 

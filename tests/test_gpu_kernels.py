@@ -169,6 +169,23 @@ def test_layernorm(ops):
     _close_bf16(ops.layernorm(x, g, b, 1e-5), R.layernorm_ref(x, g, b, 1e-5), ulps=1.0, atol=1e-4)
 
 
+def test_layernorm_folds_pending_delta_in_place(ops):
+    x = _randn((600, 1280), 130, scale=3.0, dtype=torch.float32)
+    d = _randn((600, 1280), 131)
+    g = _randn((1280,), 132, dtype=torch.float32)
+    b = _randn((1280,), 133, dtype=torch.float32)
+    want_x = x + d.float()
+    got = ops.layernorm(x, g, b, 1e-5, delta=d)
+    assert torch.equal(x, want_x)
+    _close_bf16(got, R.layernorm_ref(want_x, g, b, 1e-5), ulps=1.0, atol=1e-4)
+    # final LN + pool with a pending delta
+    cu = torch.tensor([0, 200, 600], dtype=torch.int32).cuda()
+    pooled, _, hidden = ops.final_ln_meanpool(x, cu, g, b, 1e-5, want_hidden=True, delta=d)
+    h_want = R.layernorm_ref(x + d.float(), g, b)
+    assert torch.allclose(hidden, h_want, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(pooled, R.meanpool_ref(h_want, cu.tolist()), rtol=1e-4, atol=1e-4)
+
+
 def test_rmsnorm_exact(ops):
     x = _randn((777, 4096), 33, scale=2.0)
     w = _randn((4096,), 34)
