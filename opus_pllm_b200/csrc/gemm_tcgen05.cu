@@ -74,6 +74,24 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
   *reinterpret_cast<uint4*>(dst) = q;
 }
 
+// Transposed-form bf16 stores. Thread = accumulator row (consecutive lanes = consecutive output addresses), so a plain
+// store is 2 bytes per lane — measured ~10 us slower per tile than 4-byte stores. Lane pairs therefore exchange one value
+// per column pair: even lanes write column i for rows (l, l+1), odd lanes write column i+1 for rows (l-1, l), 4 bytes each.
+// x[i] = value of (this thread's row, column i); `base` points at (column 0, this thread's row); requires even `row`
+// alignment of the pair (row of an even lane is even) and an even number of valid rows.
+__device__ __forceinline__ void store_bf16_transposed_paired(__nv_bfloat16* base, size_t ld, const float (&x)[32],
+                                                            int n_valid, int lane) {
+  const bool odd = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float send = odd ? x[i] : x[i + 1];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    const int col = odd ? i + 1 : i;
+    const uint32_t packed = odd ? pack_bf16x2(recv, x[i + 1]) : pack_bf16x2(x[i], recv);
+    if (col < n_valid) *reinterpret_cast<uint32_t*>(base + (size_t)col * ld - (odd ? 1 : 0)) = packed;
+  }
+}
+
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], int row, int col0,
                                                int split) {
   float v[32];
@@ -177,48 +195,77 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   // ---- transposed (swap-AB): accumulator row = output feature `row`, column = batch row n -> out[n*ldo + row] ----
   const bool row_ok = row < p.M;
   if (p.epi == EPI_PARTIAL_F32) {
-    float* base = reinterpret_cast<float*>(p.out) + (size_t)split * p.N * p.ldo;
+    float* base = reinterpret_cast<float*>(p.out) + ((size_t)split * p.N + col0) * p.ldo + row;
+    const int nv = row_ok ? min(32, p.N - col0) : 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int n = col0 + i;
-      if (row_ok && n < p.N) base[(size_t)n * p.ldo + row] = v[i];
-    }
+    for (int i = 0; i < 32; ++i)
+      if (i < nv) base[(size_t)i * p.ldo] = v[i];
     return;
   }
   if (p.epi == EPI_SWIGLU) {
     // rows (2j, 2j+1) = (gate_j, up_j) live in adjacent lanes
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)col0 * p.ldo + (row >> 1);
+    float o[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float other = __shfl_down_sync(0xffffffffu, v[i], 1);
-      const int n = col0 + i;
-      if (((row & 1) == 0) && row + 1 < p.M && n < p.N) {
-        const float g = bf16_round(v[i]);
-        const float u = bf16_round(other);
-        reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + (row >> 1)] =
-            __float2bfloat16_rn(bf16_round(silu_f(g)) * u);
-      }
+      o[i] = bf16_round(silu_f(bf16_round(v[i]))) * bf16_round(other);  // meaningful on even lanes only
+    }
+    // even lanes hold out[row/2]; lanes l and l+2 pair up so that every store is 4 bytes (see the note above)
+    const int lane = row & 31;
+    const bool hi = lane & 2;
+    const int nv = (((lane & 1) == 0) && (row | 3) < p.M) ? min(32, p.N - col0) : 0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float send = hi ? o[i] : o[i + 1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      const int col = hi ? i + 1 : i;
+      const uint32_t packed = hi ? pack_bf16x2(recv, o[i + 1]) : pack_bf16x2(o[i], recv);
+      if (col < nv) *reinterpret_cast<uint32_t*>(base + (size_t)col * p.ldo - (hi ? 1 : 0)) = packed;
     }
     return;
   }
+  // Remaining modes: one specialised, branch-free store loop per epilogue (mode checks hoisted out of the element loop;
+  // residual values are all loaded before the first store because `out` may alias `residual`).
   const float b = (p.bias != nullptr && row_ok) ? p.bias[row] : 0.0f;
+  const int n_valid = row_ok ? min(32, p.N - col0) : 0;  // columns (batch rows) of this chunk that exist
+  if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU) {
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)col0 * p.ldo + row;
+    const bool gelu = p.epi == EPI_BF16_GELU;
+    float x[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int n = col0 + i;
-    if (!(row_ok && n < p.N)) continue;
-    float x = v[i] + b;
-    if (p.epi == EPI_BF16) {
-      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + row] = __float2bfloat16_rn(x);
-    } else if (p.epi == EPI_BF16_GELU) {
-      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + row] = __float2bfloat16_rn(gelu_erf(x));
-    } else if (p.epi == EPI_RES_F32) {
-      const float rres = reinterpret_cast<const float*>(p.residual)[(size_t)n * p.ldr + row];
-      reinterpret_cast<float*>(p.out)[(size_t)n * p.ldo + row] = rres + x;
-    } else if (p.epi == EPI_RES_BF16) {
-      const float rres = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[(size_t)n * p.ldr + row]);
-      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)n * p.ldo + row] = __float2bfloat16_rn(rres + bf16_round(x));
-    } else if (p.epi == EPI_F32) {
-      reinterpret_cast<float*>(p.out)[(size_t)n * p.ldo + row] = x;
+    for (int i = 0; i < 32; ++i) {
+      x[i] = v[i] + b;
+      if (gelu) x[i] = gelu_erf(x[i]);
     }
+    // M (features) is even and tiles start at multiples of 128, so a lane pair is either fully valid or fully invalid
+    const int nv = (row | 1) < p.M ? min(32, p.N - col0) : 0;
+    store_bf16_transposed_paired(base, (size_t)p.ldo, x, nv, row & 31);
+  } else if (p.epi == EPI_F32) {
+    float* base = reinterpret_cast<float*>(p.out) + (size_t)col0 * p.ldo + row;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n_valid) base[(size_t)i * p.ldo] = v[i] + b;
+  } else if (p.epi == EPI_RES_BF16) {
+    const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)col0 * p.ldr + row;
+    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)col0 * p.ldo + row;
+    float rr[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) rr[i] = (i < n_valid) ? __bfloat162float(rbase[(size_t)i * p.ldr]) : 0.f;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = rr[i] + bf16_round(v[i] + b);
+    const int nv = (row | 1) < p.M ? min(32, p.N - col0) : 0;
+    store_bf16_transposed_paired(base, (size_t)p.ldo, x, nv, row & 31);
+  } else if (p.epi == EPI_RES_F32) {
+    const float* rbase = reinterpret_cast<const float*>(p.residual) + (size_t)col0 * p.ldr + row;
+    float* base = reinterpret_cast<float*>(p.out) + (size_t)col0 * p.ldo + row;
+    float rr[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) rr[i] = (i < n_valid) ? rbase[(size_t)i * p.ldr] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < n_valid) base[(size_t)i * p.ldo] = rr[i] + (v[i] + b);
   }
 }
 
@@ -470,6 +517,10 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return OPUS_ERR_ARG;
   if (!a.transposed && (a.N % 8)) return OPUS_ERR_ARG;
   if (a.epi == EPI_SWIGLU && ((a.transposed ? a.M : a.N) % 16)) return OPUS_ERR_ARG;
+  if (a.transposed && (a.M % 2) && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU || a.epi == EPI_RES_BF16))
+    return OPUS_ERR_ARG;  // paired 4-byte stores need an even feature count
+  if (a.transposed && (a.ldo % 2) && a.epi != EPI_PARTIAL_F32 && a.epi != EPI_F32 && a.epi != EPI_RES_F32)
+    return OPUS_ERR_ARG;
   if ((a.epi == EPI_RES_F32 || a.epi == EPI_RES_BF16) && a.residual == nullptr) return OPUS_ERR_ARG;
   if (a.epi == EPI_F32 && !a.transposed) return OPUS_ERR_ARG;
 
