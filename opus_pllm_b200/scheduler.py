@@ -1,0 +1,176 @@
+"""Continuous batching over the paged KV cache (BASELINE config 5: long generations, 512 new tokens).
+
+The reference has no scheduler: `run_opus_ddp.py` walks the prompt list in fixed batches of 8 and every batch runs until
+its slowest row stops (`eval/run_opus_ddp.py:75,88-134`). Here a fixed number of decode *slots* is kept busy instead:
+whenever a sequence emits EOS (or reaches max_new_tokens) its pages go back to the allocator and the slot is refilled by
+prefilling the next waiting prompt, while the other slots keep decoding. Outputs are returned in input order, so the
+call stays a drop-in for the per-batch `generate` loop of the eval scripts. Greedy only.
+
+All device work reuses the C ABI entry points (`opus_llama_prefill`, `opus_llama_select`, `opus_llama_decode_loop`); the
+scheduler itself is host logic over the decode-state arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import deque
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+from .llama import BLOCK
+from .model import B200OpusLlama, SplicePlan
+
+
+class ContinuousBatcher:
+    def __init__(self, model: B200OpusLlama, max_slots: int = 64, round_steps: int = 8, encoder_chunk: int = 64):
+        self.model, self.llama = model, model.llama
+        self.S, self.R, self.enc_chunk = max_slots, round_steps, encoder_chunk
+        self.dev = model.device
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _soft_tokens(self, seqs):
+        outs = []
+        for i in range(0, len(seqs), self.enc_chunk):
+            outs.append(self.model._soft_tokens(list(seqs[i: i + self.enc_chunk]), None))
+        return torch.cat(outs, 0)  # [n, n_soft, H]
+
+    def _state(self, n: int, max_blocks: int, out_ld: int, eos_ids, pad_id: int):
+        i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=self.dev)  # noqa: E731
+        bufs = dict(next_tok=i32(n), ctx_len=i32(n), pos=i32(n), slot=i32(n), block_table=i32(n, max_blocks),
+                    finished=i32(n), n_unfinished=i32(1), step=i32(1), out_ids=i32(n, out_ld),
+                    eos=torch.tensor(list(eos_ids) or [-1], dtype=torch.int32, device=self.dev))
+        s = L.DecodeState()
+        for k in ("next_tok", "ctx_len", "pos", "slot", "block_table", "finished", "n_unfinished", "step", "out_ids"):
+            setattr(s, k, bufs[k].data_ptr())
+        s.max_blocks, s.out_ld = max_blocks, out_ld
+        s.eos_ids, s.n_eos, s.pad_id = bufs["eos"].data_ptr(), len(eos_ids), pad_id
+        return s, bufs
+
+    # ------------------------------------------------------------------------------------------ main entry
+    @torch.no_grad()
+    def generate(self, prompts: list[torch.Tensor], seqs: list[str], max_new_tokens: int, eos_ids=(), pad_id: int = 0,
+                 use_graph: bool = True) -> list[torch.Tensor]:
+        """prompts[i]: 1-D int64 ids with one -200 sentinel (no padding); seqs[i]: its protein. Returns, per prompt, the
+        new tokens (int64, cut after the first EOS, at most max_new_tokens) — same content as generate() row by row."""
+        lib, ll = L.load(), self.llama
+        lib.opus_release_graphs()  # decode graphs are keyed by buffer addresses; ours are private to this call
+        n_req = len(prompts)
+        eos_set = set(int(e) for e in eos_ids)
+        soft = self._soft_tokens(seqs)
+        soft2d = soft.reshape(-1, soft.shape[-1]).contiguous()
+        n_soft = soft.shape[1]
+        # per-request splice plans (request i uses protein slot i)
+        plans = []
+        for i, p in enumerate(prompts):
+            ids = p.detach().cpu().numpy()[None, :]
+            sp = SplicePlan(ids, None, n_soft, 1)
+            src = sp.src.copy()
+            neg = src < 0
+            src[neg] -= i * n_soft            # -(j+1) -> -(i*n_soft + j + 1)
+            plans.append(src)
+        lens = np.array([len(s) for s in plans], dtype=np.int64)
+        margin = self.R + 1
+        max_blocks = int((lens.max() + max_new_tokens + margin + BLOCK - 1) // BLOCK)
+        need_pages = lambda ln: int((ln + max_new_tokens + margin + BLOCK - 1) // BLOCK)  # noqa: E731
+        S = min(self.S, n_req)
+        # worst case all slots hold the longest prompts, +1 scratch page for idle slots
+        ll._ensure_cache(S * max_blocks + 1)
+        ll._ensure_ws(int(max(lens.max() * min(S, 8), S)), S)
+        scratch = ll._alloc.alloc(1)[0]
+
+        st, bufs = self._state(S, max_blocks, self.R, eos_ids, pad_id)
+        bufs["block_table"].fill_(scratch)
+        bufs["finished"].fill_(1)
+        slot_req = [-1] * S                   # request id held by each slot
+        slot_pages: list[list[int]] = [[] for _ in range(S)]
+        results: list[list[int]] = [[] for _ in range(n_req)]
+        done = [False] * n_req
+        waiting = deque(range(n_req))
+        stream = torch.cuda.current_stream().cuda_stream
+        active = 0
+
+        def retire(slot):
+            nonlocal active
+            r = slot_req[slot]
+            done[r] = True
+            ll._alloc.release(slot_pages[slot])
+            slot_pages[slot], slot_req[slot] = [], -1
+            bufs["block_table"][slot].fill_(scratch)
+            bufs["finished"][slot] = 1
+            bufs["ctx_len"][slot] = 0
+            active -= 1
+
+        def absorb(r, toks) -> bool:
+            """append tokens of request r; True when the request is complete"""
+            for t in toks:
+                results[r].append(int(t))
+                if int(t) in eos_set or len(results[r]) >= max_new_tokens:
+                    return True
+            return False
+
+        while waiting or active:
+            # ---- admit: prefill waiting prompts into free slots (bounded by workspace rows)
+            free = [s for s in range(S) if slot_req[s] < 0]
+            adm = []
+            budget = ll._ws_rows
+            while free and waiting and lens[waiting[0]] <= budget:
+                r = waiting.popleft()
+                adm.append((free.pop(0), r))
+                budget -= int(lens[r])
+            if adm:
+                cu = np.zeros(len(adm) + 1, dtype=np.int32)
+                np.cumsum([lens[r] for _, r in adm], out=cu[1:])
+                n_tok = int(cu[-1])
+                bt = np.full((len(adm), max_blocks), scratch, dtype=np.int32)
+                for j, (s, r) in enumerate(adm):
+                    pages = ll._alloc.alloc(need_pages(int(lens[r])))
+                    slot_pages[s] = pages
+                    bt[j, : len(pages)] = pages
+                seq_of = np.repeat(np.arange(len(adm), dtype=np.int32), np.diff(cu))
+                pos = (np.arange(n_tok, dtype=np.int32) - cu[:-1][seq_of]).astype(np.int32)
+                slot_map = (bt[seq_of, pos // BLOCK] * BLOCK + pos % BLOCK).astype(np.int32)
+                src = np.concatenate([plans[r] for _, r in adm]).astype(np.int32)
+                embeds = ops.splice_gather(ops.h2d(src, self.dev), ll.embed, soft2d)
+                d_pos, d_slot, d_cu = (ops.h2d(a, self.dev) for a in (pos, slot_map, cu))
+                d_last = ops.h2d((cu[1:] - 1).astype(np.int32), self.dev)
+                L.check(lib.opus_llama_prefill(C.byref(ll._model), C.byref(ll._cache), C.byref(ll._ws),
+                                               embeds.data_ptr(), d_pos.data_ptr(), d_slot.data_ptr(), d_cu.data_ptr(),
+                                               d_last.data_ptr(), len(adm), n_tok, int(np.diff(cu).max()), stream),
+                        "opus_llama_prefill")
+                ast, ab = self._state(len(adm), max_blocks, 1, eos_ids, pad_id)
+                ab["n_unfinished"].fill_(len(adm))
+                L.check(lib.opus_llama_select(C.byref(ll._model), C.byref(ll._ws), C.byref(ast), len(adm), stream),
+                        "opus_llama_select")
+                first = ops.d2h(ab["next_tok"]).tolist()
+                idx = torch.tensor([s for s, _ in adm], dtype=torch.long, device=self.dev)
+                bufs["next_tok"][idx] = ab["next_tok"]
+                bufs["ctx_len"][idx] = torch.tensor([int(lens[r]) for _, r in adm], dtype=torch.int32, device=self.dev)
+                bufs["block_table"][idx] = ops.h2d(bt, self.dev)
+                bufs["finished"][idx] = 0
+                for j, (s, r) in enumerate(adm):
+                    slot_req[s] = r
+                    active += 1
+                    if absorb(r, [first[j]]):
+                        retire(s)
+            if not active:
+                continue
+            # ---- one round of R decode steps over all slots (idle slots spin on the scratch page)
+            idle = [s for s in range(S) if slot_req[s] < 0]
+            if idle:
+                bufs["ctx_len"][torch.tensor(idle, device=self.dev)] = 0
+            bufs["step"].fill_(-1)
+            bufs["n_unfinished"].fill_(active)
+            rc = lib.opus_llama_decode_loop(C.byref(ll._model), C.byref(ll._cache), C.byref(ll._ws), C.byref(st), S,
+                                            self.R, 0, int(use_graph), stream)
+            L.check(rc, "opus_llama_decode_loop")
+            toks = ops.d2h(bufs["out_ids"]).numpy()          # [S, R]; synchronises
+            for s in range(S):
+                r = slot_req[s]
+                if r >= 0 and absorb(r, toks[s]):
+                    retire(s)
+        ll._alloc.release([scratch])
+        torch.cuda.current_stream().synchronize()
+        lib.opus_release_graphs()
+        return [torch.tensor(r, dtype=torch.int64) for r in results]
