@@ -1,0 +1,175 @@
+"""Model loading for real OPUS-PLLM weights: counterpart of `multi_modality_v1/model/builder.py::load_pretrained_model`.
+
+Same signature and return value `(tokenizer, model, context_len)`; the files read are the ones the reference reads
+("Weight formats to load"):
+  1. HF Llama-3 directory: `config.json` + `*.safetensors` shards                       (builder.py:61-65)
+  2. `<weights>/lora_adapter/{adapter_config.json, adapter_model.safetensors|.bin}`     (builder.py:105-109, peft)
+  3. `<weights>/modality_refinement_projector/modality_refinement_projection.bin`       (builder.py:111, opus_arch.py:85-89)
+  4. `<weights>/modality_encoder/modality_encoding_adapter.ckpt` (Lightning checkpoint)  (protein_projector/builder.py:16-25)
+  5. ESM-2 t33 650M weights: a fair-esm `.pt` (hub cache) or an HF `EsmModel` directory  (cstp_v3/modelling.py:21)
+No peft / lightning / fair-esm import is needed: the readers below only parse the state dicts.
+`load_8bit` / `load_4bit` are accepted and ignored (this backend is bf16, the north star excludes bitsandbytes).
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+import re
+import warnings
+
+import torch
+
+
+def return_cstp_path(args_path: str, file_name: str) -> str:
+    return f"{args_path}{file_name}" if args_path.endswith("/") else f"{args_path}/{file_name}"
+
+
+# ------------------------------------------------------------------------------------------------ readers (CPU only)
+def _load_any(path: str) -> dict:
+    if path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        return load_file(path)
+    return torch.load(path, map_location="cpu", weights_only=False)
+
+
+def read_hf_llama(model_dir: str) -> tuple[dict, dict]:
+    """-> (state dict with HF names, config kwargs for B200Llama)"""
+    cfg = json.load(open(os.path.join(model_dir, "config.json")))
+    sd = {}
+    shards = sorted(glob.glob(os.path.join(model_dir, "*.safetensors"))) or \
+        sorted(glob.glob(os.path.join(model_dir, "pytorch_model*.bin")))
+    if not shards:
+        raise FileNotFoundError(f"no *.safetensors / pytorch_model*.bin under {model_dir}")
+    for sh in shards:
+        sd.update(_load_any(sh))
+    if "lm_head.weight" not in sd and cfg.get("tie_word_embeddings", False):
+        sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    n_heads = cfg["num_attention_heads"]
+    kw = dict(n_layers=cfg["num_hidden_layers"], dim=cfg["hidden_size"], n_q_heads=n_heads,
+              n_kv_heads=cfg.get("num_key_value_heads", n_heads),
+              head_dim=cfg.get("head_dim") or cfg["hidden_size"] // n_heads, ffn_dim=cfg["intermediate_size"],
+              vocab=cfg["vocab_size"], rms_eps=cfg.get("rms_norm_eps", 1e-5),
+              rope_theta=cfg.get("rope_theta", 500000.0))
+    scaling = cfg.get("rope_scaling")
+    if scaling and scaling.get("rope_type", scaling.get("type")) not in (None, "default"):
+        warnings.warn(f"rope_scaling {scaling} is not applied (Llama-3-8B base uses the default rope)")
+    extra = dict(eos_token_id=cfg.get("eos_token_id"), max_sequence_length=cfg.get("max_sequence_length"))
+    return sd, dict(kw, **{"_extra": extra})
+
+
+def read_peft_lora(adapter_dir: str) -> tuple[dict, float, int]:
+    """peft adapter dir -> ({'model.layers.N.<mod>.lora_A.weight': ..., '...lora_B.weight': ...}, alpha, r)"""
+    cfg = json.load(open(os.path.join(adapter_dir, "adapter_config.json")))
+    f = [p for p in (os.path.join(adapter_dir, "adapter_model.safetensors"), os.path.join(adapter_dir, "adapter_model.bin"))
+         if os.path.exists(p)]
+    if not f:
+        raise FileNotFoundError(f"no adapter_model.safetensors/.bin under {adapter_dir}")
+    raw = _load_any(f[0])
+    out = {}
+    for k, v in raw.items():
+        k = re.sub(r"^base_model\.model\.", "", k)
+        k = k.replace(".lora_A.default.", ".lora_A.").replace(".lora_B.default.", ".lora_B.")
+        if ".lora_A." in k or ".lora_B." in k:
+            out[k] = v
+    if cfg.get("fan_in_fan_out"):
+        raise NotImplementedError("fan_in_fan_out LoRA adapters are not supported")
+    return out, float(cfg["lora_alpha"]), int(cfg["r"])
+
+
+def read_switch_projector(path: str) -> dict:
+    """`.bin` with keys containing 'switch_projector.' -> {'0.weight','0.bias','2.weight','2.bias'} (opus_arch.py:85-89)"""
+    raw = _load_any(path)
+    return {k.split("switch_projector.")[1]: v for k, v in raw.items() if "switch_projector" in k}
+
+
+def read_cstp_checkpoint(path: str) -> dict:
+    """Lightning checkpoint -> {'protein_projection.linear.weight', 'protein_projection.linear.bias'}"""
+    raw = _load_any(path)
+    sd = raw.get("state_dict", raw)
+    out = {k: v for k, v in sd.items() if k.startswith("protein_projection.linear.")}
+    if len(out) != 2:
+        raise KeyError(f"{path}: protein_projection.linear.{{weight,bias}} not found")
+    return out
+
+
+_HF_ESM = (("attention.self.query", "self_attn.q_proj"), ("attention.self.key", "self_attn.k_proj"),
+           ("attention.self.value", "self_attn.v_proj"), ("attention.output.dense", "self_attn.out_proj"),
+           ("attention.LayerNorm", "self_attn_layer_norm"), ("intermediate.dense", "fc1"), ("output.dense", "fc2"),
+           ("LayerNorm", "final_layer_norm"))
+
+
+def read_esm2(path: str) -> tuple[dict, dict]:
+    """fair-esm `.pt` (keys optionally prefixed 'encoder.sentence_encoder.') or HF EsmModel dir/file ->
+    (state dict with fair-esm names, config kwargs for B200ProteinEncoder)"""
+    if os.path.isdir(path):
+        raw = {}
+        for sh in sorted(glob.glob(os.path.join(path, "*.safetensors"))) or sorted(glob.glob(os.path.join(path, "*.bin"))):
+            raw.update(_load_any(sh))
+    else:
+        raw = _load_any(path)
+        raw = raw.get("model", raw)
+    sd = {}
+    for k, v in raw.items():
+        k = re.sub(r"^(encoder\.sentence_encoder\.|esm\.|model\.)", "", k)
+        if k.startswith("embeddings.word_embeddings."):
+            k = k.replace("embeddings.word_embeddings.", "embed_tokens.")
+        elif k.startswith("encoder.emb_layer_norm_after."):
+            k = k.replace("encoder.emb_layer_norm_after.", "emb_layer_norm_after.")
+        elif k.startswith("encoder.layer."):
+            m = re.match(r"encoder\.layer\.(\d+)\.(.*)\.(weight|bias)$", k)
+            if not m:
+                continue
+            for hf, fe in _HF_ESM:
+                if m.group(2) == hf:
+                    k = f"layers.{m.group(1)}.{fe}.{m.group(3)}"
+                    break
+            else:
+                continue
+        if k.startswith(("embed_tokens.", "layers.", "emb_layer_norm_after.")):
+            sd[k] = v
+    n_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("layers."))
+    dim = sd["embed_tokens.weight"].shape[1]
+    ffn = sd["layers.0.fc1.weight"].shape[0]
+    return sd, dict(n_layers=n_layers, dim=dim, n_heads=dim // 64, ffn_dim=ffn)
+
+
+# ------------------------------------------------------------------------------------------------ reference entry point
+def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=False, load_4bit=False,
+                          accelerator=None, switch_projector_type="mlp2x_gelu", cstp_path=True, esm_path=None,
+                          tokenizer=None, **kwargs):
+    """multi_modality_v1/model/builder.py:29-131 contract -> (tokenizer, model, context_len)."""
+    from .model import build_from_state_dicts
+    if model_name is None or not model_base_path:
+        raise NotImplementedError
+    if "llama" not in model_base_path.lower():
+        raise NotImplementedError("opus_pllm_b200 implements the Llama-3 family only")
+    if load_8bit or load_4bit:
+        warnings.warn("load_8bit/load_4bit are ignored: opus_pllm_b200 runs bf16 weights")
+    device = "cuda:0" if accelerator is None else f"cuda:{accelerator.process_index}"
+    llama_sd, llama_cfg = read_hf_llama(model_base_path)
+    extra = llama_cfg.pop("_extra")
+    if tokenizer is None:
+        import transformers
+        tokenizer = transformers.AutoTokenizer.from_pretrained(model_base_path, use_fast=False)
+        tokenizer.pad_token = tokenizer.unk_token = tokenizer.eos_token                 # builder.py:69-70
+        tokenizer.pad_token_id = tokenizer.unk_token_id = tokenizer.eos_token_id
+    if accelerator is not None:
+        accelerator.wait_for_everyone()                                                 # builder.py:102-103
+    lora_sd, alpha, r, switch_sd = None, 32.0, 16, None
+    if adapter_path is not None:
+        lora_sd, alpha, r = read_peft_lora(return_cstp_path(adapter_path, "lora_adapter"))
+        switch_sd = read_switch_projector(return_cstp_path(
+            adapter_path, "modality_refinement_projector/modality_refinement_projection.bin"))
+    else:
+        print("No adapter path!")
+    cstp_sd = read_cstp_checkpoint(cstp_path) if isinstance(cstp_path, str) else None
+    if esm_path is None:
+        esm_path = os.path.expanduser("~/.cache/torch/hub/checkpoints/esm2_t33_650M_UR50D.pt")  # fair-esm hub cache
+    esm_sd, esm_cfg = read_esm2(esm_path)
+    model = build_from_state_dicts(llama_sd, llama_cfg, esm_sd, esm_cfg, cstp_sd, switch_sd,
+                                   switch_type=switch_projector_type, lora_sd=lora_sd, lora_alpha=alpha, lora_r=r,
+                                   eos_token_id=extra["eos_token_id"] if extra["eos_token_id"] is not None else (),
+                                   device=device)
+    context_len = extra["max_sequence_length"] or 512                                  # builder.py:126-131
+    return tokenizer, model, context_len

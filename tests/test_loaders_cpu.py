@@ -1,0 +1,108 @@
+"""CPU tests of the weight-file readers (builder.py) and prompt helpers against the reference's semantics."""
+import json
+import os
+
+import torch
+from safetensors.torch import save_file
+
+from opus_pllm_b200 import builder, mm_utils, synth
+from oracle import esm2_ref
+
+
+def _write_llama_dir(d, cfg, sd):
+    os.makedirs(d, exist_ok=True)
+    json.dump(dict(num_hidden_layers=cfg["n_layers"], hidden_size=cfg["dim"], num_attention_heads=cfg["n_q_heads"],
+                   num_key_value_heads=cfg["n_kv_heads"], head_dim=cfg["head_dim"], intermediate_size=cfg["ffn_dim"],
+                   vocab_size=cfg["vocab"], rms_norm_eps=1e-5, rope_theta=500000.0, eos_token_id=[2, 3],
+                   model_type="llama"), open(os.path.join(d, "config.json"), "w"))
+    keys = sorted(sd)
+    save_file({k: sd[k].contiguous() for k in keys[: len(keys) // 2]}, os.path.join(d, "model-00001-of-00002.safetensors"))
+    save_file({k: sd[k].contiguous() for k in keys[len(keys) // 2:]}, os.path.join(d, "model-00002-of-00002.safetensors"))
+
+
+def write_fake_release(root, cfg, esm_cfg, seed=3):
+    """Lay out tiny synthetic weights exactly like an OPUS-PLLM release + its Llama base dir."""
+    lw = synth.llama_weights(cfg["n_layers"], cfg["dim"], cfg["n_q_heads"], cfg["n_kv_heads"], cfg["head_dim"],
+                             cfg["ffn_dim"], cfg["vocab"], seed=seed, peaked=True)
+    base = os.path.join(root, "Meta-Llama-3-tiny")
+    _write_llama_dir(base, cfg, lw)
+    w = os.path.join(root, "opus_weights")
+    os.makedirs(os.path.join(w, "lora_adapter")); os.makedirs(os.path.join(w, "modality_refinement_projector"))
+    os.makedirs(os.path.join(w, "modality_encoder"))
+    lora = synth.lora_adapters(lw, cfg["n_layers"], r=4, seed=seed)
+    json.dump(dict(r=4, lora_alpha=8, target_modules=["q_proj", "v_proj"], fan_in_fan_out=False, peft_type="LORA"),
+              open(os.path.join(w, "lora_adapter", "adapter_config.json"), "w"))
+    save_file({"base_model.model." + k: v.contiguous() for k, v in lora.items()},
+              os.path.join(w, "lora_adapter", "adapter_model.safetensors"))
+    pw = synth.projector_weights(esm_cfg["dim"], 256, 8 * cfg["dim"], seed=seed)
+    torch.save({"model.switch_projector." + k: pw[k] for k in ("0.weight", "0.bias", "2.weight", "2.bias")},
+               os.path.join(w, "modality_refinement_projector", "modality_refinement_projection.bin"))
+    torch.save({"state_dict": {"protein_projection.linear.weight": pw["protein_projection.linear.weight"],
+                               "protein_projection.linear.bias": pw["protein_projection.linear.bias"],
+                               "text_projection.linear.weight": torch.zeros(2, 2)}, "epoch": 1},
+               os.path.join(w, "modality_encoder", "modality_encoding_adapter.ckpt"))
+    ew = synth.esm2_weights(esm_cfg["n_layers"], esm_cfg["dim"], esm_cfg["ffn_dim"], seed=seed)
+    esm_pt = os.path.join(root, "esm2_tiny.pt")
+    torch.save({"model": {"encoder.sentence_encoder." + k: v for k, v in ew.items()}, "cfg": {}}, esm_pt)
+    return dict(base=base, weights=w, esm=esm_pt, llama=lw, lora=lora, proj=pw, esm_sd=ew)
+
+
+CFG = dict(n_layers=2, dim=256, n_q_heads=2, n_kv_heads=1, head_dim=128, ffn_dim=512, vocab=512)
+ESM = dict(n_layers=2, dim=128, n_heads=2, ffn_dim=256)
+
+
+def test_readers_roundtrip(tmp_path):
+    rel = write_fake_release(str(tmp_path), CFG, ESM)
+    sd, kw = builder.read_hf_llama(rel["base"])
+    extra = kw.pop("_extra")
+    assert kw == dict(CFG, rms_eps=1e-5, rope_theta=500000.0) and extra["eos_token_id"] == [2, 3]
+    assert set(sd) == set(rel["llama"]) and all(torch.equal(sd[k], rel["llama"][k]) for k in sd)
+    lora, alpha, r = builder.read_peft_lora(os.path.join(rel["weights"], "lora_adapter"))
+    assert (alpha, r) == (8.0, 4) and set(lora) == set(rel["lora"])
+    sw = builder.read_switch_projector(os.path.join(rel["weights"], "modality_refinement_projector",
+                                                    "modality_refinement_projection.bin"))
+    assert set(sw) == {"0.weight", "0.bias", "2.weight", "2.bias"} and torch.equal(sw["2.bias"], rel["proj"]["2.bias"])
+    cs = builder.read_cstp_checkpoint(builder.return_cstp_path(rel["weights"], "modality_encoder/modality_encoding_adapter.ckpt"))
+    assert set(cs) == {"protein_projection.linear.weight", "protein_projection.linear.bias"}
+    esd, ecfg = builder.read_esm2(rel["esm"])
+    assert ecfg == ESM and set(esd) == set(rel["esm_sd"])
+
+
+def test_read_esm2_accepts_hf_names(tmp_path):
+    ew = synth.esm2_weights(2, 128, 256, seed=1)
+    hf = {"esm." + k: v.contiguous() for k, v in esm2_ref.to_hf_esm_state_dict(ew, 2).items()}
+    d = tmp_path / "hf_esm"
+    d.mkdir()
+    save_file(hf, str(d / "model.safetensors"))
+    sd, cfg = builder.read_esm2(str(d))
+    assert cfg == dict(n_layers=2, dim=128, n_heads=2, ffn_dim=256)
+    assert set(sd) == set(ew) and all(torch.equal(sd[k], ew[k]) for k in ew)
+
+
+class ToyTokenizer:
+    """whitespace tokenizer with a BOS, enough for the prompt-helper semantics"""
+    bos_token_id, eos_token_id, pad_token_id = 1, 2, 2
+
+    def __call__(self, text):
+        from types import SimpleNamespace
+        return SimpleNamespace(input_ids=[self.bos_token_id] + [3 + (hash(w) % 400) for w in text.split()])
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return [" ".join(f"t{int(t)}" for t in row if int(t) not in (1, 2)) for row in ids]
+
+
+def test_prompt_helpers_match_reference_semantics():
+    tok = ToyTokenizer()
+    ids = mm_utils.tokenizer_seq_token("a b <seq>\nc d <seq> e", tok)
+    assert ids[0] == 1 and ids.count(-200) == 2 and ids.count(1) == 1
+    a, b = tok("a b").input_ids[1:], tok("\nc d").input_ids[1:]
+    assert ids[1:3] == a and ids[3] == -200 and ids[4:6] == b
+    padded = mm_utils.left_pad_sequence([torch.tensor([5, 6, 7]), torch.tensor([8])], 2, batch_first=True)
+    assert padded.tolist() == [[5, 6, 7], [2, 2, 8]]
+    assert mm_utils.after_process_output("  Nucleus ### Student: next", "###") == "Nucleus"
+    assert mm_utils.after_process_output("Cytoplasm", "###") == "Cytoplasm"
+    assert mm_utils.get_model_name_from_path("/x/llama3/checkpoint-12/") == "llama3_checkpoint-12"
+    from opus_pllm_b200 import eval_ddp
+    p = eval_ddp.build_prompt("Where is it?", "SYS", "data/localization.json")
+    assert p == "SYS\n\n### Student: <seq>\nWhere is it?Kindly reply with only one word.\n### Professor:"
+    assert eval_ddp.max_new_tokens_for("x/keywords.json", 32) == 128 and eval_ddp.max_new_tokens_for("x/f.json", 32) == 256
