@@ -54,9 +54,8 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
 }
 
 // ---------------------------------------------------------------------------------------------- varlen / prefill
-constexpr int BM = 128;  // query rows per CTA (8 warps x 16)
 constexpr int BN = 64;   // keys per pipeline step
-constexpr int ATT_THREADS = 256;
+// query rows per CTA = BM (16 per warp): 128 for long sequences, 64 when that wastes fewer rows (e.g. T = 258)
 
 struct AttnParams {
   const __nv_bfloat16* q;
@@ -69,11 +68,11 @@ struct AttnParams {
   float scale_log2;        // softmax scale * log2(e)
 };
 
-template <int D, int ROWS>
+template <int D, int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_bfloat16* g, int ld, int row0, int len,
                                                 int tid) {
   constexpr int CH = D / 8;  // 16-byte chunks per row
-  for (int i = tid; i < ROWS * CH; i += ATT_THREADS) {
+  for (int i = tid; i < ROWS * CH; i += THREADS) {
     const int r = i / CH, c = i - r * CH;
     const int gr = row0 + r;
     const bool valid = gr < len;
@@ -82,8 +81,9 @@ __device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_b
   }
 }
 
-template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_varlen_kernel(const AttnParams p) {
+template <int D, bool CAUSAL, int BM>
+__global__ void __launch_bounds__(BM * 2, (D == 64) ? (BM == 64 ? 3 : 2) : 1) attn_varlen_kernel(const AttnParams p) {
+  constexpr int ATT_THREADS = BM * 2;
   grid_dep_launch();
   grid_dep_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -109,9 +109,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_varlen_kernel(const AttnP
   const int kv_end = CAUSAL ? min(len, q0 + BM) : len;
   const int n_blocks = (kv_end + BN - 1) / BN;
 
-  load_tile_async<D, BM>(sQ, gq, p.ldq, q0, len, tid);
-  load_tile_async<D, BN>(sK, gk, p.ldk, 0, len, tid);
-  load_tile_async<D, BN>(sV, gv, p.ldv, 0, len, tid);
+  load_tile_async<D, BM, ATT_THREADS>(sQ, gq, p.ldq, q0, len, tid);
+  load_tile_async<D, BN, ATT_THREADS>(sK, gk, p.ldk, 0, len, tid);
+  load_tile_async<D, BN, ATT_THREADS>(sV, gv, p.ldv, 0, len, tid);
   cp_async_commit();
 
   uint32_t qf[D / 16][4];
@@ -126,8 +126,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_varlen_kernel(const AttnP
   for (int j = 0; j < n_blocks; ++j) {
     const int st = j & 1;
     if (j + 1 < n_blocks) {
-      load_tile_async<D, BN>(sK + (st ^ 1) * KV_BYTES, gk, p.ldk, (j + 1) * BN, len, tid);
-      load_tile_async<D, BN>(sV + (st ^ 1) * KV_BYTES, gv, p.ldv, (j + 1) * BN, len, tid);
+      load_tile_async<D, BN, ATT_THREADS>(sK + (st ^ 1) * KV_BYTES, gk, p.ldk, (j + 1) * BN, len, tid);
+      load_tile_async<D, BN, ATT_THREADS>(sV + (st ^ 1) * KV_BYTES, gv, p.ldv, (j + 1) * BN, len, tid);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -423,18 +423,19 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
   }
 }
 
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, int BM>
 int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st) {
   constexpr int SMEM = BM * D * 2 + 4 * BN * D * 2;
+  constexpr int ATT_THREADS = BM * 2;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_varlen_kernel<D, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
+    if (cudaFuncSetAttribute(attn_varlen_kernel<D, CAUSAL, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) !=
         cudaSuccess)
       return OPUS_ERR_CUDA;
     configured = true;
   }
   dim3 grid((max_len + BM - 1) / BM, p.n_q_heads, n_seqs);
-  launch_pdl(false, attn_varlen_kernel<D, CAUSAL>, dim3(grid), dim3(ATT_THREADS), SMEM, st, p);
+  launch_pdl(false, attn_varlen_kernel<D, CAUSAL, BM>, dim3(grid), dim3(ATT_THREADS), SMEM, st, p);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -454,10 +455,12 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
   p.n_q_heads = n_q_heads;
   p.group = n_q_heads / n_kv_heads;
   p.scale_log2 = scale * 1.4426950408889634f;
-  if (head_dim == 64 && !causal) return launch_varlen<64, false>(p, n_seqs, max_len, st);
-  if (head_dim == 64 && causal) return launch_varlen<64, true>(p, n_seqs, max_len, st);
-  if (head_dim == 128 && !causal) return launch_varlen<128, false>(p, n_seqs, max_len, st);
-  if (head_dim == 128 && causal) return launch_varlen<128, true>(p, n_seqs, max_len, st);
+  // 64-row query tiles when they waste fewer padded rows than 128-row tiles (or the sequences are short)
+  const bool bm64 = ((max_len + 63) / 64) * 64 < ((max_len + 127) / 128) * 128;
+  if (head_dim == 64 && !causal) return bm64 ? launch_varlen<64, false, 64>(p, n_seqs, max_len, st) : launch_varlen<64, false, 128>(p, n_seqs, max_len, st);
+  if (head_dim == 64 && causal) return bm64 ? launch_varlen<64, true, 64>(p, n_seqs, max_len, st) : launch_varlen<64, true, 128>(p, n_seqs, max_len, st);
+  if (head_dim == 128 && !causal) return bm64 ? launch_varlen<128, false, 64>(p, n_seqs, max_len, st) : launch_varlen<128, false, 128>(p, n_seqs, max_len, st);
+  if (head_dim == 128 && causal) return bm64 ? launch_varlen<128, true, 64>(p, n_seqs, max_len, st) : launch_varlen<128, true, 128>(p, n_seqs, max_len, st);
   return OPUS_ERR_ARG;
 }
 
