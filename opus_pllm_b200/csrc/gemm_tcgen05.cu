@@ -79,11 +79,12 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v)
 // per column pair: even lanes write column i for rows (l, l+1), odd lanes write column i+1 for rows (l-1, l), 4 bytes each.
 // x[i] = value of (this thread's row, column i); `base` points at (column 0, this thread's row); requires even `row`
 // alignment of the pair (row of an even lane is even) and an even number of valid rows.
-__device__ __forceinline__ void store_bf16_transposed_paired(__nv_bfloat16* base, size_t ld, const float (&x)[32],
+template <int NC>
+__device__ __forceinline__ void store_bf16_transposed_paired(__nv_bfloat16* base, size_t ld, const float (&x)[NC],
                                                             int n_valid, int lane) {
   const bool odd = lane & 1;
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
+  for (int i = 0; i < NC; i += 2) {
     const float send = odd ? x[i] : x[i + 1];
     const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
     const int col = odd ? i + 1 : i;
@@ -192,31 +193,45 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     return;
   }
 
-  // ---- transposed (swap-AB): accumulator row = output feature `row`, column = batch row n -> out[n*ldo + row] ----
+}
+
+// out-of-line activation functions for the small-footprint (decode-sized) epilogue: one copy of the expf / erff code
+__device__ __noinline__ float silu_call(float x) { return silu_f(x); }
+__device__ __noinline__ float gelu_call(float x) { return gelu_erf(x); }
+
+// ---- transposed (swap-AB) epilogue: accumulator row = output feature `row`, column = batch row n -> out[n*ldo + row].
+// NC columns per call. It is instantiated with NC = 8 and driven by a ROLLED loop: a decode-sized launch executes this
+// code exactly once per CTA with a cold instruction cache, and a 32-way unrolled body cost ~6-18 us per launch.
+template <int NC>
+__device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const uint32_t (&r)[NC], int row, int col0,
+                                                    int split) {
+  float v[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
   const bool row_ok = row < p.M;
   if (p.epi == EPI_PARTIAL_F32) {
     float* base = reinterpret_cast<float*>(p.out) + ((size_t)split * p.N + col0) * p.ldo + row;
-    const int nv = row_ok ? min(32, p.N - col0) : 0;
+    const int nv = row_ok ? min(NC, p.N - col0) : 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < NC; ++i)
       if (i < nv) base[(size_t)i * p.ldo] = v[i];
     return;
   }
   if (p.epi == EPI_SWIGLU) {
     // rows (2j, 2j+1) = (gate_j, up_j) live in adjacent lanes
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)col0 * p.ldo + (row >> 1);
-    float o[32];
+    float o[NC];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < NC; ++i) {
       const float other = __shfl_down_sync(0xffffffffu, v[i], 1);
-      o[i] = bf16_round(silu_f(bf16_round(v[i]))) * bf16_round(other);  // meaningful on even lanes only
+      o[i] = bf16_round(silu_call(bf16_round(v[i]))) * bf16_round(other);  // meaningful on even lanes only
     }
     // even lanes hold out[row/2]; lanes l and l+2 pair up so that every store is 4 bytes (see the note above)
     const int lane = row & 31;
     const bool hi = lane & 2;
-    const int nv = (((lane & 1) == 0) && (row | 3) < p.M) ? min(32, p.N - col0) : 0;
+    const int nv = (((lane & 1) == 0) && (row | 3) < p.M) ? min(NC, p.N - col0) : 0;
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < NC; i += 2) {
       const float send = hi ? o[i] : o[i + 1];
       const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
       const int col = hi ? i + 1 : i;
@@ -228,43 +243,43 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   // Remaining modes: one specialised, branch-free store loop per epilogue (mode checks hoisted out of the element loop;
   // residual values are all loaded before the first store because `out` may alias `residual`).
   const float b = (p.bias != nullptr && row_ok) ? p.bias[row] : 0.0f;
-  const int n_valid = row_ok ? min(32, p.N - col0) : 0;  // columns (batch rows) of this chunk that exist
+  const int n_valid = row_ok ? min(NC, p.N - col0) : 0;  // columns (batch rows) of this chunk that exist
   if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU) {
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)col0 * p.ldo + row;
     const bool gelu = p.epi == EPI_BF16_GELU;
-    float x[32];
+    float x[NC];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < NC; ++i) {
       x[i] = v[i] + b;
-      if (gelu) x[i] = gelu_erf(x[i]);
+      if (gelu) x[i] = gelu_call(x[i]);
     }
     // M (features) is even and tiles start at multiples of 128, so a lane pair is either fully valid or fully invalid
-    const int nv = (row | 1) < p.M ? min(32, p.N - col0) : 0;
+    const int nv = (row | 1) < p.M ? min(NC, p.N - col0) : 0;
     store_bf16_transposed_paired(base, (size_t)p.ldo, x, nv, row & 31);
   } else if (p.epi == EPI_F32) {
     float* base = reinterpret_cast<float*>(p.out) + (size_t)col0 * p.ldo + row;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < NC; ++i)
       if (i < n_valid) base[(size_t)i * p.ldo] = v[i] + b;
   } else if (p.epi == EPI_RES_BF16) {
     const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)col0 * p.ldr + row;
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)col0 * p.ldo + row;
-    float rr[32];
+    float rr[NC];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) rr[i] = (i < n_valid) ? __bfloat162float(rbase[(size_t)i * p.ldr]) : 0.f;
-    float x[32];
+    for (int i = 0; i < NC; ++i) rr[i] = (i < n_valid) ? __bfloat162float(rbase[(size_t)i * p.ldr]) : 0.f;
+    float x[NC];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = rr[i] + bf16_round(v[i] + b);
-    const int nv = (row | 1) < p.M ? min(32, p.N - col0) : 0;
+    for (int i = 0; i < NC; ++i) x[i] = rr[i] + bf16_round(v[i] + b);
+    const int nv = (row | 1) < p.M ? min(NC, p.N - col0) : 0;
     store_bf16_transposed_paired(base, (size_t)p.ldo, x, nv, row & 31);
   } else if (p.epi == EPI_RES_F32) {
     const float* rbase = reinterpret_cast<const float*>(p.residual) + (size_t)col0 * p.ldr + row;
     float* base = reinterpret_cast<float*>(p.out) + (size_t)col0 * p.ldo + row;
-    float rr[32];
+    float rr[NC];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) rr[i] = (i < n_valid) ? rbase[(size_t)i * p.ldr] : 0.f;
+    for (int i = 0; i < NC; ++i) rr[i] = (i < n_valid) ? rbase[(size_t)i * p.ldr] : 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
+    for (int i = 0; i < NC; ++i)
       if (i < n_valid) base[(size_t)i * p.ldo] = rr[i] + (v[i] + b);
   }
 }
@@ -398,13 +413,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_after();
       const int row = tc.m * BM + quad * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      if (p.transposed) {
+        // rolled loop over 8-column groups: small code footprint (decode-sized launches run it once, I-cache cold)
 #pragma unroll 1
-      for (int c = chunk0; c < BN / 32; c += 2) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int col0 = tc.n * BN + c * 32;
-        if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
+        for (int g = chunk0; g < BN / 8; g += 2) {
+          uint32_t r8[8];
+          tmem_ld_32x8(taddr + g * 8, r8);
+          tmem_ld_wait();
+          const int col0 = tc.n * BN + g * 8;
+          if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = chunk0; c < BN / 32; c += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = tc.n * BN + c * 32;
+          if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
+        }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
