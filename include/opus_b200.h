@@ -267,6 +267,11 @@ int opus_llama_decode_loop(const opus_llama_model* model, const opus_kv_cache* c
                            void* stream);
 /* Drop cached CUDA graphs (call before freeing buffers they reference). */
 int opus_release_graphs(void);
+/* Profiling aid: between opus_trace_begin(stream) and opus_trace_end the composite forwards record a CUDA event after
+ * every kernel launch (not inside graph capture); opus_trace_end synchronises and writes "label<TAB>microseconds\n"
+ * lines (time since the previous launch completed) into the HOST buffer buf, returning the bytes written. */
+int opus_trace_begin(void* stream);
+int opus_trace_end(char* buf, int cap);
 /* Number of kernel launches issued by this library since the last call (bench.py's gpu_launches counter). */
 long long opus_launch_count(int reset);
 

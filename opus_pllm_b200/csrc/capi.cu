@@ -215,6 +215,10 @@ int opus_llama_decode_loop(const opus_llama_model* model, const opus_kv_cache* c
 
 int opus_release_graphs(void) { return release_graphs(); }
 
+int opus_trace_begin(void* stream) { return trace_begin(ST(stream)); }
+
+int opus_trace_end(char* buf, int cap) { return trace_end(buf, cap); }
+
 long long opus_launch_count(int reset) { return launch_count(reset != 0); }
 
 }  // extern "C"

@@ -3,7 +3,9 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <cstdio>
 #include <tuple>
+#include <vector>
 
 #include "common.h"
 #include "gemm.h"
@@ -16,7 +18,50 @@ namespace opus {
   do {                                                   \
     const int _rc = (expr);                              \
     if (_rc != OPUS_OK) return fail(_rc, #expr);         \
+    if (g_trace_on) trace_mark(#expr, st);               \
   } while (0)
+
+// ---- optional in-situ kernel timeline (debug / profiling aid; off by default, never active inside graph capture) ----
+bool g_trace_on = false;
+namespace {
+struct TraceMark { const char* label; cudaEvent_t ev; };
+std::vector<TraceMark> g_trace;
+}  // namespace
+void trace_mark(const char* label, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  g_trace.push_back({label, ev});
+}
+int trace_begin(cudaStream_t st) {
+  for (auto& m : g_trace) cudaEventDestroy(m.ev);
+  g_trace.clear();
+  g_trace_on = true;
+  trace_mark("begin", st);
+  return OPUS_OK;
+}
+// writes "label<TAB>microseconds\n" per mark (time since the previous mark) into buf; returns bytes written
+int trace_end(char* buf, int cap) {
+  g_trace_on = false;
+  if (g_trace.empty()) return 0;
+  cudaEventSynchronize(g_trace.back().ev);
+  int n = 0;
+  for (size_t i = 1; i < g_trace.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace[i - 1].ev, g_trace[i].ev);
+    char label[48];
+    snprintf(label, sizeof(label), "%.40s", g_trace[i].label);
+    for (char* c = label; *c; ++c) if (*c == '(') { *c = 0; break; }
+    const int w = snprintf(buf + n, cap > n ? cap - n : 0, "%s\t%.2f\n", label, ms * 1e3f);
+    if (w < 0 || n + w >= cap) break;
+    n += w;
+  }
+  for (auto& m : g_trace) cudaEventDestroy(m.ev);
+  g_trace.clear();
+  return n;
+}
 
 namespace {
 
