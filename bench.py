@@ -121,7 +121,7 @@ def cpu_reference_runner(sd, wl, torch):
     ocfg = llama_ref.LlamaCfg(n_layers=n_layers, dim=lcfg["dim"], n_q_heads=lcfg["n_q_heads"],
                               n_kv_heads=lcfg["n_kv_heads"], head_dim=lcfg["head_dim"], ffn_dim=lcfg["ffn_dim"],
                               vocab=lcfg["vocab"])
-    B, T, new = 2, min(128, wl["prompt_len"]), min(8, wl["new_tokens"])
+    B, T, new = 4, min(128, wl["prompt_len"]), min(16, wl["new_tokens"])
     seqs = synth.proteins(B, wl["protein_len"])
     prompts = synth.prompt_ids(B, T - 7, vocab=lcfg["vocab"])
     ids = torch.stack(prompts)
