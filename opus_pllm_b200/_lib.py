@@ -94,7 +94,7 @@ _SIGNATURES = {
     "opus_embed_gather_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "opus_lora_merge_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "opus_attn_varlen_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int,
-                                      c_int, c_int, c_float, _P]),
+                                      c_int, c_int, c_int, c_float, _P]),
     "opus_attn_decode_paged_bf16": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                             c_int, c_float, _P]),
     "opus_esm2_forward": (c_int, [C.POINTER(Esm2Model), C.POINTER(Esm2Workspace), _P, _P, _P, _P, c_int, c_int,

@@ -15,6 +15,8 @@
 #include "launch.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace opus {
 
 namespace {
@@ -443,10 +445,26 @@ int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st)
 }  // namespace
 
 int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
-                __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int max_len, int n_q_heads,
+                __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int n_tok, int max_len, int n_q_heads,
                 int n_kv_heads, int head_dim, int causal, float scale, cudaStream_t st) {
   if (n_seqs == 0 || max_len == 0) return OPUS_OK;
   if (n_kv_heads <= 0 || n_q_heads % n_kv_heads) return OPUS_ERR_ARG;
+  {
+    // implementation choice: tcgen05 kernel (attention_tc.cu) for 128-row tiles that are reasonably full, the mma.sync
+    // kernel below for short sequences. OPUS_ATTN=mma|tc forces one of them (A/B measurements, tests).
+    static int mode = -1;
+    if (mode < 0) {
+      const char* e = std::getenv("OPUS_ATTN");
+      mode = (e == nullptr) ? 0 : (e[0] == 't' ? 2 : 1);
+    }
+    const bool aligned = ((ldq | ldk | ldv | ldo) % 8) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                           reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+    const bool want_tc = mode == 2 || (mode == 0 && max_len >= 384);
+    if (want_tc && aligned && (head_dim == 64 || head_dim == 128))
+      return attn_varlen_tc(q, ldq, k, ldk, v, ldv, o, ldo, cu_seqlens, n_seqs, n_tok, max_len, n_q_heads, n_kv_heads,
+                            head_dim, causal, scale, st);
+  }
   if ((ldq | ldk | ldv) % 8 || ldo % 2) return OPUS_ERR_ARG;
   AttnParams p;
   p.q = q; p.k = k; p.v = v; p.o = o;

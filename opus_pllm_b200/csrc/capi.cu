@@ -161,10 +161,10 @@ int opus_lora_merge_bf16(void* W, const void* A, const void* B, int out_features
 }
 
 int opus_attn_varlen_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                          const int32_t* cu_seqlens, int n_seqs, int max_len, int n_q_heads, int n_kv_heads,
+                          const int32_t* cu_seqlens, int n_seqs, int n_tok, int max_len, int n_q_heads, int n_kv_heads,
                           int head_dim, int causal, float scale, void* stream) {
   RET(attn_varlen(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(k), ldk, static_cast<const bf16*>(v), ldv,
-                  static_cast<bf16*>(o), ldo, cu_seqlens, n_seqs, max_len, n_q_heads, n_kv_heads, head_dim, causal,
+                  static_cast<bf16*>(o), ldo, cu_seqlens, n_seqs, n_tok, max_len, n_q_heads, n_kv_heads, head_dim, causal,
                   scale, ST(stream)),
       "opus_attn_varlen_bf16");
 }

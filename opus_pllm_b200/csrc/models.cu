@@ -133,7 +133,7 @@ int esm2_forward(const opus_esm2_model* m, const opus_esm2_workspace* ws, const 
     OPUS_TRY(layernorm_f32_bf16(ws->x, pending, L.ln1_g, L.ln1_b, xn, n_tok, d, m->ln_eps, st));
     OPUS_TRY(linear(xn, n_tok, L.wqkv, 3 * d, d, EPI_BF16, qkv, 3 * d, L.bqkv, nullptr, 0, nullptr, 0, st));
     OPUS_TRY(rope_esm(qkv, pos, m->rope_cos, m->rope_sin, n_tok, m->n_heads, hd, 3 * d, 0.125f, st));
-    OPUS_TRY(attn_varlen(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu_seqlens, n_seqs, max_len,
+    OPUS_TRY(attn_varlen(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu_seqlens, n_seqs, n_tok, max_len,
                          m->n_heads, m->n_heads, hd, 0, 1.0f, st));
     OPUS_TRY(linear(attn, n_tok, L.wo, d, d, EPI_BF16, xn, d, L.bo, nullptr, 0, nullptr, 0, st));
     OPUS_TRY(layernorm_f32_bf16(ws->x, xn, L.ln2_g, L.ln2_b, xn, n_tok, d, m->ln_eps, st));
@@ -203,7 +203,7 @@ int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus
                                  static_cast<const bf16*>(m->rope_sin), kc, vc, n_tok, Hq, Hkv, hd, qkv_n,
                                  kv->block_size, st));
     OPUS_TRY(attn_varlen(qkv, qkv_n, qkv + Hq * hd, qkv_n, qkv + (Hq + Hkv) * hd, qkv_n, attn, Hq * hd, cu_seqlens,
-                         n_seqs, max_len, Hq, Hkv, hd, 1, scale, st));
+                         n_seqs, n_tok, max_len, Hq, Hkv, hd, 1, scale, st));
     OPUS_TRY(linear(attn, n_tok, L.wo, d, Hq * hd, EPI_RES_BF16, h, d, nullptr, h, d, nullptr, 0, st));
     OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(L.ln2_w), xn, n_tok, d, m->rms_eps,
                           st));

@@ -226,7 +226,7 @@ def attn_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens: t
             raise L.OpusError(f"{n}: inner stride must be 1")
     o = torch.empty((q.shape[0], n_q_heads * head_dim), dtype=BF16, device=q.device)
     L.check(L.load().opus_attn_varlen_bf16(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o),
-                                           o.stride(0), _p(cu_seqlens), cu_seqlens.numel() - 1, max_len, n_q_heads,
+                                           o.stride(0), _p(cu_seqlens), cu_seqlens.numel() - 1, q.shape[0], max_len, n_q_heads,
                                            n_kv_heads, head_dim, int(causal), scale, _stream()),
             "opus_attn_varlen_bf16")
     return o
