@@ -109,6 +109,7 @@ _SIGNATURES = {
     "opus_llama_decode_loop": (c_int, [C.POINTER(LlamaModel), C.POINTER(KvCache), C.POINTER(LlamaWorkspace),
                                        C.POINTER(DecodeState), c_int, c_int, c_int, c_int, _P]),
     "opus_release_graphs": (c_int, []),
+    "opus_set_tunable": (c_int, [C.c_char_p, c_int]),
     "opus_trace_begin": (c_int, [_P]),
     "opus_trace_end": (c_int, [C.c_char_p, c_int]),
     "opus_launch_count": (c_longlong, [c_int]),

@@ -1,13 +1,18 @@
 // Flash attention forward on tcgen05 tensor cores (variable-length packed sequences; bidirectional or causal GQA).
 //
-// One CTA = one 128-row query tile of one (sequence, head). Warp roles:
-//   warp 0     TMA producer: Q tile once, then K/V blocks of 128 keys into a 2-stage ring (SWIZZLE_128B panels of 64 cols)
-//   warp 1     MMA issuer (one thread) + TMEM owner:  S = Q K^T  (UMMA 128x128x16, both operands K-major from smem)
-//                                                     O_blk = P V (UMMA 128xDx16, A = P K-major, B = V MN-major)
-//   warps 2-5  softmax: thread = query row (TMEM lane), so row max / row sum need no shuffles. S is read twice from TMEM
-//              (max pass, exp pass), P is written to shared memory in the UMMA K-major swizzled layout, O is kept in
-//              REGISTERS (fp32, D values per thread) and updated as O = O * corr + O_blk after every block.
-// TMEM: S [128 lanes x 128 cols] + O_blk [128 x D]  (256 columns allocated).
+// One CTA = TWO 128-row query tiles (A, B) of one (sequence, head), processed ping-pong so that the tensor pipe works on
+// one tile while the softmax warps of the other tile are busy. Warp roles (320 threads):
+//   warp 0      TMA producer: both Q tiles once, then K blocks and V blocks (128 keys) into two independent rings
+//               (SWIZZLE_128B panels of 64 columns);
+//   warp 1      MMA issuer (one thread) + TMEM owner:
+//                 S_X = Q_X K^T        UMMA 128x128x16, both operands K-major from shared memory
+//                 O_X (+)= P_X V       UMMA 128xDx16, A = P read from TENSOR MEMORY, B = V MN-major from shared memory
+//   warps 2-5   softmax of tile A, warps 6-9 softmax of tile B: thread = query row (TMEM lane), so row max / row sum need
+//               no shuffles. One pass: S (128 fp32) -> registers, max, exp2, row sum, bf16 P written back with
+//               tcgen05.st over the first 64 columns of S (P aliases S). O stays in TMEM across key blocks; the softmax
+//               warps rescale it in place only when a row's running maximum grew by more than 2^8 (lazy rescaling:
+//               O and the row sum always share one reference maximum, so the result is exact).
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,256+D) O_B [256+D,256+2D).
 // Nothing T x T is materialised; K/V rows beyond the sequence end (next packed sequence / OOB zero fill) are masked in S.
 #include "common.h"
 #include "kernels.h"
@@ -22,10 +27,11 @@ namespace opus {
 
 namespace {
 
-constexpr int TBM = 128;   // query rows per CTA
+constexpr int TBM = 128;   // query rows per tile (two tiles per CTA)
 constexpr int TBN = 128;   // keys per block
 constexpr int PANEL = 128 * 128;  // bytes of one [128 rows x 64 bf16] swizzled panel
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnTcParams {
   const int* cu_seqlens;
@@ -38,11 +44,12 @@ struct AttnTcParams {
 template <int D>
 struct TcCfg {
   static constexpr int NP = D / 64;                       // panels per operand tile
-  static constexpr int Q_BYTES = NP * PANEL;
-  static constexpr int KV_BYTES = NP * PANEL;             // K (or V) block
-  static constexpr int P_BYTES = (TBN / 64) * PANEL;
-  static constexpr int SMEM = Q_BYTES + 2 * 2 * KV_BYTES + P_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 256;                   // S: 128, O_blk: D (<= 128)
+  static constexpr int TILE_BYTES = NP * PANEL;           // one Q tile / one K block / one V block
+  static constexpr int KS = (D == 128) ? 2 : 3;           // K ring stages
+  static constexpr int VS = (D == 128) ? 2 : 3;           // V ring stages
+  static constexpr int SMEM = (2 + KS + VS) * TILE_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int COL_S = 0, COL_O = 256;
 };
 
 // instruction descriptor with selectable B major-ness (bit 16: 1 = MN-major)
@@ -62,6 +69,33 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (bf16, K-major, two K elements per 32-bit column) lives in tensor memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -69,39 +103,39 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   using C = TcCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + C::Q_BYTES;            // [2 stages][KV_BYTES]
-  uint8_t* sV = sK + 2 * C::KV_BYTES;       // [2 stages][KV_BYTES]
-  uint8_t* sP = sV + 2 * C::KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + C::P_BYTES);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint64_t* o_empty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sQ = smem;                                  // [2 tiles][TILE_BYTES]
+  uint8_t* sK = sQ + 2 * C::TILE_BYTES;                // [KS][TILE_BYTES]
+  uint8_t* sV = sK + C::KS * C::TILE_BYTES;            // [VS][TILE_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::VS * C::TILE_BYTES);
+  uint64_t* q_full = bars;                  // 1
+  uint64_t* k_full = bars + 1;              // [KS]
+  uint64_t* k_empty = k_full + C::KS;       // [KS]
+  uint64_t* v_full = k_empty + C::KS;       // [VS]
+  uint64_t* v_empty = v_full + C::VS;       // [VS]
+  uint64_t* s_full = v_empty + C::VS;       // [2]  MMA -> softmax: S_X(j) complete
+  uint64_t* p_full = s_full + 2;            // [2]  softmax -> MMA: P_X(j) stored (and O_X rescaled)
+  uint64_t* o_done = p_full + 2;            // [2]  MMA -> softmax: O_X includes block j
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y;
   const int seq_start = p.cu_seqlens[b];
   const int len = p.cu_seqlens[b + 1] - seq_start;
-  const int mblk = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-  const int q0 = mblk * TBM;
+  const int mblk = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // causal: heavy tiles first
+  const int q0 = mblk * 2 * TBM;
   if (q0 >= len) return;
   const int kvh = h / p.group;
-  const int kv_end = CAUSAL ? min(len, q0 + TBM) : len;
-  const int n_blocks = (kv_end + TBN - 1) / TBN;
+  // key blocks per tile
+  const int n_a = ((CAUSAL ? min(len, q0 + TBM) : len) + TBN - 1) / TBN;
+  const int n_b = (q0 + TBM < len) ? ((CAUSAL ? min(len, q0 + 2 * TBM) : len) + TBN - 1) / TBN : 0;
+  const int n_max = n_b > 0 ? n_b : n_a;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
+    for (int s = 0; s < C::KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < C::VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&o_done[x], 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -112,149 +146,184 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;          // columns [0, 128)
-  const uint32_t tmem_o = tmem_base + TBN;    // columns [128, 128 + D)
 
   if (warp == 0) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+      mbar_arrive_expect_tx(q_full, 2 * C::TILE_BYTES);
 #pragma unroll
-      for (int pn = 0; pn < C::NP; ++pn) tma_load_2d(sQ + pn * PANEL, &tm_q, q_full, h * D + pn * 64, seq_start + q0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * C::KV_BYTES);
+      for (int x = 0; x < 2; ++x)
 #pragma unroll
-        for (int pn = 0; pn < C::NP; ++pn) {
-          tma_load_2d(sK + st * C::KV_BYTES + pn * PANEL, &tm_k, &kv_full[st], kvh * D + pn * 64, seq_start + j * TBN);
-          tma_load_2d(sV + st * C::KV_BYTES + pn * PANEL, &tm_v, &kv_full[st], kvh * D + pn * 64, seq_start + j * TBN);
-        }
+        for (int pn = 0; pn < C::NP; ++pn)
+          tma_load_2d(sQ + x * C::TILE_BYTES + pn * PANEL, &tm_q, q_full, h * D + pn * 64, seq_start + q0 + x * TBM);
+      for (int j = 0; j < n_max; ++j) {
+        const int ks = j % C::KS, vs = j % C::VS;
+        mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[ks], C::TILE_BYTES);
+#pragma unroll
+        for (int pn = 0; pn < C::NP; ++pn)
+          tma_load_2d(sK + ks * C::TILE_BYTES + pn * PANEL, &tm_k, &k_full[ks], kvh * D + pn * 64, seq_start + j * TBN);
+        mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[vs], C::TILE_BYTES);
+#pragma unroll
+        for (int pn = 0; pn < C::NP; ++pn)
+          tma_load_2d(sV + vs * C::TILE_BYTES + pn * PANEL, &tm_v, &v_full[vs], kvh * D + pn * 64, seq_start + j * TBN);
       }
     }
   } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(TBM, TBN, 0);
       constexpr uint32_t idesc_o = idesc_bf16(TBM, D, 1);
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        // ---- S = Q K^T
-        const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK + st * C::KV_BYTES);
+      const int n_x[2] = {n_a, n_b};
+      auto issue_s = [&](int x, int ks) {
+        const uint32_t aq = smem_u32(sQ + x * C::TILE_BYTES), bk = smem_u32(sK + ks * C::TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * PANEL + (kk & 3) * 32;
-          umma_bf16_ss(tmem_s, umma_smem_desc_sw128(aq + off), umma_smem_desc_sw128(bk + off), idesc_s, kk > 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_base + C::COL_S + x * TBN, umma_smem_desc_sw128(aq + off), umma_smem_desc_sw128(bk + off),
+                       idesc_s, kk > 0 ? 1u : 0u);
         }
-        umma_commit(s_full);
-        // ---- O_blk = P V   (needs P(j) in smem and O_blk(j-1) drained)
-        mbar_wait(p_full, j & 1);
-        mbar_wait(o_empty, (j & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t ap = smem_u32(sP), bv = smem_u32(sV + st * C::KV_BYTES);
+        umma_commit(&s_full[x]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      if (n_b > 0) issue_s(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_max; ++j) {
+        const int vs = j % C::VS, ks1 = (j + 1) % C::KS;
+        mbar_wait(&v_full[vs], (j / C::VS) & 1);
+        bool k_ready = false;
 #pragma unroll
-        for (int kk = 0; kk < TBN / 16; ++kk) {
-          const uint64_t da = umma_smem_desc_sw128(ap + (kk >> 2) * PANEL + (kk & 3) * 32);
-          const uint64_t db = umma_desc_mn_sw128(bv + kk * 2048, PANEL, 1024);
-          umma_bf16_ss(tmem_o, da, db, idesc_o, kk > 0 ? 1u : 0u);
+        for (int x = 0; x < 2; ++x) {
+          if (j >= n_x[x]) continue;
+          mbar_wait(&p_full[x], j & 1);
+          tc_fence_after();
+          const uint32_t bv = smem_u32(sV + vs * C::TILE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < TBN / 16; ++kk) {
+            // P: 16 keys = 8 packed columns per step; V: 16 key rows = two 8-row swizzle groups (2048 B) per step
+            umma_bf16_ts(tmem_base + C::COL_O + x * D, tmem_base + C::COL_S + x * TBN + kk * 8,
+                         umma_desc_mn_sw128(bv + kk * 2048, PANEL, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&o_done[x]);
+          if (j + 1 < n_x[x]) {
+            if (!k_ready) {
+              mbar_wait(&k_full[ks1], ((j + 1) / C::KS) & 1);
+              tc_fence_after();
+              k_ready = true;
+            }
+            issue_s(x, ks1);   // overwrites S_X / P_X(j): ordered after the PV MMAs above (same issuing thread)
+          }
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[vs]);
+        if (k_ready) umma_commit(&k_empty[ks1]);
       }
     }
   } else {
-    // ===================== softmax / accumulate warps: thread = query row =====================
-    const int quad = warp & 3;
+    // ===================== softmax warps: thread = query row =====================
+    const int x = (warp - 2) >> 2;             // tile A (warps 2-5) or B (warps 6-9)
+    const int n_blocks = x == 0 ? n_a : n_b;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access (warp id % 4)
     const int row = quad * 32 + lane;          // row inside the tile == TMEM lane
-    const int qrow = q0 + row;                 // sequence-relative query index
+    const int qt0 = q0 + x * TBM;              // first query row of the tile (sequence-relative)
+    const int qrow = qt0 + row;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-    float o_acc[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    const uint32_t sp_row = smem_u32(sP) + row * 128;
+    const uint32_t t_s = tmem_base + lane_addr + C::COL_S + x * TBN;
+    const uint32_t t_o = tmem_base + lane_addr + C::COL_O + x * D;
+    float m_run = -INFINITY, l_run = 0.f;      // m_run in scaled log2 units
 
     for (int j = 0; j < n_blocks; ++j) {
       const int k0 = j * TBN;
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
-      // pass 1: row maximum over the valid keys of this block
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait();
+      uint32_t s[128];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int key = k0 + c * 32 + i;
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_ld_wait();
+      const bool need_mask = (k0 + TBN > len) || (CAUSAL && k0 + TBN - 1 > qt0);
+      if (need_mask) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          const int key = k0 + i;
           const bool ok = key < len && (!CAUSAL || key <= qrow);
-          if (ok) mx = fmaxf(mx, __uint_as_float(r[i]));
+          if (!ok) s[i] = 0xff800000u;  // -inf
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f((m_run - m_use) * p.scale_log2);   // m_run = -inf -> 0
-      const float msl = m_use * p.scale_log2;
-      m_run = m_new;
-      // pass 2: p = exp2(s*scale - m*scale), row sum, bf16 P into the K-major swizzled smem tile
-      float ls = 0.f;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+      }
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
+      float corr = 1.0f;
+      bool rescale = false;
+      if (m_blk > m_run + kRescaleThreshold) {   // also true for the first block (m_run = -inf)
+        corr = exp2f(m_run - m_blk);             // 0 when m_run = -inf
+        rescale = j > 0;
+        m_run = m_blk;
+      }
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+      float ls0 = 0.f, ls1 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        const float p0 = exp2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_use));
+        const float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_use));
+        ls0 += p0;
+        ls1 += p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      l_run = l_run * corr + (ls0 + ls1);
+      tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      if (j > 0) {
+        // O_X must include block j-1 before it may be rescaled / before PV(j) accumulates on top of it
+        mbar_wait(&o_done[x], (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
-      for (int c = 0; c < TBN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_o + c * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int key = k0 + c * 32 + i;
-          const bool ok0 = key < len && (!CAUSAL || key <= qrow);
-          const bool ok1 = key + 1 < len && (!CAUSAL || key + 1 <= qrow);
-          const float p0 = ok0 ? exp2f(__uint_as_float(r[i]) * p.scale_log2 - msl) : 0.f;
-          const float p1 = ok1 ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2 - msl) : 0.f;
-          ls += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        // 32 keys = 4 chunks of 16 bytes; chunk index inside the 64-key panel = (c & 1) * 4 + q
-        const uint32_t panel = sp_row + (c >> 1) * PANEL;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = ((c & 1) * 4 + q) ^ (row & 7);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(panel + ch * 16), "r"(pk[q * 4]),
-                       "r"(pk[q * 4 + 1]), "r"(pk[q * 4 + 2]), "r"(pk[q * 4 + 3])
-                       : "memory");
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+            tmem_st_32x32(t_o + c * 32, r);
+          }
         }
       }
-      l_run = l_run * corr + ls;
-      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
-      // O = O * corr + O_blk
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_o + lane_addr + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * corr + __uint_as_float(r[i]);
-      }
-      tc_fence_before();
-      mbar_arrive(o_empty);
+      mbar_arrive(&p_full[x]);
     }
-    if (qrow < len) {
+    if (n_blocks > 0) {
+      mbar_wait(&o_done[x], (n_blocks - 1) & 1);
+      tc_fence_after();
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
       __nv_bfloat16* dst = p.o + (size_t)(seq_start + qrow) * p.ldo + (size_t)h * D;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_o + c * 32, r);
+        tmem_ld_wait();
+        if (qrow < len) {
 #pragma unroll
-      for (int g = 0; g < D / 8; ++g) {
-        uint4 q;
-        q.x = pack_bf16x2(o_acc[g * 8] * inv, o_acc[g * 8 + 1] * inv);
-        q.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
-        q.z = pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
-        q.w = pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + g * 8) = q;
+          for (int g = 0; g < 4; ++g) {
+            uint4 q;
+            q.x = pack_bf16x2(__uint_as_float(r[g * 8]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
+            q.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
+            q.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
+            q.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = q;
+          }
+        }
       }
     }
   }
@@ -309,7 +378,7 @@ int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
       return OPUS_ERR_CUDA;
     configured = true;
   }
-  dim3 grid((max_len + TBM - 1) / TBM, n_q_heads, n_seqs);
+  dim3 grid((max_len + 2 * TBM - 1) / (2 * TBM), n_q_heads, n_seqs);
   const cudaError_t le =
       launch_pdl(false, attn_fwd_tcgen05_kernel<D, CAUSAL>, grid, dim3(TC_THREADS), C::SMEM, st, tq, tk, tv, p);
   note_launch();

@@ -215,6 +215,8 @@ int opus_llama_decode_loop(const opus_llama_model* model, const opus_kv_cache* c
 
 int opus_release_graphs(void) { return release_graphs(); }
 
+int opus_set_tunable(const char* name, int value) { return set_tunable(name, value); }
+
 int opus_trace_begin(void* stream) { return trace_begin(ST(stream)); }
 
 int opus_trace_end(char* buf, int cap) { return trace_end(buf, cap); }

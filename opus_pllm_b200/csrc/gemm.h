@@ -32,6 +32,16 @@ struct GemmParams {
   const void* residual;
   int ldr;
   uint64_t hint_a, hint_b;
+  // next-weight L2 prefetch (swap-AB chains): work item t of the NEXT launch = (m tile t / pf_split_k, k-split
+  // t % pf_split_k); the first pf_depth k-blocks of items [0, pf_items) are requested into L2 at this CTA's tail.
+  int pf_items, pf_split_k, pf_k_blocks, pf_depth;
+  // stream-K tail: the last sk_tiles output tiles (a partial wave) are cut along K into gridDim.x equal unit ranges.
+  // A CTA whose range does not contain a tile's last k-block dumps its fp32 accumulator to sk_ws[cta]; the CTA that
+  // does ("owner") waits on sk_cnt[tile], adds the partials in CTA order (deterministic) and runs the epilogue.
+  int dp_items;   // work items walked round-robin (full tiles x split_k) before the stream-K tail
+  int sk_tiles;
+  float* sk_ws;
+  int* sk_cnt;
 };
 
 // D[M,N] = A[M,K] * B[N,K]^T, both operands bf16 row-major with K contiguous.
@@ -54,11 +64,18 @@ struct GemmArgs {
   int ldr;
   int split_k;  // 0/1 = none
   int block_n;  // 0 = auto
+  // Optional hint: the weight matrix [pf_rows, pf_K] (row stride pf_K) that the NEXT swap-AB launch on this stream will
+  // stream with split factor pf_split_k. When pf_w != nullptr every CTA, after issuing its last own load, asks the TMA
+  // unit to prefetch the first pf_depth k-blocks of "its" work item of that launch into L2, so HBM stays busy while
+  // this kernel drains, the small kernels in between run, and the next GEMM ramps up.
+  const void* pf_w;
+  int pf_rows, pf_K, pf_split_k, pf_depth;
 };
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 int gemm_pick_bn(int N, int transposed);
 int gemm_pick_split_k(int M, int N, int K, int bn);
 size_t gemm_workspace_bytes(int M, int N, int split_k);
+void gemm_set_streamk_fill(int percent);  // 0 disables the stream-K tail
 
 }  // namespace opus

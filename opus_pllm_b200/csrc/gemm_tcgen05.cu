@@ -44,24 +44,76 @@ struct Cfg {
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+enum WorkKind : int { WORK_TILE = 0, WORK_SK_PARTIAL = 1, WORK_SK_OWNER = 2 };
+
 struct TileCoord {
   int m, n, kb_begin, kb_end, split;
+  int kind;       // WorkKind
+  int sk_tile;    // index of the stream-K tile (counter slot)
+  int first_cta;  // owner only: partials of CTAs [first_cta, blockIdx.x) belong to this tile
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t) {
-  TileCoord c;
-  const int mn = t / p.split_k;
-  c.split = t - mn * p.split_k;
+// (m, n) of output tile `mn` in the grouped-M raster
+__device__ __forceinline__ void raster_mn(const GemmParams& p, int mn, int& m, int& n) {
   const int per_group = p.group_m * p.num_n_tiles;
   const int g = mn / per_group;
   const int r = mn - g * per_group;
   const int first_m = g * p.group_m;
   const int gsz = min(p.num_m_tiles - first_m, p.group_m);
-  c.m = first_m + r % gsz;
-  c.n = r / gsz;
-  c.kb_begin = (int)(((long long)c.split * p.k_blocks) / p.split_k);
-  c.kb_end = (int)(((long long)(c.split + 1) * p.k_blocks) / p.split_k);
-  return c;
+  m = first_m + r % gsz;
+  n = r / gsz;
+}
+
+// Work item number `it` (0, 1, 2, ...) of this CTA; false when the CTA is done. The producer, the MMA issuer and the
+// epilogue warps all walk the same sequence:
+//   * round-robin items t = blockIdx.x + it * gridDim.x < dp_items: whole (m, n, k-split) tiles;
+//   * then the CTA's share of the stream-K tail: unit range [b*U/ge, (b+1)*U/ge) of U = sk_tiles * k_blocks k-block units
+//     (ge = min(g, U) CTAs take part).
+//     The range is shorter than one tile's K extent (sk_tiles < g), so it touches at most two tiles: the head of a tile
+//     it does not finish (partial dump, walked FIRST so that no CTA ever waits on a CTA that is itself waiting) and the
+//     tail of a tile it finishes (owner: fix-up + epilogue).
+__device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord& c) {
+  const int b = blockIdx.x, g = gridDim.x;
+  const int t = b + it * g;
+  c.kind = WORK_TILE; c.sk_tile = 0; c.first_cta = 0;
+  if (t < p.dp_items) {
+    const int mn = t / p.split_k;
+    c.split = t - mn * p.split_k;
+    raster_mn(p, mn, c.m, c.n);
+    c.kb_begin = (int)(((long long)c.split * p.k_blocks) / p.split_k);
+    c.kb_end = (int)(((long long)(c.split + 1) * p.k_blocks) / p.split_k);
+    return true;
+  }
+  if (p.sk_tiles == 0) return false;
+  const int n_dp = b < p.dp_items ? (p.dp_items - b + g - 1) / g : 0;
+  const int j = it - n_dp;  // 0 or 1
+  const int kb = p.k_blocks;
+  const long long U = (long long)p.sk_tiles * kb;
+  const int ge = U < g ? (int)U : g;  // CTAs sharing the tail: every one of them gets at least one unit
+  if (b >= ge || j > 1) return false;
+  const int u0 = (int)((long long)b * U / ge), u1 = (int)((long long)(b + 1) * U / ge);
+  const int tA = u0 / kb, tB = (u1 - 1) / kb;
+  int tile, k0, k1;
+  if (tA == tB) {
+    if (j > 0) return false;
+    tile = tA; k0 = u0 - tA * kb; k1 = u1 - tA * kb;
+  } else if (j == 0) {
+    tile = tB; k0 = 0; k1 = u1 - tB * kb;          // head of the next tile: not finished here
+  } else {
+    tile = tA; k0 = u0 - tA * kb; k1 = kb;         // tail of the previous tile: finished here
+  }
+  c.split = 0;
+  raster_mn(p, p.dp_items + tile, c.m, c.n);       // stream-K is only used with split_k == 1
+  c.kb_begin = k0; c.kb_end = k1;
+  c.sk_tile = tile;
+  if (k1 == kb) {
+    // CTA holding unit x is ((x + 1) * g - 1) / U
+    c.first_cta = (int)((((long long)tile * kb + 1) * ge - 1) / U);
+    c.kind = (c.first_cta == b) ? WORK_TILE : WORK_SK_OWNER;  // whole tile in this CTA's range: nothing to fix up
+  } else {
+    c.kind = WORK_SK_PARTIAL;
+  }
+  return true;
 }
 
 // ---- epilogue for one 32-column chunk held by one thread (= one accumulator row) ----
@@ -287,7 +339,7 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_pf, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases
@@ -301,8 +353,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
-
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -334,8 +384,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // tiles is requested before waiting for it; only the activation operand has to wait. At decode batch sizes this
       // keeps HBM busy across kernel boundaries.
       int pre = 0;
-      if ((int)blockIdx.x < num_tiles) {
-        const TileCoord tc = decode_tile(p, blockIdx.x);
+      TileCoord tc;
+      if (get_work(p, 0, tc)) {
         pre = min(C::STAGES, tc.kb_end - tc.kb_begin);
         for (int i = 0; i < pre; ++i) {
           uint8_t* sa = smem + i * C::STAGE;
@@ -353,9 +403,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       } else {
         grid_dep_wait();
       }
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
-        for (int kb = tc.kb_begin + (t == (int)blockIdx.x ? pre : 0); kb < tc.kb_end; ++kb) {
+      for (int it = 0; get_work(p, it, tc); ++it) {
+        for (int kb = tc.kb_begin + (it == 0 ? pre : 0); kb < tc.kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE;
           uint8_t* sb = sa + C::STAGE_A;
@@ -364,6 +413,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tma_load_2d_hint(sb, &tmap_b, &full_bar[stage], kb * BK, tc.n * BN, p.hint_b);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+      // Next-weight prefetch: this CTA's own stream is fully requested; keep HBM busy through the drain / launch gap.
+      for (int t = blockIdx.x; t < p.pf_items; t += gridDim.x) {
+        const int m = t / p.pf_split_k;
+        const int s = t - m * p.pf_split_k;
+        const int kb0 = (int)(((long long)s * p.pf_k_blocks) / p.pf_split_k);
+        const int kb1 = (int)(((long long)(s + 1) * p.pf_k_blocks) / p.pf_split_k);
+        const int n = min(p.pf_depth, kb1 - kb0);
+        for (int i = 0; i < n; ++i) tma_prefetch_l2_2d(&tmap_pf, (kb0 + i) * BK, m * BM);
       }
       // PDL trigger, issued LATE (all loads of this CTA are in flight): dependents that became resident earlier would
       // only sit in griddepcontrol.wait next to a long-running GEMM.
@@ -377,8 +435,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t);
+      TileCoord tc;
+      for (int it = 0; get_work(p, it, tc); ++it) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -407,12 +465,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     grid_dep_wait();            // residual / output buffers may still be in use by the preceding kernel
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(p, t);
+    const int epi_tid = threadIdx.x - 64;  // 0..255
+    TileCoord tc;
+    for (int it = 0; get_work(p, it, tc); ++it) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const int row = tc.m * BM + quad * 32 + lane;
+      const int lrow = quad * 32 + lane;  // accumulator row inside the tile
+      const int row = tc.m * BM + lrow;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+      // stream-K partials of this tile: sk_ws[cta][column][row] fp32 (lanes = consecutive rows -> coalesced)
+      float* my_part = p.sk_ws + (size_t)blockIdx.x * (BM * BN) + lrow;
+      if (tc.kind == WORK_SK_OWNER) {
+        if (epi_tid == 0) {
+          const int need = (int)blockIdx.x - tc.first_cta;
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(p.sk_cnt + tc.sk_tile) < need) {
+            if (clock64() - t0 > 20000000000LL) {
+              printf("opus_b200: stream-K fix-up wait timed out (block %d, tile %d)\n", (int)blockIdx.x, tc.sk_tile);
+              __trap();
+            }
+          }
+          p.sk_cnt[tc.sk_tile] = 0;  // re-armed for the next launch (stream order separates launches)
+        }
+        named_bar_sync(1, NUM_EPI_THREADS);
+      }
       if (p.transposed) {
         // rolled loop over 8-column groups: small code footprint (decode-sized launches run it once, I-cache cold)
 #pragma unroll 1
@@ -420,6 +496,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint32_t r8[8];
           tmem_ld_32x8(taddr + g * 8, r8);
           tmem_ld_wait();
+          if (tc.kind == WORK_SK_PARTIAL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(r8[i]);
+            continue;
+          }
+          if (tc.kind == WORK_SK_OWNER) {
+            for (int c = tc.first_cta; c < (int)blockIdx.x; ++c) {
+              const float* src = p.sk_ws + (size_t)c * (BM * BN) + (size_t)(g * 8) * BM + lrow;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r8[i] = __float_as_uint(__uint_as_float(r8[i]) + __ldcg(src + (size_t)i * BM));
+            }
+          }
           const int col0 = tc.n * BN + g * 8;
           if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split);
         }
@@ -429,9 +517,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint32_t r[32];
           tmem_ld_32x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if (tc.kind == WORK_SK_PARTIAL) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) my_part[(size_t)(c * 32 + i) * BM] = __uint_as_float(r[i]);
+            continue;
+          }
+          if (tc.kind == WORK_SK_OWNER) {
+            for (int cc = tc.first_cta; cc < (int)blockIdx.x; ++cc) {
+              const float* src = p.sk_ws + (size_t)cc * (BM * BN) + (size_t)(c * 32) * BM + lrow;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldcg(src + (size_t)i * BM));
+            }
+          }
           const int col0 = tc.n * BN + c * 32;
           if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
         }
+      }
+      if (tc.kind == WORK_SK_PARTIAL) {
+        __threadfence();
+        named_bar_sync(1, NUM_EPI_THREADS);
+        if (epi_tid == 0) red_release_gpu_add(p.sk_cnt + tc.sk_tile, 1);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
@@ -482,7 +587,8 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t col
 }
 
 template <int BN>
-int launch(const GemmParams& p, const void* A, int lda, const void* B, int ldb, int grid, cudaStream_t stream) {
+int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, const void* B, int ldb, int grid,
+           cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -496,7 +602,12 @@ int launch(const GemmParams& p, const void* A, int lda, const void* B, int ldb, 
   if (rc) return rc;
   rc = make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN);
   if (rc) return rc;
-  const cudaError_t le = launch_pdl(p.transposed != 0, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, p);
+  CUtensorMap tp = ta;  // unused unless p.pf_items > 0
+  if (p.pf_items > 0) {
+    rc = make_tmap_bf16(&tp, pf.pf_w, pf.pf_rows, pf.pf_K, pf.pf_K, BM);
+    if (rc) return rc;
+  }
+  const cudaError_t le = launch_pdl(p.transposed != 0, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, p);
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -512,7 +623,37 @@ int num_sms() {
   return g_num_sms;
 }
 
+// Stream-K fix-up workspace: one fp32 accumulator tile (128 x 256 max) per CTA plus one counter per tail tile.
+// Allocated once per process on first use (19.4 MB); the library serialises its work on one stream per process, and
+// consecutive launches on that stream reuse it in stream order.
+struct SkWorkspace {
+  float* ws = nullptr;
+  int* cnt = nullptr;
+  int state = 0;  // 0 = not tried, 1 = ready, -1 = unavailable
+};
+SkWorkspace g_sk;
+std::mutex g_sk_mu;
+
+bool ensure_sk_workspace() {
+  std::lock_guard<std::mutex> lk(g_sk_mu);
+  if (g_sk.state != 0) return g_sk.state > 0;
+  const char* e = std::getenv("OPUS_STREAMK");
+  if (e != nullptr && e[0] == '0') { g_sk.state = -1; return false; }
+  const size_t bytes = (size_t)num_sms() * BM * 256 * sizeof(float);
+  if (cudaMalloc(&g_sk.ws, bytes) != cudaSuccess || cudaMalloc(&g_sk.cnt, 1024 * sizeof(int)) != cudaSuccess ||
+      cudaMemset(g_sk.cnt, 0, 1024 * sizeof(int)) != cudaSuccess) {
+    cudaGetLastError();  // e.g. first call inside a stream capture: stay on the plain schedule
+    return false;       // state stays 0: retried on the next eager call
+  }
+  g_sk.state = 1;
+  return true;
+}
+
+int g_sk_max_fill = 90;  // use the stream-K tail when the partial wave fills <= this percentage of the SMs
+
 }  // namespace
+
+void gemm_set_streamk_fill(int percent) { g_sk_max_fill = percent; }
 
 int gemm_pick_bn(int N, int transposed) {
   if (transposed) {
@@ -576,13 +717,36 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   p.hint_a = a.transposed ? kCacheEvictFirst : kCacheEvictNormal;
   p.hint_b = a.transposed ? kCacheEvictLast : kCacheEvictNormal;
 
+  if (a.pf_w != nullptr && a.pf_depth > 0 && a.pf_rows > 0 && a.pf_K > 0 && (a.pf_K % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(a.pf_w) & 15) == 0) {
+    p.pf_split_k = a.pf_split_k > 0 ? a.pf_split_k : 1;
+    p.pf_k_blocks = (a.pf_K + BK - 1) / BK;
+    p.pf_depth = a.pf_depth;
+    const int items = ((a.pf_rows + BM - 1) / BM) * p.pf_split_k;
+    p.pf_items = items < num_sms() ? items : num_sms();  // first wave of the next launch
+  }
+
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  p.dp_items = tiles;
+  p.sk_tiles = 0;
+  {
+    // wave quantisation: a last wave that fills only part of the machine is cut along K over all CTAs instead
+    const int rem = tiles % num_sms();
+    const bool sk_ready = ensure_sk_workspace();  // also on launches that do not need it: never first inside a capture
+    if (p.split_k == 1 && tiles > num_sms() && rem != 0 && rem * 100 <= g_sk_max_fill * num_sms() &&
+        a.epi != EPI_PARTIAL_F32 && sk_ready) {
+      p.sk_tiles = rem;
+      p.dp_items = tiles - rem;
+      p.sk_ws = g_sk.ws;
+      p.sk_cnt = g_sk.cnt;
+    }
+  }
   switch (bn) {
-    case 32: return launch<32>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
-    case 64: return launch<64>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
-    case 128: return launch<128>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
-    case 256: return launch<256>(p, a.A, a.lda, a.B, a.ldb, grid, stream);
+    case 32: return launch<32>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
+    case 64: return launch<64>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
+    case 128: return launch<128>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
+    case 256: return launch<256>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
     default: return OPUS_ERR_ARG;
   }
 }

@@ -4,6 +4,8 @@
 #include <map>
 #include <mutex>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <tuple>
 #include <vector>
 
@@ -67,10 +69,40 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 
+// Next-weight L2 prefetch hint for a chain of swap-AB GEMMs (see GemmArgs::pf_w).
+struct Prefetch {
+  const void* w = nullptr;
+  int rows = 0, K = 0, split_k = 1, depth = 0;
+};
+void apply_prefetch(GemmArgs& a, const Prefetch* pf) {
+  if (pf == nullptr || pf->w == nullptr || pf->depth <= 0) return;
+  a.pf_w = pf->w; a.pf_rows = pf->rows; a.pf_K = pf->K; a.pf_split_k = pf->split_k; a.pf_depth = pf->depth;
+}
+// k-blocks to prefetch per work item for the decode chain; OPUS_PF=0 disables, OPUS_PF_<QKV|O|GU|DOWN|LM>=n overrides,
+// opus_set_tunable("pf_qkv", n) etc. changes them at run time (tools/bench_decode.py sweeps them).
+int g_pf_depth[5] = {-1, -1, -1, -1, -1};
+void pf_init() {
+  if (g_pf_depth[0] >= 0) return;
+  static const char* names[5] = {"OPUS_PF_QKV", "OPUS_PF_O", "OPUS_PF_GU", "OPUS_PF_DOWN", "OPUS_PF_LM"};
+  static const int defaults[5] = {64, 64, 16, 24, 16};
+  const char* off = std::getenv("OPUS_PF");
+  const bool enabled = !(off != nullptr && off[0] == '0');
+  for (int i = 0; i < 5; ++i) {
+    const char* e = std::getenv(names[i]);
+    g_pf_depth[i] = !enabled ? 0 : (e != nullptr ? atoi(e) : defaults[i]);
+  }
+}
+int pf_depth_for(int which) {
+  pf_init();
+  return g_pf_depth[which];
+}
+enum { PF_QKV = 0, PF_O = 1, PF_GU = 2, PF_DOWN = 3, PF_LM = 4 };
+
 // activations [rows, K] x weight [N, K]^T -> out, choosing the weight-streaming (swap-AB) form for small `rows`.
 int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* out, int ldo, const float* bias,
-           const void* residual, int ldr, float* ws, size_t ws_bytes, cudaStream_t st) {
+           const void* residual, int ldr, float* ws, size_t ws_bytes, cudaStream_t st, const Prefetch* pf = nullptr) {
   GemmArgs a{};
+  apply_prefetch(a, pf);
   a.K = K;
   a.epi = epi;
   a.out = out; a.ldo = ldo;
@@ -90,13 +122,19 @@ int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* 
 }
 
 // swap-AB GEMM with split-K partials into `partial` ([s][rows][N] fp32). Returns the split count via *splits.
-int linear_splitk(const void* x, int rows, const void* w, int N, int K, float* partial, size_t partial_bytes,
-                  int* splits, cudaStream_t st) {
+int splitk_for(int rows, int N, int K, size_t partial_bytes) {
   const int bn = gemm_pick_bn(rows, 1);
   int s = gemm_pick_split_k(N, rows, K, bn);
   while (s > 1 && gemm_workspace_bytes(rows, N, s) > partial_bytes) --s;
+  return s;
+}
+
+int linear_splitk(const void* x, int rows, const void* w, int N, int K, float* partial, size_t partial_bytes,
+                  int* splits, cudaStream_t st, const Prefetch* pf = nullptr) {
+  const int s = splitk_for(rows, N, K, partial_bytes);
   if (gemm_workspace_bytes(rows, N, s) > partial_bytes) return OPUS_ERR_ARG;
   GemmArgs a{};
+  apply_prefetch(a, pf);
   a.transposed = 1;
   a.A = w; a.lda = K; a.M = N;
   a.B = x; a.ldb = K; a.N = rows;
@@ -245,25 +283,47 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
   OPUS_TRY(embed_gather(s->next_tok, static_cast<const bf16*>(m->embed), h, B, d, st));
   OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(m->layers[0].ln1_w), xn, B, d,
                         m->rms_eps, st));
+  // Each weight-streaming GEMM asks for the head of the NEXT GEMM's weight stream at its tail (L2 prefetch), so HBM
+  // does not idle while it drains, the small kernels between run, and the next GEMM ramps up.
+  const bool swap = B <= 256;
+  Prefetch pf_o, pf_gu, pf_down, pf_next;
+  if (swap) {
+    pf_o.rows = d; pf_o.K = Hq * hd; pf_o.split_k = splitk_for(B, d, Hq * hd, ws->partial_bytes); pf_o.depth = pf_depth_for(PF_O);
+    pf_gu.rows = 2 * ffn; pf_gu.K = d; pf_gu.split_k = 1; pf_gu.depth = pf_depth_for(PF_GU);
+    pf_down.rows = d; pf_down.K = ffn; pf_down.split_k = splitk_for(B, d, ffn, ws->partial_bytes); pf_down.depth = pf_depth_for(PF_DOWN);
+  }
   for (int l = 0; l < m->n_layers; ++l) {
     const opus_llama_layer& L = m->layers[l];
     bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
     bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
     int sp = 1;
-    OPUS_TRY(linear_splitk(xn, B, L.wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st));
+    pf_o.w = L.wo; pf_gu.w = L.wgu; pf_down.w = L.wdown;
+    if (swap && l + 1 < m->n_layers) {
+      pf_next.w = m->layers[l + 1].wqkv; pf_next.rows = qkv_n; pf_next.K = d;
+      pf_next.split_k = splitk_for(B, qkv_n, d, ws->partial_bytes); pf_next.depth = pf_depth_for(PF_QKV);
+    } else if (swap) {
+      pf_next.w = m->lm_head; pf_next.rows = m->vocab; pf_next.K = d; pf_next.split_k = 1; pf_next.depth = pf_depth_for(PF_LM);
+    }
+    OPUS_TRY(linear_splitk(xn, B, L.wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st, &pf_o));
     OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
                                  static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n, kv->block_size,
                                  st));
     OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv,
                                hd, kv->block_size, scale, st));
-    OPUS_TRY(linear_splitk(attn, B, L.wo, d, Hq * hd, ws->partial, ws->partial_bytes, &sp, st));
+    OPUS_TRY(linear_splitk(attn, B, L.wo, d, Hq * hd, ws->partial, ws->partial_bytes, &sp, st, &pf_gu));
     OPUS_TRY(rmsnorm_bf16(nullptr, ws->partial, sp, h, h, static_cast<const bf16*>(L.ln2_w), xn, B, d, m->rms_eps, st));
-    OPUS_TRY(linear(xn, B, L.wgu, 2 * ffn, d, EPI_SWIGLU, act, ffn, nullptr, nullptr, 0, nullptr, 0, st));
-    OPUS_TRY(linear_splitk(act, B, L.wdown, d, ffn, ws->partial, ws->partial_bytes, &sp, st));
+    OPUS_TRY(linear(xn, B, L.wgu, 2 * ffn, d, EPI_SWIGLU, act, ffn, nullptr, nullptr, 0, nullptr, 0, st, &pf_down));
+    OPUS_TRY(linear_splitk(act, B, L.wdown, d, ffn, ws->partial, ws->partial_bytes, &sp, st, &pf_next));
     const bf16* next_w = static_cast<const bf16*>(l + 1 < m->n_layers ? m->layers[l + 1].ln1_w : m->norm_w);
     OPUS_TRY(rmsnorm_bf16(nullptr, ws->partial, sp, h, h, next_w, xn, B, d, m->rms_eps, st));
   }
-  OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st));
+  Prefetch pf_first;  // the next decode step starts with layer 0's qkv weights
+  if (swap) {
+    pf_first.w = m->layers[0].wqkv; pf_first.rows = qkv_n; pf_first.K = d;
+    pf_first.split_k = splitk_for(B, qkv_n, d, ws->partial_bytes); pf_first.depth = pf_depth_for(PF_QKV);
+  }
+  OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st,
+                  &pf_first));
   OPUS_TRY(llama_select(m, ws, s, B, st));
   return OPUS_OK;
 }
@@ -278,6 +338,23 @@ using GraphKey = std::tuple<const void*, const void*, const void*, const void*, 
 std::map<GraphKey, GraphEntry> g_graphs;
 std::mutex g_graph_mu;
 }  // namespace
+
+int set_tunable(const char* name, int value) {
+  static const char* names[5] = {"pf_qkv", "pf_o", "pf_gu", "pf_down", "pf_lm"};
+  if (name == nullptr) return fail(OPUS_ERR_ARG, "set_tunable: null name");
+  pf_init();
+  if (std::strcmp(name, "streamk_fill") == 0) {
+    gemm_set_streamk_fill(value);
+    return release_graphs();
+  }
+  for (int i = 0; i < 5; ++i) {
+    if (std::strcmp(name, names[i]) == 0) {
+      g_pf_depth[i] = value < 0 ? 0 : value;
+      return release_graphs();  // captured decode graphs bake the old value in
+    }
+  }
+  return fail(OPUS_ERR_ARG, "set_tunable: unknown name");
+}
 
 int release_graphs() {
   std::lock_guard<std::mutex> lk(g_graph_mu);

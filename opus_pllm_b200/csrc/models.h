@@ -20,6 +20,7 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
 int llama_decode_loop(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
                       const opus_decode_state* s, int B, int n_steps, int check_every, int use_graph, cudaStream_t st);
 int release_graphs();
+int set_tunable(const char* name, int value);
 int trace_begin(cudaStream_t st);
 int trace_end(char* buf, int cap);
 }  // namespace opus

@@ -73,6 +73,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------- cross-CTA flags (stream-K fix-up) -------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// named barrier among `count` threads of the CTA (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // ---------------------------------------------- TMA ----------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
@@ -93,6 +107,12 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* des
       "%4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1), "l"(cache_hint)
       : "memory");
+}
+// 2D tiled prefetch of one box into L2 only (no shared-memory destination, no completion tracking): a hint.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* desc, int32_t crd0, int32_t crd1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+               "r"(crd0), "r"(crd1)
+               : "memory");
 }
 constexpr uint64_t kCacheEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kCacheEvictLast = 0x14F0000000000000ull;

@@ -145,6 +145,43 @@ def test_gemm_split_k_partials(ops, transposed, rows):
     _close_bf16(red, want)
 
 
+# Stream-K tail (gemm_tcgen05.cu: get_work): shapes whose tile count is not a multiple of the SM count, so the last
+# partial wave is cut along K across all CTAs and fixed up by the tile owners. Tail sizes: 76, 2, 140 (off: > 90 %),
+# 114 tiles (transposed); 645 / 1935 tiles (plain form, the encoder's out_proj / qkv shapes at C1).
+@pytest.mark.parametrize("tiles,K,rows", [(224, 4096, 64), (150, 1024, 64), (288, 512, 16), (262, 2048, 256),
+                                          (299, 320, 33)])
+def test_gemm_streamk_tail_transposed(ops, tiles, K, rows):
+    from opus_pllm_b200._lib import EPI_BF16, EPI_F32, EPI_SWIGLU
+    x = _randn((rows, K), 40)
+    w = _randn((tiles * 128, K), 41, scale=K ** -0.5)
+    b = _randn((tiles * 128,), 42, dtype=torch.float32)
+    want = R.linear_ref(x, w, b)
+    for rep in range(3):   # the tail-tile counters must be re-armed by every launch
+        got32 = ops.gemm(x, w, epilogue=EPI_F32, bias=b, transposed=True)
+        assert torch.allclose(got32, want, rtol=1e-4, atol=2e-3), float((got32 - want).abs().max())
+    _close_bf16(ops.gemm(x, w, epilogue=EPI_BF16, bias=b, transposed=True), want)
+    got = ops.gemm(x, w, epilogue=EPI_SWIGLU, transposed=True)
+    _close_bf16(got, R.swiglu_interleaved_ref(R.linear_ref(x, w)), ulps=3.0, atol=2e-2)
+    # deterministic: partials are added in CTA order
+    assert torch.equal(ops.gemm(x, w, epilogue=EPI_F32, bias=b, transposed=True), got32)
+
+
+@pytest.mark.parametrize("rows,N,K", [(16512, 1280, 1280), (16512, 3840, 1280), (5000, 1280, 5120), (2100, 2560, 192)])
+def test_gemm_streamk_tail_plain(ops, rows, N, K):
+    from opus_pllm_b200._lib import EPI_BF16, EPI_BF16_GELU, EPI_RES_BF16
+    x = _randn((rows, K), 43)
+    w = _randn((N, K), 44, scale=K ** -0.5)
+    b = _randn((N,), 45, dtype=torch.float32)
+    want = R.linear_ref(x, w, b)
+    for rep in range(2):
+        _close_bf16(ops.gemm(x, w, epilogue=EPI_BF16, bias=b, transposed=False), want)
+    _close_bf16(ops.gemm(x, w, epilogue=EPI_BF16_GELU, bias=b, transposed=False), R.gelu_erf(want))
+    res = _randn((rows, N), 46)
+    h = res.clone()
+    ops.gemm(x, w, epilogue=EPI_RES_BF16, residual=h, out=h, transposed=False)   # in place, like o_proj / down_proj
+    _close_bf16(h, R.bf16r(res.float() + R.bf16r(R.linear_ref(x, w))), ulps=2.0, atol=2e-2)
+
+
 def test_gemm_linearity_full_size(ops):
     """size-independent property at a BASELINE-sized weight: f(x1 + x2) == f(x1) + f(x2) up to bf16 rounding."""
     from opus_pllm_b200._lib import EPI_F32

@@ -166,3 +166,34 @@ def test_dp_gather_world_size_2_gloo():
         assert p.exitcode == 0
     want = [[p * 10 + t for t in range(3)] + [-1] for p in range(4)] + [[p * 10 + t for t in range(4)] for p in range(4, 7)]
     assert res[0] == want and res[1] == want
+
+
+def test_streamk_tail_partition_covers_every_unit_once():
+    """Python restatement of gemm_tcgen05.cu::get_work's stream-K tail partition: every k-block unit of the tail tiles is
+    computed exactly once, a CTA touches at most two tiles, and the owner's [first_cta, owner) range is exactly the set
+    of CTAs that dump a partial for that tile (so the counter it waits on reaches the expected value)."""
+    def sim(sk_tiles, kb, g):
+        U = sk_tiles * kb
+        ge = min(g, U)
+        cover, contrib, owners = [0] * U, {}, {}
+        for b in range(ge):
+            u0, u1 = b * U // ge, (b + 1) * U // ge
+            assert 0 < u1 - u0 <= kb
+            tA, tB = u0 // kb, (u1 - 1) // kb
+            segs = [(tA, u0 - tA * kb, u1 - tA * kb)] if tA == tB else [(tB, 0, u1 - tB * kb), (tA, u0 - tA * kb, kb)]
+            assert tB - tA <= 1
+            for t, k0, k1 in segs:
+                for k in range(k0, k1):
+                    cover[t * kb + k] += 1
+                if k1 == kb:
+                    owners[t] = (b, ((t * kb + 1) * ge - 1) // U)
+                else:
+                    contrib.setdefault(t, []).append(b)
+        assert all(c == 1 for c in cover)
+        for t in range(sk_tiles):
+            b, first = owners[t]
+            assert contrib.get(t, []) == list(range(first, b))
+    for g in (148, 132):
+        for sk in (1, 2, 3, 53, 76, 114, g - 1):
+            for kb in (1, 2, 5, 16, 20, 64, 80, 224):
+                sim(sk, kb, g)

@@ -1,0 +1,59 @@
+"""Decode-only timing (CUDA-graph replays) of the Llama-3-8B greedy loop, with run-time sweeps of the L2-prefetch depths.
+
+usage: python tools/bench_decode.py [B] [T] [new]     env SWEEP=1 sweeps the opus_set_tunable knobs.
+"""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from opus_pllm_b200 import _lib as L, presets, synth
+from opus_pllm_b200.llama import B200Llama
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+new = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+cfg = presets.LLAMA3_8B
+sd = synth.llama_weights(cfg["n_layers"], cfg["dim"], cfg["n_q_heads"], cfg["n_kv_heads"], cfg["head_dim"],
+                         cfg["ffn_dim"], cfg["vocab"], seed=0, peaked=False, dtype=torch.bfloat16, device="cuda")
+ll = B200Llama(sd, **cfg, device="cuda")
+del sd
+torch.cuda.empty_cache()
+lib = L.load()
+cu = np.arange(B + 1, dtype=np.int32) * T
+emb = (torch.randn(B * T, cfg["dim"], device="cuda") * 0.02).bfloat16()
+plan = ll.make_plan(cu, new)
+st = ll.prefill(emb, plan=plan)
+bytes_step = 15009316864 + 131072.0 * B * (T + (new + 1) / 2.0) + 131072.0 * B
+
+
+def run(label):
+    for _ in range(2):
+        ll.generate_from_prefill(st, new)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    a.record()
+    for _ in range(reps):
+        ll.generate_from_prefill(st, new)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps / (new - 1)
+    print(f"{label:40s} {ms:7.3f} ms/step  {bytes_step / ms / 1e6:7.0f} GB/s  frac {bytes_step / ms / 1e6 / 6551.4:.3f}", flush=True)
+    return ms
+
+
+def setk(**kw):
+    for k, v in kw.items():
+        L.check(lib.opus_set_tunable(k.encode(), v), k)
+
+
+run("defaults")
+if os.environ.get("SWEEP"):
+    setk(pf_qkv=0, pf_o=0, pf_gu=0, pf_down=0, pf_lm=0); base = run("all off")
+    for name in ("pf_qkv", "pf_o", "pf_gu", "pf_down", "pf_lm"):
+        for v in (8, 16, 32, 64):
+            setk(**{name: v}); run(f"only {name}={v}")
+        setk(**{name: 0})
+    for combo in [dict(pf_qkv=64, pf_o=64, pf_gu=8, pf_down=8, pf_lm=8), dict(pf_qkv=64, pf_o=64, pf_gu=16, pf_down=16, pf_lm=16),
+                  dict(pf_qkv=64, pf_o=64, pf_gu=32, pf_down=32, pf_lm=16), dict(pf_qkv=64, pf_o=64, pf_gu=64, pf_down=56, pf_lm=32),
+                  dict(pf_qkv=32, pf_o=32, pf_gu=32, pf_down=32, pf_lm=16), dict(pf_qkv=16, pf_o=16, pf_gu=16, pf_down=16, pf_lm=16)]:
+        setk(**combo); run(str(combo).replace("'", "").replace("pf_", ""))
