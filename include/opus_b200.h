@@ -271,7 +271,9 @@ int opus_llama_decode_loop(const opus_llama_model* model, const opus_kv_cache* c
 int opus_release_graphs(void);
 /* Run-time tunables of the composite forwards (measurement aid; defaults are the tuned values). Names: "pf_qkv",
  * "pf_o", "pf_gu", "pf_down", "pf_lm" = k-blocks (64 K-elements each) per work item that a decode GEMM prefetches into
- * L2 for the NEXT weight matrix of the chain (0 = off). Drops cached graphs. */
+ * L2 for the NEXT weight matrix of the chain (0 = off); "streamk_fill" = largest partial-wave fill (percent of the SMs)
+ * for which a swap-AB GEMM cuts its last wave along K (0 = off); "streamk_plain" = 1 enables the same for the plain
+ * form (off by default: it would make a token's rounding depend on its position in the batch). Drops cached graphs. */
 int opus_set_tunable(const char* name, int value);
 /* Profiling aid: between opus_trace_begin(stream) and opus_trace_end the composite forwards record a CUDA event after
  * every kernel launch (not inside graph capture); opus_trace_end synchronises and writes "label<TAB>microseconds\n"

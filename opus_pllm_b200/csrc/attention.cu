@@ -450,8 +450,10 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
   if (n_seqs == 0 || max_len == 0) return OPUS_OK;
   if (n_kv_heads <= 0 || n_q_heads % n_kv_heads) return OPUS_ERR_ARG;
   {
-    // implementation choice: tcgen05 kernel (attention_tc.cu) for 128-row tiles that are reasonably full, the mma.sync
-    // kernel below for short sequences. OPUS_ATTN=mma|tc forces one of them (A/B measurements, tests).
+    // implementation choice: the tcgen05 kernel (attention_tc.cu; two 128-row query tiles per work item) unless every
+    // sequence is short, where the 64-row mma.sync tiles below waste fewer padded rows. Measured (tools/sweep_attn.py):
+    // tcgen05 wins from T = 258 (153 vs 164 us, encoder C1) to T = 2048 (363 vs 1143 us, causal hd 128).
+    // OPUS_ATTN=mma|tc forces one of them (A/B measurements, tests).
     static int mode = -1;
     if (mode < 0) {
       const char* e = std::getenv("OPUS_ATTN");
@@ -460,7 +462,7 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
     const bool aligned = ((ldq | ldk | ldv | ldo) % 8) == 0 &&
                          ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                            reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
-    const bool want_tc = mode == 2 || (mode == 0 && max_len >= 384);
+    const bool want_tc = mode == 2 || (mode == 0 && max_len >= 192);
     if (want_tc && aligned && (head_dim == 64 || head_dim == 128))
       return attn_varlen_tc(q, ldq, k, ldk, v, ldv, o, ldo, cu_seqlens, n_seqs, n_tok, max_len, n_q_heads, n_kv_heads,
                             head_dim, causal, scale, st);

@@ -39,6 +39,7 @@ struct AttnTcParams {
   int ldo;
   int group;          // q heads per kv head
   float scale_log2;   // softmax scale * log2(e)
+  int n_seqs, n_q_heads, n_mblk, n_items;  // work list: n_mblk tile pairs x n_seqs x n_q_heads
 };
 
 template <int D>
@@ -96,6 +97,33 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// One unit of work: two adjacent 128-row query tiles of one (sequence, head).
+struct Item {
+  int seq_start, len, h, kvh, q0;
+  int n_a, n_b, n_max;  // key blocks of tile A, tile B, and of the pair
+  bool valid;
+};
+
+template <bool CAUSAL>
+__device__ __forceinline__ Item get_item(const AttnTcParams& p, int w) {
+  Item it;
+  const int per_mblk = p.n_seqs * p.n_q_heads;
+  const int mb = w / per_mblk;
+  const int rem = w - mb * per_mblk;
+  const int b = rem / p.n_q_heads;
+  it.h = rem - b * p.n_q_heads;
+  it.kvh = it.h / p.group;
+  const int mblk = CAUSAL ? (p.n_mblk - 1 - mb) : mb;   // causal: heavy tiles first
+  it.q0 = mblk * 2 * TBM;
+  it.seq_start = p.cu_seqlens[b];
+  it.len = p.cu_seqlens[b + 1] - it.seq_start;
+  it.valid = it.q0 < it.len;
+  it.n_a = ((CAUSAL ? min(it.len, it.q0 + TBM) : it.len) + TBN - 1) / TBN;
+  it.n_b = (it.q0 + TBM < it.len) ? ((CAUSAL ? min(it.len, it.q0 + 2 * TBM) : it.len) + TBN - 1) / TBN : 0;
+  it.n_max = it.n_b > 0 ? it.n_b : it.n_a;
+  return it;
+}
+
 template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -107,8 +135,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint8_t* sK = sQ + 2 * C::TILE_BYTES;                // [KS][TILE_BYTES]
   uint8_t* sV = sK + C::KS * C::TILE_BYTES;            // [VS][TILE_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::VS * C::TILE_BYTES);
-  uint64_t* q_full = bars;                  // 1
-  uint64_t* k_full = bars + 1;              // [KS]
+  uint64_t* q_full = bars;                  // 1   TMA -> MMA
+  uint64_t* q_empty = bars + 1;             // 1   MMA -> TMA: every S MMA of the item has read Q
+  uint64_t* k_full = bars + 2;              // [KS]
   uint64_t* k_empty = k_full + C::KS;       // [KS]
   uint64_t* v_full = k_empty + C::KS;       // [VS]
   uint64_t* v_empty = v_full + C::VS;       // [VS]
@@ -118,21 +147,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int seq_start = p.cu_seqlens[b];
-  const int len = p.cu_seqlens[b + 1] - seq_start;
-  const int mblk = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // causal: heavy tiles first
-  const int q0 = mblk * 2 * TBM;
-  if (q0 >= len) return;
-  const int kvh = h / p.group;
-  // key blocks per tile
-  const int n_a = ((CAUSAL ? min(len, q0 + TBM) : len) + TBN - 1) / TBN;
-  const int n_b = (q0 + TBM < len) ? ((CAUSAL ? min(len, q0 + 2 * TBM) : len) + TBN - 1) / TBN : 0;
-  const int n_max = n_b > 0 ? n_b : n_a;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < C::KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < C::VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&o_done[x], 1); }
@@ -147,27 +166,41 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Persistent CTA: every role walks the same static list of work items; barrier phases are tracked with running use
+  // counters, so the O read-out of one item overlaps the loads and the first S MMA of the next.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * C::TILE_BYTES);
+      uint32_t kc = 0, vc = 0, qc = 0;   // K blocks, V blocks, items issued so far
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        const Item it = get_item<CAUSAL>(p, w);
+        if (!it.valid) continue;
+        mbar_wait(q_empty, (qc & 1) ^ 1);
+        mbar_arrive_expect_tx(q_full, 2 * C::TILE_BYTES);
 #pragma unroll
-      for (int x = 0; x < 2; ++x)
+        for (int x = 0; x < 2; ++x)
 #pragma unroll
-        for (int pn = 0; pn < C::NP; ++pn)
-          tma_load_2d(sQ + x * C::TILE_BYTES + pn * PANEL, &tm_q, q_full, h * D + pn * 64, seq_start + q0 + x * TBM);
-      for (int j = 0; j < n_max; ++j) {
-        const int ks = j % C::KS, vs = j % C::VS;
-        mbar_wait(&k_empty[ks], ((j / C::KS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[ks], C::TILE_BYTES);
+          for (int pn = 0; pn < C::NP; ++pn)
+            tma_load_2d(sQ + x * C::TILE_BYTES + pn * PANEL, &tm_q, q_full, it.h * D + pn * 64,
+                        it.seq_start + it.q0 + x * TBM);
+        ++qc;
+        for (int j = 0; j < it.n_max; ++j) {
+          const uint32_t ks = kc % C::KS, vs = vc % C::VS;
+          mbar_wait(&k_empty[ks], ((kc / C::KS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[ks], C::TILE_BYTES);
 #pragma unroll
-        for (int pn = 0; pn < C::NP; ++pn)
-          tma_load_2d(sK + ks * C::TILE_BYTES + pn * PANEL, &tm_k, &k_full[ks], kvh * D + pn * 64, seq_start + j * TBN);
-        mbar_wait(&v_empty[vs], ((j / C::VS) & 1) ^ 1);
-        mbar_arrive_expect_tx(&v_full[vs], C::TILE_BYTES);
+          for (int pn = 0; pn < C::NP; ++pn)
+            tma_load_2d(sK + ks * C::TILE_BYTES + pn * PANEL, &tm_k, &k_full[ks], it.kvh * D + pn * 64,
+                        it.seq_start + j * TBN);
+          ++kc;
+          mbar_wait(&v_empty[vs], ((vc / C::VS) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[vs], C::TILE_BYTES);
 #pragma unroll
-        for (int pn = 0; pn < C::NP; ++pn)
-          tma_load_2d(sV + vs * C::TILE_BYTES + pn * PANEL, &tm_v, &v_full[vs], kvh * D + pn * 64, seq_start + j * TBN);
+          for (int pn = 0; pn < C::NP; ++pn)
+            tma_load_2d(sV + vs * C::TILE_BYTES + pn * PANEL, &tm_v, &v_full[vs], it.kvh * D + pn * 64,
+                        it.seq_start + j * TBN);
+          ++vc;
+        }
       }
     }
   } else if (warp == 1) {
@@ -175,8 +208,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc_s = idesc_bf16(TBM, TBN, 0);
       constexpr uint32_t idesc_o = idesc_bf16(TBM, D, 1);
-      const int n_x[2] = {n_a, n_b};
-      auto issue_s = [&](int x, int ks) {
+      uint32_t kc = 0, vc = 0, qc = 0, pc[2] = {0, 0};
+      auto issue_s = [&](int x, uint32_t ks) {
         const uint32_t aq = smem_u32(sQ + x * C::TILE_BYTES), bk = smem_u32(sK + ks * C::TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -186,128 +219,151 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
         umma_commit(&s_full[x]);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      if (n_b > 0) issue_s(1, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_max; ++j) {
-        const int vs = j % C::VS, ks1 = (j + 1) % C::KS;
-        mbar_wait(&v_full[vs], (j / C::VS) & 1);
-        bool k_ready = false;
+      for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+        const Item it = get_item<CAUSAL>(p, w);
+        if (!it.valid) continue;
+        const int n_x[2] = {it.n_a, it.n_b};
+        mbar_wait(q_full, qc & 1);
+        ++qc;
+        mbar_wait(&k_full[kc % C::KS], (kc / C::KS) & 1);
+        tc_fence_after();
+        // S_X(0) overwrites P_X of the previous item: ordered after that item's last PV MMA (same issuing thread)
+        issue_s(0, kc % C::KS);
+        if (it.n_b > 0) issue_s(1, kc % C::KS);
+        umma_commit(&k_empty[kc % C::KS]);
+        ++kc;
+        if (it.n_max == 1) umma_commit(q_empty);
+        for (int j = 0; j < it.n_max; ++j) {
+          const uint32_t vs = vc % C::VS, ks1 = kc % C::KS;
+          mbar_wait(&v_full[vs], (vc / C::VS) & 1);
+          bool k_ready = false;
 #pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          if (j >= n_x[x]) continue;
-          mbar_wait(&p_full[x], j & 1);
-          tc_fence_after();
-          const uint32_t bv = smem_u32(sV + vs * C::TILE_BYTES);
+          for (int x = 0; x < 2; ++x) {
+            if (j >= n_x[x]) continue;
+            mbar_wait(&p_full[x], pc[x] & 1);
+            ++pc[x];
+            tc_fence_after();
+            const uint32_t bv = smem_u32(sV + vs * C::TILE_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < TBN / 16; ++kk) {
-            // P: 16 keys = 8 packed columns per step; V: 16 key rows = two 8-row swizzle groups (2048 B) per step
-            umma_bf16_ts(tmem_base + C::COL_O + x * D, tmem_base + C::COL_S + x * TBN + kk * 8,
-                         umma_desc_mn_sw128(bv + kk * 2048, PANEL, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(&o_done[x]);
-          if (j + 1 < n_x[x]) {
-            if (!k_ready) {
-              mbar_wait(&k_full[ks1], ((j + 1) / C::KS) & 1);
-              tc_fence_after();
-              k_ready = true;
+            for (int kk = 0; kk < TBN / 16; ++kk) {
+              // P: 16 keys = 8 packed columns per step; V: 16 key rows = two 8-row swizzle groups (2048 B) per step
+              umma_bf16_ts(tmem_base + C::COL_O + x * D, tmem_base + C::COL_S + x * TBN + kk * 8,
+                           umma_desc_mn_sw128(bv + kk * 2048, PANEL, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
             }
-            issue_s(x, ks1);   // overwrites S_X / P_X(j): ordered after the PV MMAs above (same issuing thread)
+            umma_commit(&o_done[x]);
+            if (j + 1 < n_x[x]) {
+              if (!k_ready) {
+                mbar_wait(&k_full[ks1], (kc / C::KS) & 1);
+                tc_fence_after();
+                k_ready = true;
+              }
+              issue_s(x, ks1);   // overwrites S_X / P_X(j): ordered after the PV MMAs above
+            }
+          }
+          umma_commit(&v_empty[vs]);
+          ++vc;
+          if (k_ready) {
+            umma_commit(&k_empty[ks1]);
+            ++kc;
+            if (j + 2 == it.n_max) umma_commit(q_empty);   // the last S MMAs of this item have been issued
           }
         }
-        umma_commit(&v_empty[vs]);
-        if (k_ready) umma_commit(&k_empty[ks1]);
       }
     }
   } else {
     // ===================== softmax warps: thread = query row =====================
     const int x = (warp - 2) >> 2;             // tile A (warps 2-5) or B (warps 6-9)
-    const int n_blocks = x == 0 ? n_a : n_b;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access (warp id % 4)
     const int row = quad * 32 + lane;          // row inside the tile == TMEM lane
-    const int qt0 = q0 + x * TBM;              // first query row of the tile (sequence-relative)
-    const int qrow = qt0 + row;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr + C::COL_S + x * TBN;
     const uint32_t t_o = tmem_base + lane_addr + C::COL_O + x * D;
-    float m_run = -INFINITY, l_run = 0.f;      // m_run in scaled log2 units
+    uint32_t g = 0;                            // key blocks processed by this warp group so far (barrier phases)
 
-    for (int j = 0; j < n_blocks; ++j) {
-      const int k0 = j * TBN;
-      mbar_wait(&s_full[x], j & 1);
-      tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-      tmem_ld_wait();
-      const bool need_mask = (k0 + TBN > len) || (CAUSAL && k0 + TBN - 1 > qt0);
-      if (need_mask) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          const int key = k0 + i;
-          const bool ok = key < len && (!CAUSAL || key <= qrow);
-          if (!ok) s[i] = 0xff800000u;  // -inf
-        }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
-      }
-      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
-      // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
-      float corr = 1.0f;
-      bool rescale = false;
-      if (m_blk > m_run + kRescaleThreshold) {   // also true for the first block (m_run = -inf)
-        corr = exp2f(m_run - m_blk);             // 0 when m_run = -inf
-        rescale = j > 0;
-        m_run = m_blk;
-      }
-      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-      float ls0 = 0.f, ls1 = 0.f;
-      uint32_t pk[64];
-#pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        const float p0 = exp2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_use));
-        const float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_use));
-        ls0 += p0;
-        ls1 += p1;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-      }
-      l_run = l_run * corr + (ls0 + ls1);
-      tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-      tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
-      if (j > 0) {
-        // O_X must include block j-1 before it may be rescaled / before PV(j) accumulates on top of it
-        mbar_wait(&o_done[x], (j - 1) & 1);
+    for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
+      const Item it = get_item<CAUSAL>(p, w);
+      if (!it.valid) continue;
+      const int n_blocks = x == 0 ? it.n_a : it.n_b;
+      if (n_blocks == 0) continue;
+      const int len = it.len;
+      const int qt0 = it.q0 + x * TBM;           // first query row of the tile (sequence-relative)
+      const int qrow = qt0 + row;
+      float m_run = -INFINITY, l_run = 0.f;      // m_run in scaled log2 units
+
+      for (int j = 0; j < n_blocks; ++j, ++g) {
+        const int k0 = j * TBN;
+        mbar_wait(&s_full[x], g & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, rescale)) {
-#pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(t_o + c * 32, r);
-            tmem_ld_wait();
+        uint32_t s[128];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
-            tmem_st_32x32(t_o + c * 32, r);
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+        tmem_ld_wait();
+        const bool need_mask = (k0 + TBN > len) || (CAUSAL && k0 + TBN - 1 > qt0);
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) {
+            const int key = k0 + i;
+            const bool ok = key < len && (!CAUSAL || key <= qrow);
+            if (!ok) s[i] = 0xff800000u;  // -inf
           }
         }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+        }
+        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
+        float corr = 1.0f;
+        bool rescale = false;
+        if (m_blk > m_run + kRescaleThreshold) {   // also true for the first block (m_run = -inf)
+          corr = exp2f(m_run - m_blk);             // 0 when m_run = -inf
+          rescale = j > 0;
+          m_run = m_blk;
+        }
+        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+        float ls0 = 0.f, ls1 = 0.f;
+        uint32_t pk[64];
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) {
+          const float p0 = exp2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_use));
+          const float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_use));
+          ls0 += p0;
+          ls1 += p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        l_run = l_run * corr + (ls0 + ls1);
+        tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+        tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+        if (j > 0) {
+          // O_X must include block j-1 before it may be rescaled / before PV(j) accumulates on top of it
+          mbar_wait(&o_done[x], (g - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32(t_o + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+              tmem_st_32x32(t_o + c * 32, r);
+            }
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[x]);
-    }
-    if (n_blocks > 0) {
-      mbar_wait(&o_done[x], (n_blocks - 1) & 1);
+      // O_X is complete once the PV MMA of the last block retires; the next item's PV_X(0) cannot start before this
+      // warp group has produced that item's P_X(0), i.e. after this read-out.
+      mbar_wait(&o_done[x], (g - 1) & 1);
       tc_fence_after();
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      __nv_bfloat16* dst = p.o + (size_t)(seq_start + qrow) * p.ldo + (size_t)h * D;
+      __nv_bfloat16* dst = p.o + (size_t)(it.seq_start + qrow) * p.ldo + (size_t)it.h * D;
 #pragma unroll 1
       for (int c = 0; c < D / 32; ++c) {
         uint32_t r[32];
@@ -315,16 +371,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tmem_ld_wait();
         if (qrow < len) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int gq = 0; gq < 4; ++gq) {
             uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(r[g * 8]) * inv, __uint_as_float(r[g * 8 + 1]) * inv);
-            q.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]) * inv, __uint_as_float(r[g * 8 + 3]) * inv);
-            q.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]) * inv, __uint_as_float(r[g * 8 + 5]) * inv);
-            q.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]) * inv, __uint_as_float(r[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = q;
+            q.x = pack_bf16x2(__uint_as_float(r[gq * 8]) * inv, __uint_as_float(r[gq * 8 + 1]) * inv);
+            q.y = pack_bf16x2(__uint_as_float(r[gq * 8 + 2]) * inv, __uint_as_float(r[gq * 8 + 3]) * inv);
+            q.z = pack_bf16x2(__uint_as_float(r[gq * 8 + 4]) * inv, __uint_as_float(r[gq * 8 + 5]) * inv);
+            q.w = pack_bf16x2(__uint_as_float(r[gq * 8 + 6]) * inv, __uint_as_float(r[gq * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + c * 32 + gq * 8) = q;
           }
         }
       }
+      tc_fence_before();
     }
   }
 
@@ -378,7 +435,10 @@ int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
       return OPUS_ERR_CUDA;
     configured = true;
   }
-  dim3 grid((max_len + 2 * TBM - 1) / (2 * TBM), n_q_heads, n_seqs);
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  dim3 grid(p.n_items < sms ? p.n_items : sms);
   const cudaError_t le =
       launch_pdl(false, attn_fwd_tcgen05_kernel<D, CAUSAL>, grid, dim3(TC_THREADS), C::SMEM, st, tq, tk, tv, p);
   note_launch();
@@ -408,6 +468,9 @@ int attn_varlen_tc(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int 
   p.o = o; p.ldo = ldo;
   p.group = n_q_heads / n_kv_heads;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.n_seqs = n_seqs; p.n_q_heads = n_q_heads;
+  p.n_mblk = (max_len + 2 * TBM - 1) / (2 * TBM);
+  p.n_items = p.n_mblk * n_seqs * n_q_heads;
   if (head_dim == 128 && causal) return launch_tc<128, true>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);
   if (head_dim == 128 && !causal) return launch_tc<128, false>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);
   if (head_dim == 64 && causal) return launch_tc<64, true>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);

@@ -77,5 +77,6 @@ int gemm_pick_bn(int N, int transposed);
 int gemm_pick_split_k(int M, int N, int K, int bn);
 size_t gemm_workspace_bytes(int M, int N, int split_k);
 void gemm_set_streamk_fill(int percent);  // 0 disables the stream-K tail
+void gemm_set_streamk_plain(int on);     // stream-K tail in the plain (non swap-AB) form, off by default
 
 }  // namespace opus

@@ -650,10 +650,15 @@ bool ensure_sk_workspace() {
 }
 
 int g_sk_max_fill = 90;  // use the stream-K tail when the partial wave fills <= this percentage of the SMs
+// The plain (activations = A) form keeps one summation order for every token row by default, so a token's result does
+// not depend on where it sits in the batch (bitwise batch invariance); the tail is opt-in there. In the swap-AB form the
+// tiles partition the FEATURES, every batch row is treated alike, and the tail is on by default.
+int g_sk_plain = 0;
 
 }  // namespace
 
 void gemm_set_streamk_fill(int percent) { g_sk_max_fill = percent; }
+void gemm_set_streamk_plain(int on) { g_sk_plain = on; }
 
 int gemm_pick_bn(int N, int transposed) {
   if (transposed) {
@@ -734,7 +739,8 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
     // wave quantisation: a last wave that fills only part of the machine is cut along K over all CTAs instead
     const int rem = tiles % num_sms();
     const bool sk_ready = ensure_sk_workspace();  // also on launches that do not need it: never first inside a capture
-    if (p.split_k == 1 && tiles > num_sms() && rem != 0 && rem * 100 <= g_sk_max_fill * num_sms() &&
+    if (p.split_k == 1 && (a.transposed || g_sk_plain) && tiles > num_sms() && rem != 0 &&
+        rem * 100 <= g_sk_max_fill * num_sms() &&
         a.epi != EPI_PARTIAL_F32 && sk_ready) {
       p.sk_tiles = rem;
       p.dp_items = tiles - rem;

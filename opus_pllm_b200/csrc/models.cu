@@ -343,6 +343,10 @@ int set_tunable(const char* name, int value) {
   static const char* names[5] = {"pf_qkv", "pf_o", "pf_gu", "pf_down", "pf_lm"};
   if (name == nullptr) return fail(OPUS_ERR_ARG, "set_tunable: null name");
   pf_init();
+  if (std::strcmp(name, "streamk_plain") == 0) {
+    gemm_set_streamk_plain(value);
+    return release_graphs();
+  }
   if (std::strcmp(name, "streamk_fill") == 0) {
     gemm_set_streamk_fill(value);
     return release_graphs();

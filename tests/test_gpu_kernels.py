@@ -166,8 +166,17 @@ def test_gemm_streamk_tail_transposed(ops, tiles, K, rows):
     assert torch.equal(ops.gemm(x, w, epilogue=EPI_F32, bias=b, transposed=True), got32)
 
 
+@pytest.fixture
+def streamk_plain():
+    """The plain-form stream-K tail is opt-in (it trades bitwise batch invariance for wave balance)."""
+    from opus_pllm_b200 import _lib as L
+    L.check(L.load().opus_set_tunable(b"streamk_plain", 1))
+    yield
+    L.check(L.load().opus_set_tunable(b"streamk_plain", 0))
+
+
 @pytest.mark.parametrize("rows,N,K", [(16512, 1280, 1280), (16512, 3840, 1280), (5000, 1280, 5120), (2100, 2560, 192)])
-def test_gemm_streamk_tail_plain(ops, rows, N, K):
+def test_gemm_streamk_tail_plain(ops, rows, N, K, streamk_plain):
     from opus_pllm_b200._lib import EPI_BF16, EPI_BF16_GELU, EPI_RES_BF16
     x = _randn((rows, K), 43)
     w = _randn((N, K), 44, scale=K ** -0.5)
