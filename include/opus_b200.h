@@ -273,11 +273,19 @@ int opus_release_graphs(void);
  * "pf_o", "pf_gu", "pf_down", "pf_lm" = k-blocks (64 K-elements each) per work item that a decode GEMM prefetches into
  * L2 for the NEXT weight matrix of the chain (0 = off); "streamk_fill" = largest partial-wave fill (percent of the SMs)
  * for which a swap-AB GEMM cuts its last wave along K (0 = off); "streamk_plain" = 1 enables the same for the plain
- * form (off by default: it would make a token's rounding depend on its position in the batch). Drops cached graphs. */
+ * form (off by default: it would make a token's rounding depend on its position in the batch); "decode_fused" = 1
+ * runs o_proj -> norm -> gate/up -> down -> norm -> next qkv / lm_head of a decode step as one persistent chain kernel,
+ * 0 (default) = one kernel per GEMM / norm; "chain_l2_depth" = k-blocks the chain kernel prefetches into L2 per phase.
+ * Drops cached graphs. */
 int opus_set_tunable(const char* name, int value);
 /* Profiling aid: between opus_trace_begin(stream) and opus_trace_end the composite forwards record a CUDA event after
  * every kernel launch (not inside graph capture); opus_trace_end synchronises and writes "label<TAB>microseconds\n"
  * lines (time since the previous launch completed) into the HOST buffer buf, returning the bytes written. */
+/* Profiling aid for the fused decode chain kernel: enable != 0 makes every following chain launch record globaltimer
+ * stamps per (CTA, phase): [0] producer passed the phase's barrier, [1] first accumulator ready, [2] phase finished,
+ * [3] norm phase started. out != NULL copies the last launch's [n_sms][6][4] stamps to the host (synchronises).
+ * Returns the SM count or a negative error. */
+int opus_chain_trace(int enable, unsigned long long* out, int cap_words);
 int opus_trace_begin(void* stream);
 int opus_trace_end(char* buf, int cap);
 /* Number of kernel launches issued by this library since the last call (bench.py's gpu_launches counter). */

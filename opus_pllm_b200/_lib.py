@@ -110,6 +110,7 @@ _SIGNATURES = {
                                        C.POINTER(DecodeState), c_int, c_int, c_int, c_int, _P]),
     "opus_release_graphs": (c_int, []),
     "opus_set_tunable": (c_int, [C.c_char_p, c_int]),
+    "opus_chain_trace": (c_int, [c_int, _P, c_int]),
     "opus_trace_begin": (c_int, [_P]),
     "opus_trace_end": (c_int, [C.c_char_p, c_int]),
     "opus_launch_count": (c_longlong, [c_int]),

@@ -217,6 +217,10 @@ int opus_release_graphs(void) { return release_graphs(); }
 
 int opus_set_tunable(const char* name, int value) { return set_tunable(name, value); }
 
+int opus_chain_trace(int enable, unsigned long long* out, int cap_words) {
+  return gemm_chain_trace(enable, out, cap_words);
+}
+
 int opus_trace_begin(void* stream) { return trace_begin(ST(stream)); }
 
 int opus_trace_end(char* buf, int cap) { return trace_end(buf, cap); }

@@ -73,6 +73,33 @@ struct GemmArgs {
 };
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
+
+// ---- fused chain of swap-AB GEMMs and split-K-reduce + residual + RMSNorm steps in ONE persistent kernel ----
+// Decode runs o_proj -> norm -> gate/up(SwiGLU) -> down -> norm -> next qkv (or lm_head) as one launch: phases are
+// separated by a device-wide barrier (one CTA per SM, all resident), the TMA producer runs one ring pass ahead into the
+// next phase's WEIGHTS, and barriers / TMEM / tensor maps are set up once instead of once per GEMM.
+constexpr int kMaxChainPhases = 6;
+enum ChainPhaseKind : int { CHAIN_GEMM = 0, CHAIN_NORM = 1 };
+struct ChainNorm {
+  // h = bf16(residual + bf16(sum_s partial[s]));  h_out = h;  y = w * bf16(h * rsqrt(mean(h^2) + eps))   (rmsnorm_bf16)
+  const float* partial;
+  int n_partial;
+  const void* residual;  // bf16 [rows, cols]
+  void* h_out;           // bf16 [rows, cols] (may alias residual)
+  const void* w;         // bf16 [cols]
+  void* y;               // bf16 [rows, cols]
+  int rows, cols;
+  float eps;
+};
+struct ChainPhase {
+  int kind;
+  GemmArgs gemm;   // CHAIN_GEMM: transposed form only (weights = A); split_k as given (0/1 = none)
+  ChainNorm norm;  // CHAIN_NORM
+};
+// All GEMM phases must share the batch size (B operand rows <= 256). Returns OPUS_OK or an error code.
+int gemm_chain(const ChainPhase* phases, int n_phases, cudaStream_t stream);
+int gemm_chain_trace(int enable, unsigned long long* out, int cap_words);
+void gemm_set_chain_l2_depth(int kblocks);
 int gemm_pick_bn(int N, int transposed);
 int gemm_pick_split_k(int M, int N, int K, int bn);
 size_t gemm_workspace_bytes(int M, int N, int split_k);

@@ -248,7 +248,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 }
 
 // out-of-line activation functions for the small-footprint (decode-sized) epilogue: one copy of the expf / erff code
-__device__ __noinline__ float silu_call(float x) { return silu_f(x); }
 __device__ __noinline__ float gelu_call(float x) { return gelu_erf(x); }
 
 // ---- transposed (swap-AB) epilogue: accumulator row = output feature `row`, column = batch row n -> out[n*ldo + row].
@@ -276,7 +275,7 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       const float other = __shfl_down_sync(0xffffffffu, v[i], 1);
-      o[i] = bf16_round(silu_call(bf16_round(v[i]))) * bf16_round(other);  // meaningful on even lanes only
+      o[i] = bf16_round(silu_f(bf16_round(v[i]))) * bf16_round(other);  // meaningful on even lanes only
     }
     // even lanes hold out[row/2]; lanes l and l+2 pair up so that every store is 4 bytes (see the note above)
     const int lane = row & 31;
@@ -333,6 +332,130 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
 #pragma unroll
     for (int i = 0; i < NC; ++i)
       if (i < n_valid) base[(size_t)i * p.ldo] = rr[i] + (v[i] + b);
+  }
+}
+
+// Epilogue of one work item by the 8 epilogue warps: drain the accumulator buffer `acc` (TMEM -> registers) and either
+// run the fused epilogue, dump a stream-K partial, or (owner) add the other CTAs' partials first.
+template <int BN>
+__device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoord& tc, uint32_t tmem_base, int acc,
+                                              int quad, int lane, int chunk0, int epi_tid) {
+  const int lrow = quad * 32 + lane;  // accumulator row inside the tile
+  const int row = tc.m * BM + lrow;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+  // stream-K partials of this tile: sk_ws[cta][column][row] fp32 (lanes = consecutive rows -> coalesced)
+  float* my_part = p.sk_ws + (size_t)blockIdx.x * (BM * BN) + lrow;
+  if (tc.kind == WORK_SK_OWNER) {
+    if (epi_tid == 0) {
+      const int need = (int)blockIdx.x - tc.first_cta;
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(p.sk_cnt + tc.sk_tile) < need) {
+        if (clock64() - t0 > 20000000000LL) {
+          printf("opus_b200: stream-K fix-up wait timed out (block %d, tile %d)\n", (int)blockIdx.x, tc.sk_tile);
+          __trap();
+        }
+      }
+      p.sk_cnt[tc.sk_tile] = 0;  // re-armed for the next launch (stream order separates launches)
+    }
+    named_bar_sync(1, NUM_EPI_THREADS);
+  }
+  if (p.transposed) {
+    // Owner fix-up, decode-sized tiles: the partial sums of ALL column groups of this thread are requested at once per
+    // contributing CTA (one L2 round trip per contributor instead of one per group), summed in CTA order.
+    constexpr int NG = BN / 16;                 // 8-column groups per warp (the two warps of a quadrant interleave)
+    constexpr bool kPrefetchFix = NG <= 4;      // BN <= 64: 32 registers
+    float fix[kPrefetchFix ? NG : 1][8];
+    if (kPrefetchFix && tc.kind == WORK_SK_OWNER) {
+#pragma unroll
+      for (int q = 0; q < NG; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fix[q][i] = 0.f;
+      for (int c = tc.first_cta; c < (int)blockIdx.x; ++c) {
+        const float* src = p.sk_ws + (size_t)c * (BM * BN) + lrow;
+        float t[kPrefetchFix ? NG : 1][8];
+#pragma unroll
+        for (int q = 0; q < NG; ++q)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t[q][i] = __ldcg(src + (size_t)((chunk0 + 2 * q) * 8 + i) * BM);
+#pragma unroll
+        for (int q = 0; q < NG; ++q)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) fix[q][i] += t[q][i];
+      }
+    }
+    if constexpr (kPrefetchFix) {
+      // Decode-sized tiles: every TMEM load of this warp is issued before the first global store. (A tcgen05.ld issued
+      // after stores waits for them: with one load per 8-column group each group cost a store round trip, ~1.9 us.)
+      uint32_t av[NG][8];
+#pragma unroll
+      for (int q = 0; q < NG; ++q) tmem_ld_32x8(taddr + (chunk0 + 2 * q) * 8, av[q]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < NG; ++q) {
+        const int g = chunk0 + 2 * q;
+        if (tc.kind == WORK_SK_PARTIAL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(av[q][i]);
+          continue;
+        }
+        if (tc.kind == WORK_SK_OWNER) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av[q][i] = __float_as_uint(__uint_as_float(av[q][i]) + fix[q][i]);
+        }
+        const int col0 = tc.n * BN + g * 8;
+        if (col0 < p.N) epilogue_transposed<8>(p, av[q], row, col0, tc.split);
+      }
+    } else {
+      // rolled loop over 8-column groups (batch > 64)
+#pragma unroll 1
+      for (int g = chunk0; g < BN / 8; g += 2) {
+        uint32_t r8[8];
+        tmem_ld_32x8(taddr + g * 8, r8);
+        tmem_ld_wait();
+        if (tc.kind == WORK_SK_PARTIAL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(r8[i]);
+          continue;
+        }
+        if (tc.kind == WORK_SK_OWNER) {
+          for (int c = tc.first_cta; c < (int)blockIdx.x; ++c) {
+            const float* src = p.sk_ws + (size_t)c * (BM * BN) + (size_t)(g * 8) * BM + lrow;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r8[i] = __float_as_uint(__uint_as_float(r8[i]) + __ldcg(src + (size_t)i * BM));
+          }
+        }
+        const int col0 = tc.n * BN + g * 8;
+        if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split);
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c = chunk0; c < BN / 32; c += 2) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c * 32, r);
+      tmem_ld_wait();
+      if (tc.kind == WORK_SK_PARTIAL) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) my_part[(size_t)(c * 32 + i) * BM] = __uint_as_float(r[i]);
+        continue;
+      }
+      if (tc.kind == WORK_SK_OWNER) {
+        for (int cc = tc.first_cta; cc < (int)blockIdx.x; ++cc) {
+          const float* src = p.sk_ws + (size_t)cc * (BM * BN) + (size_t)(c * 32) * BM + lrow;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldcg(src + (size_t)i * BM));
+        }
+      }
+      const int col0 = tc.n * BN + c * 32;
+      if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
+    }
+  }
+  if (tc.kind == WORK_SK_PARTIAL) {
+    named_bar_sync(1, NUM_EPI_THREADS);   // every thread's partial stores happen-before thread 0's fence + release
+    if (epi_tid == 0) {
+      __threadfence();
+      red_release_gpu_add(p.sk_cnt + tc.sk_tile, 1);
+    }
   }
 }
 
@@ -470,77 +593,329 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int it = 0; get_work(p, it, tc); ++it) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const int lrow = quad * 32 + lane;  // accumulator row inside the tile
-      const int row = tc.m * BM + lrow;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-      // stream-K partials of this tile: sk_ws[cta][column][row] fp32 (lanes = consecutive rows -> coalesced)
-      float* my_part = p.sk_ws + (size_t)blockIdx.x * (BM * BN) + lrow;
-      if (tc.kind == WORK_SK_OWNER) {
-        if (epi_tid == 0) {
-          const int need = (int)blockIdx.x - tc.first_cta;
-          const long long t0 = clock64();
-          while (ld_acquire_gpu(p.sk_cnt + tc.sk_tile) < need) {
-            if (clock64() - t0 > 20000000000LL) {
-              printf("opus_b200: stream-K fix-up wait timed out (block %d, tile %d)\n", (int)blockIdx.x, tc.sk_tile);
-              __trap();
-            }
-          }
-          p.sk_cnt[tc.sk_tile] = 0;  // re-armed for the next launch (stream order separates launches)
-        }
-        named_bar_sync(1, NUM_EPI_THREADS);
-      }
-      if (p.transposed) {
-        // rolled loop over 8-column groups: small code footprint (decode-sized launches run it once, I-cache cold)
-#pragma unroll 1
-        for (int g = chunk0; g < BN / 8; g += 2) {
-          uint32_t r8[8];
-          tmem_ld_32x8(taddr + g * 8, r8);
-          tmem_ld_wait();
-          if (tc.kind == WORK_SK_PARTIAL) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(r8[i]);
-            continue;
-          }
-          if (tc.kind == WORK_SK_OWNER) {
-            for (int c = tc.first_cta; c < (int)blockIdx.x; ++c) {
-              const float* src = p.sk_ws + (size_t)c * (BM * BN) + (size_t)(g * 8) * BM + lrow;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) r8[i] = __float_as_uint(__uint_as_float(r8[i]) + __ldcg(src + (size_t)i * BM));
-            }
-          }
-          const int col0 = tc.n * BN + g * 8;
-          if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split);
-        }
-      } else {
-#pragma unroll 1
-        for (int c = chunk0; c < BN / 32; c += 2) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if (tc.kind == WORK_SK_PARTIAL) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) my_part[(size_t)(c * 32 + i) * BM] = __uint_as_float(r[i]);
-            continue;
-          }
-          if (tc.kind == WORK_SK_OWNER) {
-            for (int cc = tc.first_cta; cc < (int)blockIdx.x; ++cc) {
-              const float* src = p.sk_ws + (size_t)cc * (BM * BN) + (size_t)(c * 32) * BM + lrow;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldcg(src + (size_t)i * BM));
-            }
-          }
-          const int col0 = tc.n * BN + c * 32;
-          if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
-        }
-      }
-      if (tc.kind == WORK_SK_PARTIAL) {
-        __threadfence();
-        named_bar_sync(1, NUM_EPI_THREADS);
-        if (epi_tid == 0) red_release_gpu_add(p.sk_cnt + tc.sk_tile, 1);
-      }
+      epilogue_item<BN>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid);
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused chain kernel (see gemm.h: gemm_chain)
+// ------------------------------------------------------------------------------------------------
+struct ChainTmaps {
+  CUtensorMap a[kMaxChainPhases];
+  CUtensorMap b[kMaxChainPhases];
+};
+struct ChainProgram {
+  int n_phases;
+  int kind[kMaxChainPhases];
+  GemmParams g[kMaxChainPhases];
+  ChainNorm n[kMaxChainPhases];
+  int* bar;  // [0] arrivals (monotonic within a launch), [1] CTAs that left the kernel (last one re-arms both)
+  int l2_depth;               // k-blocks per CTA requested into L2 ahead of a phase barrier (beyond the smem ring)
+  unsigned long long* trace;  // optional [grid][kMaxChainPhases][4] globaltimer stamps (tools/trace_chain.py), else null
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void chain_stamp(const ChainProgram& prog, int ph, int slot) {
+  if (prog.trace != nullptr) prog.trace[((size_t)blockIdx.x * kMaxChainPhases + ph) * 4 + slot] = global_ns();
+}
+
+// spin until `target` CTAs have arrived at the device-wide barrier counter
+__device__ __forceinline__ void chain_barrier_wait(const int* bar, int target) {
+  if (ld_acquire_gpu(bar) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(bar) < target) {
+    if (clock64() - t0 > 20000000000LL) {
+      printf("opus_b200: chain barrier wait timed out (block %d, target %d)\n", (int)blockIdx.x, target);
+      __trap();
+    }
+  }
+}
+
+// split-K reduce + residual + RMSNorm of one row by the 256 epilogue threads (same rounding points as
+// rmsnorm_bf16_kernel in bandwidth.cu, so the fused and the unfused decode paths agree bit for bit)
+__device__ __forceinline__ void chain_norm_row(const ChainNorm& n, int row, int tid, float* red /* smem [8] */) {
+  constexpr int MAXG = 2;  // 8-column groups per thread: cols <= 256 * 8 * 2 = 4096 per pass
+  const size_t slice = (size_t)n.rows * n.cols;
+  const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(n.residual);
+  const __nv_bfloat16* wv = static_cast<const __nv_bfloat16*>(n.w);
+  uint4 raw[MAXG], wq[MAXG], rq[MAXG];
+  float4 pa[MAXG][4], pb[MAXG][4];
+  // every load of the row (first four partial slices, residual, norm weight) is in flight before the first use
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i) {
+    const int c = (i * NUM_EPI_THREADS + tid) * 8;
+    const bool ok = c < n.cols;
+    const size_t off = (size_t)row * n.cols + (ok ? c : 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool pok = ok && u < n.n_partial;
+      const float* pp = n.partial + (size_t)(pok ? u : 0) * slice + off;
+      pa[i][u] = pok ? __ldcg(reinterpret_cast<const float4*>(pp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      pb[i][u] = pok ? __ldcg(reinterpret_cast<const float4*>(pp + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    rq[i] = (ok && res != nullptr) ? __ldcg(reinterpret_cast<const uint4*>(res + off)) : make_uint4(0, 0, 0, 0);
+    wq[i] = ok ? *reinterpret_cast<const uint4*>(wv + c) : make_uint4(0, 0, 0, 0);
+  }
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i) {
+    const int c = (i * NUM_EPI_THREADS + tid) * 8;
+    raw[i] = make_uint4(0, 0, 0, 0);
+    if (c < n.cols) {
+      const size_t off = (size_t)row * n.cols + c;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {   // left-to-right over the slices, like rmsnorm_bf16_kernel
+        if (u < n.n_partial) {
+          acc[0] += pa[i][u].x; acc[1] += pa[i][u].y; acc[2] += pa[i][u].z; acc[3] += pa[i][u].w;
+          acc[4] += pb[i][u].x; acc[5] += pb[i][u].y; acc[6] += pb[i][u].z; acc[7] += pb[i][u].w;
+        }
+      }
+      for (int u = 4; u < n.n_partial; ++u) {
+        const float* pp = n.partial + (size_t)u * slice + off;
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(pp)), b = __ldcg(reinterpret_cast<const float4*>(pp + 4));
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = bf16_round(acc[j]);
+      if (res != nullptr) {
+        const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rq[i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 rf = __bfloat1622float2(rb[j]);
+          v[2 * j] = bf16_round(v[2 * j] + rf.x);
+          v[2 * j + 1] = bf16_round(v[2 * j + 1] + rf.y);
+        }
+      }
+      raw[i].x = pack_bf16x2(v[0], v[1]); raw[i].y = pack_bf16x2(v[2], v[3]);
+      raw[i].z = pack_bf16x2(v[4], v[5]); raw[i].w = pack_bf16x2(v[6], v[7]);
+      if (n.h_out != nullptr) *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(n.h_out) + off) = raw[i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sq += v[j] * v[j];
+    }
+  }
+  sq = warp_sum(sq);
+  if ((tid & 31) == 0) red[tid >> 5] = sq;
+  named_bar_sync(1, NUM_EPI_THREADS);
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NUM_EPI_THREADS / 32; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / n.cols + n.eps);
+#pragma unroll
+  for (int i = 0; i < MAXG; ++i) {
+    const int c = (i * NUM_EPI_THREADS + tid) * 8;
+    if (c < n.cols) {
+      const __nv_bfloat162* wb = reinterpret_cast<const __nv_bfloat162*>(&wq[i]);
+      const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+      uint4 o;
+      uint32_t* op = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 hf = __bfloat1622float2(hb[j]);
+        const float2 wf = __bfloat1622float2(wb[j]);
+        op[j] = pack_bf16x2(wf.x * bf16_round(hf.x * rstd), wf.y * bf16_round(hf.y * rstd));
+      }
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(n.y) + (size_t)row * n.cols + c) = o;
+    }
+  }
+  named_bar_sync(1, NUM_EPI_THREADS);  // `red` is reused by the next row
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_chain_tcgen05_kernel(const __grid_constant__ ChainTmaps tm, const __grid_constant__ ChainProgram prog) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* acc_full = bars + 2 * C::STAGES;
+  uint64_t* acc_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // [8] RMSNorm block reduction
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int ph = 0; ph < prog.n_phases; ++ph) {
+      if (prog.kind[ph] == CHAIN_GEMM) { tma_prefetch_desc(&tm.a[ph]); tma_prefetch_desc(&tm.b[ph]); }
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], NUM_EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: one ring across all phases =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ph = 0; ph < prog.n_phases; ++ph) {
+        if (prog.kind[ph] != CHAIN_GEMM) continue;
+        const GemmParams& p = prog.g[ph];
+        TileCoord tc;
+        int pre = 0;
+        const bool have = get_work(p, 0, tc);
+        // weights never depend on earlier phases: request the first ring pass of A tiles before the barrier
+        if (have) {
+          pre = min(C::STAGES, tc.kb_end - tc.kb_begin);
+          int st = stage;
+          uint32_t phs = phase;
+          for (int i = 0; i < pre; ++i) {
+            mbar_wait(&empty_bar[st], phs ^ 1);
+            mbar_arrive_expect_tx(&full_bar[st], C::STAGE);
+            tma_load_2d_hint(smem + st * C::STAGE, &tm.a[ph], &full_bar[st], (tc.kb_begin + i) * BK, tc.m * BM, p.hint_a);
+            if (++st == C::STAGES) { st = 0; phs ^= 1; }
+          }
+        }
+        // ... and, beyond the ring, ask for the following k-blocks of that item in L2: HBM keeps streaming while this
+        // CTA sits at the barrier (norm phases, stragglers), and the phase then starts from L2-resident weights
+        if (have) {
+          const int kb_pf_end = min(tc.kb_end, tc.kb_begin + pre + prog.l2_depth);
+          for (int kb = tc.kb_begin + pre; kb < kb_pf_end; ++kb) tma_prefetch_l2_2d(&tm.a[ph], kb * BK, tc.m * BM);
+        }
+        // activations: produced by the preceding kernel (phase 0) or by every CTA's previous phase
+        if (ph == 0) grid_dep_wait();
+        else chain_barrier_wait(prog.bar, G * ph);
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> this thread's TMA reads
+        chain_stamp(prog, ph, 0);
+        if (have) {
+          for (int i = 0; i < pre; ++i) {
+            tma_load_2d_hint(smem + stage * C::STAGE + C::STAGE_A, &tm.b[ph], &full_bar[stage], (tc.kb_begin + i) * BK,
+                             tc.n * BN, p.hint_b);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        for (int it = 0; get_work(p, it, tc); ++it) {
+          for (int kb = tc.kb_begin + (it == 0 ? pre : 0); kb < tc.kb_end; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * C::STAGE;
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
+            tma_load_2d_hint(sa, &tm.a[ph], &full_bar[stage], kb * BK, tc.m * BM, p.hint_a);
+            tma_load_2d_hint(sa + C::STAGE_A, &tm.b[ph], &full_bar[stage], kb * BK, tc.n * BN, p.hint_b);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      grid_dep_launch();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int ph = 0; ph < prog.n_phases; ++ph) {
+        if (prog.kind[ph] != CHAIN_GEMM) continue;
+        const GemmParams& p = prog.g[ph];
+        TileCoord tc;
+        for (int it = 0; get_work(p, it, tc); ++it) {
+          mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+            const uint64_t da = umma_smem_desc_sw128(sa);
+            const uint64_t db = umma_smem_desc_sw128(sa + C::STAGE_A);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > tc.kb_begin || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..9): GEMM epilogues, norm phases, barrier arrivals =====================
+    const int quad = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const int epi_tid = threadIdx.x - 64;
+    grid_dep_wait();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int ph = 0; ph < prog.n_phases; ++ph) {
+      if (prog.kind[ph] == CHAIN_GEMM) {
+        const GemmParams& p = prog.g[ph];
+        TileCoord tc;
+        for (int it = 0; get_work(p, it, tc); ++it) {
+          mbar_wait(&acc_full[acc], acc_phase);
+          tc_fence_after();
+          if (epi_tid == 0) chain_stamp(prog, ph, it == 0 ? 1 : 3);   // [3] = last item's accumulator ready
+          epilogue_item<BN>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid);
+          tc_fence_before();
+          mbar_arrive(&acc_empty[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      } else {
+        // every earlier phase of every CTA must be complete (its partial sums are this phase's input)
+        if (ph > 0) {
+          if (epi_tid == 0) chain_barrier_wait(prog.bar, G * ph);
+          named_bar_sync(1, NUM_EPI_THREADS);
+        }
+        if (epi_tid == 0) chain_stamp(prog, ph, 3);
+        const ChainNorm& n = prog.n[ph];
+        for (int row = blockIdx.x; row < n.rows; row += G) chain_norm_row(n, row, epi_tid, red);
+      }
+      // arrive at the device-wide barrier that closes this phase: the CTA barrier orders every epilogue thread's
+      // stores before thread 0's gpu-scope fence + release (cumulative), so one fence per CTA suffices
+      named_bar_sync(1, NUM_EPI_THREADS);
+      if (epi_tid == 0) {
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        chain_stamp(prog, ph, 2);
+        red_release_gpu_add(prog.bar, 1);
+      }
+    }
+    // leave: the last CTA out re-arms the counters for the next launch (nobody waits on them any more)
+    if (epi_tid == 0) {
+      const int left = atomicAdd(prog.bar + 1, 1);
+      if (left == G - 1) {
+        chain_barrier_wait(prog.bar, G * prog.n_phases);
+        prog.bar[0] = 0;
+        prog.bar[1] = 0;
+        __threadfence();
+      }
     }
   }
 
@@ -683,8 +1058,8 @@ int gemm_pick_split_k(int M, int N, int K, int bn) {
 
 size_t gemm_workspace_bytes(int M, int N, int split_k) { return (size_t)split_k * M * N * sizeof(float); }
 
-// D = epi(A * B^T). See gemm.h for the contract.
-int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
+// Validates `a` and fills the device parameter block (tiling, split-K, stream-K tail, prefetch hint). bn = tile width.
+static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return OPUS_ERR_ARG;
   if ((a.lda % 8) || (a.ldb % 8) || (a.K % 8)) return OPUS_ERR_ARG;  // TMA: 16-byte aligned rows
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return OPUS_ERR_ARG;
@@ -697,8 +1072,8 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   if ((a.epi == EPI_RES_F32 || a.epi == EPI_RES_BF16) && a.residual == nullptr) return OPUS_ERR_ARG;
   if (a.epi == EPI_F32 && !a.transposed) return OPUS_ERR_ARG;
 
-  const int bn = a.block_n > 0 ? a.block_n : gemm_pick_bn(a.N, a.transposed);
-  GemmParams p{};
+  bn = a.block_n > 0 ? a.block_n : gemm_pick_bn(a.N, a.transposed);
+  p = GemmParams{};
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.num_m_tiles = (a.M + BM - 1) / BM;
   p.num_n_tiles = (a.N + bn - 1) / bn;
@@ -732,27 +1107,127 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   }
 
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
   p.dp_items = tiles;
   p.sk_tiles = 0;
-  {
-    // wave quantisation: a last wave that fills only part of the machine is cut along K over all CTAs instead
-    const int rem = tiles % num_sms();
-    const bool sk_ready = ensure_sk_workspace();  // also on launches that do not need it: never first inside a capture
-    if (p.split_k == 1 && (a.transposed || g_sk_plain) && tiles > num_sms() && rem != 0 &&
-        rem * 100 <= g_sk_max_fill * num_sms() &&
-        a.epi != EPI_PARTIAL_F32 && sk_ready) {
-      p.sk_tiles = rem;
-      p.dp_items = tiles - rem;
-      p.sk_ws = g_sk.ws;
-      p.sk_cnt = g_sk.cnt;
-    }
+  // wave quantisation: a last wave that fills only part of the machine is cut along K over all CTAs instead
+  const int rem = tiles % num_sms();
+  const bool sk_ready = ensure_sk_workspace();  // also on launches that do not need it: never first inside a capture
+  if (p.split_k == 1 && (a.transposed || g_sk_plain) && tiles > num_sms() && rem != 0 &&
+      rem * 100 <= g_sk_max_fill * num_sms() && a.epi != EPI_PARTIAL_F32 && sk_ready) {
+    p.sk_tiles = rem;
+    p.dp_items = tiles - rem;
+    p.sk_ws = g_sk.ws;
+    p.sk_cnt = g_sk.cnt;
   }
+  return OPUS_OK;
+}
+
+// D = epi(A * B^T). See gemm.h for the contract.
+int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
+  GemmParams p;
+  int bn = 0;
+  const int rc = prepare_gemm(a, p, bn);
+  if (rc != OPUS_OK) return rc;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {
     case 32: return launch<32>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
     case 64: return launch<64>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
     case 128: return launch<128>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
     case 256: return launch<256>(p, a, a.A, a.lda, a.B, a.ldb, grid, stream);
+    default: return OPUS_ERR_ARG;
+  }
+}
+
+namespace {
+template <int BN>
+int launch_chain(const ChainTmaps& tm, const ChainProgram& prog, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_chain_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
+        cudaSuccess)
+      return OPUS_ERR_CUDA;
+    configured = true;
+  }
+  // one CTA per SM: the device-wide barriers need every CTA resident (C::SMEM > half an SM, so never two per SM)
+  const cudaError_t le = launch_pdl(true, gemm_chain_tcgen05_kernel<BN>, dim3(num_sms()), dim3(NUM_THREADS), C::SMEM,
+                                    stream, tm, prog);
+  note_launch();
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
+}
+}  // namespace
+
+int g_chain_l2_depth = 0;  // measured: prefetching beyond the ring only adds traffic (tools/bench_decode.py)
+void gemm_set_chain_l2_depth(int kblocks) { g_chain_l2_depth = kblocks < 0 ? 0 : kblocks; }
+unsigned long long* g_chain_trace = nullptr;
+// enable != 0: allocate the stamp buffer (once) and record every following chain launch (the last one wins);
+// out != nullptr: copy [num_sms][kMaxChainPhases][4] stamps to the host (synchronises the device). Returns the SM count.
+int gemm_chain_trace(int enable, unsigned long long* out, int cap_words) {
+  const int words = num_sms() * kMaxChainPhases * 4;
+  if (enable && g_chain_trace == nullptr) {
+    if (cudaMalloc(&g_chain_trace, words * sizeof(unsigned long long)) != cudaSuccess) return OPUS_ERR_CUDA;
+    cudaMemset(g_chain_trace, 0, words * sizeof(unsigned long long));
+  }
+  if (out != nullptr && g_chain_trace != nullptr) {
+    cudaDeviceSynchronize();
+    const int n = cap_words < words ? cap_words : words;
+    if (cudaMemcpy(out, g_chain_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return OPUS_ERR_CUDA;
+  }
+  if (!enable && g_chain_trace != nullptr && out == nullptr) { cudaFree(g_chain_trace); g_chain_trace = nullptr; }
+  return num_sms();
+}
+
+int gemm_chain(const ChainPhase* phases, int n_phases, cudaStream_t stream) {
+  if (phases == nullptr || n_phases <= 0 || n_phases > kMaxChainPhases) return OPUS_ERR_ARG;
+  if (!ensure_sk_workspace()) return OPUS_ERR_CUDA;
+  ChainTmaps tm;
+  ChainProgram prog{};
+  prog.n_phases = n_phases;
+  prog.bar = g_sk.cnt + 1000;
+  prog.trace = g_chain_trace;
+  prog.l2_depth = g_chain_l2_depth;
+  int bn_all = 0;
+  for (int i = 0; i < n_phases; ++i) {
+    prog.kind[i] = phases[i].kind;
+    if (phases[i].kind == CHAIN_NORM) {
+      const ChainNorm& n = phases[i].norm;
+      if (n.partial == nullptr || n.n_partial <= 0 || n.y == nullptr || n.w == nullptr || n.rows <= 0 ||
+          n.cols <= 0 || (n.cols % 8) || n.cols > NUM_EPI_THREADS * 8 * 2)
+        return OPUS_ERR_ARG;
+      prog.n[i] = n;
+      continue;
+    }
+    if (phases[i].kind != CHAIN_GEMM) return OPUS_ERR_ARG;
+    const GemmArgs& a = phases[i].gemm;
+    if (!a.transposed || a.pf_w != nullptr) return OPUS_ERR_ARG;
+    int bn = 0;
+    int rc = prepare_gemm(a, prog.g[i], bn);
+    if (rc != OPUS_OK) return rc;
+    if (bn_all == 0) bn_all = bn;
+    if (bn != bn_all) return OPUS_ERR_ARG;  // one batch size (tile width) for the whole chain
+    rc = make_tmap_bf16(&tm.a[i], a.A, a.M, a.K, a.lda, BM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tm.b[i], a.B, a.N, a.K, a.ldb, bn);
+    if (rc) return rc;
+  }
+  if (bn_all == 0) return OPUS_ERR_ARG;
+  for (int i = 0; i < n_phases; ++i)   // unused slots still need valid descriptors
+    if (prog.kind[i] != CHAIN_GEMM) { tm.a[i] = tm.a[0]; tm.b[i] = tm.b[0]; }
+  if (prog.kind[0] != CHAIN_GEMM) {
+    // slot 0 must hold a real map for the copies above
+    for (int i = 0; i < n_phases; ++i)
+      if (prog.kind[i] == CHAIN_GEMM) { tm.a[0] = tm.a[i]; tm.b[0] = tm.b[i]; break; }
+    for (int i = 1; i < n_phases; ++i)
+      if (prog.kind[i] != CHAIN_GEMM) { tm.a[i] = tm.a[0]; tm.b[i] = tm.b[0]; }
+  }
+  for (int i = n_phases; i < kMaxChainPhases; ++i) { tm.a[i] = tm.a[0]; tm.b[i] = tm.b[0]; }
+  switch (bn_all) {
+    case 32: return launch_chain<32>(tm, prog, stream);
+    case 64: return launch_chain<64>(tm, prog, stream);
+    case 128: return launch_chain<128>(tm, prog, stream);
+    case 256: return launch_chain<256>(tm, prog, stream);
     default: return OPUS_ERR_ARG;
   }
 }

@@ -98,6 +98,18 @@ int pf_depth_for(int which) {
 }
 enum { PF_QKV = 0, PF_O = 1, PF_GU = 2, PF_DOWN = 3, PF_LM = 4 };
 
+// fused decode chain (gemm_chain): opt-in with OPUS_DECODE_FUSED=1 / opus_set_tunable("decode_fused", 1). Measured on
+// B200 at batch 64 it is not yet faster than one PDL-chained kernel per op (4.48 vs 4.40 ms per step: its device-wide
+// barriers and norm phases cost what the kernel boundaries did; tools/trace_chain.py prints the phase timeline).
+int g_decode_fused = -1;
+bool decode_fused() {
+  if (g_decode_fused < 0) {
+    const char* e = std::getenv("OPUS_DECODE_FUSED");
+    g_decode_fused = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_decode_fused != 0;
+}
+
 // activations [rows, K] x weight [N, K]^T -> out, choosing the weight-streaming (swap-AB) form for small `rows`.
 int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* out, int ldo, const float* bias,
            const void* residual, int ldr, float* ws, size_t ws_bytes, cudaStream_t st, const Prefetch* pf = nullptr) {
@@ -283,6 +295,62 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
   OPUS_TRY(embed_gather(s->next_tok, static_cast<const bf16*>(m->embed), h, B, d, st));
   OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(m->layers[0].ln1_w), xn, B, d,
                         m->rms_eps, st));
+  if (B <= 256 && decode_fused()) {
+    // Fused form: per layer  rope+append -> paged attention -> ONE chain kernel
+    //   { o_proj (split-K) | reduce+residual+RMSNorm | gate/up+SwiGLU | down (split-K) | reduce+residual+RMSNorm |
+    //     next layer's qkv (split-K)  or  lm_head }
+    // i.e. 3 launches per layer instead of 8, with the weight stream running across the phase boundaries.
+    const int sp_qkv = splitk_for(B, qkv_n, d, ws->partial_bytes);
+    const int sp_o = splitk_for(B, d, Hq * hd, ws->partial_bytes);
+    const int sp_down = splitk_for(B, d, ffn, ws->partial_bytes);
+    auto gemm_phase = [&](ChainPhase& ph, const void* w, int N, int K, const void* x, int epi, void* out, int ldo,
+                          int split) {
+      ph = ChainPhase{};
+      ph.kind = CHAIN_GEMM;
+      GemmArgs& a = ph.gemm;
+      a.transposed = 1;
+      a.A = w; a.lda = K; a.M = N;
+      a.B = x; a.ldb = K; a.N = B;
+      a.K = K;
+      a.epi = epi;
+      a.out = out; a.ldo = ldo;
+      a.split_k = split;
+    };
+    auto norm_phase = [&](ChainPhase& ph, int n_partial, const void* w) {
+      ph = ChainPhase{};
+      ph.kind = CHAIN_NORM;
+      ph.norm.partial = ws->partial; ph.norm.n_partial = n_partial;
+      ph.norm.residual = h; ph.norm.h_out = h;
+      ph.norm.w = w; ph.norm.y = xn;
+      ph.norm.rows = B; ph.norm.cols = d; ph.norm.eps = m->rms_eps;
+    };
+    {
+      int sp = 1;
+      OPUS_TRY(linear_splitk(xn, B, m->layers[0].wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st));
+    }
+    for (int l = 0; l < m->n_layers; ++l) {
+      const opus_llama_layer& L = m->layers[l];
+      bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
+      bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
+      OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp_qkv, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
+                                   static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n, kv->block_size,
+                                   st));
+      OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq,
+                                 Hkv, hd, kv->block_size, scale, st));
+      ChainPhase ph[6];
+      const bool last = l + 1 == m->n_layers;
+      gemm_phase(ph[0], L.wo, d, Hq * hd, attn, EPI_PARTIAL_F32, ws->partial, d, sp_o);
+      norm_phase(ph[1], sp_o, L.ln2_w);
+      gemm_phase(ph[2], L.wgu, 2 * ffn, d, xn, EPI_SWIGLU, act, ffn, 1);
+      gemm_phase(ph[3], L.wdown, d, ffn, act, EPI_PARTIAL_F32, ws->partial, d, sp_down);
+      norm_phase(ph[4], sp_down, last ? m->norm_w : m->layers[l + 1].ln1_w);
+      if (last) gemm_phase(ph[5], m->lm_head, m->vocab, d, xn, EPI_BF16, ws->logits, m->vocab, 1);
+      else gemm_phase(ph[5], m->layers[l + 1].wqkv, qkv_n, d, xn, EPI_PARTIAL_F32, ws->partial, qkv_n, sp_qkv);
+      OPUS_TRY(gemm_chain(ph, 6, st));
+    }
+    OPUS_TRY(llama_select(m, ws, s, B, st));
+    return OPUS_OK;
+  }
   // Each weight-streaming GEMM asks for the head of the NEXT GEMM's weight stream at its tail (L2 prefetch), so HBM
   // does not idle while it drains, the small kernels between run, and the next GEMM ramps up.
   const bool swap = B <= 256;
@@ -343,6 +411,14 @@ int set_tunable(const char* name, int value) {
   static const char* names[5] = {"pf_qkv", "pf_o", "pf_gu", "pf_down", "pf_lm"};
   if (name == nullptr) return fail(OPUS_ERR_ARG, "set_tunable: null name");
   pf_init();
+  if (std::strcmp(name, "chain_l2_depth") == 0) {
+    gemm_set_chain_l2_depth(value);
+    return release_graphs();
+  }
+  if (std::strcmp(name, "decode_fused") == 0) {
+    g_decode_fused = value != 0;
+    return release_graphs();
+  }
   if (std::strcmp(name, "streamk_plain") == 0) {
     gemm_set_streamk_plain(value);
     return release_graphs();

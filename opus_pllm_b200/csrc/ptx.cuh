@@ -203,7 +203,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// silu on the fast pipes, branch-free: ex2.approx and rcp.approx (2 ulp each, no slow-path subroutine). Every caller
+// rounds the result to bf16, so it differs from x / (1 + expf(-x)) only next to bf16 rounding ties (~2^-14 of inputs).
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -193,6 +193,38 @@ def test_greedy_decode_token_parity_peaked():
     assert len(torch.unique(got)) > 32  # not a degenerate constant stream
 
 
+@pytest.mark.parametrize("cfg,batch", [(SMALL, 32), (SMALL, 5),
+                                       (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
+                                             ffn_dim=14336, vocab=32768), 64)])
+def test_decode_fused_chain_matches_kernel_per_op(cfg, batch):
+    """The fused decode chain (one persistent kernel for o_proj .. next qkv / lm_head, device-wide barriers between its
+    phases) must reproduce the kernel-per-op path: same tokens, and the same last-step logits up to the one place where
+    the two differ (the order of the RMSNorm sum of squares). The fused form is opt-in (tunable decode_fused)."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    w = synth.llama_weights(seed=4, peaked=True, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [17 + (i * 5) % 40 for i in range(batch)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(6))
+    emb = w["model.embed_tokens.weight"][tok].cuda().to(torch.bfloat16)
+    lib = L.load()
+    try:
+        L.check(lib.opus_set_tunable(b"decode_fused", 1))
+        fused = model.generate_packed(emb, cu, 12)
+        fused_logits = model._ws_bufs["logits"][:batch].float().clone()
+        fused_eager = model.generate_packed(emb, cu, 12, use_graph=False)
+        L.check(lib.opus_set_tunable(b"decode_fused", 0))
+        plain = model.generate_packed(emb, cu, 12)
+        plain_logits = model._ws_bufs["logits"][:batch].float().clone()
+    finally:
+        L.check(lib.opus_set_tunable(b"decode_fused", 0))
+    assert torch.equal(fused, fused_eager)
+    assert torch.equal(fused, plain), float((fused == plain).float().mean())
+    # 12 steps of bf16 one-ulp differences (RMSNorm reduction order) compound through the KV cache
+    assert _cos(fused_logits, plain_logits) >= 0.995
+
+
 def test_greedy_decode_default_init_margin_aware():
     """HF-init statistics: random logits have tiny top-1 margins, so token identity is fragile by construction
     (SURVEY.md §7); every disagreement must be explained by a near-tie in the oracle's own logits."""

@@ -46,7 +46,9 @@ def setk(**kw):
         L.check(lib.opus_set_tunable(k.encode(), v), k)
 
 
-run("defaults")
+run("defaults (kernel per op, PDL chain)")
+if os.environ.get("FUSED"):
+    setk(decode_fused=1); run("decode_fused=1 (chain kernel)"); setk(decode_fused=0)
 if os.environ.get("SWEEP"):
     setk(pf_qkv=0, pf_o=0, pf_gu=0, pf_down=0, pf_lm=0); base = run("all off")
     for name in ("pf_qkv", "pf_o", "pf_gu", "pf_down", "pf_lm"):

@@ -9,8 +9,8 @@ rows = int(os.environ.get("ROWS", "64"))
 NL = 16
 
 
-def bench(name, n_out, K, split, epi, block_n=0):
-    nw = max(2, int(600e6 // (n_out * K * 2)) + 1)
+def bench(name, n_out, K, split, epi, block_n=0, nw=None):
+    nw = nw or max(2, int(600e6 // (n_out * K * 2)) + 1)
     ws = [torch.randn(n_out, K, device="cuda").bfloat16() * 0.02 for _ in range(nw)]
     x = torch.randn(rows, K, device="cuda").bfloat16()
     if epi == L.EPI_PARTIAL_F32:
@@ -36,6 +36,21 @@ def bench(name, n_out, K, split, epi, block_n=0):
 
 
 P = L.EPI_PARTIAL_F32
+if os.environ.get("L2_TEST"):
+    # same weight every launch (L2-resident after the first) vs distinct weights (HBM): what does a boundary cost?
+    for nw in (1, None):
+        print("weights:", "one buffer (L2 hits)" if nw else "distinct buffers (HBM)")
+        bench("o_proj s4", 4096, 4096, 4, P, nw=nw)
+        bench("qkv s3", 6144, 4096, 3, P, nw=nw)
+        bench("16 tiles s8", 2048, 4096, 8, P, nw=nw)
+    sys.exit(0)
+if os.environ.get("DEPTH_TEST"):
+    # weight bytes in flight per SM: bn 64 -> 8 stages x 16 KB, bn 128 -> 6 x 16 KB, bn 256 -> 4 x 16 KB
+    for bn in (64, 128, 256):
+        bench("lm_head", 128256, 4096, 1, L.EPI_BF16, block_n=bn)
+        bench("gate_up bf16", 28672, 4096, 1, L.EPI_BF16, block_n=bn)
+        bench("down s4", 4096, 14336, 4, P, block_n=bn)
+    sys.exit(0)
 if os.environ.get("SK_ONLY"):
     for fill in (0, 90):
         L.check(L.load().opus_set_tunable(b"streamk_fill", fill))
