@@ -122,6 +122,13 @@ int opus_splice_gather_bf16(const int32_t* src, const void* embed, const void* s
 int opus_argmax_eos(const void* logits, int ld, int vocab, int n_rows, int32_t* finished, const int32_t* eos_ids,
                     int n_eos, int pad_id, int32_t* next_tok, int32_t* out_ids, int out_ld, int step,
                     int32_t* n_unfinished, void* stream);
+/* Temperature + nucleus sampling with the same bookkeeping (HF GenerationMixin._sample, do_sample=True: scores / T, then
+ * TopPLogitsWarper(top_p, min_tokens_to_keep=1), then one draw per row). Deterministic in (seed, row, step).
+ * kept_count (nullable, [n_rows]) receives the size of each row's nucleus. */
+int opus_sample_top_p(const void* logits, int ld, int vocab, int n_rows, float temperature, float top_p, uint64_t seed,
+                      int32_t* finished, const int32_t* eos_ids, int n_eos, int pad_id, int32_t* next_tok,
+                      int32_t* out_ids, int out_ld, int step, int32_t* n_unfinished, int32_t* kept_count,
+                      void* stream);
 int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n_rows, int dim, void* stream);
 /* W += scale * (B @ A): peft merge_and_unload (multi_modality_v1/model/builder.py:107-109). */
 int opus_lora_merge_bf16(void* W, const void* A, const void* B, int out_features, int in_features, int r, float scale,
@@ -245,6 +252,8 @@ typedef struct {
   int32_t* out_ids;     /* [n_seqs, out_ld] */
   int32_t out_ld;
   const int32_t* eos_ids; int32_t n_eos; int32_t pad_id;
+  /* token selection: do_sample == 0 -> argmax (greedy); else temperature / top-p sampling, u = hash(seed, row, step) */
+  uint64_t seed; float temperature; float top_p; int32_t do_sample; int32_t reserved_;
 } opus_decode_state;
 
 /* Prefill over packed prompt embeddings (already spliced): embeds bf16 [n_tok, dim] is copied into ws->h; K/V of every

@@ -68,7 +68,9 @@ class DecodeState(C.Structure):
     _fields_ = [("next_tok", c_void_p), ("ctx_len", c_void_p), ("pos", c_void_p), ("slot", c_void_p),
                 ("block_table", c_void_p), ("max_blocks", C.c_int32), ("finished", c_void_p),
                 ("n_unfinished", c_void_p), ("step", c_void_p), ("out_ids", c_void_p), ("out_ld", C.c_int32),
-                ("eos_ids", c_void_p), ("n_eos", C.c_int32), ("pad_id", C.c_int32)]
+                ("eos_ids", c_void_p), ("n_eos", C.c_int32), ("pad_id", C.c_int32),
+                ("seed", C.c_uint64), ("temperature", c_float), ("top_p", c_float), ("do_sample", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 # ---------------------------------------------------------------------------------------------- signatures
@@ -91,6 +93,8 @@ _SIGNATURES = {
     "opus_l2norm_f32_bf16": (c_int, [_P, _P, c_int, c_int, _P]),
     "opus_splice_gather_bf16": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     "opus_argmax_eos": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
+    "opus_sample_top_p": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, C.c_uint64, _P, _P, c_int, c_int, _P, _P,
+                                  c_int, c_int, _P, _P, _P]),
     "opus_embed_gather_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "opus_lora_merge_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "opus_attn_varlen_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int,

@@ -566,6 +566,192 @@ __global__ void argmax_eos_kernel(const __nv_bfloat16* __restrict__ logits, int 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// L10b: temperature + nucleus (top-p) sampling with the same EOS bookkeeping as argmax_eos_kernel.
+// HF semantics (GenerationMixin._sample, do_sample=True; TemperatureLogitsWarper then TopPLogitsWarper with
+// min_tokens_to_keep = 1; the reference's default decode is temperature 0.1 / top_p 0.7, run_opus_ddp.py:126-128,156-157):
+// scores = fp32(logits) / T; a token is KEPT iff the probability mass of the tokens ranked strictly above it is < top_p;
+// the next token is drawn from the renormalised kept set.
+// One CTA per row. The logits are bf16, so ranks are decided on their 16-bit order-preserving keys: a 16-step bisection
+// finds the smallest key k* with mass(key > k*) < top_p * Z (every pass re-reads the row from L2, 256 KB). Ties at k* are
+// kept lowest-index first (HF keeps them by its sort order; equal logits have equal probability). The draw uses a
+// counter-based generator, u = hash(seed, row, step), so a (seed, prompt batch) pair always yields the same tokens; it
+// cannot reproduce torch.multinomial's stream, tests compare the kept set and the sampling frequencies instead.
+// ------------------------------------------------------------------------------------------------
+constexpr int SAMPLE_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t bf16_key(uint16_t b) { return (b & 0x8000u) ? (uint16_t)~b : (uint16_t)(b | 0x8000u); }
+__device__ __forceinline__ float key_value(uint32_t key) {
+  const uint16_t b = (key & 0x8000u) ? (uint16_t)(key & 0x7fffu) : (uint16_t)~key;
+  return __uint_as_float((uint32_t)b << 16);
+}
+
+// block-wide sum in a fixed order (deterministic); result broadcast to every thread. `red` = 33 floats of smem.
+__device__ __forceinline__ float block_sum_1024(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = red[lane];
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+sample_top_p_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int vocab, float inv_temp, float top_p,
+                    unsigned long long seed, int* __restrict__ finished, const int* __restrict__ eos_ids, int n_eos,
+                    int pad_id, int* __restrict__ next_tok, int* __restrict__ out_ids, int out_ld, int step_imm,
+                    const int* __restrict__ step_ptr, int* __restrict__ n_unfinished, int* __restrict__ kept_count) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ float red[33];
+  __shared__ float scan_m[SAMPLE_THREADS];
+  __shared__ int scan_c[SAMPLE_THREADS];
+  const int b = blockIdx.x;
+  const uint16_t* row = reinterpret_cast<const uint16_t*>(logits) + (size_t)b * ld;
+  const int tid = threadIdx.x;
+  const float c = inv_temp * 1.4426950408889634f;
+
+  // pass 1: maximum key
+  uint32_t kmax = 0;
+  for (int i = tid; i < vocab; i += SAMPLE_THREADS) kmax = max(kmax, bf16_key(row[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  __shared__ uint32_t s_k[32];
+  if ((tid & 31) == 0) s_k[tid >> 5] = kmax;
+  __syncthreads();
+  kmax = s_k[0];
+#pragma unroll
+  for (int w = 1; w < SAMPLE_THREADS / 32; ++w) kmax = max(kmax, s_k[w]);
+  const float vmax = key_value(kmax);
+
+  // mass of the tokens whose key is strictly greater than k (k = -1: everything = Z)
+  auto mass_gt = [&](int k) {
+    float acc = 0.f;
+    for (int i = tid; i < vocab; i += SAMPLE_THREADS) {
+      const uint32_t key = bf16_key(row[i]);
+      if ((int)key > k) acc += exp2f((key_value(key) - vmax) * c);
+    }
+    return block_sum_1024(acc, red);
+  };
+  const float Z = mass_gt(-1);
+  const float need = top_p * Z;
+  // smallest key k* with mass_gt(k*) < need  (mass_gt(kmax) = 0 always qualifies)
+  int lo = -1, hi = (int)kmax;          // invariant: mass_gt(lo) >= need (or lo = -1 and top_p >= 1), mass_gt(hi) < need
+  float g_hi = 0.f;
+  if (Z < need || !(top_p < 1.0f)) {     // top_p >= 1: keep everything
+    hi = 0;
+    g_hi = mass_gt(0);
+    lo = -1;
+    // all keys >= 0 kept: treat k* = 0 with every tie kept (handled below by n_keep = INT_MAX)
+  } else {
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      const float g = mass_gt(mid);
+      if (g < need) { hi = mid; g_hi = g; } else { lo = mid; }
+    }
+  }
+  const int kstar = hi;
+  float w_star = exp2f((key_value((uint32_t)kstar) - vmax) * c);
+  if (!(w_star >= 0.f) || !(w_star <= 1.f)) w_star = 0.f;   // k* need not be a key that occurs (e.g. a NaN pattern)
+  int n_keep = INT_MAX;
+  if (top_p < 1.0f && Z >= need) {
+    const float room = need - g_hi;                       // > 0
+    const float q = w_star > 0.f ? ceilf(room / w_star) : 1.0f;
+    n_keep = q < 1.f ? 1 : (q > 2.0e9f ? INT_MAX : (int)q);   // min_tokens_to_keep = 1
+  }
+
+  // final pass, index order: each thread owns a contiguous range
+  const int per = (vocab + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+  const int i0 = min(tid * per, vocab), i1 = min(i0 + per, vocab);
+  float m1 = 0.f;
+  int c1 = 0, g1 = 0;
+  for (int i = i0; i < i1; ++i) {
+    const int key = (int)bf16_key(row[i]);
+    if (key > kstar) { m1 += exp2f((key_value((uint32_t)key) - vmax) * c); ++g1; }
+    else if (key == kstar) ++c1;
+  }
+  scan_m[tid] = m1;
+  scan_c[tid] = c1;
+  const float n_above = block_sum_1024((float)g1, red);   // exact: counts <= 2^24
+  __syncthreads();
+  if (tid == 0) {
+    // sequential exclusive scan by one thread: 1024 steps, deterministic, negligible next to the 18 passes above
+    const int step = step_ptr != nullptr ? *step_ptr : step_imm;
+    float M = 0.f;
+    int Cn = 0;
+    for (int t = 0; t < SAMPLE_THREADS; ++t) {
+      const float mt = scan_m[t];
+      const int ct = scan_c[t];
+      scan_m[t] = M;
+      scan_c[t] = Cn;
+      M += mt;
+      Cn += ct;
+    }
+    const int ties_kept = min(Cn, n_keep);
+    const float K = M + (float)ties_kept * w_star;        // kept mass
+    const uint64_t h = splitmix64(seed ^ splitmix64(((uint64_t)(uint32_t)b << 32) | (uint32_t)step));
+    const float u = (float)(h >> 40) * (1.0f / 16777216.0f);   // [0, 1)
+    const float target = u * K;
+    // kept mass in front of range t: scan_m[t] + min(scan_c[t], n_keep) * w*. The draw falls into the last range whose
+    // front mass is <= target; walk that range token by token.
+    int tr = 0;
+    for (int t = 1; t < SAMPLE_THREADS; ++t)
+      if (scan_m[t] + (float)min(scan_c[t], n_keep) * w_star <= target) tr = t;
+    int tok = -1, last_kept = -1;
+    for (; tr < SAMPLE_THREADS && tok < 0; ++tr) {   // normally one range; continues only across rounding slack
+      float cum = scan_m[tr] + (float)min(scan_c[tr], n_keep) * w_star;
+      int ties_seen = scan_c[tr];
+      const int j0 = min(tr * per, vocab), j1 = min(j0 + per, vocab);
+      for (int i = j0; i < j1; ++i) {
+        const int key = (int)bf16_key(row[i]);
+        bool kept = false;
+        float wi = 0.f;
+        if (key > kstar) { kept = true; wi = exp2f((key_value((uint32_t)key) - vmax) * c); }
+        else if (key == kstar) { kept = ties_seen < n_keep; wi = kept ? w_star : 0.f; ++ties_seen; }
+        if (kept) {
+          last_kept = i;
+          cum += wi;
+          if (cum > target) { tok = i; break; }
+        }
+      }
+    }
+    if (tok < 0) {
+      // target sat in the rounding slack at the very end of the kept mass: take the last kept token
+      if (last_kept < 0) {
+        for (int i = vocab - 1; i >= 0 && last_kept < 0; --i)
+          if ((int)bf16_key(row[i]) > kstar) last_kept = i;
+      }
+      tok = last_kept >= 0 ? last_kept : 0;
+    }
+    if (kept_count != nullptr) kept_count[b] = (int)n_above + ties_kept;
+    const int fin = finished[b];
+    if (fin) tok = pad_id;
+    next_tok[b] = tok;
+    out_ids[(size_t)b * out_ld + step] = tok;
+    if (!fin) {
+      bool is_eos = false;
+      for (int e = 0; e < n_eos; ++e) is_eos |= (tok == eos_ids[e]);
+      if (is_eos) {
+        finished[b] = 1;
+        if (n_unfinished != nullptr) atomicSub(n_unfinished, 1);
+      }
+    }
+  }
+}
+
 // decode input: x[b,:] = table[tok[b],:]; also advances positions / cache slots for the step (one launch per step).
 __global__ void embed_gather_kernel(const int* __restrict__ tok, const __nv_bfloat16* __restrict__ table,
                                     __nv_bfloat16* __restrict__ x, int n_rows, int dim) {
@@ -725,6 +911,19 @@ int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* 
   launch_pdl(true, argmax_eos_kernel, dim3(n_rows), dim3(1024), 0, st, logits, ld, vocab, finished, eos_ids, n_eos, pad_id, next_tok, out_ids,
                                             out_ld, step, step_ptr, n_unfinished);
   return ok();
+}
+
+int sample_top_p(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, float temperature, float top_p,
+                 unsigned long long seed, int* finished, const int* eos_ids, int n_eos, int pad_id, int* next_tok,
+                 int* out_ids, int out_ld, int step, int* n_unfinished, cudaStream_t st, const int* step_ptr,
+                 int* kept_count) {
+  if (n_rows == 0) return OPUS_OK;
+  if (!(temperature > 0.f) || !(top_p > 0.f) || vocab <= 0) return OPUS_ERR_ARG;
+  launch_pdl(true, sample_top_p_kernel, dim3(n_rows), dim3(SAMPLE_THREADS), 0, st, logits, ld, vocab, 1.0f / temperature,
+             top_p, seed, finished, eos_ids, n_eos, pad_id, next_tok, out_ids, out_ld, step, step_ptr, n_unfinished,
+             kept_count);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
 }
 
 int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, int n_rows, int dim, cudaStream_t st) {

@@ -148,6 +148,15 @@ int opus_argmax_eos(const void* logits, int ld, int vocab, int n_rows, int32_t* 
       "opus_argmax_eos");
 }
 
+int opus_sample_top_p(const void* logits, int ld, int vocab, int n_rows, float temperature, float top_p, uint64_t seed,
+                      int32_t* finished, const int32_t* eos_ids, int n_eos, int pad_id, int32_t* next_tok,
+                      int32_t* out_ids, int out_ld, int step, int32_t* n_unfinished, int32_t* kept_count,
+                      void* stream) {
+  RET(sample_top_p(static_cast<const bf16*>(logits), ld, vocab, n_rows, temperature, top_p, seed, finished, eos_ids,
+                   n_eos, pad_id, next_tok, out_ids, out_ld, step, n_unfinished, ST(stream), nullptr, kept_count),
+      "opus_sample_top_p");
+}
+
 int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n_rows, int dim, void* stream) {
   RET(embed_gather(tok, static_cast<const bf16*>(table), static_cast<bf16*>(x), n_rows, dim, ST(stream)),
       "opus_embed_gather_bf16");

@@ -37,6 +37,12 @@ int splice_gather(const int* src, const __nv_bfloat16* embed, const __nv_bfloat1
 int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* finished, const int* eos_ids, int n_eos,
                int pad_id, int* next_tok, int* out_ids, int out_ld, int step, int* n_unfinished, cudaStream_t st,
                const int* step_ptr = nullptr);
+// temperature / top-p sampling with the EOS bookkeeping of argmax_eos (HF do_sample=True); kept_count (nullable) receives
+// the number of boundary-key ties kept per row (diagnostics)
+int sample_top_p(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, float temperature, float top_p,
+                 unsigned long long seed, int* finished, const int* eos_ids, int n_eos, int pad_id, int* next_tok,
+                 int* out_ids, int out_ld, int step, int* n_unfinished, cudaStream_t st,
+                 const int* step_ptr = nullptr, int* kept_count = nullptr);
 int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, int n_rows, int dim, cudaStream_t st);
 int decode_advance(int* ctx_len, int* pos, int* slot, const int* block_table, int max_blocks, int block_size, int n,
                    cudaStream_t st, int* step = nullptr);

@@ -272,6 +272,10 @@ int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus
 
 int llama_select(const opus_llama_model* m, const opus_llama_workspace* ws, const opus_decode_state* s, int n_seqs,
                  cudaStream_t st) {
+  if (s->do_sample)
+    return sample_top_p(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->temperature, s->top_p,
+                        s->seed, s->finished, s->eos_ids, s->n_eos, s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1,
+                        s->n_unfinished, st, s->step);
   return argmax_eos(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->finished, s->eos_ids, s->n_eos,
                     s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1, s->n_unfinished, st, s->step);
 }

@@ -198,9 +198,10 @@ class B200Llama:
         d["embeds"] = embeds
         return d
 
-    def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int):
+    def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int, sampling=None):
+        """sampling = None (greedy) or (temperature, top_p, seed)."""
         n, dev = st["n_seqs"], self.device
-        key = (n, max_new_tokens, tuple(eos_ids), pad_id)
+        key = (n, max_new_tokens, tuple(eos_ids), pad_id, sampling)
         cached = getattr(self, "_state_cache", None)
         if cached is None or cached[0] != key:
             i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
@@ -224,19 +225,21 @@ class B200Llama:
             setattr(s, k, bufs[k].data_ptr())
         s.max_blocks, s.out_ld = st["max_blocks"], max_new_tokens
         s.eos_ids, s.n_eos, s.pad_id = bufs["eos"].data_ptr(), len(eos_ids), pad_id
+        if sampling is not None:
+            s.do_sample, s.temperature, s.top_p, s.seed = 1, float(sampling[0]), float(sampling[1]), int(sampling[2])
         return s, bufs
 
     @torch.no_grad()
     def generate_packed(self, embeds: torch.Tensor, cu_seqlens, max_new_tokens: int, eos_ids=(), pad_id: int = 0,
                         use_graph: bool = True, check_every: int = 16, return_prefill_logits: bool = False,
-                        plan: dict | None = None):
+                        plan: dict | None = None, sampling=None):
         """Greedy generation from packed prompt embeddings. Returns int64 [n_seqs, n_new] (new tokens only; finished
         rows padded with pad_id; trimmed at the step where every row had finished, like HF)."""
         own_plan = plan is None
         st = self.prefill(embeds, cu_seqlens, max_new_tokens, plan=plan)
         try:
             prefill_logits = st["logits"].clone() if return_prefill_logits else None
-            out = self.generate_from_prefill(st, max_new_tokens, eos_ids, pad_id, use_graph, check_every)
+            out = self.generate_from_prefill(st, max_new_tokens, eos_ids, pad_id, use_graph, check_every, sampling)
         finally:
             if own_plan:
                 self.release_plan(st)
@@ -244,10 +247,11 @@ class B200Llama:
 
     @torch.no_grad()
     def generate_from_prefill(self, st: dict, max_new_tokens: int, eos_ids=(), pad_id: int = 0,
-                              use_graph: bool = True, check_every: int = 16) -> torch.Tensor:
-        """Select the first token from the prefill logits, then run the greedy decode loop (CUDA-graph replays)."""
+                              use_graph: bool = True, check_every: int = 16, sampling=None) -> torch.Tensor:
+        """Select the first token from the prefill logits, then run the decode loop (CUDA-graph replays). Greedy unless
+        sampling = (temperature, top_p, seed): HF do_sample=True semantics, drawn on the device."""
         lib = L.load()
-        s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id)
+        s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id, sampling)
         stream = torch.cuda.current_stream().cuda_stream
         L.check(lib.opus_llama_select(C.byref(self._model), C.byref(self._ws), C.byref(s), st["n_seqs"], stream),
                 "opus_llama_select")

@@ -5,8 +5,8 @@ Keeps the call surface the eval scripts use (multi_modality_v1/eval/run_opus_ddp
 ``LongTensor[B, n_new]`` (new tokens only), plus the mixin methods of `OpusMetaModelForCauselLM`
 (multi_modality_v1/model/opus_arch.py:103-294): encode_seq2embedding / encode_projector_embedding /
 switch_projector_embedding / prepare_inputs_labels_for_multimodal. Error conventions follow the reference
-(NotImplementedError for non-str `seq`, for `inputs_embeds=` and for sampling/beam options this backend does not
-implement).
+(NotImplementedError for non-str `seq`, for `inputs_embeds=` and for beam search / top-k, which this backend does not
+implement). Greedy and temperature / top-p sampling are both drawn on the device.
 """
 from __future__ import annotations
 
@@ -192,16 +192,34 @@ class B200OpusLlama:
     # ---- generation
     @torch.no_grad()
     def generate(self, inputs=None, seq=None, seq_embedding=None, **kwargs):
-        """opus_llama.py:95-132 contract. Greedy only (north star): do_sample must be False / temperature 0."""
+        """opus_llama.py:95-132 contract. do_sample=False: greedy (north star). do_sample=True: temperature / top-p
+        sampling on the device (the reference's default eval setting, run_opus_ddp.py:126-128: temperature 0.1,
+        top_p 0.7); `seed=` pins the draw, otherwise torch.initial_seed() and a per-call counter are used."""
         kwargs.pop("position_ids", None)
         attention_mask = kwargs.pop("attention_mask", None)
         if "inputs_embeds" in kwargs:
             raise NotImplementedError("`inputs_embeds` is not supported")
-        if kwargs.pop("do_sample", False):
-            raise NotImplementedError("opus_pllm_b200 implements greedy decoding only (do_sample=False)")
+        do_sample = bool(kwargs.pop("do_sample", False))
         if int(kwargs.pop("num_beams", 1) or 1) != 1:
             raise NotImplementedError("beam search is not implemented")
-        kwargs.pop("temperature", None); kwargs.pop("top_p", None); kwargs.pop("use_cache", None)
+        temperature = kwargs.pop("temperature", None)
+        top_p = kwargs.pop("top_p", None)
+        seed = kwargs.pop("seed", None)
+        if kwargs.pop("top_k", None) not in (None, 0):
+            raise NotImplementedError("top_k sampling is not implemented")
+        kwargs.pop("use_cache", None)
+        sampling = None
+        if do_sample:
+            temperature = 1.0 if temperature is None else float(temperature)
+            top_p = 1.0 if top_p is None else float(top_p)
+            if not temperature > 0.0:
+                raise ValueError("`temperature` has to be a strictly positive float")   # HF's message
+            if not 0.0 < top_p <= 1.0:
+                raise ValueError("`top_p` has to be a float > 0 and <= 1")
+            if seed is None:
+                self._sample_calls = getattr(self, "_sample_calls", 0) + 1
+                seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._sample_calls) & (2 ** 64 - 1)
+            sampling = (temperature, top_p, int(seed) & (2 ** 64 - 1))
         max_new = int(kwargs.pop("max_new_tokens", 20))
         pad_id = kwargs.pop("pad_token_id", None)
         eos = kwargs.pop("eos_token_id", None)
@@ -225,7 +243,7 @@ class B200OpusLlama:
         src_d = ops.h2d(plan.src, self.device)
         embeds = ops.splice_gather(src_d, self.llama.embed, soft2d)
         return self.llama.generate_packed(embeds, plan.cu, max_new, eos_ids=eos_ids, pad_id=int(pad_id),
-                                          use_graph=use_graph, return_prefill_logits=return_logits)
+                                          use_graph=use_graph, return_prefill_logits=return_logits, sampling=sampling)
 
 
 def build_from_state_dicts(llama_sd: dict, llama_cfg: dict, esm_sd: dict | None, esm_cfg: dict | None,

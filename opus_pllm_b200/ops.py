@@ -201,6 +201,18 @@ def argmax_eos(logits: torch.Tensor, finished: torch.Tensor, eos_ids: torch.Tens
             "opus_argmax_eos")
 
 
+
+def sample_top_p(logits: torch.Tensor, temperature: float, top_p: float, seed: int, finished: torch.Tensor,
+                 eos_ids: torch.Tensor | None, pad_id: int, next_tok: torch.Tensor, out_ids: torch.Tensor, step: int,
+                 n_unfinished: torch.Tensor | None = None, kept_count: torch.Tensor | None = None):
+    """Temperature / nucleus sampling of one token per row (HF do_sample=True semantics), EOS bookkeeping included."""
+    _chk(logits, BF16, "logits"); _chk(finished, I32, "finished"); _chk(out_ids, I32, "out_ids")
+    L.check(L.load().opus_sample_top_p(_p(logits), logits.stride(0), logits.shape[1], logits.shape[0],
+                                       float(temperature), float(top_p), int(seed) & (2 ** 64 - 1), _p(finished),
+                                       _p(eos_ids), 0 if eos_ids is None else eos_ids.numel(), pad_id, _p(next_tok),
+                                       _p(out_ids), out_ids.stride(0), step, _p(n_unfinished), _p(kept_count),
+                                       _stream()), "opus_sample_top_p")
+
 def embed_gather(tok: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     _chk(tok, I32, "tok"); _chk(table, BF16, "table")
     x = torch.empty((tok.numel(), table.shape[1]), dtype=BF16, device=tok.device)

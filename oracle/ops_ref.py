@@ -127,3 +127,22 @@ def greedy_select_ref(logits: torch.Tensor, finished: torch.Tensor, eos_ids, pad
     for e in eos_ids:
         is_eos |= tok == e
     return tok, finished.bool() | is_eos
+
+
+def top_p_keep_mask(logits: torch.Tensor, temperature: float, top_p: float) -> torch.Tensor:
+    """Nucleus of every row, as HF builds it (transformers generation/logits_process.py: TemperatureLogitsWarper then
+    TopPLogitsWarper with min_tokens_to_keep=1; reached from the reference through generate(do_sample=True,
+    temperature, top_p), run_opus_ddp.py:126-128). logits [B, V] -> bool [B, V], True = kept."""
+    scores = logits.float() / temperature
+    sorted_logits, sorted_indices = torch.sort(scores, descending=False)
+    cumulative_probs = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+    remove = cumulative_probs <= (1 - top_p)
+    remove[..., -1:] = False
+    remove = remove.scatter(1, sorted_indices, remove)
+    return ~remove
+
+
+def top_p_probs(logits: torch.Tensor, temperature: float, top_p: float) -> torch.Tensor:
+    """Distribution HF samples the next token from: softmax of the warped scores (-inf outside the nucleus)."""
+    scores = (logits.float() / temperature).masked_fill(~top_p_keep_mask(logits, temperature, top_p), float("-inf"))
+    return scores.softmax(-1)

@@ -358,6 +358,64 @@ def test_argmax_eos(ops):
     assert int(n_unf) == B - 2
 
 
+@pytest.mark.parametrize("temperature,top_p,vocab", [(0.1, 0.7, 128256), (1.0, 0.9, 1000), (0.7, 0.5, 4099), (1.5, 1.0, 517)])
+def test_sample_top_p_nucleus_and_frequencies(ops, temperature, top_p, vocab):
+    """do_sample=True path (the reference's default decode, run_opus_ddp.py:126-128): the nucleus must be HF's, every
+    draw must come from it, and the draw frequencies must follow the renormalised probabilities."""
+    g = torch.Generator().manual_seed(vocab)
+    base = (torch.randn(4, vocab, generator=g) * (2.0 if temperature >= 0.5 else 0.3)).to(torch.bfloat16)
+    reps = 2048
+    logits = base.repeat_interleave(reps, 0).cuda().contiguous()          # 4 distinct rows x 2048 independent draws
+    n = logits.shape[0]
+    fin = torch.zeros(n, dtype=torch.int32, device="cuda")
+    nxt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    out = torch.zeros(n, 2, dtype=torch.int32, device="cuda")
+    kept = torch.zeros(n, dtype=torch.int32, device="cuda")
+    ops.sample_top_p(logits, temperature, top_p, 1234, fin, None, 0, nxt, out, 1, kept_count=kept)
+    tok = out[:, 1].long().cpu()
+    assert torch.equal(tok, nxt.long().cpu())
+    keep = R.top_p_keep_mask(base, temperature, top_p)                    # [4, V]
+    probs = R.top_p_probs(base, temperature, top_p)
+    for r in range(4):
+        t = tok[r * reps:(r + 1) * reps]
+        # nucleus size (ties between equal bf16 logits at the boundary may be resolved differently: +-1)
+        assert abs(int(kept[r * reps]) - int(keep[r].sum())) <= 1, (int(kept[r * reps]), int(keep[r].sum()))
+        # every draw is at least as probable as the least probable token of HF's nucleus
+        floor = base[r].float()[keep[r]].min()
+        assert bool((base[r].float()[t] >= floor).all())
+        # frequencies follow the renormalised distribution: total variation distance of 2048 draws
+        freq = torch.bincount(t, minlength=vocab).float() / reps
+        tv = 0.5 * float((freq - probs[r]).abs().sum())
+        support = int(keep[r].sum())
+        assert tv <= 0.04 + 0.6 * (support / reps) ** 0.5, (tv, support)
+    # deterministic in the seed, different across seeds (when the nucleus has more than one token)
+    out2 = torch.zeros_like(out)
+    ops.sample_top_p(logits, temperature, top_p, 1234, fin, None, 0, nxt, out2, 1)
+    assert torch.equal(out2[:, 1], out[:, 1])
+    ops.sample_top_p(logits, temperature, top_p, 99, fin, None, 0, nxt, out2, 1)
+    if int(keep.sum(1).min()) > 1:
+        assert not torch.equal(out2[:, 1], out[:, 1])
+
+
+def test_sample_top_p_limits_and_eos(ops):
+    g = torch.Generator().manual_seed(7)
+    logits = (torch.randn(16, 3001, generator=g) * 2).to(torch.bfloat16).cuda()
+    fin = torch.zeros(16, dtype=torch.int32, device="cuda"); fin[3] = 1
+    nxt = torch.zeros(16, dtype=torch.int32, device="cuda")
+    out = torch.full((16, 1), -1, dtype=torch.int32, device="cuda")
+    left = torch.tensor([15], dtype=torch.int32, device="cuda")
+    greedy = logits.float().argmax(-1)
+    eos = torch.tensor([int(greedy[5])], dtype=torch.int32, device="cuda")
+    # temperature -> 0 (or a nucleus of one token) degenerates to greedy; finished rows emit pad; EOS rows finish
+    ops.sample_top_p(logits, 1e-3, 0.9, 5, fin, eos, 77, nxt, out, 0, left)
+    want = greedy.clone(); want[3] = 77
+    assert torch.equal(out[:, 0].long(), want)
+    assert int(fin[5]) == 1 and int(left) == 15 - int((greedy == greedy[5]).sum() - (1 if int(greedy[3]) == int(greedy[5]) else 0))
+    out.fill_(-1); fin.zero_()
+    ops.sample_top_p(logits, 1.0, 1e-6, 5, fin, None, 0, nxt, out, 0)
+    assert torch.equal(out[:, 0].long(), greedy)
+
+
 def test_lora_merge(ops):
     W = _randn((512, 256), 49, scale=0.05)
     A = _randn((16, 256), 50, scale=0.02)

@@ -246,6 +246,32 @@ def test_greedy_decode_default_init_margin_aware():
     assert _cos(logits, wl[:, 0]) >= 0.999
 
 
+def test_generate_sampling_default_eval_settings():
+    """generate(do_sample=True, temperature=0.1, top_p=0.7) — the reference eval scripts' default (run_opus_ddp.py:
+    126-128,156-157): runs on the device, is reproducible for a given seed, graph replay == plain launches, and at this
+    temperature the peaked-logit model's draws coincide with greedy on nearly every position."""
+    from opus_pllm_b200 import presets
+    model = presets.build_synthetic_model("tiny", "cuda", peaked=True)
+    B, new = 6, 10
+    seqs = synth.proteins(B, 20, 40, seed=3)
+    ids = torch.stack(synth.prompt_ids(B, 30, vocab=2048, sentinel_at=5)).cuda()
+    kw = dict(pad_token_id=1, max_new_tokens=new)
+    greedy = model.generate(ids, seqs, do_sample=False, **kw)
+    a = model.generate(ids, seqs, do_sample=True, temperature=0.1, top_p=0.7, seed=11, **kw)
+    b = model.generate(ids, seqs, do_sample=True, temperature=0.1, top_p=0.7, seed=11, use_graph=False, **kw)
+    assert a.shape == (B, new) and a.dtype == torch.int64 and torch.equal(a, b)
+    assert float((a == greedy).float().mean()) >= 0.9
+    flat = presets.build_synthetic_model("tiny", "cuda", peaked=False)      # HF-init statistics: flat next-token distribution
+    flat_greedy = flat.generate(ids, seqs, do_sample=False, **kw)
+    hot = flat.generate(ids, seqs, do_sample=True, temperature=1.0, top_p=1.0, seed=11, **kw)
+    hot2 = flat.generate(ids, seqs, do_sample=True, temperature=1.0, top_p=1.0, seed=12, **kw)
+    assert not torch.equal(hot, flat_greedy) and not torch.equal(hot, hot2)
+    with pytest.raises(ValueError):
+        model.generate(ids, seqs, do_sample=True, temperature=0.0, **kw)
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, seqs, do_sample=False, num_beams=4, **kw)
+
+
 def test_eos_and_pad_semantics():
     from opus_pllm_b200.llama import B200Llama
     cfg = SMALL

@@ -126,3 +126,16 @@ def test_lora_merge_and_op_refs():
     assert torch.allclose(ops_ref.gelu_erf(x), torch.nn.functional.gelu(x), atol=1e-6)
     tok, fin = ops_ref.greedy_select_ref(torch.tensor([[0., 3., 3.], [9., 1., 0.]]), torch.tensor([0, 1]), [1], 7)
     assert tok.tolist() == [1, 7] and fin.tolist() == [True, True]
+
+
+def test_top_p_oracle_matches_hf_warpers():
+    """oracle/ops_ref.py::top_p_keep_mask / top_p_probs restate HF's TemperatureLogitsWarper + TopPLogitsWarper (what
+    the reference's generate(do_sample=True, temperature, top_p) applies): pin them against transformers itself."""
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopPLogitsWarper
+    from oracle import ops_ref as R
+    g = torch.Generator().manual_seed(0)
+    for T, P in [(0.1, 0.7), (1.0, 0.9), (0.7, 0.5), (2.0, 1.0)]:
+        lg = (torch.randn(6, 3000, generator=g) * 3).bfloat16()
+        sc = TopPLogitsWarper(top_p=P)(None, TemperatureLogitsWarper(T)(None, lg.float()))
+        assert torch.equal(torch.isfinite(sc), R.top_p_keep_mask(lg, T, P))
+        assert torch.allclose(sc.softmax(-1), R.top_p_probs(lg, T, P))
