@@ -1,9 +1,9 @@
 """Batch annotation driver: counterpart of `multi_modality_v1/eval/run_opus_ddp.py` on the B200 backend.
 
 Same flags, same prompt construction, same data-parallel scheme (contiguous shards of the prompt list, one gather at the
-end). Differences: `--temperature` defaults to 0 (greedy is what this backend implements), the collective is a tensor
-all-gather of token ids instead of `gather_object`, and `--continuous-batching` keeps a fixed number of decode slots busy
-instead of walking fixed batches of 8. Launch with torchrun (one process per GPU) or plain python (one GPU).
+end; `--temperature 0.1 --top_p 0.7` sampling by default like the reference, `--temperature 0` = greedy). Differences:
+the collective is a tensor all-gather of token ids instead of `gather_object`, `--seed` pins the sampling stream, and
+`--continuous-batching` (greedy only) keeps a fixed number of decode slots busy instead of walking fixed batches of 8. Launch with torchrun (one process per GPU) or plain python (one GPU).
 
   torchrun --nproc-per-node 8 -m opus_pllm_b200.eval_ddp --model-base-path <llama3 dir> \
       --opus-pllm-weights-path <weights dir> --input_path data.json --save_path out.json
@@ -79,8 +79,8 @@ def eval_model(args, tokenizer=None, model=None):
     seqs_all, instr_all, gt_all = [q["input"] for q in qs], [q["instruction"] for q in qs], [q["output"] for q in qs]
     seqs, instrs = split_between_processes(seqs_all, rank, world), split_between_processes(instr_all, rank, world)
     max_new = args.max_new_tokens if args.max_new_tokens_fixed else max_new_tokens_for(args.input_path, args.max_new_tokens)
-    if args.temperature > 0:
-        raise NotImplementedError("opus_pllm_b200 implements greedy decoding; run with --temperature 0")
+    if args.temperature > 0 and args.continuous_batching:
+        raise NotImplementedError("--continuous-batching decodes greedily; run it with --temperature 0")
     dev = model.device
     prompts = [build_prompt(i, system, args.input_path) for i in instrs]
     ids = [tokenizer_seq_token(p, tokenizer, DEFAULT_SEQ_TOKEN_INDEX, return_tensors="pt") for p in prompts]
@@ -95,8 +95,10 @@ def eval_model(args, tokenizer=None, model=None):
         for i in range(0, len(ids), args.batch_size):
             batch = left_pad_sequence(ids[i: i + args.batch_size], tokenizer.pad_token_id, batch_first=True)
             out = model.generate(batch, seqs[i: i + args.batch_size], attention_mask=batch != tokenizer.pad_token_id,
-                                 pad_token_id=tokenizer.eos_token_id, do_sample=False, temperature=0,
-                                 top_p=args.top_p, num_beams=args.num_beams, max_new_tokens=max_new, use_cache=True)
+                                 pad_token_id=tokenizer.eos_token_id, do_sample=args.temperature > 0,
+                                 temperature=args.temperature, top_p=args.top_p, num_beams=args.num_beams,
+                                 max_new_tokens=max_new, use_cache=True,
+                                 **({"seed": args.seed + 1000003 * rank + i} if args.temperature > 0 else {}))
             rows.extend(torch.nn.functional.pad(o, (0, max_new - o.numel()), value=tokenizer.eos_token_id) for o in out.cpu())
     local = torch.stack(rows).to(dev) if rows else torch.zeros((0, max_new), dtype=torch.int64, device=dev)
     gathered = gather_token_ids(local, tokenizer.eos_token_id)
@@ -119,7 +121,8 @@ def main():
     ap.add_argument("--is_json", type=bool, default=True)
     ap.add_argument("--input_path", type=str, required=True)
     ap.add_argument("--save_path", type=str, required=True)
-    ap.add_argument("--temperature", type=float, default=0.0)
+    ap.add_argument("--temperature", type=float, default=0.1)      # run_opus_ddp.py:156
+    ap.add_argument("--seed", type=int, default=0, help="sampling stream (per rank and batch offsets are added)")
     ap.add_argument("--top_p", type=float, default=0.7)
     ap.add_argument("--num_beams", type=int, default=1)
     ap.add_argument("--max_new_tokens", type=int, default=32)

@@ -410,6 +410,10 @@ def test_load_pretrained_model_and_eval_driver(tmp_path):
     args.continuous_batching = True
     res_cb = eval_ddp.eval_model(args, tokenizer=tok, model=model)
     assert res_cb == res
+    # the reference's default decode (temperature 0.1, top_p 0.7) through the same driver: reproducible per --seed
+    args.continuous_batching, args.temperature, args.seed = False, 0.1, 3
+    res_s = eval_ddp.eval_model(args, tokenizer=tok, model=model)
+    assert len(res_s) == 5 and res_s == eval_ddp.eval_model(args, tokenizer=tok, model=model)
     # same tokens from the model assembled directly from the tensors
     prompt = eval_ddp.build_prompt(data[0]["instruction"], args.system_prompt, str(inp))
     from opus_pllm_b200.mm_utils import tokenizer_seq_token
