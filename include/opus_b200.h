@@ -129,6 +129,10 @@ int opus_sample_top_p(const void* logits, int ld, int vocab, int n_rows, float t
                       int32_t* finished, const int32_t* eos_ids, int n_eos, int pad_id, int32_t* next_tok,
                       int32_t* out_ids, int out_ld, int step, int32_t* n_unfinished, int32_t* kept_count,
                       void* stream);
+/* Teacher-forced scoring (HF LlamaForCausalLM.forward(labels=...), reached from language_model/opus_llama.py:41-93):
+ * loss[r] = logsumexp(fp32(logits[r,:])) - logits[r, target[r]]; 0 where target[r] < 0 (ignore_index). */
+int opus_cross_entropy_bf16(const void* logits, int ld, int vocab, const int32_t* target, float* loss, int n_rows,
+                            void* stream);
 int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n_rows, int dim, void* stream);
 /* W += scale * (B @ A): peft merge_and_unload (multi_modality_v1/model/builder.py:107-109). */
 int opus_lora_merge_bf16(void* W, const void* A, const void* B, int out_features, int in_features, int r, float scale,

@@ -95,6 +95,7 @@ _SIGNATURES = {
     "opus_argmax_eos": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
     "opus_sample_top_p": (c_int, [_P, c_int, c_int, c_int, c_float, c_float, C.c_uint64, _P, _P, c_int, c_int, _P, _P,
                                   c_int, c_int, _P, _P, _P]),
+    "opus_cross_entropy_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P]),
     "opus_embed_gather_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "opus_lora_merge_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "opus_attn_varlen_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int,

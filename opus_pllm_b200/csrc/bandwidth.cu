@@ -752,6 +752,55 @@ sample_top_p_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int vocab,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Teacher-forced scoring tail (HF LlamaForCausalLM.forward with labels=, reached from opus_llama.py:41-93): per-row
+// cross entropy in fp32 over bf16 logits, loss[r] = logsumexp(logits[r, :]) - logits[r, target[r]]; rows whose target is
+// negative (HF's ignore_index = -100) get 0. One CTA per row; the mean over the counted rows is the caller's.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+cross_entropy_rows_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int vocab,
+                          const int* __restrict__ target, float* __restrict__ loss) {
+  const int r = blockIdx.x;
+  const int tgt = target[r];
+  if (tgt < 0 || tgt >= vocab) {
+    if (threadIdx.x == 0) loss[r] = 0.f;
+    return;
+  }
+  const __nv_bfloat16* row = logits + (size_t)r * ld;
+  __shared__ float red[17];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x * 8; c < vocab; c += blockDim.x * 8) {
+    float f[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (c + j < vocab) mx = fmaxf(mx, f[j]);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 16; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x * 8; c < vocab; c += blockDim.x * 8) {
+    float f[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(row + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (c + j < vocab) sum += expf(f[j] - mx);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) tot += red[w];
+    loss[r] = logf(tot) + mx - __bfloat162float(row[tgt]);
+  }
+}
+
 // decode input: x[b,:] = table[tok[b],:]; also advances positions / cache slots for the step (one launch per step).
 __global__ void embed_gather_kernel(const int* __restrict__ tok, const __nv_bfloat16* __restrict__ table,
                                     __nv_bfloat16* __restrict__ x, int n_rows, int dim) {
@@ -922,6 +971,15 @@ int sample_top_p(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, flo
   launch_pdl(true, sample_top_p_kernel, dim3(n_rows), dim3(SAMPLE_THREADS), 0, st, logits, ld, vocab, 1.0f / temperature,
              top_p, seed, finished, eos_ids, n_eos, pad_id, next_tok, out_ids, out_ld, step, step_ptr, n_unfinished,
              kept_count);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
+}
+
+int cross_entropy_rows(const __nv_bfloat16* logits, int ld, int vocab, const int* target, float* loss, int n_rows,
+                       cudaStream_t st) {
+  if (n_rows == 0) return OPUS_OK;
+  if (vocab <= 0 || (ld % 8) || (reinterpret_cast<uintptr_t>(logits) & 15)) return OPUS_ERR_ARG;
+  cross_entropy_rows_kernel<<<n_rows, 512, 0, st>>>(logits, ld, vocab, target, loss);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
 }

@@ -157,6 +157,12 @@ int opus_sample_top_p(const void* logits, int ld, int vocab, int n_rows, float t
       "opus_sample_top_p");
 }
 
+int opus_cross_entropy_bf16(const void* logits, int ld, int vocab, const int32_t* target, float* loss, int n_rows,
+                            void* stream) {
+  RET(cross_entropy_rows(static_cast<const bf16*>(logits), ld, vocab, target, loss, n_rows, ST(stream)),
+      "opus_cross_entropy_bf16");
+}
+
 int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n_rows, int dim, void* stream) {
   RET(embed_gather(tok, static_cast<const bf16*>(table), static_cast<bf16*>(x), n_rows, dim, ST(stream)),
       "opus_embed_gather_bf16");

@@ -43,6 +43,9 @@ int sample_top_p(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, flo
                  unsigned long long seed, int* finished, const int* eos_ids, int n_eos, int pad_id, int* next_tok,
                  int* out_ids, int out_ld, int step, int* n_unfinished, cudaStream_t st,
                  const int* step_ptr = nullptr, int* kept_count = nullptr);
+// loss[r] = logsumexp(logits[r,:]) - logits[r, target[r]] in fp32 (0 where target[r] < 0)
+int cross_entropy_rows(const __nv_bfloat16* logits, int ld, int vocab, const int* target, float* loss, int n_rows,
+                       cudaStream_t st);
 int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, int n_rows, int dim, cudaStream_t st);
 int decode_advance(int* ctx_len, int* pos, int* slot, const int* block_table, int max_blocks, int block_size, int n,
                    cudaStream_t st, int* step = nullptr);

@@ -198,6 +198,29 @@ class B200Llama:
         d["embeds"] = embeds
         return d
 
+    @torch.no_grad()
+    def score_packed(self, embeds: torch.Tensor, cu_seqlens, targets: torch.Tensor, return_logits: bool = False,
+                     chunk_rows: int = 4096):
+        """Teacher-forced scoring of packed sequences: `targets` int32 [n_tok] holds, for every row, the id the model
+        should predict NEXT (already shifted; < 0 = not counted). Returns (per-row fp32 losses, logits bf16 | None).
+        All-position logits are produced chunk by chunk (final RMSNorm -> lm_head -> fp32 cross entropy), so the
+        [n_tok, vocab] matrix only exists when return_logits is set."""
+        st = self.prefill(embeds, cu_seqlens, 1)
+        try:
+            n_tok = st["n_tok"]
+            hidden = self._ws_bufs["h"][:n_tok]                    # residual stream after the last layer
+            losses = torch.empty((n_tok,), dtype=torch.float32, device=self.device)
+            all_logits = torch.empty((n_tok, self.vocab), dtype=torch.bfloat16, device=self.device) if return_logits else None
+            targets = targets.to(self.device, torch.int32).contiguous()
+            for r0 in range(0, n_tok, chunk_rows):
+                r1 = min(n_tok, r0 + chunk_rows)
+                xn = ops.rmsnorm(hidden[r0:r1], self.norm_w, self.rms_eps)
+                logits = ops.gemm(xn, self.lm_head, out=None if all_logits is None else all_logits[r0:r1])
+                losses[r0:r1] = ops.cross_entropy_rows(logits, targets[r0:r1])
+        finally:
+            self.release_plan(st)
+        return losses, all_logits
+
     def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int, sampling=None):
         """sampling = None (greedy) or (temperature, top_p, seed)."""
         n, dev = st["n_seqs"], self.device

@@ -189,6 +189,58 @@ class B200OpusLlama:
         out_mask = None if attention_mask is None else new_mask.to(attention_mask.dtype)
         return None, new_pos, out_mask, past_key_values, embeds, new_labels
 
+    # ---- teacher-forced scoring
+    @torch.no_grad()
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, labels=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, seq=None, input_embed=None,
+                return_dict=None, return_logits: bool = True, **kwargs):
+        """opus_llama.py:41-93 contract for the scoring use (`model(input_ids, labels=..., seq=...)`): splice the soft
+        tokens with RIGHT padding semantics (opus_arch.py:259-269), run the prompt, and return an object with `.loss`
+        (HF: mean fp32 cross entropy of position t predicting label t+1 over labels != -100) and `.logits`
+        ([B, L', V] bf16, right-padded with zeros; None when return_logits=False to save the 2*V bytes per token).
+        Inference only: there is no autograd graph behind the loss."""
+        if kwargs.get("inputs_embeds") is not None or past_key_values is not None:
+            raise NotImplementedError("forward(): `inputs_embeds` / `past_key_values` are not supported")
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("forward(): attention maps / hidden states are not materialised")
+        n_prompts = input_ids.shape[0]
+        if seq is not None and self.protein_encoder is not None and input_ids.shape[1] != 1:
+            soft = self._soft_tokens(seq, input_embed)
+            plan = self._plan(input_ids, attention_mask, soft.shape[0])
+            soft2d = soft.reshape(-1, soft.shape[-1]).contiguous()
+        else:
+            ids = input_ids.detach().cpu().numpy()
+            mask = None if attention_mask is None else attention_mask.detach().bool().cpu().numpy()
+            plan = SplicePlan(np.where(ids == DEFAULT_SEQ_TOKEN_INDEX, 0, ids), mask, self.n_soft, 1 << 30)
+            soft2d = torch.zeros((1, self.llama.dim), dtype=torch.bfloat16, device=self.device)
+        # labels follow the splice (IGNORE_INDEX under the soft tokens), then shift by one inside every sequence
+        n_tok = int(plan.cu[-1])
+        tgt = np.full((n_tok,), IGNORE_INDEX, dtype=np.int32)
+        if labels is not None:
+            lab_in = labels.detach().cpu().numpy()
+            ids_in = input_ids.detach().cpu().numpy()
+            mk = np.ones_like(ids_in, dtype=bool) if attention_mask is None else attention_mask.detach().bool().cpu().numpy()
+            for b in range(n_prompts):
+                row_ids, row_lab = ids_in[b][mk[b]], lab_in[b][mk[b]]
+                reps = np.where(row_ids == DEFAULT_SEQ_TOKEN_INDEX, self.n_soft, 1)
+                spliced = np.repeat(np.where(row_ids == DEFAULT_SEQ_TOKEN_INDEX, IGNORE_INDEX, row_lab), reps)
+                n = int(plan.lens[b])
+                spliced = spliced[:n]
+                tgt[plan.cu[b]: plan.cu[b] + n - 1] = spliced[1:n]
+        embeds = ops.splice_gather(ops.h2d(plan.src, self.device), self.llama.embed, soft2d)
+        losses, logits = self.llama.score_packed(embeds, plan.cu, torch.from_numpy(tgt), return_logits=return_logits)
+        counted = int((tgt >= 0).sum())
+        loss = (losses.sum() / counted) if (labels is not None and counted > 0) else None
+        padded = None
+        if logits is not None:
+            Lm = int(plan.lens.max())
+            padded = torch.zeros((n_prompts, Lm, logits.shape[-1]), dtype=logits.dtype, device=self.device)
+            for b in range(n_prompts):
+                padded[b, : int(plan.lens[b])] = logits[plan.cu[b]: plan.cu[b + 1]]
+        return SimpleNamespace(loss=loss, logits=padded, token_losses=losses, past_key_values=None)
+
+    __call__ = forward
+
     # ---- generation
     @torch.no_grad()
     def generate(self, inputs=None, seq=None, seq_embedding=None, **kwargs):

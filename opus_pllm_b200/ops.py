@@ -202,6 +202,15 @@ def argmax_eos(logits: torch.Tensor, finished: torch.Tensor, eos_ids: torch.Tens
 
 
 
+def cross_entropy_rows(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """fp32 per-row cross entropy over bf16 logits [rows, vocab]; rows with target < 0 contribute 0."""
+    _chk(logits, BF16, "logits"); _chk(target, I32, "target")
+    loss = torch.empty((logits.shape[0],), dtype=F32, device=logits.device)
+    L.check(L.load().opus_cross_entropy_bf16(_p(logits), logits.stride(0), logits.shape[1], _p(target), _p(loss),
+                                             logits.shape[0], _stream()), "opus_cross_entropy_bf16")
+    return loss
+
+
 def sample_top_p(logits: torch.Tensor, temperature: float, top_p: float, seed: int, finished: torch.Tensor,
                  eos_ids: torch.Tensor | None, pad_id: int, next_tok: torch.Tensor, out_ids: torch.Tensor, step: int,
                  n_unfinished: torch.Tensor | None = None, kept_count: torch.Tensor | None = None):

@@ -67,7 +67,7 @@ def rotate_half(x):
 
 
 def llama_forward(w: dict, cfg: LlamaCfg, embeds: torch.Tensor, attention_mask: torch.Tensor,
-                  position_ids: torch.Tensor, past=None):
+                  position_ids: torch.Tensor, past=None, all_positions: bool = False):
     """embeds [B, T, D]; attention_mask bool [B, S] over (past + current) keys, S = past_len + T; position_ids [B, T].
     Returns (last-position logits fp32 [B, V], new past). `past` = list of (k, v) each [B, Hkv, S_past, hd]."""
     B, T, D = embeds.shape
@@ -108,9 +108,19 @@ def llama_forward(w: dict, cfg: LlamaCfg, embeds: torch.Tensor, attention_mask: 
         g = F.linear(x, w[p + "mlp.gate_proj.weight"])
         u = F.linear(x, w[p + "mlp.up_proj.weight"])
         h = res + F.linear(F.silu(g) * u, w[p + "mlp.down_proj.weight"])
+    if all_positions:   # teacher-forced scoring: HF returns logits for every position when labels are given
+        return F.linear(rmsnorm(h, w["model.norm.weight"], cfg.rms_eps), w["lm_head.weight"]).float(), new_past
     h = rmsnorm(h[:, -1:, :], w["model.norm.weight"], cfg.rms_eps)
     logits = F.linear(h, w["lm_head.weight"])[:, -1, :]
     return logits.float(), new_past
+
+
+def causal_lm_loss(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """HF LlamaForCausalLM loss (reached from opus_llama.py:82-93 when labels are passed): position t predicts label
+    t+1; mean fp32 cross entropy over the labels != ignore_index. logits [B, T, V], labels [B, T]."""
+    shift_logits = logits[..., :-1, :].float().reshape(-1, logits.shape[-1])
+    shift_labels = labels[..., 1:].reshape(-1)
+    return F.cross_entropy(shift_logits, shift_labels, ignore_index=ignore_index)
 
 
 def greedy_generate(w: dict, cfg: LlamaCfg, embeds: torch.Tensor, attention_mask: torch.Tensor, max_new_tokens: int,

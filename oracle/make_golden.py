@@ -156,6 +156,14 @@ def golden_mm_and_llama(esm_w, seqs, pooled):
         # prefill logits of the last position straight from the reference forward
         logits = model(inputs_embeds=e_ref, attention_mask=m_ref).logits[:, -1, :].float()
 
+        # teacher-forced scoring through the reference forward (opus_llama.py:41-93; right padding, labels spliced)
+        labels = ids.clone()
+        labels[~mask] = -100
+        labels[:, :Lm - 12] = -100                          # only the last dozen positions are scored
+        labels[ids == -200] = -100
+        scored = model(input_ids=ids, attention_mask=mask, labels=labels, seq=list(seqs))
+        score_loss, score_logits = scored.loss.float(), scored.logits.float()
+
     # ---- oracle restatements on the same inputs
     c_mine = mm_ref.protein_forward(pooled, pw["protein_projection.linear.weight"], pw["protein_projection.linear.bias"])
     s_mine = mm_ref.switch_projector(c_mine, pw, H)
@@ -175,6 +183,21 @@ def golden_mm_and_llama(esm_w, seqs, pooled):
     out_mine = llama_ref.greedy_generate(lw, ocfg, e_ref.float(), m_mine, 12, eos_ids=(2,), pad_id=2)
     assert d_l < 2e-4, d_l
     assert out_mine.shape == out.shape and torch.equal(out_mine, out), (out_mine, out)
+    # scoring path: right-padded splice + all-position logits + shifted cross entropy
+    lab_mine = mm_ref.splice_labels(ids, mask, labels)
+    pos_r = (m_mine_r.long().cumsum(-1) - 1).masked_fill(~m_mine_r, 1)
+    lg_all, _ = llama_ref.llama_forward(lw, ocfg, e_mine_r, m_mine_r, pos_r, all_positions=True)
+    loss_mine = llama_ref.causal_lm_loss(lg_all, lab_mine)
+    d_loss = float((loss_mine - score_loss).abs())
+    d_lg = float(((lg_all - score_logits) * m_mine_r[..., None]).abs().max())
+    assert d_loss < 1e-4 and d_lg < 5e-4, (d_loss, d_lg)
+    torch.save(dict(cfg=c, seed=13, input_ids=ids, attention_mask=mask, labels=labels, seqs=list(seqs), loss=score_loss,
+                    logits=score_logits.to(torch.bfloat16), mask_right=m_mine_r, labels_spliced=lab_mine,
+                    oracle_dev=dict(loss=d_loss, logits=d_lg),
+                    source="reference OpusLlamaForCausalLM.forward(labels=...) over transformers " +
+                           __import__("transformers").__version__),
+               os.path.join(GOLD, "score_small.pt"))
+    print(f"score_small.pt: oracle vs reference forward(labels): loss |diff| {d_loss:.3g}, logits max |diff| {d_lg:.3g}")
     torch.save(dict(esm_cfg=ESM_SMALL, proj_seed=12, seqs=list(seqs), pooled=pooled, cstp_out=c_ref.float(),
                     soft=s_ref.float(), input_ids=ids, attention_mask=mask, embeds_left=e_ref.float(),
                     mask_left=m_ref.bool(), embeds_right=e_r.float(), mask_right=m_r.bool(), pos_right=p_r, lens=lens,

@@ -78,3 +78,21 @@ def splice(input_ids: torch.Tensor, attention_mask: torch.Tensor | None, soft: t
         new_mask[b, sl] = True
         pos[b, sl] = torch.arange(n, device=embed.device)
     return out, new_mask, pos, lens
+
+
+def splice_labels(input_ids: torch.Tensor, attention_mask: torch.Tensor | None, labels: torch.Tensor, n_soft: int = 8,
+                  ignore_index: int = -100, max_length: int | None = None) -> torch.Tensor:
+    """Label side of prepare_inputs_labels_for_multimodal in training / scoring mode (opus_arch.py:176-269 with
+    inference_mode=False): pad positions dropped, every <seq> sentinel replaced by n_soft ignore_index labels, rows
+    right-padded with ignore_index. Returns int64 [B, Lmax']."""
+    B = input_ids.shape[0]
+    mask = torch.ones_like(input_ids, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
+    rows = []
+    for b in range(B):
+        ids, lab = input_ids[b][mask[b]], labels[b][mask[b]]
+        out = []
+        for t, l in zip(ids.tolist(), lab.tolist()):
+            out.extend([ignore_index] * n_soft if t == SEQ_TOKEN_INDEX else [l])
+        rows.append(torch.tensor(out[:max_length] if max_length is not None else out, dtype=torch.int64))
+    Lm = max(r.numel() for r in rows)
+    return torch.stack([torch.cat([r, torch.full((Lm - r.numel(),), ignore_index, dtype=torch.int64)]) for r in rows])

@@ -92,3 +92,32 @@ def test_llama_prefill_matches_reference_generate_golden():
     margin = top2[:, 0] - top2[:, 1]
     same = out[:, 0].cpu() == g["tokens"][:, 0]
     assert bool((same | (margin < 0.05 * float(want.std()))).all())
+
+
+def test_forward_labels_scoring_matches_reference_golden():
+    """model(input_ids, labels=..., seq=..., input_embed=...) — the teacher-forced scoring path (opus_llama.py:41-93,
+    right-padded splice opus_arch.py:259-269, pre-computed ESM embeddings opus_arch.py:151-161) against the loss and
+    all-position logits the reference's own forward produced (tests/golden/score_small.pt)."""
+    from opus_pllm_b200.model import build_from_state_dicts
+    g, mm = _load("score_small.pt"), _load("mm_small.pt")
+    c = g["cfg"]
+    H = c["dim"]
+    pw = synth.projector_weights(mm["esm_cfg"]["dim"], 5120, 8 * H, seed=mm["proj_seed"])
+    lw = synth.llama_weights(c["n_layers"], H, c["n_q_heads"], c["n_kv_heads"], c["head_dim"], c["ffn_dim"], c["vocab"],
+                             seed=g["seed"])
+    ec = mm["esm_cfg"]
+    model = build_from_state_dicts(lw, c, synth.esm2_weights(ec["n_layers"], ec["dim"], ec["ffn"], seed=11),
+                                   dict(n_layers=ec["n_layers"], dim=ec["dim"], n_heads=ec["n_heads"], ffn_dim=ec["ffn"]),
+                                   pw, pw)
+    ids, mask, labels = g["input_ids"].cuda(), g["attention_mask"].cuda(), g["labels"].cuda()
+    out = model(ids, attention_mask=mask, labels=labels, seq=g["seqs"], input_embed=mm["pooled"].cuda())
+    want_logits, valid = g["logits"].float(), g["mask_right"]
+    assert out.logits.shape == want_logits.shape
+    assert _cos(out.logits.cpu()[valid], want_logits[valid]) >= 0.999
+    assert abs(float(out.loss) - float(g["loss"])) <= 0.03, (float(out.loss), float(g["loss"]))
+    assert bool((out.logits.cpu()[~valid] == 0).all())
+    # same through the protein encoder instead of pre-computed embeddings, and without materialising the logits
+    out2 = model(ids, attention_mask=mask, labels=labels, seq=g["seqs"], return_logits=False)
+    assert out2.logits is None and abs(float(out2.loss) - float(g["loss"])) <= 0.05
+    # no labels -> no loss (HF returns loss=None)
+    assert model(ids, attention_mask=mask, seq=g["seqs"], return_logits=False).loss is None

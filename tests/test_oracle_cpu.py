@@ -139,3 +139,21 @@ def test_top_p_oracle_matches_hf_warpers():
         sc = TopPLogitsWarper(top_p=P)(None, TemperatureLogitsWarper(T)(None, lg.float()))
         assert torch.equal(torch.isfinite(sc), R.top_p_keep_mask(lg, T, P))
         assert torch.allclose(sc.softmax(-1), R.top_p_probs(lg, T, P))
+
+
+def test_scoring_oracle_matches_reference_forward_golden():
+    """oracle restatement of forward(labels=...) (right-padded splice, spliced labels, all-position logits, shifted
+    cross entropy) against the reference's own forward output pinned in tests/golden/score_small.pt."""
+    g, mm = _load("score_small.pt"), _load("mm_small.pt")
+    c = g["cfg"]
+    w = synth.llama_weights(c["n_layers"], c["dim"], c["n_q_heads"], c["n_kv_heads"], c["head_dim"], c["ffn_dim"],
+                            c["vocab"], seed=g["seed"])
+    ocfg = llama_ref.LlamaCfg(n_layers=c["n_layers"], dim=c["dim"], n_q_heads=c["n_q_heads"],
+                              n_kv_heads=c["n_kv_heads"], head_dim=c["head_dim"], ffn_dim=c["ffn_dim"], vocab=c["vocab"])
+    lab = mm_ref.splice_labels(g["input_ids"], g["attention_mask"], g["labels"])
+    assert torch.equal(lab, g["labels_spliced"])
+    e, m, _, _ = mm_ref.splice(g["input_ids"], g["attention_mask"], mm["soft"], w["model.embed_tokens.weight"], False)
+    pos = (m.long().cumsum(-1) - 1).masked_fill(~m, 1)
+    logits, _ = llama_ref.llama_forward(w, ocfg, e, m, pos, all_positions=True)
+    assert float((logits - g["logits"].float())[m].abs().max()) <= 0.05          # fixture logits are stored in bf16
+    assert abs(float(llama_ref.causal_lm_loss(logits, lab)) - float(g["loss"])) <= 1e-4
