@@ -100,7 +100,8 @@ int opus_rope_esm_bf16(void* qkv, const int32_t* pos, const float* cos_t, const 
  * qkv bf16 [n_tok, ld] = q heads | k heads | v heads; q,k rotated in place; k,v of token i written to cache slot
  * slot[i] (= block*block_size + offset; < 0 skips). Cache layout [blocks][n_kv_heads][block_size][head_dim] bf16.
  * If `partial` != NULL the row is first reduced from n_partial fp32 split-K partials [s][n_tok][ld].
- * Replaces HF DynamicCache.update (torch.cat per layer per step). cos/sin bf16 [max_pos, head_dim]. */
+ * Replaces HF DynamicCache.update (torch.cat per layer per step). cos/sin bf16 [max_pos, head_dim] built like HF's
+ * LlamaRotaryEmbedding, emb = cat(freqs, freqs): only columns [0, head_dim/2) are read, the upper half is its copy. */
 int opus_rope_llama_kvappend_bf16(void* qkv, const float* partial, int n_partial, const int32_t* pos,
                                   const int32_t* slot, const void* cos_t, const void* sin_t, void* kcache, void* vcache,
                                   int n_tok, int n_q_heads, int n_kv_heads, int head_dim, int ld, int block_size,

@@ -342,16 +342,16 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
   float o1[8], o2[8];
   if (!is_v) {
     const int p = pos[tok];
-    float c1[8], s1[8], c2[8], s2[8];
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(cos_t + (size_t)p * head_dim + j0), c1);
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(sin_t + (size_t)p * head_dim + j0), s1);
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(cos_t + (size_t)p * head_dim + half + j0), c2);
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(sin_t + (size_t)p * head_dim + half + j0), s2);
+    // HF builds the tables as cat(freqs, freqs): column j + half holds the same angle as column j, so one cos / sin
+    // load serves both halves (the table loads were 2/3 of this kernel's load instructions)
+    float c1[8], s1[8];
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(cos_t + (size_t)p * head_dim + j0)), c1);
+    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(sin_t + (size_t)p * head_dim + j0)), s1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       // first half: x1*cos + (-x2)*sin ; second half: x2*cos + x1*sin ; every op rounds to bf16 like torch
       o1[i] = bf16_round(bf16_round(x1[i] * c1[i]) + bf16_round(-x2[i] * s1[i]));
-      o2[i] = bf16_round(bf16_round(x2[i] * c2[i]) + bf16_round(x1[i] * s2[i]));
+      o2[i] = bf16_round(bf16_round(x2[i] * c1[i]) + bf16_round(x1[i] * s1[i]));
     }
   } else {
 #pragma unroll

@@ -78,13 +78,13 @@ void apply_prefetch(GemmArgs& a, const Prefetch* pf) {
   if (pf == nullptr || pf->w == nullptr || pf->depth <= 0) return;
   a.pf_w = pf->w; a.pf_rows = pf->rows; a.pf_K = pf->K; a.pf_split_k = pf->split_k; a.pf_depth = pf->depth;
 }
-// k-blocks to prefetch per work item for the decode chain; OPUS_PF=0 disables, OPUS_PF_<QKV|O|GU|DOWN|LM>=n overrides,
+// k-blocks to prefetch per work item for the decode chain (default 0 = off); OPUS_PF_<QKV|O|GU|DOWN|LM>=n overrides,
 // opus_set_tunable("pf_qkv", n) etc. changes them at run time (tools/bench_decode.py sweeps them).
 int g_pf_depth[5] = {-1, -1, -1, -1, -1};
 void pf_init() {
   if (g_pf_depth[0] >= 0) return;
   static const char* names[5] = {"OPUS_PF_QKV", "OPUS_PF_O", "OPUS_PF_GU", "OPUS_PF_DOWN", "OPUS_PF_LM"};
-  static const int defaults[5] = {64, 64, 16, 24, 16};
+  static const int defaults[5] = {0, 0, 0, 0, 0};  // measured: no gain at batch 64 (the launches are not HBM-starved)
   const char* off = std::getenv("OPUS_PF");
   const bool enabled = !(off != nullptr && off[0] == '0');
   for (int i = 0; i < 5; ++i) {
