@@ -38,6 +38,7 @@ struct GemmParams {
   // stream-K tail: the last sk_tiles output tiles (a partial wave) are cut along K into gridDim.x equal unit ranges.
   // A CTA whose range does not contain a tile's last k-block dumps its fp32 accumulator to sk_ws[cta]; the CTA that
   // does ("owner") waits on sk_cnt[tile], adds the partials in CTA order (deterministic) and runs the epilogue.
+  int tma_store;  // plain form, bf16 (+bias, +GELU) epilogue: tiles leave through shared memory + TMA stores
   int dp_items;   // work items walked round-robin (full tiles x split_k) before the stream-K tail
   int sk_tiles;
   float* sk_ws;

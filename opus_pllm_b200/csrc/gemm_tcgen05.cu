@@ -41,7 +41,9 @@ struct Cfg {
   static constexpr int STAGE = STAGE_A + STAGE_B;
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STORE_BYTES = 8 * 4096;  // epilogue staging: one [32 rows x 64 bf16] swizzled box per warp
+  static constexpr int BARS_OFF = STAGES * STAGE + STORE_BYTES;
+  static constexpr int SMEM = BARS_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 enum WorkKind : int { WORK_TILE = 0, WORK_SK_PARTIAL = 1, WORK_SK_OWNER = 2 };
@@ -247,8 +249,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 
 }
 
-// out-of-line activation functions for the small-footprint (decode-sized) epilogue: one copy of the expf / erff code
-__device__ __noinline__ float gelu_call(float x) { return gelu_erf(x); }
 
 // ---- transposed (swap-AB) epilogue: accumulator row = output feature `row`, column = batch row n -> out[n*ldo + row].
 // NC columns per call. It is instantiated with NC = 8 and driven by a ROLLED loop: a decode-sized launch executes this
@@ -302,7 +302,7 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       x[i] = v[i] + b;
-      if (gelu) x[i] = gelu_call(x[i]);
+      if (gelu) x[i] = gelu_erf(x[i]);
     }
     // M (features) is even and tiles start at multiples of 128, so a lane pair is either fully valid or fully invalid
     const int nv = (row | 1) < p.M ? min(NC, p.N - col0) : 0;
@@ -339,7 +339,8 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
 // run the fused epilogue, dump a stream-K partial, or (owner) add the other CTAs' partials first.
 template <int BN>
 __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoord& tc, uint32_t tmem_base, int acc,
-                                              int quad, int lane, int chunk0, int epi_tid) {
+                                              int quad, int lane, int chunk0, int epi_tid,
+                                              const CUtensorMap* tm_out = nullptr, uint8_t* stage = nullptr) {
   const int lrow = quad * 32 + lane;  // accumulator row inside the tile
   const int row = tc.m * BM + lrow;
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
@@ -428,6 +429,48 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
         if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split);
       }
     }
+  } else if (p.tma_store && tm_out != nullptr && tc.kind == WORK_TILE) {
+    // bf16 (+bias, +GELU) tiles leave through shared memory: a thread owns one accumulator ROW, so direct stores put 32
+    // different 128-byte lines behind every store instruction (measured: the K = 1280 encoder GEMMs ran at the pace of
+    // their output bytes, 0.7 TB/s). Each warp packs a [32 rows x 64 columns] box into its own swizzled staging buffer
+    // and lane 0 hands it to the TMA unit, which writes whole lines and clips at the M / N edges.
+    uint8_t* my_stage = stage + (quad + 4 * chunk0) * 4096;
+    const uint32_t st_row = smem_u32(my_stage) + lane * 128;
+#pragma unroll 1
+    for (int gi = chunk0; gi < BN / 64; gi += 2) {
+      const int col0 = tc.n * BN + gi * 64;
+      if (col0 >= p.N) break;
+      uint32_t r[64];
+      tmem_ld_32x32(taddr + gi * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+      tmem_ld_32x32(taddr + gi * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+      tmem_ld_wait();
+      uint32_t pk[32];
+#pragma unroll
+      for (int g4 = 0; g4 < 16; ++g4) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && col0 + g4 * 4 + 4 <= p.N) b = *reinterpret_cast<const float4*>(p.bias + col0 + g4 * 4);
+        float v0 = __uint_as_float(r[g4 * 4]) + b.x, v1 = __uint_as_float(r[g4 * 4 + 1]) + b.y;
+        float v2 = __uint_as_float(r[g4 * 4 + 2]) + b.z, v3 = __uint_as_float(r[g4 * 4 + 3]) + b.w;
+        if (p.epi == EPI_BF16_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3); }
+        pk[g4 * 2] = pack_bf16x2(v0, v1);
+        pk[g4 * 2 + 1] = pack_bf16x2(v2, v3);
+      }
+      if (lane == 0) tma_store_wait_read();   // the previous box of this warp has left the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int ch = q ^ (lane & 7);          // SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ch * 16), "r"(pk[q * 4]), "r"(pk[q * 4 + 1]),
+                     "r"(pk[q * 4 + 2]), "r"(pk[q * 4 + 3])
+                     : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tm_out, my_stage, col0, tc.m * BM + quad * 32);
+        tma_store_commit();
+      }
+    }
   } else {
 #pragma unroll 1
     for (int c = chunk0; c < BN / 32; c += 2) {
@@ -462,12 +505,13 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const __grid_constant__ CUtensorMap tmap_pf, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_pf, const __grid_constant__ CUtensorMap tmap_out,
+                         const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BARS_OFF);
   uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * C::STAGES;     // [2]       MMA -> epilogue
@@ -593,11 +637,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int it = 0; get_work(p, it, tc); ++it) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_item<BN>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid);
+      epilogue_item<BN>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out,
+                        smem + C::STAGES * C::STAGE);
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();   // the staging buffers die with the CTA
   }
 
   tc_fence_before();
@@ -744,7 +790,7 @@ gemm_chain_tcgen05_kernel(const __grid_constant__ ChainTmaps tm, const __grid_co
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BARS_OFF);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + C::STAGES;
   uint64_t* acc_full = bars + 2 * C::STAGES;
@@ -982,7 +1028,12 @@ int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, cons
     rc = make_tmap_bf16(&tp, pf.pf_w, pf.pf_rows, pf.pf_K, pf.pf_K, BM);
     if (rc) return rc;
   }
-  const cudaError_t le = launch_pdl(p.transposed != 0, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, p);
+  CUtensorMap to = ta;  // unused unless p.tma_store
+  if (p.tma_store) {
+    rc = make_tmap_bf16(&to, p.out, p.M, p.N, p.ldo, 32);   // box = 32 rows x 64 columns, one per epilogue warp
+    if (rc) return rc;
+  }
+  const cudaError_t le = launch_pdl(p.transposed != 0, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, to, p);
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -1108,6 +1159,14 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     const int items = ((a.pf_rows + BM - 1) / BM) * p.pf_split_k;
     p.pf_items = items < num_sms() ? items : num_sms();  // first wave of the next launch
   }
+
+  static int tma_store_on = -1;
+  if (tma_store_on < 0) {
+    const char* e = std::getenv("OPUS_TMA_STORE");
+    tma_store_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  p.tma_store = tma_store_on && !a.transposed && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU) && (a.ldo % 8) == 0 &&
+                (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && bn >= 64;
 
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   p.dp_items = tiles;
