@@ -166,11 +166,23 @@ rmsnorm_bf16_kernel(const __nv_bfloat16* x,                            // [rows,
         float v[8];
         if (partial != nullptr) {
           float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int s = 0; s < n_partial; ++s) {
-            const float* pp = partial + (size_t)s * rows * cols + off;
-            const float4 a = ld4(pp), b = ld4(pp + 4);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+          // four slices per round: all eight loads are in flight before the first add (one L2 round trip instead of
+          // n_partial); the adds keep the slice order, so the result is unchanged
+          for (int s0 = 0; s0 < n_partial; s0 += 4) {
+            float4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool ok = s0 + u < n_partial;
+              const float* pp = partial + (size_t)(ok ? s0 + u : s0) * rows * cols + off;
+              a[u] = ld4(pp); b[u] = ld4(pp + 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (s0 + u < n_partial) {
+                acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+                acc[4] += b[u].x; acc[5] += b[u].y; acc[6] += b[u].z; acc[7] += b[u].w;
+              }
+            }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = bf16_round(acc[j]);
@@ -325,11 +337,23 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
   if (partial != nullptr) {
     const size_t off = (size_t)tok * ld + (size_t)hsel * head_dim;
     float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int s = 0; s < n_partial; ++s) {
-      const float* pp = partial + (size_t)s * n_tok * ld + off;
-      const float4 t1 = ld4(pp + j0), t2 = ld4(pp + j0 + 4), t3 = ld4(pp + half + j0), t4 = ld4(pp + half + j0 + 4);
-      a[0] += t1.x; a[1] += t1.y; a[2] += t1.z; a[3] += t1.w; a[4] += t2.x; a[5] += t2.y; a[6] += t2.z; a[7] += t2.w;
-      b[0] += t3.x; b[1] += t3.y; b[2] += t3.z; b[3] += t3.w; b[4] += t4.x; b[5] += t4.y; b[6] += t4.z; b[7] += t4.w;
+    for (int s0 = 0; s0 < n_partial; s0 += 3) {   // three slices per round, loads first (see rmsnorm_bf16_kernel)
+      float4 t1[3], t2[3], t3[3], t4[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const bool ok = s0 + u < n_partial;
+        const float* pp = partial + (size_t)(ok ? s0 + u : s0) * n_tok * ld + off;
+        t1[u] = ld4(pp + j0); t2[u] = ld4(pp + j0 + 4); t3[u] = ld4(pp + half + j0); t4[u] = ld4(pp + half + j0 + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        if (s0 + u < n_partial) {
+          a[0] += t1[u].x; a[1] += t1[u].y; a[2] += t1[u].z; a[3] += t1[u].w;
+          a[4] += t2[u].x; a[5] += t2[u].y; a[6] += t2[u].z; a[7] += t2[u].w;
+          b[0] += t3[u].x; b[1] += t3[u].y; b[2] += t3[u].z; b[3] += t3[u].w;
+          b[4] += t4[u].x; b[5] += t4[u].y; b[6] += t4[u].z; b[7] += t4[u].w;
+        }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x1[i] = bf16_round(a[i]); x2[i] = bf16_round(b[i]); }
