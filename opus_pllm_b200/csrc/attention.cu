@@ -506,10 +506,11 @@ int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcac
   const int smem = DEC_WARPS * 4 * DEC_PANEL + DEC_WARPS * group * (DEC_D + 2) * 4;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(attn_decode_paged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(attn_decode_paged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(attn_decode_paged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(attn_decode_paged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    auto bytes_for = [](int g) { return DEC_WARPS * 4 * DEC_PANEL + DEC_WARPS * g * (DEC_D + 2) * 4; };
+    cudaFuncSetAttribute(attn_decode_paged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(1));
+    cudaFuncSetAttribute(attn_decode_paged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(2));
+    cudaFuncSetAttribute(attn_decode_paged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(4));
+    cudaFuncSetAttribute(attn_decode_paged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(8));
     configured = true;
   }
   switch (group) {

@@ -95,7 +95,75 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// keys of block j that exist, rounded up to the UMMA N / K granularity: the tail block of a sequence is computed narrow
+// (S = Q K^T with N = nk, O += P V over nk keys) instead of as a full 128-key block
+__device__ __forceinline__ int block_keys(int len, int j) { return min(TBN, ((len - j * TBN + 15) >> 4) << 4); }
+
+// Softmax of one row over NC (= 128, or 32 for narrow tail blocks) S columns: S -> registers, mask, row maximum, lazy
+// reference-maximum update, exp2, row sum, bf16 P written back over S. Returns whether O must be rescaled by `corr`.
+template <int NC, bool CAUSAL>
+__device__ __forceinline__ bool softmax_block(uint32_t t_s, int k0, int len, int qrow, int qt0, float scale_log2,
+                                              bool first, float& m_run, float& l_run, float& corr) {
+  uint32_t s[NC];
+#pragma unroll
+  for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+  tmem_ld_wait();
+  const bool need_mask = (k0 + NC > len) || (CAUSAL && k0 + NC - 1 > qt0);
+  if (need_mask) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int key = k0 + i;
+      const bool ok = key < len && (!CAUSAL || key <= qrow);
+      if (!ok) s[i] = 0xff800000u;  // -inf
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NC; i += 4) {
+    mx0 = fmaxf(mx0, __uint_as_float(s[i]));
+    mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
+    mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
+    mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
+  }
+  const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+  // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
+  corr = 1.0f;
+  bool rescale = false;
+  if (m_blk > m_run + kRescaleThreshold) {   // also true for the first block (m_run = -inf)
+    corr = exp2f(m_run - m_blk);             // 0 when m_run = -inf
+    rescale = !first;
+    m_run = m_blk;
+  }
+  const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+  float ls0 = 0.f, ls1 = 0.f;
+  uint32_t pk[NC / 2];
+#pragma unroll
+  for (int i = 0; i < NC; i += 2) {
+    const float p0 = exp2f(fmaf(__uint_as_float(s[i]), scale_log2, -m_use));
+    const float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), scale_log2, -m_use));
+    ls0 += p0;
+    ls1 += p1;
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+  }
+  l_run = l_run * corr + (ls0 + ls1);
+  if constexpr (NC == 128) {
+    tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+    tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+  } else {
+    tmem_st_32x16(t_s, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+  }
+  return rescale;
+}
 
 // One unit of work: two adjacent 128-row query tiles of one (sequence, head).
 struct Item {
@@ -124,7 +192,9 @@ __device__ __forceinline__ Item get_item(const AttnTcParams& p, int w) {
   return it;
 }
 
-template <int D, bool CAUSAL>
+// NARROW: tail key blocks are computed with N = K-extent = the keys that exist (worth it for short sequences such as the
+// 258-token encoder batch, where the third block holds 2 keys; it costs ~8 % on long sequences, so the host picks).
+template <int D, bool CAUSAL, bool NARROW>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const AttnTcParams p) {
@@ -206,11 +276,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = idesc_bf16(TBM, TBN, 0);
       constexpr uint32_t idesc_o = idesc_bf16(TBM, D, 1);
       uint32_t kc = 0, vc = 0, qc = 0, pc[2] = {0, 0};
-      auto issue_s = [&](int x, uint32_t ks) {
+      auto issue_s = [&](int x, uint32_t ks, int nk) {   // nk = keys of the block (multiple of 16) = UMMA N
         const uint32_t aq = smem_u32(sQ + x * C::TILE_BYTES), bk = smem_u32(sK + ks * C::TILE_BYTES);
+        const uint32_t idesc_s = idesc_bf16(TBM, (uint32_t)nk, 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * PANEL + (kk & 3) * 32;
@@ -228,8 +298,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         mbar_wait(&k_full[kc % C::KS], (kc / C::KS) & 1);
         tc_fence_after();
         // S_X(0) overwrites P_X of the previous item: ordered after that item's last PV MMA (same issuing thread)
-        issue_s(0, kc % C::KS);
-        if (it.n_b > 0) issue_s(1, kc % C::KS);
+        issue_s(0, kc % C::KS, NARROW ? block_keys(it.len, 0) : TBN);
+        if (it.n_b > 0) issue_s(1, kc % C::KS, NARROW ? block_keys(it.len, 0) : TBN);
         umma_commit(&k_empty[kc % C::KS]);
         ++kc;
         if (it.n_max == 1) umma_commit(q_empty);
@@ -244,11 +314,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             ++pc[x];
             tc_fence_after();
             const uint32_t bv = smem_u32(sV + vs * C::TILE_BYTES);
+            const int ksteps = NARROW ? (block_keys(it.len, j) >> 4) : (TBN / 16);
 #pragma unroll
             for (int kk = 0; kk < TBN / 16; ++kk) {
               // P: 16 keys = 8 packed columns per step; V: 16 key rows = two 8-row swizzle groups (2048 B) per step
-              umma_bf16_ts(tmem_base + C::COL_O + x * D, tmem_base + C::COL_S + x * TBN + kk * 8,
-                           umma_desc_mn_sw128(bv + kk * 2048, PANEL, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+              if (kk < ksteps)
+                umma_bf16_ts(tmem_base + C::COL_O + x * D, tmem_base + C::COL_S + x * TBN + kk * 8,
+                             umma_desc_mn_sw128(bv + kk * 2048, PANEL, 1024), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
             }
             umma_commit(&o_done[x]);
             if (j + 1 < n_x[x]) {
@@ -257,7 +329,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                 tc_fence_after();
                 k_ready = true;
               }
-              issue_s(x, ks1);   // overwrites S_X / P_X(j): ordered after the PV MMAs above
+              issue_s(x, ks1, NARROW ? block_keys(it.len, j + 1) : TBN);   // overwrites S_X / P_X(j): ordered after the PV MMAs above
             }
           }
           umma_commit(&v_empty[vs]);
@@ -294,50 +366,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         const int k0 = j * TBN;
         mbar_wait(&s_full[x], g & 1);
         tc_fence_after();
-        uint32_t s[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-        tmem_ld_wait();
-        const bool need_mask = (k0 + TBN > len) || (CAUSAL && k0 + TBN - 1 > qt0);
-        if (need_mask) {
-#pragma unroll
-          for (int i = 0; i < 128; ++i) {
-            const int key = k0 + i;
-            const bool ok = key < len && (!CAUSAL || key <= qrow);
-            if (!ok) s[i] = 0xff800000u;  // -inf
-          }
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
-        }
-        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
-        // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
-        float corr = 1.0f;
-        bool rescale = false;
-        if (m_blk > m_run + kRescaleThreshold) {   // also true for the first block (m_run = -inf)
-          corr = exp2f(m_run - m_blk);             // 0 when m_run = -inf
-          rescale = j > 0;
-          m_run = m_blk;
-        }
-        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-        float ls0 = 0.f, ls1 = 0.f;
-        uint32_t pk[64];
-#pragma unroll
-        for (int i = 0; i < 128; i += 2) {
-          const float p0 = exp2f(fmaf(__uint_as_float(s[i]), p.scale_log2, -m_use));
-          const float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -m_use));
-          ls0 += p0;
-          ls1 += p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        l_run = l_run * corr + (ls0 + ls1);
-        tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-        tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+        float corr;
+        const bool rescale = (NARROW && block_keys(len, j) <= 32)
+                                 ? softmax_block<32, CAUSAL>(t_s, k0, len, qrow, qt0, p.scale_log2, j == 0, m_run, l_run, corr)
+                                 : softmax_block<128, CAUSAL>(t_s, k0, len, qrow, qt0, p.scale_log2, j == 0, m_run, l_run, corr);
         if (j > 0) {
           // O_X must include block j-1 before it may be rescaled / before PV(j) accumulates on top of it
           mbar_wait(&o_done[x], (g - 1) & 1);
@@ -424,13 +456,13 @@ int make_map(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uin
              : OPUS_ERR_TMAP;
 }
 
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, bool NARROW>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int n_seqs,
               int max_len, int n_q_heads, cudaStream_t st) {
   using C = TcCfg<D>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<D, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
+    if (cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<D, CAUSAL, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
         cudaSuccess)
       return OPUS_ERR_CUDA;
     configured = true;
@@ -440,7 +472,7 @@ int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   dim3 grid(p.n_items < sms ? p.n_items : sms);
   const cudaError_t le =
-      launch_pdl(false, attn_fwd_tcgen05_kernel<D, CAUSAL>, grid, dim3(TC_THREADS), C::SMEM, st, tq, tk, tv, p);
+      launch_pdl(false, attn_fwd_tcgen05_kernel<D, CAUSAL, NARROW>, grid, dim3(TC_THREADS), C::SMEM, st, tq, tk, tv, p);
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -471,10 +503,16 @@ int attn_varlen_tc(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int 
   p.n_seqs = n_seqs; p.n_q_heads = n_q_heads;
   p.n_mblk = (max_len + 2 * TBM - 1) / (2 * TBM);
   p.n_items = p.n_mblk * n_seqs * n_q_heads;
-  if (head_dim == 128 && causal) return launch_tc<128, true>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);
-  if (head_dim == 128 && !causal) return launch_tc<128, false>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);
-  if (head_dim == 64 && causal) return launch_tc<64, true>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);
-  if (head_dim == 64 && !causal) return launch_tc<64, false>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);
+  const bool narrow = max_len <= 384;
+#define OPUS_TC_CASE(HD, C)                                                                                     \
+  if (head_dim == HD && (causal != 0) == C)                                                                     \
+    return narrow ? launch_tc<HD, C, true>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st)                      \
+                  : launch_tc<HD, C, false>(tq, tk, tv, p, n_seqs, max_len, n_q_heads, st);
+  OPUS_TC_CASE(128, true)
+  OPUS_TC_CASE(128, false)
+  OPUS_TC_CASE(64, true)
+  OPUS_TC_CASE(64, false)
+#undef OPUS_TC_CASE
   return OPUS_ERR_ARG;
 }
 
