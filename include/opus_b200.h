@@ -289,7 +289,9 @@ int opus_release_graphs(void);
  * for which a swap-AB GEMM cuts its last wave along K (0 = off); "streamk_plain" = 1 enables the same for the plain
  * form (off by default: it would make a token's rounding depend on its position in the batch); "decode_fused" = 1
  * runs o_proj -> norm -> gate/up -> down -> norm -> next qkv / lm_head of a decode step as one persistent chain kernel,
- * 0 (default) = one kernel per GEMM / norm; "chain_l2_depth" = k-blocks the chain kernel prefetches into L2 per phase.
+ * 0 (default) = one kernel per GEMM / norm; "chain_l2_depth" = k-blocks the chain kernel prefetches into L2 per phase;
+ * "tma_store" = 0 sends the plain bf16 / GELU GEMM epilogues back to direct row-per-thread stores (and the encoder's rotary
+ * embedding back to its own kernel).
  * Drops cached graphs. */
 int opus_set_tunable(const char* name, int value);
 /* Profiling aid: between opus_trace_begin(stream) and opus_trace_end the composite forwards record a CUDA event after

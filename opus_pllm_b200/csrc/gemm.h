@@ -39,6 +39,13 @@ struct GemmParams {
   // A CTA whose range does not contain a tile's last k-block dumps its fp32 accumulator to sk_ws[cta]; the CTA that
   // does ("owner") waits on sk_cnt[tile], adds the partials in CTA order (deterministic) and runs the epilogue.
   int tma_store;  // plain form, bf16 (+bias, +GELU) epilogue: tiles leave through shared memory + TMA stores
+  // ESM rotary fused into that epilogue (head_dim 64 = one 64-column store box): columns [0, rope_cols) are rotated with
+  // the row's position, columns [0, rope_q_cols) are scaled by rope_q_scale first (q <- rope(q * hd^-0.5), k <- rope(k))
+  const int* rope_pos;
+  const float* rope_cos;   // fp32 [max_pos, 32]
+  const float* rope_sin;
+  int rope_cols, rope_q_cols;
+  float rope_q_scale;
   int dp_items;   // work items walked round-robin (full tiles x split_k) before the stream-K tail
   int sk_tiles;
   float* sk_ws;
@@ -71,7 +78,15 @@ struct GemmArgs {
   // this kernel drains, the small kernels in between run, and the next GEMM ramps up.
   const void* pf_w;
   int pf_rows, pf_K, pf_split_k, pf_depth;
+  // Optional fused ESM rotary (see GemmParams); honoured only when gemm_fuses_rope(args) is true
+  const int* rope_pos;
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_cols, rope_q_cols;
+  float rope_q_scale;
 };
+// true when gemm_bf16 will apply the rope_* fields of `a` in its epilogue (plain form, EPI_BF16, TMA-store path)
+bool gemm_fuses_rope(const GemmArgs& a);
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);
 
@@ -105,6 +120,7 @@ int gemm_pick_bn(int N, int transposed);
 int gemm_pick_split_k(int M, int N, int K, int bn);
 size_t gemm_workspace_bytes(int M, int N, int split_k);
 void gemm_set_streamk_fill(int percent);  // 0 disables the stream-K tail
-void gemm_set_streamk_plain(int on);     // stream-K tail in the plain (non swap-AB) form, off by default
+void gemm_set_streamk_plain(int on);
+void gemm_set_tma_store(int on);          // TMA-store epilogue (and the rotary fusion that rides on it)     // stream-K tail in the plain (non swap-AB) form, off by default
 
 }  // namespace opus

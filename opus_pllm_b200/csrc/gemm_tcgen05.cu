@@ -337,7 +337,7 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
 
 // Epilogue of one work item by the 8 epilogue warps: drain the accumulator buffer `acc` (TMEM -> registers) and either
 // run the fused epilogue, dump a stream-K partial, or (owner) add the other CTAs' partials first.
-template <int BN>
+template <int BN, bool TR>
 __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoord& tc, uint32_t tmem_base, int acc,
                                               int quad, int lane, int chunk0, int epi_tid,
                                               const CUtensorMap* tm_out = nullptr, uint8_t* stage = nullptr) {
@@ -360,7 +360,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
     }
     named_bar_sync(1, NUM_EPI_THREADS);
   }
-  if (p.transposed) {
+  if constexpr (TR) {
     // Owner fix-up, decode-sized tiles: the partial sums of ALL column groups of this thread are requested at once per
     // contributing CTA (one L2 round trip per contributor instead of one per group), summed in CTA order.
     constexpr int NG = BN / 16;                 // 8-column groups per warp (the two warps of a quadrant interleave)
@@ -429,7 +429,8 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
         if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split);
       }
     }
-  } else if (p.tma_store && tm_out != nullptr && tc.kind == WORK_TILE) {
+  } else {
+  if (p.tma_store && tm_out != nullptr && tc.kind == WORK_TILE) {
     // bf16 (+bias, +GELU) tiles leave through shared memory: a thread owns one accumulator ROW, so direct stores put 32
     // different 128-byte lines behind every store instruction (measured: the K = 1280 encoder GEMMs ran at the pace of
     // their output bytes, 0.7 TB/s). Each warp packs a [32 rows x 64 columns] box into its own swizzled staging buffer
@@ -454,6 +455,35 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
         if (p.epi == EPI_BF16_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3); }
         pk[g4 * 2] = pack_bf16x2(v0, v1);
         pk[g4 * 2 + 1] = pack_bf16x2(v2, v3);
+      }
+      if (p.rope_cos != nullptr && col0 < p.rope_cols) {
+        // fused ESM rotary: this thread holds the whole 64-wide head of its token. Same arithmetic as rope_esm_kernel:
+        // x = bf16(acc + bias) (the value the unfused path stores), scaled, rotated in fp32, rounded once.
+        const int pos = row < p.M ? p.rope_pos[row] : 0;
+        const float sc = col0 < p.rope_q_cols ? p.rope_q_scale : 1.0f;
+        const float4* ct = reinterpret_cast<const float4*>(p.rope_cos + (size_t)pos * 32);
+        const float4* st4 = reinterpret_cast<const float4*>(p.rope_sin + (size_t)pos * 32);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 c4 = __ldg(ct + g4), s4 = __ldg(st4 + g4);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+          const __nv_bfloat162* lo = reinterpret_cast<const __nv_bfloat162*>(&pk[g4 * 2]);
+          const __nv_bfloat162* hi = reinterpret_cast<const __nv_bfloat162*>(&pk[16 + g4 * 2]);
+          const float2 l0 = __bfloat1622float2(lo[0]), l1 = __bfloat1622float2(lo[1]);
+          const float2 h0 = __bfloat1622float2(hi[0]), h1 = __bfloat1622float2(hi[1]);
+          const float x1[4] = {l0.x * sc, l0.y * sc, l1.x * sc, l1.y * sc};
+          const float x2[4] = {h0.x * sc, h0.y * sc, h1.x * sc, h1.y * sc};
+          float o1[4], o2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o1[i] = x1[i] * cc[i] - x2[i] * ss[i];
+            o2[i] = x2[i] * cc[i] + x1[i] * ss[i];
+          }
+          pk[g4 * 2] = pack_bf16x2(o1[0], o1[1]);
+          pk[g4 * 2 + 1] = pack_bf16x2(o1[2], o1[3]);
+          pk[16 + g4 * 2] = pack_bf16x2(o2[0], o2[1]);
+          pk[16 + g4 * 2 + 1] = pack_bf16x2(o2[2], o2[3]);
+        }
       }
       if (lane == 0) tma_store_wait_read();   // the previous box of this warp has left the staging buffer
       __syncwarp();
@@ -493,6 +523,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
       if (col0 < p.N) epilogue_chunk(p, r, row, col0, tc.split);
     }
   }
+  }  // plain form
   if (tc.kind == WORK_SK_PARTIAL) {
     named_bar_sync(1, NUM_EPI_THREADS);   // every thread's partial stores happen-before thread 0's fence + release
     if (epi_tid == 0) {
@@ -502,7 +533,9 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
   }
 }
 
-template <int BN>
+// TR = swap-AB ("transposed") form. The two forms are separate instantiations so that a decode-sized launch does not carry
+// the plain form's epilogues in its instruction stream (and vice versa).
+template <int BN, bool TR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_pf, const __grid_constant__ CUtensorMap tmap_out,
@@ -557,13 +590,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int i = 0; i < pre; ++i) {
           uint8_t* sa = smem + i * C::STAGE;
           mbar_arrive_expect_tx(&full_bar[i], C::STAGE);
-          if (p.transposed) tma_load_2d_hint(sa, &tmap_a, &full_bar[i], (tc.kb_begin + i) * BK, tc.m * BM, p.hint_a);
+          if (TR) tma_load_2d_hint(sa, &tmap_a, &full_bar[i], (tc.kb_begin + i) * BK, tc.m * BM, p.hint_a);
           else tma_load_2d_hint(sa + C::STAGE_A, &tmap_b, &full_bar[i], (tc.kb_begin + i) * BK, tc.n * BN, p.hint_b);
         }
         grid_dep_wait();
         for (int i = 0; i < pre; ++i) {
           uint8_t* sa = smem + i * C::STAGE;
-          if (p.transposed) tma_load_2d_hint(sa + C::STAGE_A, &tmap_b, &full_bar[i], (tc.kb_begin + i) * BK, tc.n * BN, p.hint_b);
+          if (TR) tma_load_2d_hint(sa + C::STAGE_A, &tmap_b, &full_bar[i], (tc.kb_begin + i) * BK, tc.n * BN, p.hint_b);
           else tma_load_2d_hint(sa, &tmap_a, &full_bar[i], (tc.kb_begin + i) * BK, tc.m * BM, p.hint_a);
         }
         if (pre == C::STAGES) { stage = 0; phase = 1; } else { stage = pre; }
@@ -637,7 +670,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int it = 0; get_work(p, it, tc); ++it) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_item<BN>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out,
+      epilogue_item<BN, TR>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out,
                         smem + C::STAGES * C::STAGE);
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
@@ -928,7 +961,7 @@ gemm_chain_tcgen05_kernel(const __grid_constant__ ChainTmaps tm, const __grid_co
           mbar_wait(&acc_full[acc], acc_phase);
           tc_fence_after();
           if (epi_tid == 0) chain_stamp(prog, ph, it == 0 ? 1 : 3);   // [3] = last item's accumulator ready
-          epilogue_item<BN>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid);
+          epilogue_item<BN, true>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid);
           tc_fence_before();
           mbar_arrive(&acc_empty[acc]);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1013,8 +1046,10 @@ int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, cons
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
+            cudaSuccess)
       return OPUS_ERR_CUDA;
     configured = true;
   }
@@ -1033,7 +1068,9 @@ int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, cons
     rc = make_tmap_bf16(&to, p.out, p.M, p.N, p.ldo, 32);   // box = 32 rows x 64 columns, one per epilogue warp
     if (rc) return rc;
   }
-  const cudaError_t le = launch_pdl(p.transposed != 0, gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, to, p);
+  const cudaError_t le =
+      p.transposed ? launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, to, p)
+                   : launch_pdl(false, gemm_bf16_tcgen05_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, to, p);
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -1080,10 +1117,12 @@ int g_sk_max_fill = 90;  // use the stream-K tail when the partial wave fills <=
 // not depend on where it sits in the batch (bitwise batch invariance); the tail is opt-in there. In the swap-AB form the
 // tiles partition the FEATURES, every batch row is treated alike, and the tail is on by default.
 int g_sk_plain = 0;
+int g_tma_store_on = -1;  // plain bf16 / GELU epilogues through shared memory + TMA stores (OPUS_TMA_STORE=0 disables)
 
 }  // namespace
 
 void gemm_set_streamk_fill(int percent) { g_sk_max_fill = percent; }
+void gemm_set_tma_store(int on) { g_tma_store_on = on != 0; }
 void gemm_set_streamk_plain(int on) { g_sk_plain = on; }
 
 int gemm_pick_bn(int N, int transposed) {
@@ -1160,13 +1199,19 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     p.pf_items = items < num_sms() ? items : num_sms();  // first wave of the next launch
   }
 
-  static int tma_store_on = -1;
-  if (tma_store_on < 0) {
+  if (g_tma_store_on < 0) {
     const char* e = std::getenv("OPUS_TMA_STORE");
-    tma_store_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_tma_store_on = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  p.tma_store = tma_store_on && !a.transposed && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU) && (a.ldo % 8) == 0 &&
+  p.tma_store = g_tma_store_on && !a.transposed && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU) && (a.ldo % 8) == 0 &&
                 (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && bn >= 64;
+  if (a.rope_cos != nullptr) {
+    if (!(p.tma_store && a.epi == EPI_BF16 && a.rope_pos != nullptr && a.rope_sin != nullptr && (a.rope_cols % 64) == 0 &&
+          (a.rope_q_cols % 64) == 0))
+      return OPUS_ERR_ARG;   // callers check gemm_fuses_rope() first
+    p.rope_pos = a.rope_pos; p.rope_cos = a.rope_cos; p.rope_sin = a.rope_sin;
+    p.rope_cols = a.rope_cols; p.rope_q_cols = a.rope_q_cols; p.rope_q_scale = a.rope_q_scale;
+  }
 
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   p.dp_items = tiles;
@@ -1182,6 +1227,16 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     p.sk_cnt = g_sk.cnt;
   }
   return OPUS_OK;
+}
+
+bool gemm_fuses_rope(const GemmArgs& a) {
+  GemmParams p;
+  int bn = 0;
+  GemmArgs probe = a;
+  probe.rope_cos = nullptr;
+  if (prepare_gemm(probe, p, bn) != OPUS_OK) return false;
+  return p.tma_store && a.epi == EPI_BF16 && a.rope_pos != nullptr && a.rope_cos != nullptr && a.rope_sin != nullptr &&
+         (a.rope_cols % 64) == 0 && (a.rope_q_cols % 64) == 0;
 }
 
 // D = epi(A * B^T). See gemm.h for the contract.

@@ -181,8 +181,26 @@ int esm2_forward(const opus_esm2_model* m, const opus_esm2_workspace* ws, const 
   for (int l = 0; l < m->n_layers; ++l) {
     const opus_esm2_layer& L = m->layers[l];
     OPUS_TRY(layernorm_f32_bf16(ws->x, pending, L.ln1_g, L.ln1_b, xn, n_tok, d, m->ln_eps, st));
-    OPUS_TRY(linear(xn, n_tok, L.wqkv, 3 * d, d, EPI_BF16, qkv, 3 * d, L.bqkv, nullptr, 0, nullptr, 0, st));
-    OPUS_TRY(rope_esm(qkv, pos, m->rope_cos, m->rope_sin, n_tok, m->n_heads, hd, 3 * d, 0.125f, st));
+    {
+      // q|k|v projection with the rotary embedding applied in the GEMM epilogue (a 64-wide head is exactly one store box
+      // of the row-owning epilogue thread); the separate RoPE kernel remains for shapes the fused path does not take
+      GemmArgs a{};
+      a.transposed = 0;
+      a.A = xn; a.lda = d; a.M = n_tok;
+      a.B = L.wqkv; a.ldb = d; a.N = 3 * d;
+      a.K = d;
+      a.epi = EPI_BF16;
+      a.out = qkv; a.ldo = 3 * d;
+      a.bias = L.bqkv;
+      a.rope_pos = pos; a.rope_cos = m->rope_cos; a.rope_sin = m->rope_sin;
+      a.rope_cols = 2 * d; a.rope_q_cols = d; a.rope_q_scale = 0.125f;
+      if (n_tok > 256 && gemm_fuses_rope(a)) {
+        OPUS_TRY(gemm_bf16(a, st));
+      } else {
+        OPUS_TRY(linear(xn, n_tok, L.wqkv, 3 * d, d, EPI_BF16, qkv, 3 * d, L.bqkv, nullptr, 0, nullptr, 0, st));
+        OPUS_TRY(rope_esm(qkv, pos, m->rope_cos, m->rope_sin, n_tok, m->n_heads, hd, 3 * d, 0.125f, st));
+      }
+    }
     OPUS_TRY(attn_varlen(qkv, 3 * d, qkv + d, 3 * d, qkv + 2 * d, 3 * d, attn, d, cu_seqlens, n_seqs, n_tok, max_len,
                          m->n_heads, m->n_heads, hd, 0, 1.0f, st));
     OPUS_TRY(linear(attn, n_tok, L.wo, d, d, EPI_BF16, xn, d, L.bo, nullptr, 0, nullptr, 0, st));
@@ -421,6 +439,10 @@ int set_tunable(const char* name, int value) {
   }
   if (std::strcmp(name, "decode_fused") == 0) {
     g_decode_fused = value != 0;
+    return release_graphs();
+  }
+  if (std::strcmp(name, "tma_store") == 0) {
+    gemm_set_tma_store(value);
     return release_graphs();
   }
   if (std::strcmp(name, "streamk_plain") == 0) {

@@ -56,6 +56,28 @@ def test_encoder_vs_oracle(n_layers, dim, heads, ffn, lens):
     assert enc.get_protein_seq_embeddings(seqs).dtype == torch.float32
 
 
+def test_encoder_fused_rope_epilogue_matches_separate_kernel():
+    """The q|k|v GEMM applies ESM's rotary embedding in its TMA-store epilogue; with the tunable off the same forward
+    runs the plain epilogue + rope_esm_kernel. Both must agree to bf16 rounding (one FMA contraction apart)."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.encoder import B200ProteinEncoder
+    n_layers, dim, heads, ffn = 3, 1280, 20, 5120
+    w = synth.esm2_weights(n_layers, dim, ffn, seed=21, device="cuda")
+    enc = B200ProteinEncoder(w, n_layers, dim, heads, ffn)
+    seqs = synth.proteins(5, 60, 300, seed=17)
+    lib = L.load()
+    try:
+        fused, _, hid_f, _ = enc.encode(seqs, want_hidden=True)
+        fused, hid_f = fused.clone(), hid_f.clone()
+        L.check(lib.opus_set_tunable(b"tma_store", 0))
+        plain, _, hid_p, _ = enc.encode(seqs, want_hidden=True)
+    finally:
+        L.check(lib.opus_set_tunable(b"tma_store", 1))
+    assert _cos(hid_f, hid_p) >= 0.99999 and float((fused - plain).abs().max()) <= 5e-3
+    want = esm2_ref.get_protein_seq_embeddings(w, seqs, n_layers, heads)
+    assert _cos(fused, want) >= 0.9995 and float((fused - want).abs().max()) <= 3e-2
+
+
 def test_encoder_padded_equals_varlen():
     """key-padding mask semantics: a sequence's embedding does not depend on what it is batched with."""
     from opus_pllm_b200.encoder import B200ProteinEncoder
