@@ -46,6 +46,17 @@ struct GemmParams {
   const float* rope_sin;
   int rope_cols, rope_q_cols;
   float rope_q_scale;
+  // Llama rotary + paged KV-cache append fused into the same epilogue (head_dim 128 = two store boxes; BN = 256 = two
+  // heads per tile, one per epilogue warp pair): heads [0, rl_hq) are q (rotated), the next rl_hkv are k (rotated, also
+  // written to kcache at slot[row]), the last rl_hkv are v (copied to vcache). Same rounding points as
+  // rope_llama_kvappend_kernel (HF apply_rotary_pos_emb in bf16).
+  const int* rl_pos;
+  const int* rl_slot;
+  const void* rl_cos;   // bf16 [max_pos, 128], cat(freqs, freqs)
+  const void* rl_sin;
+  void* rl_kcache;
+  void* rl_vcache;
+  int rl_hq, rl_hkv, rl_bs;
   int dp_items;   // work items walked round-robin (full tiles x split_k) before the stream-K tail
   int sk_tiles;
   float* sk_ws;
@@ -84,8 +95,16 @@ struct GemmArgs {
   const float* rope_sin;
   int rope_cols, rope_q_cols;
   float rope_q_scale;
+  // Optional fused Llama rotary + KV append (see GemmParams); honoured only when gemm_fuses_rope(args) is true
+  const int* rl_pos;
+  const int* rl_slot;
+  const void* rl_cos;
+  const void* rl_sin;
+  void* rl_kcache;
+  void* rl_vcache;
+  int rl_hq, rl_hkv, rl_bs;
 };
-// true when gemm_bf16 will apply the rope_* fields of `a` in its epilogue (plain form, EPI_BF16, TMA-store path)
+// true when gemm_bf16 will apply the rope_* / rl_* fields of `a` in its epilogue (plain form, EPI_BF16, TMA-store path)
 bool gemm_fuses_rope(const GemmArgs& a);
 
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream);

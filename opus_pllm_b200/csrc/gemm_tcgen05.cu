@@ -118,6 +118,16 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
   return true;
 }
 
+__device__ __forceinline__ void bf16x8_unpack(const uint4 q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
 // ---- epilogue for one 32-column chunk held by one thread (= one accumulator row) ----
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
   uint4 q;
@@ -437,6 +447,84 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
     // and lane 0 hands it to the TMA unit, which writes whole lines and clips at the M / N edges.
     uint8_t* my_stage = stage + (quad + 4 * chunk0) * 4096;
     const uint32_t st_row = smem_u32(my_stage) + lane * 128;
+    if constexpr (BN == 256) {
+      if (p.rl_cos != nullptr) {
+        // ---- Llama q|k|v projection: rotary embedding + paged KV append in the epilogue. This warp pair (chunk0)
+        // owns head 2n + chunk0 of the tile; a thread holds its token's 128 accumulator columns of that head.
+        const int head = tc.n * 2 + chunk0;
+        const int colh = head * 128;
+        if (colh < p.N) {
+          const bool ok_row = row < p.M;
+          const bool is_v = head >= p.rl_hq + p.rl_hkv;
+          const bool to_cache = head >= p.rl_hq;
+          const int pos = ok_row ? p.rl_pos[row] : 0;
+          const int sl = (ok_row && to_cache && p.rl_slot != nullptr) ? p.rl_slot[row] : -1;
+          const __nv_bfloat16* cos_t = static_cast<const __nv_bfloat16*>(p.rl_cos) + (size_t)pos * 128;
+          const __nv_bfloat16* sin_t = static_cast<const __nv_bfloat16*>(p.rl_sin) + (size_t)pos * 128;
+          __nv_bfloat16* cdst = nullptr;
+          if (sl >= 0) {
+            const int kvh = is_v ? head - p.rl_hq - p.rl_hkv : head - p.rl_hq;
+            const int blk = sl / p.rl_bs, off = sl - blk * p.rl_bs;
+            cdst = static_cast<__nv_bfloat16*>(is_v ? p.rl_vcache : p.rl_kcache) +
+                   (((size_t)blk * p.rl_hkv + kvh) * p.rl_bs + off) * 128;
+          }
+          const uint32_t th = taddr + chunk0 * 128;   // TMEM columns of this head
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t pk[32];
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {        // 16 rotation pairs per step keeps the live set small
+              uint32_t a1[16], a2[16];
+              tmem_ld_32x16(th + sub * 16, a1);        // columns j      (first half of the head)
+              tmem_ld_32x16(th + 64 + sub * 16, a2);   // columns j + 64 (second half)
+              tmem_ld_wait();
+              float cs[16], sn[16];
+              if (!is_v) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  bf16x8_unpack(__ldg(reinterpret_cast<const uint4*>(cos_t + sub * 16 + q * 8)), &cs[q * 8]);
+                  bf16x8_unpack(__ldg(reinterpret_cast<const uint4*>(sin_t + sub * 16 + q * 8)), &sn[q * 8]);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                float o[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const float x1 = bf16_round(__uint_as_float(a1[i + e]));   // the bf16 value the plain epilogue stores
+                  const float x2 = bf16_round(__uint_as_float(a2[i + e]));
+                  if (is_v) o[e] = half == 0 ? x1 : x2;
+                  else if (half == 0) o[e] = bf16_round(bf16_round(x1 * cs[i + e]) + bf16_round(-x2 * sn[i + e]));
+                  else o[e] = bf16_round(bf16_round(x2 * cs[i + e]) + bf16_round(x1 * sn[i + e]));
+                }
+                pk[sub * 8 + (i >> 1)] = pack_bf16x2(o[0], o[1]);
+              }
+            }
+            if (cdst != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(cdst + half * 64 + q * 8) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+            }
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int ch = q ^ (lane & 7);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ch * 16), "r"(pk[q * 4]),
+                           "r"(pk[q * 4 + 1]), "r"(pk[q * 4 + 2]), "r"(pk[q * 4 + 3])
+                           : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(tm_out, my_stage, colh + half * 64, tc.m * BM + quad * 32);
+              tma_store_commit();
+            }
+          }
+        }
+        return;
+      }
+    }
 #pragma unroll 1
     for (int gi = chunk0; gi < BN / 64; gi += 2) {
       const int col0 = tc.n * BN + gi * 64;
@@ -1205,6 +1293,14 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   }
   p.tma_store = g_tma_store_on && !a.transposed && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU) && (a.ldo % 8) == 0 &&
                 (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && bn >= 64;
+  if (a.rl_cos != nullptr) {
+    if (!(p.tma_store && a.epi == EPI_BF16 && bn == 256 && a.rl_pos != nullptr && a.rl_sin != nullptr && a.rl_bs > 0 &&
+          a.N == (a.rl_hq + 2 * a.rl_hkv) * 128 && a.bias == nullptr))
+      return OPUS_ERR_ARG;   // callers check gemm_fuses_rope() first
+    p.rl_pos = a.rl_pos; p.rl_slot = a.rl_slot; p.rl_cos = a.rl_cos; p.rl_sin = a.rl_sin;
+    p.rl_kcache = a.rl_kcache; p.rl_vcache = a.rl_vcache;
+    p.rl_hq = a.rl_hq; p.rl_hkv = a.rl_hkv; p.rl_bs = a.rl_bs;
+  }
   if (a.rope_cos != nullptr) {
     if (!(p.tma_store && a.epi == EPI_BF16 && a.rope_pos != nullptr && a.rope_sin != nullptr && (a.rope_cols % 64) == 0 &&
           (a.rope_q_cols % 64) == 0))
@@ -1234,7 +1330,11 @@ bool gemm_fuses_rope(const GemmArgs& a) {
   int bn = 0;
   GemmArgs probe = a;
   probe.rope_cos = nullptr;
+  probe.rl_cos = nullptr;
   if (prepare_gemm(probe, p, bn) != OPUS_OK) return false;
+  if (a.rl_cos != nullptr)
+    return p.tma_store && a.epi == EPI_BF16 && bn == 256 && a.rl_pos != nullptr && a.rl_sin != nullptr && a.rl_bs > 0 &&
+           a.N == (a.rl_hq + 2 * a.rl_hkv) * 128 && a.bias == nullptr;
   return p.tma_store && a.epi == EPI_BF16 && a.rope_pos != nullptr && a.rope_cos != nullptr && a.rope_sin != nullptr &&
          (a.rope_cols % 64) == 0 && (a.rope_q_cols % 64) == 0;
 }

@@ -266,10 +266,28 @@ int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus
     bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
     OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(L.ln1_w), xn, n_tok, d, m->rms_eps,
                           st));
-    OPUS_TRY(linear(xn, n_tok, L.wqkv, qkv_n, d, EPI_BF16, qkv, qkv_n, nullptr, nullptr, 0, nullptr, 0, st));
-    OPUS_TRY(rope_llama_kvappend(qkv, nullptr, 0, pos, slot, static_cast<const bf16*>(m->rope_cos),
-                                 static_cast<const bf16*>(m->rope_sin), kc, vc, n_tok, Hq, Hkv, hd, qkv_n,
-                                 kv->block_size, st));
+    {
+      // q|k|v projection with RoPE and the paged KV append applied in the GEMM epilogue (K = 4096 leaves the epilogue
+      // idle most of the time); the separate kernel remains for shapes the fused path does not take
+      GemmArgs a{};
+      a.transposed = 0;
+      a.A = xn; a.lda = d; a.M = n_tok;
+      a.B = L.wqkv; a.ldb = d; a.N = qkv_n;
+      a.K = d;
+      a.epi = EPI_BF16;
+      a.out = qkv; a.ldo = qkv_n;
+      a.rl_pos = pos; a.rl_slot = slot; a.rl_cos = m->rope_cos; a.rl_sin = m->rope_sin;
+      a.rl_kcache = kc; a.rl_vcache = vc;
+      a.rl_hq = Hq; a.rl_hkv = Hkv; a.rl_bs = kv->block_size;
+      if (n_tok > 256 && gemm_fuses_rope(a)) {
+        OPUS_TRY(gemm_bf16(a, st));
+      } else {
+        OPUS_TRY(linear(xn, n_tok, L.wqkv, qkv_n, d, EPI_BF16, qkv, qkv_n, nullptr, nullptr, 0, nullptr, 0, st));
+        OPUS_TRY(rope_llama_kvappend(qkv, nullptr, 0, pos, slot, static_cast<const bf16*>(m->rope_cos),
+                                     static_cast<const bf16*>(m->rope_sin), kc, vc, n_tok, Hq, Hkv, hd, qkv_n,
+                                     kv->block_size, st));
+      }
+    }
     OPUS_TRY(attn_varlen(qkv, qkv_n, qkv + Hq * hd, qkv_n, qkv + (Hq + Hkv) * hd, qkv_n, attn, Hq * hd, cu_seqlens,
                          n_seqs, n_tok, max_len, Hq, Hkv, hd, 1, scale, st));
     OPUS_TRY(linear(attn, n_tok, L.wo, d, Hq * hd, EPI_RES_BF16, h, d, nullptr, h, d, nullptr, 0, st));

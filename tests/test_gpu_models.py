@@ -195,6 +195,35 @@ def test_prefill_logits_vs_oracle(cfg, lens):
         assert _cos(got[b], want32[b]) >= 0.999
 
 
+@pytest.mark.parametrize("cfg,lens", [(SMALL, [140, 37, 129, 64]),
+                                      (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
+                                            ffn_dim=14336, vocab=8192), [300, 33, 200])])
+def test_prefill_fused_rope_kvappend_epilogue_is_bit_identical(cfg, lens):
+    """The prefill q|k|v GEMM rotates q/k and appends k/v to the paged cache in its epilogue; with the tunable off the
+    plain epilogue + rope_llama_kvappend_kernel run instead. Same rounding points -> identical logits and cache."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    w = synth.llama_weights(seed=9, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    emb = synth.weight((int(cu[-1]), cfg["dim"]), "prompt_embeds_rope", 0.02).cuda().to(torch.bfloat16)
+    plan = model.make_plan(cu, 2)
+    lib = L.load()
+    try:
+        model._k.zero_(); model._v.zero_()
+        fused = model.prefill(emb, plan=plan)["logits"].clone()
+        k_f, v_f = model._k.clone(), model._v.clone()
+        L.check(lib.opus_set_tunable(b"tma_store", 0))
+        model._k.zero_(); model._v.zero_()
+        plain = model.prefill(emb, plan=plan)["logits"].clone()
+        k_p, v_p = model._k.clone(), model._v.clone()
+    finally:
+        L.check(lib.opus_set_tunable(b"tma_store", 1))
+        model.release_plan(plan)
+    assert bool(k_p.abs().sum() > 0) and torch.equal(k_f, k_p) and torch.equal(v_f, v_p)
+    assert torch.equal(fused, plain)
+
+
 def test_greedy_decode_token_parity_peaked():
     """>= 99 % of prompts token-identical over 32 new tokens (north star), peaked-logit synthetic weights."""
     from opus_pllm_b200.llama import B200Llama
