@@ -43,7 +43,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
   static constexpr int STORE_BYTES = 8 * 4096;  // epilogue staging: one [32 rows x 64 bf16] swizzled box per warp
   static constexpr int BARS_OFF = STAGES * STAGE + STORE_BYTES;
-  static constexpr int SMEM = BARS_OFF + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM = BARS_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*epilogue bias slice*/;
 };
 
 enum WorkKind : int { WORK_TILE = 0, WORK_SK_PARTIAL = 1, WORK_SK_OWNER = 2 };
@@ -525,6 +525,15 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
         return;
       }
     }
+    // the tile's bias slice goes through shared memory once (one float per epilogue thread, BN <= 256): per-group global
+    // loads showed up as long-scoreboard stalls in front of every add (ncu source view)
+    float* s_bias = reinterpret_cast<float*>(stage + Cfg<BN>::STORE_BYTES) + 64;   // after the barriers (256 B)
+    if (p.bias != nullptr) {
+      named_bar_sync(2, NUM_EPI_THREADS);                       // the previous tile's readers are done
+      const int bc = tc.n * BN + epi_tid;
+      if (epi_tid < BN) s_bias[epi_tid] = bc < p.N ? __ldg(p.bias + bc) : 0.f;
+      named_bar_sync(2, NUM_EPI_THREADS);
+    }
 #pragma unroll 1
     for (int gi = chunk0; gi < BN / 64; gi += 2) {
       const int col0 = tc.n * BN + gi * 64;
@@ -537,7 +546,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
 #pragma unroll
       for (int g4 = 0; g4 < 16; ++g4) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && col0 + g4 * 4 + 4 <= p.N) b = *reinterpret_cast<const float4*>(p.bias + col0 + g4 * 4);
+        if (p.bias != nullptr) b = *reinterpret_cast<const float4*>(s_bias + gi * 64 + g4 * 4);
         float v0 = __uint_as_float(r[g4 * 4]) + b.x, v1 = __uint_as_float(r[g4 * 4 + 1]) + b.y;
         float v2 = __uint_as_float(r[g4 * 4 + 2]) + b.z, v3 = __uint_as_float(r[g4 * 4 + 3]) + b.w;
         if (p.epi == EPI_BF16_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3); }
