@@ -260,6 +260,23 @@ constexpr int DEC_BS = 16;   // tokens per KV block (cache page)
 constexpr int DEC_D = 128;   // head dim
 constexpr int DEC_PANEL = DEC_BS * DEC_D * 2;  // 4 KB
 
+__device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+
 struct DecodeParams {
   const __nv_bfloat16* q;  // [B, ldq], head h at column h*128 (already rotated)
   int ldq;
@@ -272,6 +289,18 @@ struct DecodeParams {
   int ldo;
   int n_kv_heads, group;
   float scale_log2;
+  // Optional fused prologue (decode): the q|k|v row of this step still sits in fp32 split-K partials. The CTA of
+  // (sequence, kv head) reduces ITS heads (GROUP query heads, one key head, one value head), applies RoPE with the
+  // rounding points of rope_llama_kvappend_kernel, writes q/k/v to `qkv` and k/v to the paged cache, then attends.
+  const float* partial;  // [n_partial][B][ldq] or nullptr (q / cache already final)
+  int n_partial;
+  __nv_bfloat16* qkv;    // == q base; written when partial != nullptr
+  const int* pos;
+  const int* slot;
+  const __nv_bfloat16* cos_t;  // bf16 [max_pos, 128], cat(freqs, freqs)
+  const __nv_bfloat16* sin_t;
+  __nv_bfloat16* kcache_w;
+  __nv_bfloat16* vcache_w;
 };
 
 __device__ __forceinline__ void load_panel_async(uint32_t smem_base, const __nv_bfloat16* panel, int lane) {
@@ -296,6 +325,63 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
   const int n_blocks = (ctx + DEC_BS - 1) / DEC_BS;
   const uint32_t s_warp = smem_u32(smem) + warp * (4 * DEC_PANEL);
   float* s_merge = reinterpret_cast<float*>(smem + DEC_WARPS * 4 * DEC_PANEL);  // [warps][GROUP][128+2]
+
+  if (p.partial != nullptr) {
+    // ---- fused split-K reduce + RoPE + KV append for the heads of this (sequence, kv head) ----
+    const int B = gridDim.y, Hq = p.n_kv_heads * GROUP;
+    const int pos = p.pos[b], sl = p.slot[b];
+    for (int t = threadIdx.x; t < (GROUP + 2) * 8; t += DEC_WARPS * 32) {
+      const int hh = t >> 3, j0 = (t & 7) * 8;          // head of this CTA, first of 8 rotation pairs
+      const bool is_k = hh == GROUP, is_v = hh == GROUP + 1;
+      const int hcol = (hh < GROUP ? kvh * GROUP + hh : (is_k ? Hq + kvh : Hq + p.n_kv_heads + kvh)) * DEC_D;
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s0 = 0; s0 < p.n_partial; s0 += 3) {     // three slices per round, loads first
+        float4 t1[3], t2[3], t3[3], t4[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const bool ok = s0 + u < p.n_partial;
+          const float* pp = p.partial + ((size_t)(ok ? s0 + u : s0) * B + b) * p.ldq + hcol;
+          t1[u] = ldf4(pp + j0); t2[u] = ldf4(pp + j0 + 4); t3[u] = ldf4(pp + 64 + j0); t4[u] = ldf4(pp + 64 + j0 + 4);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          if (s0 + u < p.n_partial) {
+            a[0] += t1[u].x; a[1] += t1[u].y; a[2] += t1[u].z; a[3] += t1[u].w;
+            a[4] += t2[u].x; a[5] += t2[u].y; a[6] += t2[u].z; a[7] += t2[u].w;
+            c[0] += t3[u].x; c[1] += t3[u].y; c[2] += t3[u].z; c[3] += t3[u].w;
+            c[4] += t4[u].x; c[5] += t4[u].y; c[6] += t4[u].z; c[7] += t4[u].w;
+          }
+        }
+      }
+      float x1[8], x2[8], o1[8], o2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { x1[i] = bf16_round(a[i]); x2[i] = bf16_round(c[i]); }
+      if (!is_v) {
+        float cs[8], sn[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(p.cos_t + (size_t)pos * DEC_D + j0), cs);
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(p.sin_t + (size_t)pos * DEC_D + j0), sn);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o1[i] = bf16_round(bf16_round(x1[i] * cs[i]) + bf16_round(-x2[i] * sn[i]));
+          o2[i] = bf16_round(bf16_round(x2[i] * cs[i]) + bf16_round(x1[i] * sn[i]));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o1[i] = x1[i]; o2[i] = x2[i]; }
+      }
+      const uint4 w1 = pack_bf16x8(o1), w2 = pack_bf16x8(o2);
+      __nv_bfloat16* dst = p.qkv + (size_t)b * p.ldq + hcol;
+      *reinterpret_cast<uint4*>(dst + j0) = w1;
+      *reinterpret_cast<uint4*>(dst + 64 + j0) = w2;
+      if ((is_k || is_v) && sl >= 0) {
+        const int blk = sl / DEC_BS, off = sl - blk * DEC_BS;
+        __nv_bfloat16* cd = (is_v ? p.vcache_w : p.kcache_w) + (((size_t)blk * p.n_kv_heads + kvh) * DEC_BS + off) * DEC_D;
+        *reinterpret_cast<uint4*>(cd + j0) = w1;
+        *reinterpret_cast<uint4*>(cd + 64 + j0) = w2;
+      }
+    }
+    __syncthreads();   // q for the fragments below and the new K/V row for the page loads are visible to this CTA
+  }
 
   // Q fragments: rows 0..GROUP-1 of the m16 tile are the query heads of this KV group, the rest are zero
   uint32_t qf[DEC_D / 16][4];
@@ -491,7 +577,21 @@ int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcac
                       const int* block_table, int max_blocks, const int* ctx_len, __nv_bfloat16* o, int ldo,
                       int n_seqs, int n_q_heads, int n_kv_heads, int head_dim, int block_size, float scale,
                       cudaStream_t st) {
+  return attn_decode_paged_fused(const_cast<__nv_bfloat16*>(q), ldq, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                                 const_cast<__nv_bfloat16*>(kcache), const_cast<__nv_bfloat16*>(vcache), block_table,
+                                 max_blocks, ctx_len, o, ldo, n_seqs, n_q_heads, n_kv_heads, head_dim, block_size,
+                                 scale, st);
+}
+
+int attn_decode_paged_fused(__nv_bfloat16* qkv, int ldq, const float* partial, int n_partial, const int* pos,
+                            const int* slot, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
+                            __nv_bfloat16* kcache, __nv_bfloat16* vcache, const int* block_table, int max_blocks,
+                            const int* ctx_len, __nv_bfloat16* o, int ldo, int n_seqs, int n_q_heads, int n_kv_heads,
+                            int head_dim, int block_size, float scale, cudaStream_t st) {
+  const __nv_bfloat16* q = qkv;
   if (n_seqs == 0) return OPUS_OK;
+  if (partial != nullptr && (pos == nullptr || slot == nullptr || cos_t == nullptr || sin_t == nullptr || (ldq % 8)))
+    return OPUS_ERR_ARG;
   if (head_dim != DEC_D || block_size != DEC_BS || n_kv_heads <= 0 || n_q_heads % n_kv_heads) return OPUS_ERR_ARG;
   const int group = n_q_heads / n_kv_heads;
   DecodeParams p;
@@ -502,6 +602,9 @@ int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcac
   p.o = o; p.ldo = ldo;
   p.n_kv_heads = n_kv_heads; p.group = group;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.partial = partial; p.n_partial = n_partial;
+  p.qkv = qkv; p.pos = pos; p.slot = slot; p.cos_t = cos_t; p.sin_t = sin_t;
+  p.kcache_w = kcache; p.vcache_w = vcache;
   dim3 grid(n_kv_heads, n_seqs);
   const int smem = DEC_WARPS * 4 * DEC_PANEL + DEC_WARPS * group * (DEC_D + 2) * 4;
   static bool configured = false;

@@ -65,4 +65,12 @@ int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcac
                       int n_seqs, int n_q_heads, int n_kv_heads, int head_dim, int block_size, float scale,
                       cudaStream_t st);
 
+// Same, with the decode step's split-K reduce + RoPE + KV append done by the attention CTAs themselves: `qkv` is written
+// (bf16 q|k|v row of every sequence) from `partial` ([n_partial][n_seqs][ldq] fp32) before the heads are attended.
+int attn_decode_paged_fused(__nv_bfloat16* qkv, int ldq, const float* partial, int n_partial, const int* pos,
+                            const int* slot, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
+                            __nv_bfloat16* kcache, __nv_bfloat16* vcache, const int* block_table, int max_blocks,
+                            const int* ctx_len, __nv_bfloat16* o, int ldo, int n_seqs, int n_q_heads, int n_kv_heads,
+                            int head_dim, int block_size, float scale, cudaStream_t st);
+
 }  // namespace opus

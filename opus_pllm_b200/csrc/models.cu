@@ -101,6 +101,7 @@ enum { PF_QKV = 0, PF_O = 1, PF_GU = 2, PF_DOWN = 3, PF_LM = 4 };
 // fused decode chain (gemm_chain): opt-in with OPUS_DECODE_FUSED=1 / opus_set_tunable("decode_fused", 1). Measured on
 // B200 at batch 64 it is not yet faster than one PDL-chained kernel per op (4.48 vs 4.40 ms per step: its device-wide
 // barriers and norm phases cost what the kernel boundaries did; tools/trace_chain.py prints the phase timeline).
+int g_decode_rope_fused = 1;  // RoPE + KV append inside the decode attention kernel (tunable "decode_rope_fused")
 int g_decode_fused = -1;
 bool decode_fused() {
   if (g_decode_fused < 0) {
@@ -372,11 +373,18 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
       const opus_llama_layer& L = m->layers[l];
       bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
       bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
-      OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp_qkv, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
-                                   static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n, kv->block_size,
-                                   st));
-      OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq,
-                                 Hkv, hd, kv->block_size, scale, st));
+      if (g_decode_rope_fused) {
+        OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp_qkv, s->pos, s->slot,
+                                         static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin),
+                                         kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv,
+                                         hd, kv->block_size, scale, st));
+      } else {
+        OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp_qkv, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
+                                     static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n,
+                                     kv->block_size, st));
+        OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq,
+                                   Hkv, hd, kv->block_size, scale, st));
+      }
       ChainPhase ph[6];
       const bool last = l + 1 == m->n_layers;
       gemm_phase(ph[0], L.wo, d, Hq * hd, attn, EPI_PARTIAL_F32, ws->partial, d, sp_o);
@@ -413,11 +421,19 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
       pf_next.w = m->lm_head; pf_next.rows = m->vocab; pf_next.K = d; pf_next.split_k = 1; pf_next.depth = pf_depth_for(PF_LM);
     }
     OPUS_TRY(linear_splitk(xn, B, L.wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st, &pf_o));
-    OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
-                                 static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n, kv->block_size,
-                                 st));
-    OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv,
-                               hd, kv->block_size, scale, st));
+    if (g_decode_rope_fused) {
+      // split-K reduce + RoPE + KV append happen inside the attention CTAs (one launch less per layer)
+      OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp, s->pos, s->slot,
+                                       static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin), kc,
+                                       vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv, hd,
+                                       kv->block_size, scale, st));
+    } else {
+      OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
+                                   static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n,
+                                   kv->block_size, st));
+      OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq,
+                                 Hkv, hd, kv->block_size, scale, st));
+    }
     OPUS_TRY(linear_splitk(attn, B, L.wo, d, Hq * hd, ws->partial, ws->partial_bytes, &sp, st, &pf_gu));
     OPUS_TRY(rmsnorm_bf16(nullptr, ws->partial, sp, h, h, static_cast<const bf16*>(L.ln2_w), xn, B, d, m->rms_eps, st));
     OPUS_TRY(linear(xn, B, L.wgu, 2 * ffn, d, EPI_SWIGLU, act, ffn, nullptr, nullptr, 0, nullptr, 0, st, &pf_down));
@@ -453,6 +469,10 @@ int set_tunable(const char* name, int value) {
   pf_init();
   if (std::strcmp(name, "chain_l2_depth") == 0) {
     gemm_set_chain_l2_depth(value);
+    return release_graphs();
+  }
+  if (std::strcmp(name, "decode_rope_fused") == 0) {
+    g_decode_rope_fused = value != 0;
     return release_graphs();
   }
   if (std::strcmp(name, "decode_fused") == 0) {

@@ -276,6 +276,35 @@ def test_decode_fused_chain_matches_kernel_per_op(cfg, batch):
     assert _cos(fused_logits, plain_logits) >= 0.995
 
 
+@pytest.mark.parametrize("cfg,batch", [(SMALL, 9), (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
+                                                        ffn_dim=14336, vocab=8192), 64)])
+def test_decode_rope_fused_into_attention_is_bit_identical(cfg, batch):
+    """Decode: the attention CTAs reduce the q|k|v split-K partials of their heads, apply RoPE and append K/V themselves
+    (default) — same arithmetic as the separate rope_llama_kvappend kernel, so tokens, cache and logits are identical."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    w = synth.llama_weights(seed=12, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [21 + (i * 11) % 60 for i in range(batch)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    emb = synth.weight((int(cu[-1]), cfg["dim"]), "rope_fused_prompt", 0.02).cuda().to(torch.bfloat16)
+    lib = L.load()
+    plan = model.make_plan(cu, 10)
+    try:
+        res = {}
+        for mode in (1, 0):
+            L.check(lib.opus_set_tunable(b"decode_rope_fused", mode))
+            model._k.zero_(); model._v.zero_()
+            st = model.prefill(emb, plan=plan)
+            toks = model.generate_from_prefill(st, 10)
+            res[mode] = (toks.clone(), model._ws_bufs["logits"][:batch].clone(), model._k.clone(), model._v.clone())
+    finally:
+        L.check(lib.opus_set_tunable(b"decode_rope_fused", 1))
+        model.release_plan(plan)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
+
+
 def test_greedy_decode_default_init_margin_aware():
     """HF-init statistics: random logits have tiny top-1 margins, so token identity is fragile by construction
     (SURVEY.md §7); every disagreement must be explained by a near-tie in the oracle's own logits."""
