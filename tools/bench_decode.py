@@ -47,6 +47,19 @@ def setk(**kw):
 
 
 run("defaults (kernel per op, PDL chain)")
+if os.environ.get("AFTER_PREFILL"):
+    # the same decode loop timed right after a prefill, as inside bench.py (clock / power state carried over)
+    tot = 0.0
+    for _ in range(3):
+        st2 = ll.prefill(emb, plan=plan)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ll.generate_from_prefill(st2, new)
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    ms = tot / 3 / (new - 1)
+    print(f"{'decode timed right after a prefill':40s} {ms:7.3f} ms/step  {bytes_step / ms / 1e6:7.0f} GB/s  frac {bytes_step / ms / 1e6 / 6551.4:.3f}", flush=True)
 if os.environ.get("FUSED"):
     setk(decode_fused=1); run("decode_fused=1 (chain kernel)"); setk(decode_fused=0)
 if os.environ.get("SWEEP"):
