@@ -1281,7 +1281,10 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   // grouped-M raster: the A rows of one group (group_m x 128 x K) must stay L2-resident while the group's n-tiles are
   // walked; measured DRAM traffic per launch at M = 32768 (ncu): gate/up (K 4096) 4.96 GB at 16 -> 3.09 GB at 32, but
   // down (K 14336) 4.99 GB at 16 -> 5.65 GB at 32
-  p.group_m = a.transposed ? p.num_m_tiles : (group_override > 0 ? group_override : (a.K > 8192 ? 16 : 32));
+  // swap-AB with more than one batch tile: walk the batch tiles of one weight panel back to back (n fastest), so the
+  // panel is fetched from HBM once and re-read from L2
+  p.group_m = a.transposed ? (p.num_n_tiles > 1 ? 1 : p.num_m_tiles)
+                           : (group_override > 0 ? group_override : (a.K > 8192 ? 16 : 32));
   if (p.group_m > p.num_m_tiles) p.group_m = p.num_m_tiles;
   // weights are streamed once in the swap-AB form; activations are re-read by every tile
   p.hint_a = a.transposed ? kCacheEvictFirst : kCacheEvictNormal;

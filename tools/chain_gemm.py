@@ -44,6 +44,16 @@ if os.environ.get("L2_TEST"):
         bench("qkv s3", 6144, 4096, 3, P, nw=nw)
         bench("16 tiles s8", 2048, 4096, 8, P, nw=nw)
     sys.exit(0)
+if os.environ.get("BN_TEST"):
+    # batch 129..256: one 256-wide batch tile (4 stages) vs two 128-wide tiles sharing the weight panel through L2
+    for bn in (256, 128):
+        print("block_n", bn)
+        bench("qkv s3", 6144, 4096, 3, P, block_n=bn)
+        bench("o_proj s4", 4096, 4096, 4, P, block_n=bn)
+        bench("gate_up swiglu", 28672, 4096, 1, L.EPI_SWIGLU, block_n=bn)
+        bench("down s4", 4096, 14336, 4, P, block_n=bn)
+        bench("lm_head", 128256, 4096, 1, L.EPI_BF16, block_n=bn)
+    sys.exit(0)
 if os.environ.get("DEPTH_TEST"):
     # weight bytes in flight per SM: bn 64 -> 8 stages x 16 KB, bn 128 -> 6 x 16 KB, bn 256 -> 4 x 16 KB
     for bn in (64, 128, 256):
