@@ -215,6 +215,7 @@ typedef struct {
   const void* ln2_w;
   const void* wgu;   /* bf16 [2*ffn, dim], rows interleaved gate_0, up_0, gate_1, up_1, ... */
   const void* wdown; /* bf16 [dim, ffn] */
+  const float* bqkv; /* fp32 [(Hq+2*Hkv)*hd] q|k|v projection bias (Qwen2 family) or NULL (Llama) */
 } opus_llama_layer;
 
 typedef struct {

@@ -45,7 +45,7 @@ class ProjectorModel(C.Structure):
 
 
 class LlamaLayer(C.Structure):
-    _fields_ = [(n, c_void_p) for n in ("ln1_w", "wqkv", "wo", "ln2_w", "wgu", "wdown")]
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "wqkv", "wo", "ln2_w", "wgu", "wdown", "bqkv")]
 
 
 class LlamaModel(C.Structure):

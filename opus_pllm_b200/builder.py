@@ -2,7 +2,8 @@
 
 Same signature and return value `(tokenizer, model, context_len)`; the files read are the ones the reference reads
 ("Weight formats to load"):
-  1. HF Llama-3 directory: `config.json` + `*.safetensors` shards                       (builder.py:61-65)
+  1. HF Llama-3 (or Qwen2 / Qwen2.5: same layout + q/k/v biases, builder.py:83-94) directory: `config.json` +
+     `*.safetensors` shards                                                              (builder.py:61-65)
   2. `<weights>/lora_adapter/{adapter_config.json, adapter_model.safetensors|.bin}`     (builder.py:105-109, peft)
   3. `<weights>/modality_refinement_projector/modality_refinement_projection.bin`       (builder.py:111, opus_arch.py:85-89)
   4. `<weights>/modality_encoder/modality_encoding_adapter.ckpt` (Lightning checkpoint)  (protein_projector/builder.py:16-25)
@@ -142,8 +143,10 @@ def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=F
     from .model import build_from_state_dicts
     if model_name is None or not model_base_path:
         raise NotImplementedError
-    if "llama" not in model_base_path.lower():
-        raise NotImplementedError("opus_pllm_b200 implements the Llama-3 family only")
+    family = model_base_path.lower()
+    if "llama" not in family and "qwen" not in family:
+        # model/builder.py:71-96 also dispatches OPT / Galactica (LayerNorm, learned positions, ReLU): not built here
+        raise NotImplementedError("opus_pllm_b200 implements the Llama-3 and Qwen2 / Qwen2.5 families (head_dim 128)")
     if load_8bit or load_4bit:
         warnings.warn("load_8bit/load_4bit are ignored: opus_pllm_b200 runs bf16 weights")
     device = "cuda:0" if accelerator is None else f"cuda:{accelerator.process_index}"

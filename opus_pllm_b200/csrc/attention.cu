@@ -301,6 +301,7 @@ struct DecodeParams {
   const __nv_bfloat16* sin_t;
   __nv_bfloat16* kcache_w;
   __nv_bfloat16* vcache_w;
+  const float* bias;           // fp32 [ldq] q|k|v projection bias (Qwen2) or nullptr
 };
 
 __device__ __forceinline__ void load_panel_async(uint32_t smem_base, const __nv_bfloat16* panel, int lane) {
@@ -352,6 +353,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
             c[4] += t4[u].x; c[5] += t4[u].y; c[6] += t4[u].z; c[7] += t4[u].w;
           }
         }
+      }
+      if (p.bias != nullptr) {
+        const float* bb = p.bias + hcol;
+        const float4 b1 = ldf4(bb + j0), b2 = ldf4(bb + j0 + 4), b3 = ldf4(bb + 64 + j0), b4 = ldf4(bb + 64 + j0 + 4);
+        a[0] += b1.x; a[1] += b1.y; a[2] += b1.z; a[3] += b1.w; a[4] += b2.x; a[5] += b2.y; a[6] += b2.z; a[7] += b2.w;
+        c[0] += b3.x; c[1] += b3.y; c[2] += b3.z; c[3] += b3.w; c[4] += b4.x; c[5] += b4.y; c[6] += b4.z; c[7] += b4.w;
       }
       float x1[8], x2[8], o1[8], o2[8];
 #pragma unroll
@@ -587,7 +594,7 @@ int attn_decode_paged_fused(__nv_bfloat16* qkv, int ldq, const float* partial, i
                             const int* slot, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
                             __nv_bfloat16* kcache, __nv_bfloat16* vcache, const int* block_table, int max_blocks,
                             const int* ctx_len, __nv_bfloat16* o, int ldo, int n_seqs, int n_q_heads, int n_kv_heads,
-                            int head_dim, int block_size, float scale, cudaStream_t st) {
+                            int head_dim, int block_size, float scale, cudaStream_t st, const float* bias) {
   const __nv_bfloat16* q = qkv;
   if (n_seqs == 0) return OPUS_OK;
   if (partial != nullptr && (pos == nullptr || slot == nullptr || cos_t == nullptr || sin_t == nullptr || (ldq % 8)))
@@ -605,22 +612,21 @@ int attn_decode_paged_fused(__nv_bfloat16* qkv, int ldq, const float* partial, i
   p.partial = partial; p.n_partial = n_partial;
   p.qkv = qkv; p.pos = pos; p.slot = slot; p.cos_t = cos_t; p.sin_t = sin_t;
   p.kcache_w = kcache; p.vcache_w = vcache;
+  p.bias = partial != nullptr ? bias : nullptr;
   dim3 grid(n_kv_heads, n_seqs);
   const int smem = DEC_WARPS * 4 * DEC_PANEL + DEC_WARPS * group * (DEC_D + 2) * 4;
   static bool configured = false;
   if (!configured) {
     auto bytes_for = [](int g) { return DEC_WARPS * 4 * DEC_PANEL + DEC_WARPS * g * (DEC_D + 2) * 4; };
-    cudaFuncSetAttribute(attn_decode_paged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(1));
-    cudaFuncSetAttribute(attn_decode_paged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(2));
-    cudaFuncSetAttribute(attn_decode_paged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(4));
-    cudaFuncSetAttribute(attn_decode_paged_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(8));
+#define OPUS_DEC_CFG(G) cudaFuncSetAttribute(attn_decode_paged_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes_for(G));
+    OPUS_DEC_CFG(1) OPUS_DEC_CFG(2) OPUS_DEC_CFG(3) OPUS_DEC_CFG(4) OPUS_DEC_CFG(5) OPUS_DEC_CFG(6) OPUS_DEC_CFG(7) OPUS_DEC_CFG(8)
+#undef OPUS_DEC_CFG
     configured = true;
   }
-  switch (group) {
-    case 1: launch_pdl(true, attn_decode_paged_kernel<1>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
-    case 2: launch_pdl(true, attn_decode_paged_kernel<2>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
-    case 4: launch_pdl(true, attn_decode_paged_kernel<4>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
-    case 8: launch_pdl(true, attn_decode_paged_kernel<8>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+  switch (group) {   // the GROUP query heads of a kv head share the rows of one m16 MMA tile: any group size up to 8
+#define OPUS_DEC_CASE(G) case G: launch_pdl(true, attn_decode_paged_kernel<G>, dim3(grid), dim3(DEC_WARPS * 32), smem, st, p); break;
+    OPUS_DEC_CASE(1) OPUS_DEC_CASE(2) OPUS_DEC_CASE(3) OPUS_DEC_CASE(4) OPUS_DEC_CASE(5) OPUS_DEC_CASE(6) OPUS_DEC_CASE(7) OPUS_DEC_CASE(8)
+#undef OPUS_DEC_CASE
     default: return OPUS_ERR_ARG;
   }
   note_launch();

@@ -318,7 +318,8 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
                                            const __nv_bfloat16* __restrict__ cos_t,
                                            const __nv_bfloat16* __restrict__ sin_t, __nv_bfloat16* __restrict__ kcache,
                                            __nv_bfloat16* __restrict__ vcache, int n_tok, int n_q_heads,
-                                           int n_kv_heads, int head_dim, int ld, int block_size) {
+                                           int n_kv_heads, int head_dim, int ld, int block_size,
+                                           const float* __restrict__ bias) {
   grid_dep_launch();
   grid_dep_wait();
   const int half = head_dim / 2;
@@ -354,6 +355,12 @@ __global__ void rope_llama_kvappend_kernel(__nv_bfloat16* __restrict__ qkv, cons
           b[4] += t4[u].x; b[5] += t4[u].y; b[6] += t4[u].z; b[7] += t4[u].w;
         }
       }
+    }
+    if (bias != nullptr) {   // q|k|v projection bias (Qwen2): added to the fp32 sum before the one bf16 rounding
+      const float* bb = bias + (size_t)hsel * head_dim;
+      const float4 b1 = ld4(bb + j0), b2 = ld4(bb + j0 + 4), b3 = ld4(bb + half + j0), b4 = ld4(bb + half + j0 + 4);
+      a[0] += b1.x; a[1] += b1.y; a[2] += b1.z; a[3] += b1.w; a[4] += b2.x; a[5] += b2.y; a[6] += b2.z; a[7] += b2.w;
+      b[0] += b3.x; b[1] += b3.y; b[2] += b3.z; b[3] += b3.w; b[4] += b4.x; b[5] += b4.y; b[6] += b4.z; b[7] += b4.w;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x1[i] = bf16_round(a[i]); x2[i] = bf16_round(b[i]); }
@@ -940,13 +947,14 @@ int rope_esm(__nv_bfloat16* qkv, const int* pos, const float* cos_t, const float
 int rope_llama_kvappend(__nv_bfloat16* qkv, const float* partial, int n_partial, const int* pos, const int* slot,
                         const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t, __nv_bfloat16* kcache,
                         __nv_bfloat16* vcache, int n_tok, int n_q_heads, int n_kv_heads, int head_dim, int ld,
-                        int block_size, cudaStream_t st) {
+                        int block_size, cudaStream_t st, const float* bias) {
   if (head_dim % 16 || ld % 8) return OPUS_ERR_ARG;
+  if (bias != nullptr && partial == nullptr) return OPUS_ERR_ARG;   // a finished bf16 row already contains the bias
   if (n_tok == 0) return OPUS_OK;
   const long long total = (long long)n_tok * (n_q_heads + 2 * n_kv_heads) * (head_dim / 16);
   launch_pdl(n_tok <= 1024, rope_llama_kvappend_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, qkv, partial, n_partial, pos, slot, cos_t, sin_t, kcache,
                                                               vcache, n_tok, n_q_heads, n_kv_heads, head_dim, ld,
-                                                              block_size);
+                                                              block_size, bias);
   return ok();
 }
 

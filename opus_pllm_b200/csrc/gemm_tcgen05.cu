@@ -469,6 +469,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
                    (((size_t)blk * p.rl_hkv + kvh) * p.rl_bs + off) * 128;
           }
           const uint32_t th = taddr + chunk0 * 128;   // TMEM columns of this head
+          const float* bq = p.bias != nullptr ? p.bias + colh : nullptr;
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
             uint32_t pk[32];
@@ -491,8 +492,9 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
                 float o[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                  const float x1 = bf16_round(__uint_as_float(a1[i + e]));   // the bf16 value the plain epilogue stores
-                  const float x2 = bf16_round(__uint_as_float(a2[i + e]));
+                  // the bf16 value the plain epilogue stores (+ projection bias, Qwen2)
+                  const float x1 = bf16_round(__uint_as_float(a1[i + e]) + (bq != nullptr ? __ldg(bq + sub * 16 + i + e) : 0.f));
+                  const float x2 = bf16_round(__uint_as_float(a2[i + e]) + (bq != nullptr ? __ldg(bq + 64 + sub * 16 + i + e) : 0.f));
                   if (is_v) o[e] = half == 0 ? x1 : x2;
                   else if (half == 0) o[e] = bf16_round(bf16_round(x1 * cs[i + e]) + bf16_round(-x2 * sn[i + e]));
                   else o[e] = bf16_round(bf16_round(x2 * cs[i + e]) + bf16_round(x1 * sn[i + e]));
@@ -1307,7 +1309,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
                 (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && bn >= 64;
   if (a.rl_cos != nullptr) {
     if (!(p.tma_store && a.epi == EPI_BF16 && bn == 256 && a.rl_pos != nullptr && a.rl_sin != nullptr && a.rl_bs > 0 &&
-          a.N == (a.rl_hq + 2 * a.rl_hkv) * 128 && a.bias == nullptr))
+          a.N == (a.rl_hq + 2 * a.rl_hkv) * 128))
       return OPUS_ERR_ARG;   // callers check gemm_fuses_rope() first
     p.rl_pos = a.rl_pos; p.rl_slot = a.rl_slot; p.rl_cos = a.rl_cos; p.rl_sin = a.rl_sin;
     p.rl_kcache = a.rl_kcache; p.rl_vcache = a.rl_vcache;
@@ -1346,7 +1348,7 @@ bool gemm_fuses_rope(const GemmArgs& a) {
   if (prepare_gemm(probe, p, bn) != OPUS_OK) return false;
   if (a.rl_cos != nullptr)
     return p.tma_store && a.epi == EPI_BF16 && bn == 256 && a.rl_pos != nullptr && a.rl_sin != nullptr && a.rl_bs > 0 &&
-           a.N == (a.rl_hq + 2 * a.rl_hkv) * 128 && a.bias == nullptr;
+           a.N == (a.rl_hq + 2 * a.rl_hkv) * 128;
   return p.tma_store && a.epi == EPI_BF16 && a.rope_pos != nullptr && a.rope_cos != nullptr && a.rope_sin != nullptr &&
          (a.rope_cols % 64) == 0 && (a.rope_q_cols % 64) == 0;
 }

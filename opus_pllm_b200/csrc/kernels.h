@@ -27,7 +27,7 @@ int rope_esm(__nv_bfloat16* qkv, const int* pos, const float* cos_t, const float
 int rope_llama_kvappend(__nv_bfloat16* qkv, const float* partial, int n_partial, const int* pos, const int* slot,
                         const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t, __nv_bfloat16* kcache,
                         __nv_bfloat16* vcache, int n_tok, int n_q_heads, int n_kv_heads, int head_dim, int ld,
-                        int block_size, cudaStream_t st);
+                        int block_size, cudaStream_t st, const float* bias = nullptr /* fp32 [ld], split-K path only */);
 int final_ln_meanpool(const float* x, const __nv_bfloat16* delta, const int* cu_seqlens, const float* gamma,
                       const float* beta, float* pooled,
                       __nv_bfloat16* pooled_l2, float* hidden_out, int n_seqs, int dim, float eps, cudaStream_t st);
@@ -71,6 +71,6 @@ int attn_decode_paged_fused(__nv_bfloat16* qkv, int ldq, const float* partial, i
                             const int* slot, const __nv_bfloat16* cos_t, const __nv_bfloat16* sin_t,
                             __nv_bfloat16* kcache, __nv_bfloat16* vcache, const int* block_table, int max_blocks,
                             const int* ctx_len, __nv_bfloat16* o, int ldo, int n_seqs, int n_q_heads, int n_kv_heads,
-                            int head_dim, int block_size, float scale, cudaStream_t st);
+                            int head_dim, int block_size, float scale, cudaStream_t st, const float* bias = nullptr);
 
 }  // namespace opus

@@ -277,13 +277,14 @@ int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus
       a.K = d;
       a.epi = EPI_BF16;
       a.out = qkv; a.ldo = qkv_n;
+      a.bias = L.bqkv;
       a.rl_pos = pos; a.rl_slot = slot; a.rl_cos = m->rope_cos; a.rl_sin = m->rope_sin;
       a.rl_kcache = kc; a.rl_vcache = vc;
       a.rl_hq = Hq; a.rl_hkv = Hkv; a.rl_bs = kv->block_size;
       if (n_tok > 256 && gemm_fuses_rope(a)) {
         OPUS_TRY(gemm_bf16(a, st));
       } else {
-        OPUS_TRY(linear(xn, n_tok, L.wqkv, qkv_n, d, EPI_BF16, qkv, qkv_n, nullptr, nullptr, 0, nullptr, 0, st));
+        OPUS_TRY(linear(xn, n_tok, L.wqkv, qkv_n, d, EPI_BF16, qkv, qkv_n, L.bqkv, nullptr, 0, nullptr, 0, st));
         OPUS_TRY(rope_llama_kvappend(qkv, nullptr, 0, pos, slot, static_cast<const bf16*>(m->rope_cos),
                                      static_cast<const bf16*>(m->rope_sin), kc, vc, n_tok, Hq, Hkv, hd, qkv_n,
                                      kv->block_size, st));
@@ -377,11 +378,11 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
         OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp_qkv, s->pos, s->slot,
                                          static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin),
                                          kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv,
-                                         hd, kv->block_size, scale, st));
+                                         hd, kv->block_size, scale, st, L.bqkv));
       } else {
         OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp_qkv, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
                                      static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n,
-                                     kv->block_size, st));
+                                     kv->block_size, st, L.bqkv));
         OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq,
                                    Hkv, hd, kv->block_size, scale, st));
       }
@@ -426,11 +427,11 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
       OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp, s->pos, s->slot,
                                        static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin), kc,
                                        vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv, hd,
-                                       kv->block_size, scale, st));
+                                       kv->block_size, scale, st, L.bqkv));
     } else {
       OPUS_TRY(rope_llama_kvappend(qkv, ws->partial, sp, s->pos, s->slot, static_cast<const bf16*>(m->rope_cos),
                                    static_cast<const bf16*>(m->rope_sin), kc, vc, B, Hq, Hkv, hd, qkv_n,
-                                   kv->block_size, st));
+                                   kv->block_size, st, L.bqkv));
       OPUS_TRY(attn_decode_paged(qkv, qkv_n, kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq,
                                  Hkv, hd, kv->block_size, scale, st));
     }

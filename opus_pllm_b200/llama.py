@@ -64,6 +64,7 @@ class B200Llama:
             p = f"model.layers.{i}."
             q, k, v = (merged(p + f"self_attn.{n}") for n in ("q_proj", "k_proj", "v_proj"))
             g, u = merged(p + "mlp.gate_proj"), merged(p + "mlp.up_proj")
+            bq = [weights.get(p + f"self_attn.{n}.bias") for n in ("q_proj", "k_proj", "v_proj")]
             t = dict(ln1_w=b16(weights[p + "input_layernorm.weight"]),
                      wqkv=torch.cat([q, k, v], 0).contiguous(),
                      wo=merged(p + "self_attn.o_proj"),
@@ -71,13 +72,18 @@ class B200Llama:
                      # rows interleaved (gate_0, up_0, gate_1, up_1, ...) so SwiGLU lives in the GEMM epilogue
                      wgu=torch.stack([g, u], 1).reshape(2 * ffn_dim, dim).contiguous(),
                      wdown=merged(p + "mlp.down_proj"))
+            if any(b is not None for b in bq):   # Qwen2 family: q/k/v projections carry a bias (o_proj does not)
+                if any(b is None for b in bq):
+                    raise L.OpusError(f"layer {i}: q/k/v projection biases must be given together")
+                t["bqkv"] = torch.cat([b.detach().to(self.device, torch.float32) for b in bq]).contiguous()
             del q, k, v, g, u
             self._keep.append(t)
             for kk, vv in t.items():
                 setattr(layers[i], kk, vv.data_ptr())
         self._layers = layers
         self.norm_w = b16(weights["model.norm.weight"])
-        self.lm_head = b16(weights["lm_head.weight"])
+        # tie_word_embeddings (small Qwen2 variants): no separate lm_head tensor
+        self.lm_head = b16(weights["lm_head.weight"]) if "lm_head.weight" in weights else self.embed
         self._build_rope(max_positions)
         self._cache = None
         self._alloc = None

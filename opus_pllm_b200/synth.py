@@ -121,7 +121,7 @@ def projector_weights(in_dim: int, cstp_dim: int, hidden: int, seed: int = 0, de
 
 
 def llama_weights(n_layers: int, dim: int, n_q_heads: int, n_kv_heads: int, head_dim: int, ffn: int, vocab: int,
-                  seed: int = 0, peaked: bool = False, dtype=torch.float32, device="cpu") -> dict:
+                  seed: int = 0, peaked: bool = False, dtype=torch.float32, device="cpu", qkv_bias: bool = False) -> dict:
     """HF state-dict names. Default = HF init statistics (std 0.02). peaked=True is the token-parity recipe: damped
     residual branches and lm_head tied to a permutation of the embedding rows, so greedy argmax margins dwarf bf16
     noise (hard part 1)."""
@@ -136,6 +136,10 @@ def llama_weights(n_layers: int, dim: int, n_q_heads: int, n_kv_heads: int, head
         w[p + "self_attn.q_proj.weight"] = weight((qd, dim), f"llama.{i}.q", 0.02, seed, device=device).to(dtype)
         w[p + "self_attn.k_proj.weight"] = weight((kd, dim), f"llama.{i}.k", 0.02, seed, device=device).to(dtype)
         w[p + "self_attn.v_proj.weight"] = weight((kd, dim), f"llama.{i}.v", 0.02, seed, device=device).to(dtype)
+        if qkv_bias:   # Qwen2 family: biases on the q/k/v projections
+            w[p + "self_attn.q_proj.bias"] = weight((qd,), f"llama.{i}.qb", 0.1, seed, device=device).to(dtype)
+            w[p + "self_attn.k_proj.bias"] = weight((kd,), f"llama.{i}.kb", 0.1, seed, device=device).to(dtype)
+            w[p + "self_attn.v_proj.bias"] = weight((kd,), f"llama.{i}.vb", 0.1, seed, device=device).to(dtype)
         w[p + "self_attn.o_proj.weight"] = weight((dim, qd), f"llama.{i}.o", out_std, seed, device=device).to(dtype)
         w[p + "mlp.gate_proj.weight"] = weight((ffn, dim), f"llama.{i}.gate", 0.02, seed, device=device).to(dtype)
         w[p + "mlp.up_proj.weight"] = weight((ffn, dim), f"llama.{i}.up", 0.02, seed, device=device).to(dtype)

@@ -88,9 +88,10 @@ def llama_forward(w: dict, cfg: LlamaCfg, embeds: torch.Tensor, attention_mask: 
         p = f"model.layers.{i}."
         res = h
         x = rmsnorm(h, w[p + "input_layernorm.weight"], cfg.rms_eps)
-        q = F.linear(x, w[p + "self_attn.q_proj.weight"]).view(B, T, Hq, hd).transpose(1, 2)
-        k = F.linear(x, w[p + "self_attn.k_proj.weight"]).view(B, T, Hkv, hd).transpose(1, 2)
-        v = F.linear(x, w[p + "self_attn.v_proj.weight"]).view(B, T, Hkv, hd).transpose(1, 2)
+        # q/k/v projection biases exist in the Qwen2 family (HF modeling_qwen2.py: Linear(..., bias=True)), not in Llama
+        q = F.linear(x, w[p + "self_attn.q_proj.weight"], w.get(p + "self_attn.q_proj.bias")).view(B, T, Hq, hd).transpose(1, 2)
+        k = F.linear(x, w[p + "self_attn.k_proj.weight"], w.get(p + "self_attn.k_proj.bias")).view(B, T, Hkv, hd).transpose(1, 2)
+        v = F.linear(x, w[p + "self_attn.v_proj.weight"], w.get(p + "self_attn.v_proj.bias")).view(B, T, Hkv, hd).transpose(1, 2)
         q = (q * cos) + (rotate_half(q) * sin)
         k = (k * cos) + (rotate_half(k) * sin)
         if past is not None:
@@ -108,10 +109,11 @@ def llama_forward(w: dict, cfg: LlamaCfg, embeds: torch.Tensor, attention_mask: 
         g = F.linear(x, w[p + "mlp.gate_proj.weight"])
         u = F.linear(x, w[p + "mlp.up_proj.weight"])
         h = res + F.linear(F.silu(g) * u, w[p + "mlp.down_proj.weight"])
+    lm_head = w["lm_head.weight"] if "lm_head.weight" in w else w["model.embed_tokens.weight"]   # tied embeddings
     if all_positions:   # teacher-forced scoring: HF returns logits for every position when labels are given
-        return F.linear(rmsnorm(h, w["model.norm.weight"], cfg.rms_eps), w["lm_head.weight"]).float(), new_past
+        return F.linear(rmsnorm(h, w["model.norm.weight"], cfg.rms_eps), lm_head).float(), new_past
     h = rmsnorm(h[:, -1:, :], w["model.norm.weight"], cfg.rms_eps)
-    logits = F.linear(h, w["lm_head.weight"])[:, -1, :]
+    logits = F.linear(h, lm_head)[:, -1, :]
     return logits.float(), new_past
 
 

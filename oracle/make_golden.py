@@ -212,8 +212,63 @@ def golden_mm_and_llama(esm_w, seqs, pooled):
     print(f"llama_small.pt: oracle vs reference generate: logits max |diff| {d_l:.3g}, tokens identical {tuple(out.shape)}")
 
 
+def golden_qwen():
+    """Sibling family (model/language_model/opus_qwen.py): the reference's OpusQwenForCausalLM (Qwen2: Llama blocks +
+    q/k/v biases, GQA group 3 here, rope theta 1e6, eps 1e-6) on a tiny config with hash-seeded weights; text-only
+    greedy generate (`seq=None` branch, opus_qwen.py:124-125) and last-position prefill logits."""
+    from multi_modality_model.multi_modality_v1.model.language_model.opus_qwen import OpusQwenConfig, OpusQwenForCausalLM
+
+    class Shim(OpusQwenForCausalLM):   # same transformers-version shim as for the Llama wrapper
+        def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):
+            kwargs.pop("seq", None)
+            return super(OpusQwenForCausalLM, self).prepare_inputs_for_generation(
+                input_ids, past_key_values=past_key_values, inputs_embeds=inputs_embeds, **kwargs)
+
+    c = dict(n_layers=2, dim=384, n_q_heads=3, n_kv_heads=1, head_dim=128, ffn_dim=768, vocab=1024)
+    hf_cfg = OpusQwenConfig(vocab_size=c["vocab"], hidden_size=c["dim"], intermediate_size=c["ffn_dim"],
+                            num_hidden_layers=c["n_layers"], num_attention_heads=c["n_q_heads"],
+                            num_key_value_heads=c["n_kv_heads"], rms_norm_eps=1e-6, rope_theta=1000000.0,
+                            max_position_embeddings=512, tie_word_embeddings=False, use_sliding_window=False,
+                            bos_token_id=1, eos_token_id=2, pad_token_id=None)
+    hf_cfg._attn_implementation = "eager"
+    lw = synth.llama_weights(c["n_layers"], c["dim"], c["n_q_heads"], c["n_kv_heads"], c["head_dim"], c["ffn_dim"],
+                             c["vocab"], seed=23, qkv_bias=True)
+    model = Shim(hf_cfg).eval()
+    missing, unexpected = model.load_state_dict(lw, strict=False)
+    assert not [m for m in missing if "rotary" not in m and "inv_freq" not in m and "protein" not in m and "switch" not in m], missing
+    assert not unexpected, unexpected
+    B, L = 5, 19
+    g = torch.Generator().manual_seed(41)
+    ids = torch.randint(3, c["vocab"], (B, L), generator=g)
+    pad = 0
+    for b in range(B):                                       # left padding, ragged
+        ids[b, : b * 2] = pad
+    mask = ids != pad
+    with torch.no_grad():
+        out = model.generate(ids, None, attention_mask=mask, pad_token_id=2, do_sample=False, max_new_tokens=10,
+                             use_cache=True)
+        emb = model.get_model().embed_tokens(ids)
+        logits = model(inputs_embeds=emb, attention_mask=mask).logits[:, -1, :].float()
+    ocfg = llama_ref.LlamaCfg(n_layers=c["n_layers"], dim=c["dim"], n_q_heads=c["n_q_heads"], n_kv_heads=c["n_kv_heads"],
+                              head_dim=c["head_dim"], ffn_dim=c["ffn_dim"], vocab=c["vocab"], rms_eps=1e-6,
+                              rope_theta=1000000.0)
+    pos = (mask.long().cumsum(-1) - 1).masked_fill(~mask, 1)
+    lg_mine, _ = llama_ref.llama_forward(lw, ocfg, emb.float(), mask, pos)
+    out_mine = llama_ref.greedy_generate(lw, ocfg, emb.float(), mask, 10, eos_ids=(2,), pad_id=2)
+    d_l = float((lg_mine - logits).abs().max())
+    assert d_l < 2e-4, d_l
+    assert out_mine.shape == out.shape and torch.equal(out_mine, out), (out_mine, out)
+    torch.save(dict(cfg=c, seed=23, rms_eps=1e-6, rope_theta=1000000.0, input_ids=ids, mask=mask, prefill_logits=logits,
+                    tokens=out, eos=2, pad=2, max_new_tokens=10, oracle_dev=dict(logits=d_l, tokens=0),
+                    source="reference OpusQwenForCausalLM.generate over transformers " +
+                           __import__("transformers").__version__),
+               os.path.join(GOLD, "qwen_small.pt"))
+    print(f"qwen_small.pt: oracle vs reference OpusQwenForCausalLM: logits max |diff| {d_l:.3g}, tokens identical {tuple(out.shape)}")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     w, seqs, pooled = golden_esm()
     golden_mm_and_llama(w, seqs, pooled)
+    golden_qwen()

@@ -121,3 +121,32 @@ def test_forward_labels_scoring_matches_reference_golden():
     assert out2.logits is None and abs(float(out2.loss) - float(g["loss"])) <= 0.05
     # no labels -> no loss (HF returns loss=None)
     assert model(ids, attention_mask=mask, seq=g["seqs"], return_logits=False).loss is None
+
+
+def test_qwen_family_matches_reference_wrapper_golden():
+    """Qwen2 / Qwen2.5 (model/language_model/opus_qwen.py) through the same kernels: q/k/v projection biases (prefill
+    epilogue, decode split-K reduce), GQA group 3, rope theta 1e6, eps 1e-6 — against the reference wrapper's own
+    generate output (tests/golden/qwen_small.pt)."""
+    from opus_pllm_b200.llama import B200Llama
+    g = _load("qwen_small.pt")
+    c = g["cfg"]
+    lw = synth.llama_weights(c["n_layers"], c["dim"], c["n_q_heads"], c["n_kv_heads"], c["head_dim"], c["ffn_dim"],
+                             c["vocab"], seed=g["seed"], qkv_bias=True)
+    model = B200Llama(lw, **c, rms_eps=g["rms_eps"], rope_theta=g["rope_theta"])
+    mask = g["mask"]
+    lens = mask.sum(1).tolist()
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    packed = lw["model.embed_tokens.weight"][g["input_ids"]][mask].cuda().to(torch.bfloat16)
+    out, logits = model.generate_packed(packed, cu, g["max_new_tokens"], eos_ids=[g["eos"]], pad_id=g["pad"],
+                                        return_prefill_logits=True)
+    want = g["prefill_logits"]
+    assert _cos(logits, want) >= 0.999
+    assert float((logits.float().cpu() - want).abs().max()) <= 0.06 * float(want.std()) + 1e-3
+    top2 = want.topk(2, dim=-1).values
+    same = out[:, 0].cpu() == g["tokens"][:, 0]
+    assert bool((same | ((top2[:, 0] - top2[:, 1]) < 0.05 * float(want.std()))).all())
+    # without the biases the logits must move: the bias path is really exercised
+    nb = {k: v for k, v in lw.items() if not k.endswith(".bias")}
+    _, logits_nb = B200Llama(nb, **c, rms_eps=g["rms_eps"], rope_theta=g["rope_theta"]).generate_packed(
+        packed, cu, 2, return_prefill_logits=True)
+    assert _cos(logits_nb, want) < 0.999

@@ -455,9 +455,11 @@ def test_attn_prefill_causal_gqa(ops, lens):
         _close_bf16(got[s:e].view(-1, Hq, D), want, ulps=2.0, atol=8e-3)
 
 
-@pytest.mark.parametrize("ctxs", [[1, 16, 17, 528, 100, 33], [544] * 8])
-def test_attn_decode_paged(ops, ctxs):
-    Hq, Hkv, D, BS = 32, 8, 128, 16
+@pytest.mark.parametrize("ctxs,Hq,Hkv", [([1, 16, 17, 528, 100, 33], 32, 8), ([544] * 8, 32, 8),
+                                        ([5, 40, 300], 3, 1), ([70, 129, 16, 31], 28, 4), ([33, 257], 12, 2)])
+def test_attn_decode_paged(ops, ctxs, Hq, Hkv):
+    """GQA groups 4 (Llama-3-8B) and 3 / 7 / 6 (Qwen2.5 sizes): the group's query heads share one m16 tile."""
+    D, BS = 128, 16
     B = len(ctxs)
     max_blocks = (max(ctxs) + BS - 1) // BS
     nblk = B * max_blocks + 3

@@ -305,6 +305,37 @@ def test_decode_rope_fused_into_attention_is_bit_identical(cfg, batch):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("n_q,n_kv,batch", [(3, 1, 7), (12, 2, 33), (28, 4, 64)])
+def test_qwen_style_decode_token_parity(n_q, n_kv, batch):
+    """Qwen2-style blocks (q/k/v biases; GQA groups 3 / 6 / 7; theta 1e6) through prefill + the decode loop: tokens vs
+    the oracle on peaked-logit weights, CUDA graph == plain launches, fused RoPE paths == separate kernels."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    cfg = dict(n_layers=2, dim=n_q * 128, n_q_heads=n_q, n_kv_heads=n_kv, head_dim=128, ffn_dim=1024, vocab=2048)
+    w = synth.llama_weights(seed=6, peaked=True, device="cuda", qkv_bias=True,
+                            **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg, rms_eps=1e-6, rope_theta=1e6)
+    lens = [12 + (i * 13) % 70 for i in range(batch)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(8))
+    emb = w["model.embed_tokens.weight"][tok].cuda().to(torch.bfloat16)
+    got = model.generate_packed(emb, cu, 16)
+    assert torch.equal(got, model.generate_packed(emb, cu, 16, use_graph=False))
+    lib = L.load()
+    try:
+        L.check(lib.opus_set_tunable(b"decode_rope_fused", 0))
+        L.check(lib.opus_set_tunable(b"tma_store", 0))
+        assert torch.equal(got, model.generate_packed(emb, cu, 16))
+    finally:
+        L.check(lib.opus_set_tunable(b"decode_rope_fused", 1))
+        L.check(lib.opus_set_tunable(b"tma_store", 1))
+    e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+    ocfg = llama_ref.LlamaCfg(n_layers=2, dim=cfg["dim"], n_q_heads=n_q, n_kv_heads=n_kv, head_dim=128, ffn_dim=1024,
+                              vocab=2048, rms_eps=1e-6, rope_theta=1e6)
+    want = llama_ref.greedy_generate(_dev(w, torch.bfloat16), ocfg, e_pad, m_pad, 16)
+    assert float((got.cpu() == want.cpu()).all(1).float().mean()) >= 0.99
+
+
 def test_greedy_decode_default_init_margin_aware():
     """HF-init statistics: random logits have tiny top-1 margins, so token identity is fragile by construction
     (SURVEY.md §7); every disagreement must be explained by a near-tie in the oracle's own logits."""

@@ -157,3 +157,22 @@ def test_scoring_oracle_matches_reference_forward_golden():
     logits, _ = llama_ref.llama_forward(w, ocfg, e, m, pos, all_positions=True)
     assert float((logits - g["logits"].float())[m].abs().max()) <= 0.05          # fixture logits are stored in bf16
     assert abs(float(llama_ref.causal_lm_loss(logits, lab)) - float(g["loss"])) <= 1e-4
+
+
+def test_qwen_oracle_matches_reference_wrapper_golden():
+    """Sibling family (opus_qwen.py): the Llama restatement + q/k/v biases against the reference's own
+    OpusQwenForCausalLM.generate output pinned in tests/golden/qwen_small.pt."""
+    g = _load("qwen_small.pt")
+    c = g["cfg"]
+    w = synth.llama_weights(c["n_layers"], c["dim"], c["n_q_heads"], c["n_kv_heads"], c["head_dim"], c["ffn_dim"],
+                            c["vocab"], seed=g["seed"], qkv_bias=True)
+    ocfg = llama_ref.LlamaCfg(n_layers=c["n_layers"], dim=c["dim"], n_q_heads=c["n_q_heads"],
+                              n_kv_heads=c["n_kv_heads"], head_dim=c["head_dim"], ffn_dim=c["ffn_dim"], vocab=c["vocab"],
+                              rms_eps=g["rms_eps"], rope_theta=g["rope_theta"])
+    mask = g["mask"]
+    emb = w["model.embed_tokens.weight"][g["input_ids"]]
+    pos = (mask.long().cumsum(-1) - 1).masked_fill(~mask, 1)
+    logits, _ = llama_ref.llama_forward(w, ocfg, emb, mask, pos)
+    assert torch.allclose(logits, g["prefill_logits"], atol=5e-4)
+    out = llama_ref.greedy_generate(w, ocfg, emb, mask, g["max_new_tokens"], eos_ids=(g["eos"],), pad_id=g["pad"])
+    assert torch.equal(out, g["tokens"])
