@@ -314,7 +314,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("gemm_prefill_dram_bytes_per_launch")
-    roofline = {"kernel": "gemm_bf16_tcgen05_kernel<256> (prefill linears, M=%d)" % M, "bound": "tensor",
+    roofline = {"kernel": "tcgen05 GEMM, prefill linears at M=%d: gemm_bf16_2cta_kernel (cta_group::2; qkv, o_proj, down) + "
+                          "gemm_bf16_tcgen05_kernel<256> (gate/up, SwiGLU epilogue)" % M, "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
                 "traffic": traffic, "peak_source": peaks["source"] + ", burst figure (kernel timed alone)",
                 "per_shape": per_shape}

@@ -291,6 +291,8 @@ int opus_release_graphs(void);
  * form (off by default: it would make a token's rounding depend on its position in the batch); "decode_fused" = 1
  * runs o_proj -> norm -> gate/up -> down -> norm -> next qkv / lm_head of a decode step as one persistent chain kernel,
  * 0 (default) = one kernel per GEMM / norm; "chain_l2_depth" = k-blocks the chain kernel prefetches into L2 per phase;
+ * "gemm_2cta" = 0 single-CTA GEMM everywhere, 1 CTA-pair (cta_group::2) form for every large plain GEMM, 2 (default) the
+ * pair form except under the SwiGLU epilogue;
  * "decode_rope_fused" = 0 runs the decode step's split-K reduce + RoPE + KV append as its own kernel instead of inside
  * the paged-attention CTAs (default 1);
  * "tma_store" = 0 sends the plain bf16 / GELU GEMM epilogues back to direct row-per-thread stores (and the encoder's rotary

@@ -787,6 +787,160 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) form of the plain GEMM: a cluster of two CTAs computes a 256 x 256 output tile with one UMMA
+// of M = 256. Each CTA loads 128 rows of A and 128 of the 256 B rows per k-block (32 KB per stage instead of 48 KB, so
+// six stages fit: 50 % more bytes in flight and half the B traffic per SM); the leader CTA issues the MMAs for the pair,
+// both CTAs drain their own 128 accumulator rows. Barrier protocol (all barriers live at the same offsets in both CTAs):
+//   full[s]      leader only : expect_tx of BOTH CTAs' bytes, both producers' TMA loads complete on it
+//   empty[s]     both        : tcgen05.commit multicast when the MMAs that read stage s retire
+//   acc_full[a]  both        : tcgen05.commit multicast when a tile's accumulator is complete
+//   acc_empty[a] leader only : 2 x 256 epilogue threads (the peer arrives remotely)
+// ------------------------------------------------------------------------------------------------
+struct Cfg2 {
+  static constexpr int BN = 256;
+  static constexpr int STAGE_A = BM * BK * 2;          // this CTA's 128 rows of A
+  static constexpr int STAGE_B = (BN / 2) * BK * 2;    // this CTA's 128 rows of B
+  static constexpr int STAGE = STAGE_A + STAGE_B;      // 32 KB
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 512;                // two 256-column accumulator buffers
+  static constexpr int STORE_BYTES = 8 * 4096;
+  static constexpr int BARS_OFF = STAGES * STAGE + STORE_BYTES;
+  static constexpr int SMEM = BARS_OFF + 1024 + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+  using C = Cfg2;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BARS_OFF);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + C::STAGES;
+  uint64_t* acc_full = bars + 2 * C::STAGES;
+  uint64_t* acc_empty = bars + 2 * C::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();        // 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM);     // 256-row tiles
+  const int n_tiles = p.num_n_tiles;
+  const int total = m_tiles * n_tiles;
+  const int group = max(1, p.group_m / 2);
+  auto tile_of = [&](int t, int& m, int& n) {             // grouped-M raster over 256-row tiles
+    const int per_group = group * n_tiles;
+    const int g = t / per_group, r = t - g * per_group;
+    const int first_m = g * group;
+    const int gsz = min(m_tiles - first_m, group);
+    m = first_m + r % gsz;
+    n = r / gsz;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 2 * NUM_EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();                              // both CTAs' barriers exist before any remote arrive / TMA signal
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        int m, n;
+        tile_of(t, m, n);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE);   // bytes of both CTAs
+          tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, (2 * m + rank) * BM, p.hint_a);
+          tma_load_2d_pair(sa + C::STAGE_A, &tmap_b, &full_bar[stage], kb * BK, n * BN + rank * (BN / 2), p.hint_b);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < total; t += n_pairs) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+          const uint64_t da = umma_smem_desc_sw128(sa);
+          const uint64_t db = umma_smem_desc_sw128(sa + C::STAGE_A);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);   // both CTAs' slots
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&acc_full[acc]);        // both CTAs' epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs): this CTA's 128 rows of the tile =====================
+    const int quad = warp & 3;
+    const int chunk0 = (warp - 2) >> 2;
+    const int epi_tid = threadIdx.x - 64;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < total; t += n_pairs) {
+      TileCoord tc;
+      int m, n;
+      tile_of(t, m, n);
+      tc.m = 2 * m + rank; tc.n = n; tc.kb_begin = 0; tc.kb_end = p.k_blocks; tc.split = 0;
+      tc.kind = WORK_TILE; tc.sk_tile = 0; tc.first_cta = 0;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_item<BN, false>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out, smem + C::STAGES * C::STAGE);
+      tc_fence_before();
+      mbar_arrive_leader(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.tma_store && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();            // the peer's shared memory / TMEM stay alive until the leader's last MMA has retired
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused chain kernel (see gemm.h: gemm_chain)
 // ------------------------------------------------------------------------------------------------
 struct ChainTmaps {
@@ -1353,12 +1507,60 @@ bool gemm_fuses_rope(const GemmArgs& a) {
          (a.rope_cols % 64) == 0 && (a.rope_q_cols % 64) == 0;
 }
 
+namespace {
+int g_2cta = -1;   // CTA-pair form for large plain GEMMs (tunable "gemm_2cta", env OPUS_GEMM_2CTA; default 2)
+
+int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM) != cudaSuccess)
+      return OPUS_ERR_CUDA;
+    configured = true;
+  }
+  CUtensorMap ta, tb, to;
+  int rc = make_tmap_bf16(&ta, a.A, p.M, p.K, a.lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, a.B, p.N, p.K, a.ldb, Cfg2::BN / 2);
+  if (rc) return rc;
+  to = ta;
+  if (p.tma_store) {
+    rc = make_tmap_bf16(&to, p.out, p.M, p.N, p.ldo, 32);
+    if (rc) return rc;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(num_sms() & ~1);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg2::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_2cta_kernel, ta, tb, to, p);
+  note_launch();
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
+}
+}  // namespace
+
+void gemm_set_2cta(int on) { g_2cta = on < 0 ? 0 : (on > 2 ? 2 : on); }
+
 // D = epi(A * B^T). See gemm.h for the contract.
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   GemmParams p;
   int bn = 0;
   const int rc = prepare_gemm(a, p, bn);
   if (rc != OPUS_OK) return rc;
+  if (g_2cta < 0) {
+    const char* e = std::getenv("OPUS_GEMM_2CTA");
+    g_2cta = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  }
+  // 1 = every eligible launch, 2 = every eligible launch except the SwiGLU epilogue (measured slower there)
+  if (g_2cta && !a.transposed && bn == 256 && p.split_k == 1 && p.sk_tiles == 0 && a.M >= 1024 && a.block_n == 0 &&
+      !(g_2cta == 2 && a.epi == EPI_SWIGLU))
+    return launch_2cta(p, a, stream);
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {

@@ -480,6 +480,10 @@ int set_tunable(const char* name, int value) {
     g_decode_fused = value != 0;
     return release_graphs();
   }
+  if (std::strcmp(name, "gemm_2cta") == 0) {
+    gemm_set_2cta(value);
+    return release_graphs();
+  }
   if (std::strcmp(name, "tma_store") == 0) {
     gemm_set_tma_store(value);
     return release_graphs();

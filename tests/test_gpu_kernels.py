@@ -191,6 +191,34 @@ def test_gemm_streamk_tail_plain(ops, rows, N, K, streamk_plain):
     _close_bf16(h, R.bf16r(res.float() + R.bf16r(R.linear_ref(x, w))), ulps=2.0, atol=2e-2)
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 256, 64), (1100, 768, 1280), (4096, 5120, 1280), (16512, 1280, 1280),
+                                   (2500, 6272, 512)])
+def test_gemm_cta_pair_form_is_bit_identical(ops, M, N, K):
+    """cta_group::2 kernel (two CTAs share a 256 x 256 tile, UMMA M = 256, B split across the pair) against the
+    single-CTA kernel: same k order per output element, so every epilogue must agree bit for bit."""
+    from opus_pllm_b200 import _lib as L
+    x = _randn((M, K), 50)
+    w = _randn((N, K), 51, scale=K ** -0.5)
+    b = _randn((N,), 52, dtype=torch.float32)
+    res = _randn((M, N), 53)
+    lib = L.load()
+    out = {}
+    try:
+        for mode in (1, 0):
+            L.check(lib.opus_set_tunable(b"gemm_2cta", mode))
+            h = res.clone()
+            ops.gemm(x, w, epilogue=L.EPI_RES_BF16, residual=h, out=h, transposed=False)
+            out[mode] = (ops.gemm(x, w, epilogue=L.EPI_BF16, bias=b, transposed=False),
+                         ops.gemm(x, w, epilogue=L.EPI_BF16_GELU, bias=b, transposed=False),
+                         ops.gemm(x, w, epilogue=L.EPI_SWIGLU, transposed=False) if N % 16 == 0 else None, h)
+    finally:
+        L.check(lib.opus_set_tunable(b"gemm_2cta", 2))
+    for a, c in zip(out[1], out[0]):
+        if a is not None:
+            assert torch.equal(a, c)
+    _close_bf16(out[1][0], R.linear_ref(x, w, b))
+
+
 def test_gemm_linearity_full_size(ops):
     """size-independent property at a BASELINE-sized weight: f(x1 + x2) == f(x1) + f(x2) up to bf16 rounding."""
     from opus_pllm_b200._lib import EPI_F32

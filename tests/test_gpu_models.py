@@ -197,7 +197,9 @@ def test_prefill_logits_vs_oracle(cfg, lens):
 
 @pytest.mark.parametrize("cfg,lens", [(SMALL, [140, 37, 129, 64]),
                                       (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
-                                            ffn_dim=14336, vocab=8192), [300, 33, 200])])
+                                            ffn_dim=14336, vocab=8192), [300, 33, 200]),
+                                      (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
+                                            ffn_dim=14336, vocab=8192), [700, 512, 130])])   # >= 1024 rows: CTA-pair GEMMs
 def test_prefill_fused_rope_kvappend_epilogue_is_bit_identical(cfg, lens):
     """The prefill q|k|v GEMM rotates q/k and appends k/v to the paged cache in its epilogue; with the tunable off the
     plain epilogue + rope_llama_kvappend_kernel run instead. Same rounding points -> identical logits and cache."""
