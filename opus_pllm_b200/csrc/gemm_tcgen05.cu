@@ -448,6 +448,48 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
     uint8_t* my_stage = stage + (quad + 4 * chunk0) * 4096;
     const uint32_t st_row = smem_u32(my_stage) + lane * 128;
     if constexpr (BN == 256) {
+      if (p.epi == EPI_SWIGLU) {
+        // interleaved (gate, up) columns: this warp pair owns input columns [chunk0*128, +128) of the tile = 64 output
+        // columns = one store box. HF rounding points: bf16(silu(bf16 gate)) * bf16 up, rounded once more on the pack.
+        const int ocol0 = (tc.n * BN + chunk0 * 128) >> 1;          // first output column of the box
+        if (tc.n * BN + chunk0 * 128 < p.N) {
+          uint32_t pk[32];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[64];
+            tmem_ld_32x32(taddr + chunk0 * 128 + hf * 64, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            tmem_ld_32x32(taddr + chunk0 * 128 + hf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float o[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float g = bf16_round(__uint_as_float(r[2 * (j + e)]));
+                const float u = bf16_round(__uint_as_float(r[2 * (j + e) + 1]));
+                o[e] = bf16_round(silu_f(g)) * u;
+              }
+              pk[hf * 16 + (j >> 1)] = pack_bf16x2(o[0], o[1]);
+            }
+          }
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int ch = q ^ (lane & 7);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_row + ch * 16), "r"(pk[q * 4]),
+                         "r"(pk[q * 4 + 1]), "r"(pk[q * 4 + 2]), "r"(pk[q * 4 + 3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tm_out, my_stage, ocol0, tc.m * BM + quad * 32);
+            tma_store_commit();
+          }
+        }
+        return;
+      }
       if (p.rl_cos != nullptr) {
         // ---- Llama q|k|v projection: rotary embedding + paged KV append in the epilogue. This warp pair (chunk0)
         // owns head 2n + chunk0 of the tile; a thread holds its token's 128 accumulator columns of that head.
@@ -1318,7 +1360,8 @@ int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, cons
   }
   CUtensorMap to = ta;  // unused unless p.tma_store
   if (p.tma_store) {
-    rc = make_tmap_bf16(&to, p.out, p.M, p.N, p.ldo, 32);   // box = 32 rows x 64 columns, one per epilogue warp
+    // box = 32 rows x 64 columns, one per epilogue warp (SwiGLU halves the output width)
+    rc = make_tmap_bf16(&to, p.out, p.M, p.epi == EPI_SWIGLU ? p.N / 2 : p.N, p.ldo, 32);
     if (rc) return rc;
   }
   const cudaError_t le =
@@ -1459,8 +1502,9 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     const char* e = std::getenv("OPUS_TMA_STORE");
     g_tma_store_on = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  p.tma_store = g_tma_store_on && !a.transposed && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU) && (a.ldo % 8) == 0 &&
-                (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && bn >= 64;
+  p.tma_store = g_tma_store_on && !a.transposed && (a.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                ((bn >= 64 && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU)) ||
+                 (bn == 256 && a.epi == EPI_SWIGLU && (a.N % 128) == 0));
   if (a.rl_cos != nullptr) {
     if (!(p.tma_store && a.epi == EPI_BF16 && bn == 256 && a.rl_pos != nullptr && a.rl_sin != nullptr && a.rl_bs > 0 &&
           a.N == (a.rl_hq + 2 * a.rl_hkv) * 128))
@@ -1524,7 +1568,7 @@ int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   to = ta;
   if (p.tma_store) {
-    rc = make_tmap_bf16(&to, p.out, p.M, p.N, p.ldo, 32);
+    rc = make_tmap_bf16(&to, p.out, p.M, p.epi == EPI_SWIGLU ? p.N / 2 : p.N, p.ldo, 32);
     if (rc) return rc;
   }
   cudaLaunchConfig_t cfg{};
