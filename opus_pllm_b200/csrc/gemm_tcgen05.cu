@@ -1488,6 +1488,17 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   // weights are streamed once in the swap-AB form; activations are re-read by every tile
   p.hint_a = a.transposed ? kCacheEvictFirst : kCacheEvictNormal;
   p.hint_b = a.transposed ? kCacheEvictLast : kCacheEvictNormal;
+  {
+    // plain form: the A panel of a raster group is re-read by every n-tile of the group, B is streamed once per group
+    static int plain_hints = -1;
+    if (plain_hints < 0) {
+      const char* e = std::getenv("OPUS_GEMM_HINTS");
+      plain_hints = e ? atoi(e) : 0;
+    }
+    if (!a.transposed && plain_hints == 1) { p.hint_a = kCacheEvictLast; p.hint_b = kCacheEvictFirst; }
+    if (!a.transposed && plain_hints == 2) { p.hint_a = kCacheEvictLast; p.hint_b = kCacheEvictNormal; }
+    if (!a.transposed && plain_hints == 3) { p.hint_a = kCacheEvictNormal; p.hint_b = kCacheEvictFirst; }
+  }
 
   if (a.pf_w != nullptr && a.pf_depth > 0 && a.pf_rows > 0 && a.pf_K > 0 && (a.pf_K % 8) == 0 &&
       (reinterpret_cast<uintptr_t>(a.pf_w) & 15) == 0) {

@@ -1,0 +1,13 @@
+"""gate/up prefill GEMM (SwiGLU) once per mode for ncu: single-CTA vs CTA-pair."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from opus_pllm_b200 import ops, _lib as L
+lib = L.load()
+x = torch.randn(32768, 4096, device="cuda").bfloat16() * 0.05
+w = torch.randn(28672, 4096, device="cuda").bfloat16() * 0.02
+for mode in (0, 1, 0, 1):
+    L.check(lib.opus_set_tunable(b"gemm_2cta", mode))
+    ops.gemm(x, w, epilogue=L.EPI_SWIGLU, transposed=False)
+torch.cuda.synchronize()
+print("done")
