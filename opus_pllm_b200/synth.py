@@ -166,3 +166,39 @@ def lora_adapters(w: dict, n_layers: int, r: int = 16, seed: int = 0, device="cp
             out[key + ".lora_A.weight"] = weight((r, k), f"lora.{i}.{t}.A", 0.02, seed, device=device)
             out[key + ".lora_B.weight"] = weight((o, r), f"lora.{i}.{t}.B", 0.02, seed, device=device)
     return out
+
+
+def opt_weights(n_layers: int, dim: int, n_heads: int, ffn: int, vocab: int, max_pos: int = 2048, seed: int = 0,
+                peaked: bool = False, dtype=torch.float32, device="cpu", bias: bool = True) -> dict:
+    """HF OPT / Galactica state-dict names (`model.decoder.*`, learned positions with the offset-2 table, LayerNorm with
+    bias, fc1/fc2; the sibling family of language_model/opus_opt.py). `lm_head.weight` is tied to the embedding in real
+    OPT checkpoints; here it is a separate tensor so that peaked=True can use the token-parity recipe of llama_weights.
+    bias=False is Galactica's `enable_bias: false`."""
+    emb_std = 1.0 if peaked else 0.02
+    out_std = 0.02 / math.sqrt(2 * n_layers) if peaked else 0.02
+    p0 = "model.decoder."
+    w = {p0 + "embed_tokens.weight": weight((vocab, dim), "opt.embed", emb_std, seed, device=device).to(dtype),
+         p0 + "embed_positions.weight": weight((max_pos + 2, dim), "opt.pos", 0.3 * emb_std, seed, device=device).to(dtype)}
+    for i in range(n_layers):
+        p = f"{p0}layers.{i}."
+        for n, std in (("q_proj", 0.02), ("k_proj", 0.02), ("v_proj", 0.02), ("out_proj", out_std)):
+            w[p + f"self_attn.{n}.weight"] = weight((dim, dim), f"opt.{i}.{n}.w", std, seed, device=device).to(dtype)
+            if bias:
+                w[p + f"self_attn.{n}.bias"] = weight((dim,), f"opt.{i}.{n}.b", 0.05, seed, device=device).to(dtype)
+        w[p + "fc1.weight"] = weight((ffn, dim), f"opt.{i}.fc1.w", 0.02, seed, device=device).to(dtype)
+        w[p + "fc2.weight"] = weight((dim, ffn), f"opt.{i}.fc2.w", out_std, seed, device=device).to(dtype)
+        if bias:
+            w[p + "fc1.bias"] = weight((ffn,), f"opt.{i}.fc1.b", 0.05, seed, device=device).to(dtype)
+            w[p + "fc2.bias"] = weight((dim,), f"opt.{i}.fc2.b", 0.05 * (out_std / 0.02), seed, device=device).to(dtype)
+        for n in ("self_attn_layer_norm", "final_layer_norm"):
+            w[p + n + ".weight"] = weight((dim,), f"opt.{i}.{n}.g", 0.05, seed, mean=1.0, device=device).to(dtype)
+            w[p + n + ".bias"] = weight((dim,), f"opt.{i}.{n}.b", 0.05, seed, device=device).to(dtype)
+    w[p0 + "final_layer_norm.weight"] = weight((dim,), "opt.lnf.g", 0.05, seed, mean=1.0, device=device).to(dtype)
+    w[p0 + "final_layer_norm.bias"] = weight((dim,), "opt.lnf.b", 0.05, seed, device=device).to(dtype)
+    if peaked:
+        g = torch.Generator().manual_seed(seed + 17)
+        perm = torch.randperm(vocab, generator=g).to(device)
+        w["lm_head.weight"] = (w[p0 + "embed_tokens.weight"].float()[perm] * (8.0 / math.sqrt(dim))).to(dtype)
+    else:
+        w["lm_head.weight"] = weight((vocab, dim), "opt.lm_head", 0.02, seed, device=device).to(dtype)
+    return w

@@ -266,9 +266,61 @@ def golden_qwen():
     print(f"qwen_small.pt: oracle vs reference OpusQwenForCausalLM: logits max |diff| {d_l:.3g}, tokens identical {tuple(out.shape)}")
 
 
+def golden_opt():
+    """Sibling family (model/language_model/opus_opt.py, chosen at builder.py:71-81): the reference's OpusOPTForCausalLM
+    (OPT: learned positions, LayerNorm, biased linears, ReLU MLP; Galactica: same blocks, erf-GELU, no biases) on tiny
+    configs with hash-seeded weights; text-only greedy generate (`seq=None` branch, opus_opt.py:124-125) and
+    last-position prefill logits. The OPT wrapper needs no transformers-version shim."""
+    from multi_modality_model.multi_modality_v1.model.language_model.opus_opt import OpusOPTConfig, OpusOPTForCausalLM
+    from oracle import opt_ref
+    cases = {}
+    for name, act, bias, seed in (("opt", "relu", True, 29), ("galactica", "gelu", False, 31)):
+        c = dict(n_layers=2, dim=256, n_heads=2, ffn_dim=512, vocab=1024, max_pos=256)
+        hf_cfg = OpusOPTConfig(vocab_size=c["vocab"], hidden_size=c["dim"], ffn_dim=c["ffn_dim"],
+                               num_hidden_layers=c["n_layers"], num_attention_heads=c["n_heads"],
+                               max_position_embeddings=c["max_pos"], word_embed_proj_dim=c["dim"],
+                               do_layer_norm_before=True, activation_function=act, enable_bias=bias, dropout=0.0,
+                               bos_token_id=0, eos_token_id=2, pad_token_id=1, tie_word_embeddings=False)
+        hf_cfg._attn_implementation = "eager"
+        lw = synth.opt_weights(c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], c["max_pos"], seed=seed,
+                               bias=bias)
+        model = OpusOPTForCausalLM(hf_cfg).eval()
+        sd = dict(lw)
+        sd["model.embed_tokens.weight"] = lw["model.decoder.embed_tokens.weight"]   # opus_opt.py:24 aliases the table
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not [m for m in missing if "protein" not in m and "switch" not in m], missing
+        assert not unexpected, unexpected
+        B, L = 5, 21
+        g = torch.Generator().manual_seed(43)
+        ids = torch.randint(3, c["vocab"], (B, L), generator=g)
+        pad = 1
+        for b in range(B):                                       # left padding, ragged
+            ids[b, : b * 2] = pad
+        mask = ids != pad
+        with torch.no_grad():
+            out = model.generate(ids, None, attention_mask=mask, pad_token_id=2, do_sample=False, max_new_tokens=10,
+                                 use_cache=True)
+            emb = model.get_model().embed_tokens(ids)
+            logits = model(inputs_embeds=emb, attention_mask=mask).logits[:, -1, :].float().clone()
+        ocfg = opt_ref.OptCfg(n_layers=c["n_layers"], dim=c["dim"], n_heads=c["n_heads"], ffn_dim=c["ffn_dim"],
+                              vocab=c["vocab"], max_pos=c["max_pos"], activation=act)
+        lg_mine, _ = opt_ref.opt_forward(lw, ocfg, emb.float(), mask, opt_ref.positions_from_mask(mask))
+        out_mine = opt_ref.greedy_generate(lw, ocfg, emb.float(), mask, 10, eos_ids=(2,), pad_id=2)
+        d_l = float((lg_mine - logits).abs().max())
+        assert d_l < 2e-4, d_l
+        assert out_mine.shape == out.shape and torch.equal(out_mine, out), (out_mine, out)
+        cases[name] = dict(cfg=c, seed=seed, activation=act, bias=bias, input_ids=ids, mask=mask, prefill_logits=logits,
+                           tokens=out, eos=2, pad=2, max_new_tokens=10, oracle_dev=dict(logits=d_l, tokens=0))
+        print(f"opt_small.pt[{name}]: oracle vs reference OpusOPTForCausalLM: logits max |diff| {d_l:.3g}, "
+              f"tokens identical {tuple(out.shape)}")
+    cases["source"] = "reference OpusOPTForCausalLM.generate over transformers " + __import__("transformers").__version__
+    torch.save(cases, os.path.join(GOLD, "opt_small.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     w, seqs, pooled = golden_esm()
     golden_mm_and_llama(w, seqs, pooled)
     golden_qwen()
+    golden_opt()

@@ -176,3 +176,22 @@ def test_qwen_oracle_matches_reference_wrapper_golden():
     assert torch.allclose(logits, g["prefill_logits"], atol=5e-4)
     out = llama_ref.greedy_generate(w, ocfg, emb, mask, g["max_new_tokens"], eos_ids=(g["eos"],), pad_id=g["pad"])
     assert torch.equal(out, g["tokens"])
+
+
+@pytest.mark.parametrize("case", ["opt", "galactica"])
+def test_opt_oracle_matches_reference_wrapper_golden(case):
+    """Sibling family (opus_opt.py; builder.py:71-81): oracle/opt_ref.py against the reference's own
+    OpusOPTForCausalLM.generate output pinned in tests/golden/opt_small.pt (OPT: ReLU + biases; Galactica: GELU, none)."""
+    from oracle import opt_ref
+    g = _load("opt_small.pt")[case]
+    c = g["cfg"]
+    w = synth.opt_weights(c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], c["max_pos"], seed=g["seed"],
+                          bias=g["bias"])
+    ocfg = opt_ref.OptCfg(n_layers=c["n_layers"], dim=c["dim"], n_heads=c["n_heads"], ffn_dim=c["ffn_dim"],
+                          vocab=c["vocab"], max_pos=c["max_pos"], activation=g["activation"])
+    mask = g["mask"]
+    emb = w["model.decoder.embed_tokens.weight"][g["input_ids"]]
+    logits, _ = opt_ref.opt_forward(w, ocfg, emb, mask, opt_ref.positions_from_mask(mask))
+    assert torch.allclose(logits, g["prefill_logits"], atol=5e-4)
+    out = opt_ref.greedy_generate(w, ocfg, emb, mask, g["max_new_tokens"], eos_ids=(g["eos"],), pad_id=g["pad"])
+    assert torch.equal(out, g["tokens"])
