@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OPUS_B200_ABI_VERSION 1
+#define OPUS_B200_ABI_VERSION 2
 
 enum {
   OPUS_OK = 0,
@@ -43,7 +43,8 @@ enum {
   OPUS_EPI_RES_BF16 = 3,    /* out bf16 = bf16(residual + bf16(acc))  (Llama o_proj / down_proj) */
   OPUS_EPI_SWIGLU = 4,      /* features interleaved (gate_j, up_j) -> out bf16[.., j] = silu(gate)*up */
   OPUS_EPI_PARTIAL_F32 = 5, /* split-K partial sums, out f32 [split][rows][ldo] */
-  OPUS_EPI_F32 = 6          /* out f32 = acc (+ bias), transposed form only */
+  OPUS_EPI_F32 = 6,         /* out f32 = acc (+ bias), transposed form only */
+  OPUS_EPI_BF16_RELU = 7    /* out bf16 = relu(acc + bias)            (OPT fc1: HF OPTDecoderLayer, activation "relu") */
 };
 
 int opus_abi_version(void);
@@ -135,6 +136,18 @@ int opus_sample_top_p(const void* logits, int ld, int vocab, int n_rows, float t
 int opus_cross_entropy_bf16(const void* logits, int ld, int vocab, const int32_t* target, float* loss, int n_rows,
                             void* stream);
 int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n_rows, int dim, void* stream);
+/* OPT / Galactica family (language_model/opus_opt.py -> HF OPTDecoder). nn.LayerNorm over a bf16 residual stream with
+ * the fusions of opus_rmsnorm_bf16 plus the bias of the linear whose split-K partials are reduced:
+ *   h = x  or  bf16(sum_s partial[s] + red_bias)   (exactly one of x / partial non-null; red_bias fp32 [cols] nullable)
+ *   h = bf16(h + residual) if residual;  h_out <- h if h_out;
+ *   y <- bf16((h - mean) * rsqrt(var + eps) * gamma + beta) if y   (gamma, beta fp32 [cols]; beta nullable). */
+int opus_layernorm_bf16(const void* x, const float* partial, int n_partial, const float* red_bias, const void* residual,
+                        void* h_out, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
+                        void* stream);
+/* OPTLearnedPositionalEmbedding: h[i,:] = bf16(h[i,:] + table[pos[i] + offset, :]) in place (offset = 2 in HF);
+ * table bf16 [table_rows, dim], pos int32 [n_rows]. */
+int opus_add_pos_embed_bf16(void* h, const void* table, const int32_t* pos, int offset, int table_rows, int n_rows,
+                            int dim, void* stream);
 /* W += scale * (B @ A): peft merge_and_unload (multi_modality_v1/model/builder.py:107-109). */
 int opus_lora_merge_bf16(void* W, const void* A, const void* B, int out_features, int in_features, int r, float scale,
                          void* stream);
@@ -215,7 +228,14 @@ typedef struct {
   const void* ln2_w;
   const void* wgu;   /* bf16 [2*ffn, dim], rows interleaved gate_0, up_0, gate_1, up_1, ... */
   const void* wdown; /* bf16 [dim, ffn] */
-  const float* bqkv; /* fp32 [(Hq+2*Hkv)*hd] q|k|v projection bias (Qwen2 family) or NULL (Llama) */
+  const float* bqkv; /* fp32 [(Hq+2*Hkv)*hd] q|k|v projection bias (Qwen2 / OPT families) or NULL (Llama) */
+  /* OPT / Galactica family only (arch == OPUS_ARCH_OPT; NULL otherwise). There ln1_w / ln2_w are unused: the LayerNorm
+   * gains live in ln1_g / ln2_g as fp32, wgu holds fc1 [ffn, dim] (plain rows, no gate) and wdown holds fc2. */
+  const float* ln1_g; const float* ln1_b; /* fp32 [dim] self_attn_layer_norm weight / bias (bias NULL = none) */
+  const float* ln2_g; const float* ln2_b; /* fp32 [dim] final_layer_norm of the layer */
+  const float* bo;   /* fp32 [dim]  out_proj bias or NULL */
+  const float* b1;   /* fp32 [ffn]  fc1 bias or NULL */
+  const float* b2;   /* fp32 [dim]  fc2 bias or NULL */
 } opus_llama_layer;
 
 typedef struct {
@@ -225,8 +245,17 @@ typedef struct {
   const opus_llama_layer* layers; /* HOST array */
   const void* norm_w;             /* bf16 [dim] */
   const void* lm_head;            /* bf16 [vocab, dim] */
-  const void* rope_cos; const void* rope_sin; /* bf16 [rope_max_pos, head_dim] */
+  const void* rope_cos; const void* rope_sin; /* bf16 [rope_max_pos, head_dim] (OPT: cos = 1, sin = 0, i.e. no rotation) */
+  /* Decoder family. OPUS_ARCH_LLAMA (0): RMSNorm + RoPE + SwiGLU blocks (Llama, Qwen2; opus_llama.py / opus_qwen.py).
+   * OPUS_ARCH_OPT (1): HF OPTDecoder with do_layer_norm_before (opus_opt.py; OPT and Galactica): learned positions
+   * h = embeds + pos_embed[pos + 2], LayerNorm (eps = rms_eps), biased linears, fc1 -> ReLU | erf-GELU -> fc2, MHA. */
+  int32_t arch;
+  int32_t opt_act;                /* OPT family: 0 = ReLU, 1 = erf-GELU */
+  const void* pos_embed;          /* OPT family: bf16 [pos_rows, dim] (HF embed_positions.weight, offset 2 included) */
+  int32_t pos_rows; int32_t reserved_;
+  const float* norm_g; const float* norm_b; /* OPT family: decoder.final_layer_norm fp32 [dim] */
 } opus_llama_model;
+enum { OPUS_ARCH_LLAMA = 0, OPUS_ARCH_OPT = 1 };
 
 typedef struct {
   void* k; void* v;          /* bf16 [n_layers][num_blocks][n_kv_heads][block_size][head_dim], zero-initialised */

@@ -12,7 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libopus_b200.so")
 
 OK = 0
-EPI_BF16, EPI_BF16_GELU, EPI_RES_F32, EPI_RES_BF16, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_F32 = range(7)
+EPI_BF16, EPI_BF16_GELU, EPI_RES_F32, EPI_RES_BF16, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_F32, EPI_BF16_RELU = range(8)
+ARCH_LLAMA, ARCH_OPT = 0, 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_float, c_size_t, c_longlong = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
@@ -45,14 +47,17 @@ class ProjectorModel(C.Structure):
 
 
 class LlamaLayer(C.Structure):
-    _fields_ = [(n, c_void_p) for n in ("ln1_w", "wqkv", "wo", "ln2_w", "wgu", "wdown", "bqkv")]
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "wqkv", "wo", "ln2_w", "wgu", "wdown", "bqkv",
+                                        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "bo", "b1", "b2")]   # OPT family tail
 
 
 class LlamaModel(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dim", C.c_int32), ("n_q_heads", C.c_int32), ("n_kv_heads", C.c_int32),
                 ("head_dim", C.c_int32), ("ffn_dim", C.c_int32), ("vocab", C.c_int32), ("rope_max_pos", C.c_int32),
                 ("rms_eps", c_float), ("embed", c_void_p), ("layers", C.POINTER(LlamaLayer)),
-                ("norm_w", c_void_p), ("lm_head", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p)]
+                ("norm_w", c_void_p), ("lm_head", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p),
+                ("arch", C.c_int32), ("opt_act", C.c_int32), ("pos_embed", c_void_p), ("pos_rows", C.c_int32),
+                ("reserved_", C.c_int32), ("norm_g", c_void_p), ("norm_b", c_void_p)]
 
 
 class KvCache(C.Structure):
@@ -98,6 +103,8 @@ _SIGNATURES = {
     "opus_cross_entropy_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P]),
     "opus_embed_gather_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "opus_lora_merge_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "opus_layernorm_bf16": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
+    "opus_add_pos_embed_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "opus_attn_varlen_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_float, _P]),
     "opus_attn_decode_paged_bf16": (c_int, [_P, c_int, _P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int,
@@ -140,7 +147,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.opus_abi_version() != 1:
+    if lib.opus_abi_version() != ABI_VERSION:
         raise OpusError("libopus_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -3,7 +3,8 @@
 Same signature and return value `(tokenizer, model, context_len)`; the files read are the ones the reference reads
 ("Weight formats to load"):
   1. HF Llama-3 (or Qwen2 / Qwen2.5: same layout + q/k/v biases, builder.py:83-94) directory: `config.json` +
-     `*.safetensors` shards                                                              (builder.py:61-65)
+     `*.safetensors` shards                                                              (builder.py:61-65);
+     or an HF OPT / Galactica directory (`pytorch_model*.bin`, builder.py:71-82) -> `opt.py::B200Opt`
   2. `<weights>/lora_adapter/{adapter_config.json, adapter_model.safetensors|.bin}`     (builder.py:105-109, peft)
   3. `<weights>/modality_refinement_projector/modality_refinement_projection.bin`       (builder.py:111, opus_arch.py:85-89)
   4. `<weights>/modality_encoder/modality_encoding_adapter.ckpt` (Lightning checkpoint)  (protein_projector/builder.py:16-25)
@@ -55,6 +56,26 @@ def read_hf_llama(model_dir: str) -> tuple[dict, dict]:
     scaling = cfg.get("rope_scaling")
     if scaling and scaling.get("rope_type", scaling.get("type")) not in (None, "default"):
         warnings.warn(f"rope_scaling {scaling} is not applied (Llama-3-8B base uses the default rope)")
+    extra = dict(eos_token_id=cfg.get("eos_token_id"), max_sequence_length=cfg.get("max_sequence_length"))
+    return sd, dict(kw, **{"_extra": extra})
+
+
+def read_hf_opt(model_dir: str) -> tuple[dict, dict]:
+    """HF OPT / Galactica directory -> (state dict with HF names, kwargs for B200Opt). The reference loads these with
+    `use_safetensors=False` (builder.py:73-76), i.e. from pytorch_model*.bin; safetensors shards are read when present."""
+    cfg = json.load(open(os.path.join(model_dir, "config.json")))
+    shards = sorted(glob.glob(os.path.join(model_dir, "pytorch_model*.bin"))) or \
+        sorted(glob.glob(os.path.join(model_dir, "*.safetensors")))
+    if not shards:
+        raise FileNotFoundError(f"no pytorch_model*.bin / *.safetensors under {model_dir}")
+    sd = {}
+    for sh in shards:
+        sd.update(_load_any(sh))
+    if not cfg.get("do_layer_norm_before", True) or cfg.get("word_embed_proj_dim", cfg["hidden_size"]) != cfg["hidden_size"]:
+        raise NotImplementedError("OPT post-LN / projected-embedding variants (opt-350m) are not supported")
+    kw = dict(n_layers=cfg["num_hidden_layers"], dim=cfg["hidden_size"], n_heads=cfg["num_attention_heads"],
+              ffn_dim=cfg["ffn_dim"], vocab=cfg["vocab_size"], max_pos=cfg.get("max_position_embeddings", 2048),
+              activation=cfg.get("activation_function", "relu"))
     extra = dict(eos_token_id=cfg.get("eos_token_id"), max_sequence_length=cfg.get("max_sequence_length"))
     return sd, dict(kw, **{"_extra": extra})
 
@@ -143,20 +164,26 @@ def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=F
     from .model import build_from_state_dicts
     if model_name is None or not model_base_path:
         raise NotImplementedError
-    family = model_base_path.lower()
-    if "llama" not in family and "qwen" not in family:
-        # model/builder.py:71-96 also dispatches OPT / Galactica (LayerNorm, learned positions, ReLU): not built here
-        raise NotImplementedError("opus_pllm_b200 implements the Llama-3 and Qwen2 / Qwen2.5 families (head_dim 128)")
+    name = model_base_path.lower()
+    if "llama" in name or "qwen" in name:                                               # builder.py:59-70, 83-94
+        family = "llama"
+    elif "opt" in name or "galactica" in name:                                          # builder.py:71-82
+        family = "opt"
+    else:
+        raise NotImplementedError                                                       # builder.py:95-96
     if load_8bit or load_4bit:
         warnings.warn("load_8bit/load_4bit are ignored: opus_pllm_b200 runs bf16 weights")
     device = "cuda:0" if accelerator is None else f"cuda:{accelerator.process_index}"
-    llama_sd, llama_cfg = read_hf_llama(model_base_path)
+    llama_sd, llama_cfg = read_hf_llama(model_base_path) if family == "llama" else read_hf_opt(model_base_path)
     extra = llama_cfg.pop("_extra")
     if tokenizer is None:
         import transformers
         tokenizer = transformers.AutoTokenizer.from_pretrained(model_base_path, use_fast=False)
-        tokenizer.pad_token = tokenizer.unk_token = tokenizer.eos_token                 # builder.py:69-70
-        tokenizer.pad_token_id = tokenizer.unk_token_id = tokenizer.eos_token_id
+        if family == "opt":
+            tokenizer.pad_token, tokenizer.unk_token, tokenizer.eos_token = "<pad>", "<unk>", "</s>"   # builder.py:80-82
+        else:
+            tokenizer.pad_token = tokenizer.unk_token = tokenizer.eos_token             # builder.py:69-70
+            tokenizer.pad_token_id = tokenizer.unk_token_id = tokenizer.eos_token_id
     if accelerator is not None:
         accelerator.wait_for_everyone()                                                 # builder.py:102-103
     lora_sd, alpha, r, switch_sd = None, 32.0, 16, None
@@ -173,6 +200,6 @@ def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=F
     model = build_from_state_dicts(llama_sd, llama_cfg, esm_sd, esm_cfg, cstp_sd, switch_sd,
                                    switch_type=switch_projector_type, lora_sd=lora_sd, lora_alpha=alpha, lora_r=r,
                                    eos_token_id=extra["eos_token_id"] if extra["eos_token_id"] is not None else (),
-                                   device=device)
+                                   device=device, family=family)
     context_len = extra["max_sequence_length"] or 512                                  # builder.py:126-131
     return tokenizer, model, context_len

@@ -168,6 +168,21 @@ int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n
       "opus_embed_gather_bf16");
 }
 
+int opus_layernorm_bf16(const void* x, const float* partial, int n_partial, const float* red_bias, const void* residual,
+                        void* h_out, const float* gamma, const float* beta, void* y, int rows, int cols, float eps,
+                        void* stream) {
+  RET(layernorm_bf16(static_cast<const bf16*>(x), partial, n_partial, red_bias, static_cast<const bf16*>(residual),
+                     static_cast<bf16*>(h_out), gamma, beta, static_cast<bf16*>(y), rows, cols, eps, ST(stream)),
+      "opus_layernorm_bf16");
+}
+
+int opus_add_pos_embed_bf16(void* h, const void* table, const int32_t* pos, int offset, int table_rows, int n_rows,
+                            int dim, void* stream) {
+  RET(add_pos_embed(static_cast<bf16*>(h), static_cast<const bf16*>(table), pos, offset, table_rows, n_rows, dim,
+                    ST(stream)),
+      "opus_add_pos_embed_bf16");
+}
+
 int opus_lora_merge_bf16(void* W, const void* A, const void* B, int out_features, int in_features, int r, float scale,
                          void* stream) {
   RET(lora_merge(static_cast<bf16*>(W), static_cast<const bf16*>(A), static_cast<const bf16*>(B), out_features,

@@ -16,6 +16,7 @@ enum EpiMode : int {
   EPI_SWIGLU = OPUS_EPI_SWIGLU,            // interleaved (gate, up) features -> out bf16 = silu(gate) * up, half width
   EPI_PARTIAL_F32 = OPUS_EPI_PARTIAL_F32,  // split-K partial sums: out f32 [split][rows][ldo]
   EPI_F32 = OPUS_EPI_F32,                  // out f32 = acc (+ bias)   (transposed form only)
+  EPI_BF16_RELU = OPUS_EPI_BF16_RELU,      // out bf16 = relu(acc + bias)   (OPT fc1)
 };
 
 // Device-visible parameter block.

@@ -184,10 +184,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         }
       }
     }
-    if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU) {
+    if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU || p.epi == EPI_BF16_RELU) {
       if (p.epi == EPI_BF16_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      } else if (p.epi == EPI_BF16_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
       }
       if (row_ok) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
@@ -305,14 +308,16 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
   // residual values are all loaded before the first store because `out` may alias `residual`).
   const float b = (p.bias != nullptr && row_ok) ? p.bias[row] : 0.0f;
   const int n_valid = row_ok ? min(NC, p.N - col0) : 0;  // columns (batch rows) of this chunk that exist
-  if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU) {
+  if (p.epi == EPI_BF16 || p.epi == EPI_BF16_GELU || p.epi == EPI_BF16_RELU) {
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)col0 * p.ldo + row;
     const bool gelu = p.epi == EPI_BF16_GELU;
+    const float floor_v = p.epi == EPI_BF16_RELU ? 0.0f : -INFINITY;   // ReLU (OPT fc1) as a clamp: no extra branch
     float x[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
       x[i] = v[i] + b;
       if (gelu) x[i] = gelu_erf(x[i]);
+      x[i] = fmaxf(x[i], floor_v);
     }
     // M (features) is even and tiles start at multiples of 128, so a lane pair is either fully valid or fully invalid
     const int nv = (row | 1) < p.M ? min(NC, p.N - col0) : 0;
@@ -594,6 +599,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
         float v0 = __uint_as_float(r[g4 * 4]) + b.x, v1 = __uint_as_float(r[g4 * 4 + 1]) + b.y;
         float v2 = __uint_as_float(r[g4 * 4 + 2]) + b.z, v3 = __uint_as_float(r[g4 * 4 + 3]) + b.w;
         if (p.epi == EPI_BF16_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3); }
+        if (p.epi == EPI_BF16_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
         pk[g4 * 2] = pack_bf16x2(v0, v1);
         pk[g4 * 2 + 1] = pack_bf16x2(v2, v3);
       }
@@ -1451,7 +1457,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B)) & 15) return OPUS_ERR_ARG;
   if (!a.transposed && (a.N % 8)) return OPUS_ERR_ARG;
   if (a.epi == EPI_SWIGLU && ((a.transposed ? a.M : a.N) % 16)) return OPUS_ERR_ARG;
-  if (a.transposed && (a.M % 2) && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU || a.epi == EPI_RES_BF16))
+  if (a.transposed && (a.M % 2) && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU || a.epi == EPI_BF16_RELU || a.epi == EPI_RES_BF16))
     return OPUS_ERR_ARG;  // paired 4-byte stores need an even feature count
   if (a.transposed && (a.ldo % 2) && a.epi != EPI_PARTIAL_F32 && a.epi != EPI_F32 && a.epi != EPI_RES_F32)
     return OPUS_ERR_ARG;
@@ -1514,7 +1520,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     g_tma_store_on = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   p.tma_store = g_tma_store_on && !a.transposed && (a.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
-                ((bn >= 64 && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU)) ||
+                ((bn >= 64 && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU || a.epi == EPI_BF16_RELU)) ||
                  (bn == 256 && a.epi == EPI_SWIGLU && (a.N % 128) == 0));
   if (a.rl_cos != nullptr) {
     if (!(p.tma_store && a.epi == EPI_BF16 && bn == 256 && a.rl_pos != nullptr && a.rl_sin != nullptr && a.rl_bs > 0 &&

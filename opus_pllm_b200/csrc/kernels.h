@@ -52,6 +52,15 @@ int decode_advance(int* ctx_len, int* pos, int* slot, const int* block_table, in
 int lora_merge(__nv_bfloat16* W, const __nv_bfloat16* A, const __nv_bfloat16* B, int out_f, int in_f, int r, float scale,
                cudaStream_t st);
 
+// ---- bandwidth_opt.cu (OPT / Galactica family) ----
+// nn.LayerNorm over bf16 rows with the fusions of rmsnorm_bf16 (+ red_bias added to the reduced partial sums)
+int layernorm_bf16(const __nv_bfloat16* x, const float* partial, int n_partial, const float* red_bias,
+                   const __nv_bfloat16* residual, __nv_bfloat16* h_out, const float* gamma, const float* beta,
+                   __nv_bfloat16* y, int rows, int cols, float eps, cudaStream_t st);
+// h[i,:] = bf16(h[i,:] + table[pos[i] + offset, :])
+int add_pos_embed(__nv_bfloat16* h, const __nv_bfloat16* table, const int* pos, int offset, int table_rows, int n_rows,
+                  int dim, cudaStream_t st);
+
 // ---- attention.cu ----
 int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                 __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int n_tok, int max_len, int n_q_heads,

@@ -240,12 +240,23 @@ int projector_forward(const opus_projector_model* m, const void* x_l2, int n, vo
   return OPUS_OK;
 }
 
+namespace {
+// OPT / Galactica family (defined below, after llama_select)
+int opt_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws, const void* embeds,
+                const int* pos, const int* slot, const int* cu_seqlens, const int* last_rows, int n_seqs, int n_tok,
+                int max_len, cudaStream_t st);
+int opt_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
+                    const opus_decode_state* s, int B, cudaStream_t st);
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------ Llama prefill
 int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
                   const void* embeds, const int* pos, const int* slot, const int* cu_seqlens, const int* last_rows,
                   int n_seqs, int n_tok, int max_len, cudaStream_t st) {
   if (!m || !kv || !ws || !m->layers) return fail(OPUS_ERR_ARG, "llama_prefill: null argument");
   if (n_tok <= 0 || n_seqs <= 0) return OPUS_OK;
+  if (m->arch == OPUS_ARCH_OPT)
+    return opt_prefill(m, kv, ws, embeds, pos, slot, cu_seqlens, last_rows, n_seqs, n_tok, max_len, st);
   const int d = m->dim, hd = m->head_dim, Hq = m->n_q_heads, Hkv = m->n_kv_heads, ffn = m->ffn_dim;
   const int qkv_n = (Hq + 2 * Hkv) * hd;
   if (hd != 128) return fail(OPUS_ERR_ARG, "llama_prefill: head_dim must be 128");
@@ -318,11 +329,131 @@ int llama_select(const opus_llama_model* m, const opus_llama_workspace* ws, cons
                     s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1, s->n_unfinished, st, s->step);
 }
 
+
+// ------------------------------------------------------------------------------------------------ OPT / Galactica
+// Sibling decoder family of language_model/opus_opt.py (HF OPTDecoder, do_layer_norm_before): the same GEMM / attention /
+// paged-cache kernels as the Llama path with LayerNorm instead of RMSNorm, biased linears, a plain fc1 -> act -> fc2 MLP
+// and learned positions. The "rotary" tables of an OPT model hold cos = 1 / sin = 0, so the fused RoPE + KV-append
+// epilogues pass q and k through unchanged (x * 1 + rot(x) * 0 is exact in bf16) and only do the cache append.
+namespace {
+int opt_check(const opus_llama_model* m) {
+  if (m->pos_embed == nullptr || m->pos_rows <= 0 || m->norm_g == nullptr)
+    return fail(OPUS_ERR_ARG, "OPT family: pos_embed / final_layer_norm missing");
+  if (m->n_q_heads != m->n_kv_heads) return fail(OPUS_ERR_ARG, "OPT family: multi-head attention only");
+  if (m->head_dim != 128) return fail(OPUS_ERR_ARG, "OPT family: head_dim must be 128");
+  return OPUS_OK;
+}
+inline int opt_fc1_epi(const opus_llama_model* m) { return m->opt_act == 1 ? EPI_BF16_GELU : EPI_BF16_RELU; }
+
+int opt_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws, const void* embeds,
+                const int* pos, const int* slot, const int* cu_seqlens, const int* last_rows, int n_seqs, int n_tok,
+                int max_len, cudaStream_t st) {
+  OPUS_TRY(opt_check(m));
+  const int d = m->dim, hd = m->head_dim, H = m->n_q_heads, ffn = m->ffn_dim;
+  const int qkv_n = 3 * d;
+  bf16* h = static_cast<bf16*>(ws->h);
+  bf16* xn = static_cast<bf16*>(ws->xn);
+  bf16* qkv = static_cast<bf16*>(ws->qkv);
+  bf16* attn = static_cast<bf16*>(ws->attn);
+  bf16* act = static_cast<bf16*>(ws->act);
+  if (embeds != ws->h) {
+    if (cudaMemcpyAsync(h, embeds, (size_t)n_tok * d * sizeof(bf16), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return fail(OPUS_ERR_CUDA, "opt_prefill: copy embeds");
+    note_launch();
+  }
+  OPUS_TRY(add_pos_embed(h, static_cast<const bf16*>(m->pos_embed), pos, 2, m->pos_rows, n_tok, d, st));
+  const size_t layer_stride = (size_t)kv->num_blocks * H * kv->block_size * hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  for (int l = 0; l < m->n_layers; ++l) {
+    const opus_llama_layer& L = m->layers[l];
+    bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
+    bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
+    OPUS_TRY(layernorm_bf16(h, nullptr, 0, nullptr, nullptr, nullptr, L.ln1_g, L.ln1_b, xn, n_tok, d, m->rms_eps, st));
+    {
+      GemmArgs a{};
+      a.transposed = 0;
+      a.A = xn; a.lda = d; a.M = n_tok;
+      a.B = L.wqkv; a.ldb = d; a.N = qkv_n;
+      a.K = d;
+      a.epi = EPI_BF16;
+      a.out = qkv; a.ldo = qkv_n;
+      a.bias = L.bqkv;
+      a.rl_pos = pos; a.rl_slot = slot; a.rl_cos = m->rope_cos; a.rl_sin = m->rope_sin;
+      a.rl_kcache = kc; a.rl_vcache = vc;
+      a.rl_hq = H; a.rl_hkv = H; a.rl_bs = kv->block_size;
+      if (n_tok > 256 && gemm_fuses_rope(a)) {
+        OPUS_TRY(gemm_bf16(a, st));
+      } else {
+        OPUS_TRY(linear(xn, n_tok, L.wqkv, qkv_n, d, EPI_BF16, qkv, qkv_n, L.bqkv, nullptr, 0, nullptr, 0, st));
+        OPUS_TRY(rope_llama_kvappend(qkv, nullptr, 0, pos, slot, static_cast<const bf16*>(m->rope_cos),
+                                     static_cast<const bf16*>(m->rope_sin), kc, vc, n_tok, H, H, hd, qkv_n,
+                                     kv->block_size, st));
+      }
+    }
+    OPUS_TRY(attn_varlen(qkv, qkv_n, qkv + d, qkv_n, qkv + 2 * d, qkv_n, attn, d, cu_seqlens, n_seqs, n_tok, max_len, H,
+                         H, hd, 1, scale, st));
+    OPUS_TRY(linear(attn, n_tok, L.wo, d, d, EPI_RES_BF16, h, d, L.bo, h, d, nullptr, 0, st));
+    OPUS_TRY(layernorm_bf16(h, nullptr, 0, nullptr, nullptr, nullptr, L.ln2_g, L.ln2_b, xn, n_tok, d, m->rms_eps, st));
+    OPUS_TRY(linear(xn, n_tok, L.wgu, ffn, d, opt_fc1_epi(m), act, ffn, L.b1, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(linear(act, n_tok, L.wdown, d, ffn, EPI_RES_BF16, h, d, L.b2, h, d, nullptr, 0, st));
+  }
+  bf16* last_h = static_cast<bf16*>(ws->last_h);
+  OPUS_TRY(embed_gather(last_rows, h, last_h, n_seqs, d, st));
+  OPUS_TRY(layernorm_bf16(last_h, nullptr, 0, nullptr, nullptr, nullptr, m->norm_g, m->norm_b, last_h, n_seqs, d,
+                          m->rms_eps, st));
+  OPUS_TRY(linear(last_h, n_seqs, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr,
+                  0, st));
+  return OPUS_OK;
+}
+
+int opt_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
+                    const opus_decode_state* s, int B, cudaStream_t st) {
+  OPUS_TRY(opt_check(m));
+  const int d = m->dim, hd = m->head_dim, H = m->n_q_heads, ffn = m->ffn_dim;
+  const int qkv_n = 3 * d;
+  bf16* h = static_cast<bf16*>(ws->h);
+  bf16* xn = static_cast<bf16*>(ws->xn);
+  bf16* qkv = static_cast<bf16*>(ws->qkv);
+  bf16* attn = static_cast<bf16*>(ws->attn);
+  bf16* act = static_cast<bf16*>(ws->act);
+  const size_t layer_stride = (size_t)kv->num_blocks * H * kv->block_size * hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  OPUS_TRY(decode_advance(s->ctx_len, s->pos, s->slot, s->block_table, s->max_blocks, kv->block_size, B, st, s->step));
+  OPUS_TRY(embed_gather(s->next_tok, static_cast<const bf16*>(m->embed), h, B, d, st));
+  OPUS_TRY(add_pos_embed(h, static_cast<const bf16*>(m->pos_embed), s->pos, 2, m->pos_rows, B, d, st));
+  OPUS_TRY(layernorm_bf16(h, nullptr, 0, nullptr, nullptr, nullptr, m->layers[0].ln1_g, m->layers[0].ln1_b, xn, B, d,
+                          m->rms_eps, st));
+  for (int l = 0; l < m->n_layers; ++l) {
+    const opus_llama_layer& L = m->layers[l];
+    bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
+    bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
+    int sp = 1;
+    // q|k|v: weight-streaming split-K GEMM; the attention CTAs reduce the partials of their heads (+ bias) and append K/V
+    OPUS_TRY(linear_splitk(xn, B, L.wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st));
+    OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp, s->pos, s->slot,
+                                     static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin), kc,
+                                     vc, s->block_table, s->max_blocks, s->ctx_len, attn, d, B, H, H, hd,
+                                     kv->block_size, scale, st, L.bqkv));
+    OPUS_TRY(linear_splitk(attn, B, L.wo, d, d, ws->partial, ws->partial_bytes, &sp, st));
+    OPUS_TRY(layernorm_bf16(nullptr, ws->partial, sp, L.bo, h, h, L.ln2_g, L.ln2_b, xn, B, d, m->rms_eps, st));
+    OPUS_TRY(linear(xn, B, L.wgu, ffn, d, opt_fc1_epi(m), act, ffn, L.b1, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(linear_splitk(act, B, L.wdown, d, ffn, ws->partial, ws->partial_bytes, &sp, st));
+    const bool last = l + 1 == m->n_layers;
+    OPUS_TRY(layernorm_bf16(nullptr, ws->partial, sp, L.b2, h, h, last ? m->norm_g : m->layers[l + 1].ln1_g,
+                            last ? m->norm_b : m->layers[l + 1].ln1_b, xn, B, d, m->rms_eps, st));
+  }
+  OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st));
+  OPUS_TRY(llama_select(m, ws, s, B, st));
+  return OPUS_OK;
+}
+}  // namespace
+
 // ------------------------------------------------------------------------------------------------ Llama decode step
 int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
                       const opus_decode_state* s, int B, cudaStream_t st) {
   if (!m || !kv || !ws || !s) return fail(OPUS_ERR_ARG, "llama_decode_step: null argument");
   if (B <= 0) return OPUS_OK;
+  if (m->arch == OPUS_ARCH_OPT) return opt_decode_step(m, kv, ws, s, B, st);
   const int d = m->dim, hd = m->head_dim, Hq = m->n_q_heads, Hkv = m->n_kv_heads, ffn = m->ffn_dim;
   const int qkv_n = (Hq + 2 * Hkv) * hd;
   bf16* h = static_cast<bf16*>(ws->h);

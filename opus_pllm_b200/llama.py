@@ -220,12 +220,15 @@ class B200Llama:
             targets = targets.to(self.device, torch.int32).contiguous()
             for r0 in range(0, n_tok, chunk_rows):
                 r1 = min(n_tok, r0 + chunk_rows)
-                xn = ops.rmsnorm(hidden[r0:r1], self.norm_w, self.rms_eps)
+                xn = self._final_norm(hidden[r0:r1])
                 logits = ops.gemm(xn, self.lm_head, out=None if all_logits is None else all_logits[r0:r1])
                 losses[r0:r1] = ops.cross_entropy_rows(logits, targets[r0:r1])
         finally:
             self.release_plan(st)
         return losses, all_logits
+
+    def _final_norm(self, hidden: torch.Tensor) -> torch.Tensor:
+        return ops.rmsnorm(hidden, self.norm_w, self.rms_eps)
 
     def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int, sampling=None):
         """sampling = None (greedy) or (temperature, top_p, seed)."""

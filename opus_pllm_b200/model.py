@@ -301,9 +301,17 @@ class B200OpusLlama:
 def build_from_state_dicts(llama_sd: dict, llama_cfg: dict, esm_sd: dict | None, esm_cfg: dict | None,
                            projector_sd: dict | None, switch_sd: dict | None, switch_type: str = "mlp2x_gelu",
                            lora_sd: dict | None = None, lora_alpha: float = 32.0, lora_r: int = 16,
-                           eos_token_id=(), device="cuda", n_soft_tokens: int = 8) -> B200OpusLlama:
-    """Assemble the model from plain state dicts (HF / fair-esm / Lightning / .bin key names)."""
-    llama = B200Llama(llama_sd, device=device, lora=lora_sd, lora_alpha=lora_alpha, lora_r=lora_r, **llama_cfg)
+                           eos_token_id=(), device="cuda", n_soft_tokens: int = 8,
+                           family: str = "llama") -> B200OpusLlama:
+    """Assemble the model from plain state dicts (HF / fair-esm / Lightning / .bin key names). family = "llama" (Llama,
+    Qwen2: opus_llama.py / opus_qwen.py) or "opt" (OPT, Galactica: opus_opt.py; llama_cfg then holds B200Opt's kwargs)."""
+    if family == "opt":
+        from .opt import B200Opt
+        llama = B200Opt(llama_sd, device=device, lora=lora_sd, lora_alpha=lora_alpha, lora_r=lora_r, **llama_cfg)
+    elif family == "llama":
+        llama = B200Llama(llama_sd, device=device, lora=lora_sd, lora_alpha=lora_alpha, lora_r=lora_r, **llama_cfg)
+    else:
+        raise NotImplementedError(f"unknown decoder family {family!r}")
     enc = B200ProteinEncoder(esm_sd, device=device, **esm_cfg) if esm_sd is not None else None
     pp = None
     in_dim = esm_cfg["dim"] if esm_cfg else 1280
@@ -314,4 +322,7 @@ def build_from_state_dicts(llama_sd: dict, llama_cfg: dict, esm_sd: dict | None,
     sw = B200SwitchProjector(in_dim, llama.dim * n_soft_tokens, switch_type, device=device)
     if switch_sd is not None:
         sw.load_state_dict(switch_sd)
-    return B200OpusLlama(llama, enc, pp, sw, n_soft_tokens, eos_token_id)
+    model = B200OpusLlama(llama, enc, pp, sw, n_soft_tokens, eos_token_id)
+    if family == "opt":
+        model.config.model_type = "opus_opt"
+    return model

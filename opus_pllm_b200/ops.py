@@ -143,6 +143,34 @@ def rmsnorm(x: torch.Tensor | None, w: torch.Tensor | None, eps: float = 1e-5, *
     return y
 
 
+def layernorm_bf16(x: torch.Tensor | None, gamma: torch.Tensor | None, beta: torch.Tensor | None, eps: float = 1e-5, *,
+                   partial: torch.Tensor | None = None, red_bias: torch.Tensor | None = None,
+                   residual: torch.Tensor | None = None, h_out: torch.Tensor | None = None, normalise: bool = True):
+    """OPT-family LayerNorm over bf16 rows (fp32 gamma / beta), same fusions as rmsnorm plus the reduced linear's bias."""
+    src = x if x is not None else partial
+    rows, cols = src.shape[-2], src.shape[-1]
+    if x is not None:
+        _chk(x, BF16, "x")
+    else:
+        _chk(partial, F32, "partial")
+    for t, n in ((gamma, "gamma"), (beta, "beta"), (red_bias, "red_bias")):
+        if t is not None:
+            _chk(t, F32, n)
+    y = torch.empty((rows, cols), dtype=BF16, device=src.device) if normalise else None
+    L.check(L.load().opus_layernorm_bf16(_p(x), _p(partial), 0 if partial is None else partial.shape[0], _p(red_bias),
+                                         _p(residual), _p(h_out), _p(gamma), _p(beta), _p(y), rows, cols, eps,
+                                         _stream()), "opus_layernorm_bf16")
+    return y
+
+
+def add_pos_embed_(h: torch.Tensor, table: torch.Tensor, pos: torch.Tensor, offset: int = 2) -> torch.Tensor:
+    """h[i] += table[pos[i] + offset] in place (OPTLearnedPositionalEmbedding)."""
+    _chk(h, BF16, "h"); _chk(table, BF16, "table"); _chk(pos, I32, "pos")
+    L.check(L.load().opus_add_pos_embed_bf16(_p(h), _p(table), _p(pos), offset, table.shape[0], h.shape[0], h.shape[1],
+                                             _stream()), "opus_add_pos_embed_bf16")
+    return h
+
+
 def rope_esm_(qkv: torch.Tensor, pos: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, n_heads: int,
               head_dim: int, q_scale: float) -> torch.Tensor:
     _chk(qkv, BF16, "qkv"); _chk(pos, I32, "pos"); _chk(cos_t, F32, "cos"); _chk(sin_t, F32, "sin")

@@ -1,0 +1,220 @@
+"""GPU: the OPT / Galactica sibling family (language_model/opus_opt.py) -- its extra kernels against plain torch, and the
+whole decoder against the reference wrapper's own output (tests/golden/opt_small.pt) and the oracle (oracle/opt_ref.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from opus_pllm_b200 import synth  # noqa: E402
+from oracle import opt_ref  # noqa: E402
+from oracle import ops_ref as R  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from opus_pllm_b200 import ops as o
+    o.device_check()
+    return o
+
+
+def _randn(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def _cos(a, b):
+    a, b = a.float().flatten().cpu(), b.float().flatten().cpu()
+    return float(torch.dot(a, b) / (a.norm() * b.norm()))
+
+
+def _ln_ref(h, g, b, eps):
+    return torch.nn.functional.layer_norm(h.float(), (h.shape[-1],), g, b, eps)
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("rows,cols", [(5, 256), (64, 4096), (777, 4096), (1500, 5120), (3, 7168)])
+def test_layernorm_bf16_plain(ops, rows, cols):
+    x = _randn((rows, cols), 51, scale=2.0)
+    g = _randn((cols,), 52, dtype=torch.float32) * 0.1 + 1.0
+    b = _randn((cols,), 53, dtype=torch.float32) * 0.1
+    got = ops.layernorm_bf16(x, g, b, 1e-5)
+    want = _ln_ref(x, g, b, 1e-5)
+    # one rounding at the end, like nn.LayerNorm on bf16: half an ulp + statistics-order noise
+    err = (got.float() - want).abs()
+    assert float((err - (2.0 ** -8) * want.abs()).max()) <= 2e-3
+    got_nb = ops.layernorm_bf16(x, g, None, 1e-5)          # Galactica-style: no beta
+    assert float((got_nb.float() - _ln_ref(x, g, None, 1e-5)).abs().max()) <= 0.05
+
+
+@pytest.mark.parametrize("rows", [64, 1100])
+def test_layernorm_bf16_partials_bias_residual(ops, rows):
+    """decode tail of out_proj / fc2: h = bf16(residual + bf16(sum partial + bias)), written back, then normalised."""
+    cols = 4096
+    part = _randn((3, rows, cols), 54, dtype=torch.float32)
+    bias = _randn((cols,), 55, dtype=torch.float32)
+    res = _randn((rows, cols), 56)
+    g = _randn((cols,), 57, dtype=torch.float32) * 0.1 + 1.0
+    b = _randn((cols,), 58, dtype=torch.float32) * 0.1
+    h_out = torch.empty_like(res)
+    y = ops.layernorm_bf16(None, g, b, 1e-5, partial=part, red_bias=bias, residual=res, h_out=h_out)
+    lin = R.bf16r((part[0] + part[1] + part[2]) + bias)
+    h_want = R.bf16r(res.float() + lin)
+    flips = (h_out.float() - h_want).abs() > 0          # summation order of three fp32 slices can flip a rounding
+    assert flips.float().mean() < 2e-3
+    assert float((h_out.float() - h_want).abs().max()) <= 2.0 ** -6 * float(h_want.abs().max())
+    want = _ln_ref(h_out, g, b, 1e-5)
+    assert float(((y.float() - want).abs() - (2.0 ** -8) * want.abs()).max()) <= 2e-3
+    # in-place residual stream (h_out aliases residual), no normalisation
+    res2 = res.clone()
+    assert ops.layernorm_bf16(None, None, None, 1e-5, partial=part, red_bias=bias, residual=res2, h_out=res2,
+                              normalise=False) is None
+    assert torch.equal(res2, h_out)
+
+
+def test_add_pos_embed_bit_exact(ops):
+    h = _randn((300, 1024), 59)
+    table = _randn((130, 1024), 60)
+    pos = torch.randint(0, 128, (300,), generator=torch.Generator().manual_seed(61)).to(torch.int32).cuda()
+    want = (h.float() + table[(pos + 2).long()].float()).to(torch.bfloat16)
+    got = ops.add_pos_embed_(h.clone(), table, pos, 2)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("rows,transposed", [(300, False), (2100, False), (64, True), (7, True)])
+def test_gemm_relu_epilogue(ops, rows, transposed):
+    from opus_pllm_b200._lib import EPI_BF16_RELU
+    x = _randn((rows, 1024), 62)
+    w = _randn((4096, 1024), 63, scale=1024 ** -0.5)
+    b = _randn((4096,), 64, dtype=torch.float32)
+    got = ops.gemm(x, w, epilogue=EPI_BF16_RELU, bias=b, transposed=transposed)
+    want = torch.relu(R.linear_ref(x, w, b))
+    assert float((got.float() - want).abs().max()) <= 2e-2 + 2.0 ** -8 * float(want.abs().max())
+    assert bool((got >= 0).all()) and bool(((want > 0.05) <= (got.float() > 0)).all())
+    # ReLU is exact on top of the plain epilogue: relu(plain) == fused, bit for bit
+    plain = ops.gemm(x, w, bias=b, transposed=transposed)
+    assert torch.equal(torch.relu(plain), got)
+
+
+# ------------------------------------------------------------------------------------------------ whole decoder
+def _build(case_cfg, seed, act, bias, **kw):
+    from opus_pllm_b200.opt import B200Opt
+    c = case_cfg
+    lw = synth.opt_weights(c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], c["max_pos"], seed=seed,
+                           bias=bias, **kw)
+    return lw, B200Opt(lw, c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], max_pos=c["max_pos"],
+                       activation=act)
+
+
+@pytest.mark.parametrize("case", ["opt", "galactica"])
+def test_opt_family_matches_reference_wrapper_golden(case):
+    """Prefill logits and greedy tokens against what the reference's OpusOPTForCausalLM.generate produced in the build
+    container (fp32, HF OPTForCausalLM underneath)."""
+    g = torch.load(os.path.join(GOLD, "opt_small.pt"), weights_only=False)[case]
+    lw, model = _build(g["cfg"], g["seed"], g["activation"], g["bias"])
+    mask = g["mask"]
+    lens = mask.sum(1).tolist()
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    packed = lw["model.decoder.embed_tokens.weight"][g["input_ids"]][mask].cuda().to(torch.bfloat16)
+    out, logits = model.generate_packed(packed, cu, g["max_new_tokens"], eos_ids=[g["eos"]], pad_id=g["pad"],
+                                        return_prefill_logits=True)
+    want = g["prefill_logits"]
+    assert _cos(logits, want) >= 0.999
+    assert float((logits.float().cpu() - want).abs().max()) <= 0.06 * float(want.std()) + 1e-3
+    top2 = want.topk(2, dim=-1).values
+    same = out[:, 0].cpu() == g["tokens"][:, 0]
+    assert bool((same | ((top2[:, 0] - top2[:, 1]) < 0.05 * float(want.std()))).all())
+    if g["bias"]:   # without the biases the logits must move: the bias paths are really exercised
+        nb = {k: v for k, v in lw.items() if not (k.endswith("_proj.bias") or k.endswith("fc1.bias") or k.endswith("fc2.bias"))}
+        from opus_pllm_b200.opt import B200Opt
+        c = g["cfg"]
+        _, logits_nb = B200Opt(nb, c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], max_pos=c["max_pos"],
+                               activation=g["activation"]).generate_packed(packed, cu, 2, return_prefill_logits=True)
+        assert _cos(logits_nb, want) < 0.999
+
+
+@pytest.mark.parametrize("act,bias,B,T,new", [("relu", True, 6, 40, 12), ("gelu", False, 3, 300, 6), ("relu", True, 70, 24, 5)])
+def test_opt_greedy_tokens_match_oracle_peaked(act, bias, B, T, new):
+    """Token parity (north-star bar: >= 99 % of prompts identical) with the peaked-logit recipe, ragged prompts, prefill
+    through both GEMM forms (n_tok <= 256 swap-AB / > 256 plain with the fused KV append), decode via the CUDA graph
+    and without it (bit-identical)."""
+    c = dict(n_layers=3, dim=256, n_heads=2, ffn_dim=1024, vocab=2048, max_pos=512)
+    lw, model = _build(c, 77, act, bias, peaked=True)
+    lens = [T - (i % 5) for i in range(B)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    gen = torch.Generator().manual_seed(5)
+    ids = [torch.randint(3, c["vocab"], (n,), generator=gen) for n in lens]
+    emb_w = lw["model.decoder.embed_tokens.weight"]
+    packed = torch.cat([emb_w[i] for i in ids]).cuda().to(torch.bfloat16)
+    got = model.generate_packed(packed, cu, new)
+    got_nograph = model.generate_packed(packed, cu, new, use_graph=False)
+    assert torch.equal(got, got_nograph)
+    # oracle on the same bf16-rounded weights, fp32 arithmetic, left-padded batch
+    w32 = {k: v.to(torch.bfloat16).float() for k, v in lw.items()}
+    Lm = max(lens)
+    emb = torch.zeros(B, Lm, c["dim"])
+    mask = torch.zeros(B, Lm, dtype=torch.bool)
+    for b, i in enumerate(ids):
+        emb[b, Lm - len(i):] = w32["model.decoder.embed_tokens.weight"][i]
+        mask[b, Lm - len(i):] = True
+    ocfg = opt_ref.OptCfg(n_layers=c["n_layers"], dim=c["dim"], n_heads=c["n_heads"], ffn_dim=c["ffn_dim"],
+                          vocab=c["vocab"], max_pos=c["max_pos"], activation=act)
+    want = opt_ref.greedy_generate(w32, ocfg, emb, mask, new)
+    same_rows = (got.cpu() == want).all(1).float().mean()
+    assert float(same_rows) >= 0.99, (float(same_rows), got.cpu()[:4], want[:4])
+
+
+def test_opt_rejects_unsupported_variants():
+    from opus_pllm_b200.opt import B200Opt
+    c = dict(n_layers=1, dim=256, n_heads=4, ffn_dim=512, vocab=512, max_pos=64)     # head_dim 64
+    lw = synth.opt_weights(c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], c["max_pos"])
+    with pytest.raises(NotImplementedError):
+        B200Opt(lw, c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], max_pos=c["max_pos"])
+    lw = synth.opt_weights(1, 256, 2, 512, 512, 64)
+    del lw["model.decoder.final_layer_norm.weight"]                                 # opt-350m: post-LN, no final norm
+    with pytest.raises(NotImplementedError):
+        B200Opt(lw, 1, 256, 2, 512, 512, max_pos=64)
+    lw = synth.opt_weights(1, 256, 2, 512, 512, 64)
+    model = B200Opt(lw, 1, 256, 2, 512, 512, max_pos=64)
+    from opus_pllm_b200._lib import OpusError
+    with pytest.raises(OpusError):                                                  # beyond the learned position table
+        model.make_plan(np.array([0, 60], dtype=np.int32), 10)
+
+
+def test_opt_generate_end_to_end_vs_oracle_pipeline():
+    """proteins + prompts with -200 sentinels -> tokens through the reference-shaped generate() with an OPT decoder
+    (what `load_pretrained_model` builds for an 'opt' / 'galactica' base path, builder.py:71-82)."""
+    from oracle import esm2_ref, mm_ref
+    from opus_pllm_b200.model import build_from_state_dicts
+    c = dict(n_layers=2, dim=256, n_heads=2, ffn_dim=512, vocab=2048, max_pos=256)
+    lw = synth.opt_weights(c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], c["max_pos"], seed=3,
+                           peaked=True, device="cuda")
+    esm_cfg = dict(n_layers=2, dim=128, n_heads=2, ffn_dim=512)
+    ew = synth.esm2_weights(2, 128, 512)
+    pw = synth.projector_weights(128, 256, 8 * c["dim"])
+    model = build_from_state_dicts(lw, dict(c, activation="relu"), ew, esm_cfg, pw, pw, family="opt")
+    assert model.config.model_type == "opus_opt"
+    B, new = 8, 16
+    seqs = synth.proteins(B, 20, 90, seed=11)
+    prompts = synth.prompt_ids(B, 48, vocab=c["vocab"], ragged=5, sentinel_at=10)
+    Lm, pad = max(p.numel() for p in prompts), 1
+    ids = torch.stack([torch.cat([torch.full((Lm - p.numel(),), pad), p]) for p in prompts]).cuda()
+    mask = ids != pad
+    got = model.generate(ids, seqs, attention_mask=mask, pad_token_id=pad, do_sample=False, max_new_tokens=new)
+    assert got.dtype == torch.int64 and got.shape == (B, new)
+    dev = lambda d, dt=None: {k: (v.cuda() if dt is None else v.cuda().to(dt)) for k, v in d.items()}  # noqa: E731
+    pooled = esm2_ref.get_protein_seq_embeddings(dev(ew), seqs, 2, 2)
+    pwd = dev(pw)
+    cc = mm_ref.protein_forward(pooled, pwd["protein_projection.linear.weight"], pwd["protein_projection.linear.bias"])
+    soft = mm_ref.switch_projector(cc, pwd, c["dim"])
+    emb, m, _, _ = mm_ref.splice(ids, mask, soft.to(torch.bfloat16),
+                                 lw["model.decoder.embed_tokens.weight"].cuda().bfloat16())
+    ocfg = opt_ref.OptCfg(n_layers=c["n_layers"], dim=c["dim"], n_heads=c["n_heads"], ffn_dim=c["ffn_dim"],
+                          vocab=c["vocab"], max_pos=c["max_pos"])
+    want = opt_ref.greedy_generate(dev(lw, torch.bfloat16), ocfg, emb, m, new)
+    same = (got.cpu() == want.cpu()).all(1).float().mean()
+    assert float(same) >= 0.99, float(same)

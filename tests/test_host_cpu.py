@@ -23,7 +23,7 @@ def test_shared_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.opus_abi_version() == 1
+    assert lib.opus_abi_version() == 2
     assert isinstance(lib.opus_last_error(), bytes)
 
 

@@ -106,3 +106,28 @@ def test_prompt_helpers_match_reference_semantics():
     p = eval_ddp.build_prompt("Where is it?", "SYS", "data/localization.json")
     assert p == "SYS\n\n### Student: <seq>\nWhere is it?Kindly reply with only one word.\n### Professor:"
     assert eval_ddp.max_new_tokens_for("x/keywords.json", 32) == 128 and eval_ddp.max_new_tokens_for("x/f.json", 32) == 256
+
+
+def test_read_hf_opt_directory_and_family_dispatch(tmp_path):
+    """OPT / Galactica base dirs (model/builder.py:71-82: `use_safetensors=False`, i.e. pytorch_model*.bin)."""
+    import pytest
+    d = str(tmp_path / "opt-tiny")
+    os.makedirs(d)
+    sd = synth.opt_weights(2, 256, 2, 512, 512, max_pos=64, seed=4)
+    json.dump(dict(num_hidden_layers=2, hidden_size=256, num_attention_heads=2, ffn_dim=512, vocab_size=512,
+                   max_position_embeddings=64, word_embed_proj_dim=256, do_layer_norm_before=True,
+                   activation_function="relu", eos_token_id=2, model_type="opt"), open(os.path.join(d, "config.json"), "w"))
+    torch.save({k[len("model."):]: v for k, v in sd.items() if k != "lm_head.weight"},    # old-style `decoder.*` keys
+               os.path.join(d, "pytorch_model.bin"))
+    got, kw = builder.read_hf_opt(d)
+    extra = kw.pop("_extra")
+    assert kw == dict(n_layers=2, dim=256, n_heads=2, ffn_dim=512, vocab=512, max_pos=64, activation="relu")
+    assert extra["eos_token_id"] == 2
+    assert torch.equal(got["decoder.layers.1.fc1.weight"], sd["model.decoder.layers.1.fc1.weight"])
+    cfg = json.load(open(os.path.join(d, "config.json")))
+    cfg.update(do_layer_norm_before=False, word_embed_proj_dim=128)                       # opt-350m
+    json.dump(cfg, open(os.path.join(d, "config.json"), "w"))
+    with pytest.raises(NotImplementedError):
+        builder.read_hf_opt(d)
+    with pytest.raises(NotImplementedError):                                              # builder.py:95-96
+        builder.load_pretrained_model("/nonexistent/mistral-7b", None, "mistral-7b")   # (tmp_path itself contains "opt")
