@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OPUS_B200_ABI_VERSION 2
+#define OPUS_B200_ABI_VERSION 3
 
 enum {
   OPUS_OK = 0,
@@ -135,6 +135,12 @@ int opus_sample_top_p(const void* logits, int ld, int vocab, int n_rows, float t
  * loss[r] = logsumexp(fp32(logits[r,:])) - logits[r, target[r]]; 0 where target[r] < 0 (ignore_index). */
 int opus_cross_entropy_bf16(const void* logits, int ld, int vocab, const int32_t* target, float* loss, int n_rows,
                             void* stream);
+/* Stop-sequence check after a token selection step (column `step`, or *step_ptr when non-NULL, of out_ids has just been
+ * written): unfinished rows whose emitted tail matches one of the sequences are marked finished (n_unfinished
+ * decremented). Device-side counterpart of KeywordsStoppingCriteria (multi_modality_v1/mm_utils.py:43-75), per row. */
+int opus_stop_sequences(const int32_t* out_ids, int out_ld, int n_rows, int step, const int32_t* step_ptr,
+                        const int32_t* stop_seqs, const int32_t* stop_lens, int n_stop, int stop_ld, int32_t* finished,
+                        int32_t* n_unfinished, void* stream);
 int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n_rows, int dim, void* stream);
 /* OPT / Galactica family (language_model/opus_opt.py -> HF OPTDecoder). nn.LayerNorm over a bf16 residual stream with
  * the fusions of opus_rmsnorm_bf16 plus the bias of the linear whose split-K partials are reduced:
@@ -289,6 +295,10 @@ typedef struct {
   const int32_t* eos_ids; int32_t n_eos; int32_t pad_id;
   /* token selection: do_sample == 0 -> argmax (greedy); else temperature / top-p sampling, u = hash(seed, row, step) */
   uint64_t seed; float temperature; float top_p; int32_t do_sample; int32_t reserved_;
+  /* optional stop sequences (the "###" keyword of mm_utils.py:43-75 KeywordsStoppingCriteria, evaluated on the device):
+   * a row also finishes when its last stop_lens[j] emitted tokens equal stop_seqs[j][0 .. stop_lens[j]) for some j.
+   * stop_seqs int32 [n_stop, stop_ld] (NULL / n_stop == 0 = none). Checked by one extra small kernel per step. */
+  const int32_t* stop_seqs; const int32_t* stop_lens; int32_t n_stop; int32_t stop_ld;
 } opus_decode_state;
 
 /* Prefill over packed prompt embeddings (already spliced): embeds bf16 [n_tok, dim] is copied into ws->h; K/V of every

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libopus_b200.so")
 OK = 0
 EPI_BF16, EPI_BF16_GELU, EPI_RES_F32, EPI_RES_BF16, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_F32, EPI_BF16_RELU = range(8)
 ARCH_LLAMA, ARCH_OPT = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int, c_float, c_size_t, c_longlong = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
@@ -75,7 +75,8 @@ class DecodeState(C.Structure):
                 ("n_unfinished", c_void_p), ("step", c_void_p), ("out_ids", c_void_p), ("out_ld", C.c_int32),
                 ("eos_ids", c_void_p), ("n_eos", C.c_int32), ("pad_id", C.c_int32),
                 ("seed", C.c_uint64), ("temperature", c_float), ("top_p", c_float), ("do_sample", C.c_int32),
-                ("reserved_", C.c_int32)]
+                ("reserved_", C.c_int32),
+                ("stop_seqs", c_void_p), ("stop_lens", c_void_p), ("n_stop", C.c_int32), ("stop_ld", C.c_int32)]
 
 
 # ---------------------------------------------------------------------------------------------- signatures
@@ -103,6 +104,7 @@ _SIGNATURES = {
     "opus_cross_entropy_bf16": (c_int, [_P, c_int, c_int, _P, _P, c_int, _P]),
     "opus_embed_gather_bf16": (c_int, [_P, _P, _P, c_int, c_int, _P]),
     "opus_lora_merge_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "opus_stop_sequences": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "opus_layernorm_bf16": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float, _P]),
     "opus_add_pos_embed_bf16": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "opus_attn_varlen_bf16": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int,

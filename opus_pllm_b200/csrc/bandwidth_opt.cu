@@ -3,6 +3,7 @@
 //     same optional fusions as rmsnorm_bf16 (residual add written back, split-K partial reduction) plus the bias of the
 //     linear whose partial sums are being reduced (out_proj / fc2 carry biases in OPT);
 //   * the learned positional embedding add  h[i,:] = bf16(h[i,:] + P[pos[i] + 2, :])  (OPTLearnedPositionalEmbedding).
+// Also here: the per-row stop-sequence check of the decode loop (mm_utils.py KeywordsStoppingCriteria on the device).
 // Coalesced 128-bit accesses, the row kept in registers, warp-shuffle + shared-memory reductions.
 #include "common.h"
 #include "kernels.h"
@@ -166,6 +167,30 @@ __global__ void add_pos_embed_kernel(__nv_bfloat16* __restrict__ h, const __nv_b
   }
 }
 
+// one thread per row: does the emitted tail out_ids[b, step-len+1 .. step] equal one of the stop sequences?
+__global__ void stop_sequences_kernel(const int* __restrict__ out_ids, int out_ld, int n_rows, int step_imm,
+                                      const int* __restrict__ step_ptr, const int* __restrict__ stop_seqs,
+                                      const int* __restrict__ stop_lens, int n_stop, int stop_ld,
+                                      int* __restrict__ finished, int* __restrict__ n_unfinished) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_rows || finished[b]) return;
+  const int step = step_ptr != nullptr ? *step_ptr : step_imm;
+  const int* row = out_ids + (size_t)b * out_ld;
+  for (int j = 0; j < n_stop; ++j) {
+    const int len = stop_lens[j];
+    if (len <= 0 || len > step + 1) continue;
+    bool same = true;
+    for (int i = 0; i < len && same; ++i) same = row[step - len + 1 + i] == stop_seqs[(size_t)j * stop_ld + i];
+    if (same) {
+      finished[b] = 1;
+      if (n_unfinished != nullptr) atomicSub(n_unfinished, 1);
+      return;
+    }
+  }
+}
+
 inline int cdiv_(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline int ok_() {
   note_launch();
@@ -201,6 +226,15 @@ int add_pos_embed(__nv_bfloat16* h, const __nv_bfloat16* table, const int* pos, 
   if (dim % 8 || table_rows <= 0) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
   launch_pdl(n_rows <= 1024, add_pos_embed_kernel, dim3(cdiv_(n_rows, 4)), dim3(128), 0, st, h, table, pos, offset, table_rows, n_rows, dim);
+  return ok_();
+}
+
+int stop_sequences(const int* out_ids, int out_ld, int n_rows, int step, const int* step_ptr, const int* stop_seqs,
+                   const int* stop_lens, int n_stop, int stop_ld, int* finished, int* n_unfinished, cudaStream_t st) {
+  if (n_rows == 0 || n_stop <= 0 || stop_seqs == nullptr) return OPUS_OK;
+  if (stop_lens == nullptr || stop_ld <= 0 || finished == nullptr) return OPUS_ERR_ARG;
+  launch_pdl(true, stop_sequences_kernel, dim3(cdiv_(n_rows, 128)), dim3(128), 0, st, out_ids, out_ld, n_rows, step,
+             step_ptr, stop_seqs, stop_lens, n_stop, stop_ld, finished, n_unfinished);
   return ok_();
 }
 

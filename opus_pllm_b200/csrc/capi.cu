@@ -183,6 +183,14 @@ int opus_add_pos_embed_bf16(void* h, const void* table, const int32_t* pos, int 
       "opus_add_pos_embed_bf16");
 }
 
+int opus_stop_sequences(const int32_t* out_ids, int out_ld, int n_rows, int step, const int32_t* step_ptr,
+                        const int32_t* stop_seqs, const int32_t* stop_lens, int n_stop, int stop_ld, int32_t* finished,
+                        int32_t* n_unfinished, void* stream) {
+  RET(stop_sequences(out_ids, out_ld, n_rows, step, step_ptr, stop_seqs, stop_lens, n_stop, stop_ld, finished,
+                     n_unfinished, ST(stream)),
+      "opus_stop_sequences");
+}
+
 int opus_lora_merge_bf16(void* W, const void* A, const void* B, int out_features, int in_features, int r, float scale,
                          void* stream) {
   RET(lora_merge(static_cast<bf16*>(W), static_cast<const bf16*>(A), static_cast<const bf16*>(B), out_features,

@@ -61,6 +61,10 @@ int layernorm_bf16(const __nv_bfloat16* x, const float* partial, int n_partial, 
 int add_pos_embed(__nv_bfloat16* h, const __nv_bfloat16* table, const int* pos, int offset, int table_rows, int n_rows,
                   int dim, cudaStream_t st);
 
+// rows whose emitted tail (ending at column step / *step_ptr of out_ids) equals a stop sequence become finished
+int stop_sequences(const int* out_ids, int out_ld, int n_rows, int step, const int* step_ptr, const int* stop_seqs,
+                   const int* stop_lens, int n_stop, int stop_ld, int* finished, int* n_unfinished, cudaStream_t st);
+
 // ---- attention.cu ----
 int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                 __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int n_tok, int max_len, int n_q_heads,

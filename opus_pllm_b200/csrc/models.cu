@@ -322,13 +322,17 @@ int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus
 int llama_select(const opus_llama_model* m, const opus_llama_workspace* ws, const opus_decode_state* s, int n_seqs,
                  cudaStream_t st) {
   if (s->do_sample)
-    return sample_top_p(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->temperature, s->top_p,
-                        s->seed, s->finished, s->eos_ids, s->n_eos, s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1,
-                        s->n_unfinished, st, s->step);
-  return argmax_eos(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->finished, s->eos_ids, s->n_eos,
-                    s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1, s->n_unfinished, st, s->step);
+    OPUS_TRY(sample_top_p(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->temperature, s->top_p,
+                          s->seed, s->finished, s->eos_ids, s->n_eos, s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1,
+                          s->n_unfinished, st, s->step));
+  else
+    OPUS_TRY(argmax_eos(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->finished, s->eos_ids,
+                        s->n_eos, s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1, s->n_unfinished, st, s->step));
+  if (s->n_stop > 0 && s->stop_seqs != nullptr)
+    OPUS_TRY(stop_sequences(s->out_ids, s->out_ld, n_seqs, -1, s->step, s->stop_seqs, s->stop_lens, s->n_stop,
+                            s->stop_ld, s->finished, s->n_unfinished, st));
+  return OPUS_OK;
 }
-
 
 // ------------------------------------------------------------------------------------------------ OPT / Galactica
 // Sibling decoder family of language_model/opus_opt.py (HF OPTDecoder, do_layer_norm_before): the same GEMM / attention /

@@ -84,6 +84,10 @@ def eval_model(args, tokenizer=None, model=None):
     dev = model.device
     prompts = [build_prompt(i, system, args.input_path) for i in instrs]
     ids = [tokenizer_seq_token(p, tokenizer, DEFAULT_SEQ_TOKEN_INDEX, return_tensors="pt") for p in prompts]
+    stop_kw = {}
+    if getattr(args, "stop_keyword", False):   # opt-in: stop a row once it has emitted the "###" separator (device-side)
+        from .mm_utils import KeywordsStoppingCriteria
+        stop_kw = {"stopping_criteria": [KeywordsStoppingCriteria([SEP], tokenizer)]}
     t0 = time.time()
     rows = []
     if args.continuous_batching:
@@ -97,7 +101,7 @@ def eval_model(args, tokenizer=None, model=None):
             out = model.generate(batch, seqs[i: i + args.batch_size], attention_mask=batch != tokenizer.pad_token_id,
                                  pad_token_id=tokenizer.eos_token_id, do_sample=args.temperature > 0,
                                  temperature=args.temperature, top_p=args.top_p, num_beams=args.num_beams,
-                                 max_new_tokens=max_new, use_cache=True,
+                                 max_new_tokens=max_new, use_cache=True, **stop_kw,
                                  **({"seed": args.seed + 1000003 * rank + i} if args.temperature > 0 else {}))
             rows.extend(torch.nn.functional.pad(o, (0, max_new - o.numel()), value=tokenizer.eos_token_id) for o in out.cpu())
     local = torch.stack(rows).to(dev) if rows else torch.zeros((0, max_new), dtype=torch.int64, device=dev)
@@ -132,6 +136,8 @@ def main():
     ap.add_argument("--load-8bit", type=bool, default=False)
     ap.add_argument("--batch_size", type=int, default=64)
     ap.add_argument("--continuous-batching", action="store_true")
+    ap.add_argument("--stop-keyword", action="store_true",
+                    help='finish a row when it emits the "###" separator (mm_utils.KeywordsStoppingCriteria, on the device)')
     ap.add_argument("--esm-path", type=str, default=None)
     ap.add_argument("--system-prompt", type=str, default=None)
     eval_model(ap.parse_args())

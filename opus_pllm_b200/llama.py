@@ -230,16 +230,22 @@ class B200Llama:
     def _final_norm(self, hidden: torch.Tensor) -> torch.Tensor:
         return ops.rmsnorm(hidden, self.norm_w, self.rms_eps)
 
-    def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int, sampling=None):
-        """sampling = None (greedy) or (temperature, top_p, seed)."""
+    def _decode_state(self, st: dict, max_new_tokens: int, eos_ids, pad_id: int, sampling=None, stop_sequences=()):
+        """sampling = None (greedy) or (temperature, top_p, seed); stop_sequences = token-id sequences that finish a row."""
         n, dev = st["n_seqs"], self.device
-        key = (n, max_new_tokens, tuple(eos_ids), pad_id, sampling)
+        stops = tuple(tuple(int(t) for t in q) for q in (stop_sequences or ()) if len(q))
+        key = (n, max_new_tokens, tuple(eos_ids), pad_id, sampling, stops)
         cached = getattr(self, "_state_cache", None)
         if cached is None or cached[0] != key:
             i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
             bufs = dict(next_tok=i32(n), ctx_len=i32(n), pos=i32(n), slot=i32(n), block_table=i32(n, st["max_blocks"]),
                         finished=i32(n), n_unfinished=i32(1), step=i32(1), out_ids=i32(n, max_new_tokens),
                         eos=torch.tensor(list(eos_ids) or [-1], dtype=torch.int32, device=dev))
+            if stops:
+                ld = max(len(q) for q in stops)
+                bufs["stop_seqs"] = torch.tensor([list(q) + [-1] * (ld - len(q)) for q in stops], dtype=torch.int32,
+                                                 device=dev)
+                bufs["stop_lens"] = torch.tensor([len(q) for q in stops], dtype=torch.int32, device=dev)
             self._state_cache = (key, bufs)
             L.load().opus_release_graphs()
         bufs = self._state_cache[1]
@@ -259,19 +265,24 @@ class B200Llama:
         s.eos_ids, s.n_eos, s.pad_id = bufs["eos"].data_ptr(), len(eos_ids), pad_id
         if sampling is not None:
             s.do_sample, s.temperature, s.top_p, s.seed = 1, float(sampling[0]), float(sampling[1]), int(sampling[2])
+        if stops:
+            s.stop_seqs, s.stop_lens = bufs["stop_seqs"].data_ptr(), bufs["stop_lens"].data_ptr()
+            s.n_stop, s.stop_ld = len(stops), bufs["stop_seqs"].shape[1]
         return s, bufs
 
     @torch.no_grad()
     def generate_packed(self, embeds: torch.Tensor, cu_seqlens, max_new_tokens: int, eos_ids=(), pad_id: int = 0,
                         use_graph: bool = True, check_every: int = 16, return_prefill_logits: bool = False,
-                        plan: dict | None = None, sampling=None):
+                        plan: dict | None = None, sampling=None, stop_sequences=()):
         """Greedy generation from packed prompt embeddings. Returns int64 [n_seqs, n_new] (new tokens only; finished
-        rows padded with pad_id; trimmed at the step where every row had finished, like HF)."""
+        rows padded with pad_id; trimmed at the step where every row had finished, like HF). stop_sequences: token-id
+        sequences (e.g. the ids of "###") after which a row counts as finished -- checked on the device every step."""
         own_plan = plan is None
         st = self.prefill(embeds, cu_seqlens, max_new_tokens, plan=plan)
         try:
             prefill_logits = st["logits"].clone() if return_prefill_logits else None
-            out = self.generate_from_prefill(st, max_new_tokens, eos_ids, pad_id, use_graph, check_every, sampling)
+            out = self.generate_from_prefill(st, max_new_tokens, eos_ids, pad_id, use_graph, check_every, sampling,
+                                             stop_sequences)
         finally:
             if own_plan:
                 self.release_plan(st)
@@ -279,18 +290,19 @@ class B200Llama:
 
     @torch.no_grad()
     def generate_from_prefill(self, st: dict, max_new_tokens: int, eos_ids=(), pad_id: int = 0,
-                              use_graph: bool = True, check_every: int = 16, sampling=None) -> torch.Tensor:
+                              use_graph: bool = True, check_every: int = 16, sampling=None,
+                              stop_sequences=()) -> torch.Tensor:
         """Select the first token from the prefill logits, then run the decode loop (CUDA-graph replays). Greedy unless
         sampling = (temperature, top_p, seed): HF do_sample=True semantics, drawn on the device."""
         lib = L.load()
-        s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id, sampling)
+        s, bufs = self._decode_state(st, max_new_tokens, eos_ids, pad_id, sampling, stop_sequences)
         stream = torch.cuda.current_stream().cuda_stream
         L.check(lib.opus_llama_select(C.byref(self._model), C.byref(self._ws), C.byref(s), st["n_seqs"], stream),
                 "opus_llama_select")
         if max_new_tokens > 1:
             rc = lib.opus_llama_decode_loop(C.byref(self._model), C.byref(self._cache), C.byref(self._ws),
                                             C.byref(s), st["n_seqs"], max_new_tokens - 1,
-                                            check_every if len(eos_ids) else 0, int(use_graph), stream)
+                                            check_every if (len(eos_ids) or s.n_stop) else 0, int(use_graph), stream)
             L.check(rc, "opus_llama_decode_loop")
         out = bufs["out_ids"].to(torch.int64)
         if len(eos_ids):

@@ -44,3 +44,25 @@ def after_process_output(text: str, sep: str) -> str:
     text = text.strip()
     i = text.find(sep)
     return (text if i < 0 else text[:i]).strip()
+
+
+class KeywordsStoppingCriteria:
+    """Host half of the reference's stop-keyword criterion (mm_utils.py:43-61): keywords -> token-id sequences, a
+    leading BOS dropped. Pass it as `model.generate(..., stopping_criteria=[crit])`: the matching runs on the device,
+    once per decode step and per row (`opus_stop_sequences`), instead of the reference's per-step host loop over
+    `output_ids[0, -len:]` plus a `batch_decode` substring search (mm_utils.py:63-75). Rows stop individually -- the
+    reference's `all(outputs)` only stops when every row matches in the same step -- which leaves the text up to and
+    including the keyword unchanged, and `after_process_output` cuts there anyway."""
+
+    def __init__(self, keywords, tokenizer, input_ids=None):
+        self.keywords = list(keywords)
+        self.keyword_ids = []
+        self.max_keyword_len = 0
+        for keyword in self.keywords:
+            ids = list(tokenizer(keyword).input_ids)
+            if len(ids) > 1 and ids[0] == tokenizer.bos_token_id:
+                ids = ids[1:]
+            self.max_keyword_len = max(self.max_keyword_len, len(ids))
+            self.keyword_ids.append(torch.tensor(ids))
+        self.tokenizer = tokenizer
+        self.start_len = 0 if input_ids is None else input_ids.shape[1]

@@ -280,6 +280,13 @@ class B200OpusLlama:
             pad_id = eos_ids[0] if eos_ids else 0
         use_graph = bool(kwargs.pop("use_graph", True))
         return_logits = bool(kwargs.pop("return_prefill_logits", False))
+        # stop keywords: `stop_sequences=[[ids of "###"], ...]` or the reference's KeywordsStoppingCriteria objects
+        # (mm_utils.py:43-75) in `stopping_criteria=[...]`; rows stop individually, on the device
+        stops = [list(map(int, q)) for q in (kwargs.pop("stop_sequences", None) or [])]
+        for crit in kwargs.pop("stopping_criteria", None) or []:
+            if not hasattr(crit, "keyword_ids"):
+                raise NotImplementedError("only KeywordsStoppingCriteria-style criteria (keyword_ids) are supported")
+            stops.extend([int(t) for t in torch.as_tensor(q).reshape(-1).tolist()] for q in crit.keyword_ids)
         if kwargs:
             raise TypeError(f"generate(): unsupported arguments {sorted(kwargs)}")
 
@@ -295,7 +302,8 @@ class B200OpusLlama:
         src_d = ops.h2d(plan.src, self.device)
         embeds = ops.splice_gather(src_d, self.llama.embed, soft2d)
         return self.llama.generate_packed(embeds, plan.cu, max_new, eos_ids=eos_ids, pad_id=int(pad_id),
-                                          use_graph=use_graph, return_prefill_logits=return_logits, sampling=sampling)
+                                          use_graph=use_graph, return_prefill_logits=return_logits, sampling=sampling,
+                                          stop_sequences=stops)
 
 
 def build_from_state_dicts(llama_sd: dict, llama_cfg: dict, esm_sd: dict | None, esm_cfg: dict | None,

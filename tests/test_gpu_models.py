@@ -534,3 +534,45 @@ def test_load_pretrained_model_and_eval_driver(tmp_path):
     a = model.generate(ids, [data[0]["input"]], do_sample=False, max_new_tokens=6, pad_token_id=2)
     b = direct.generate(ids, [data[0]["input"]], do_sample=False, max_new_tokens=6, pad_token_id=2)
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ stop keywords
+def test_stop_sequences_kernel_and_generate(tmp_path):
+    """Device-side counterpart of KeywordsStoppingCriteria (mm_utils.py:43-75): a row finishes when its emitted tail equals
+    a stop sequence; afterwards it emits pad, and the loop ends early once every row has finished."""
+    from opus_pllm_b200 import _lib as L, ops
+    from opus_pllm_b200.llama import B200Llama
+    # kernel: hand-made histories
+    out = torch.tensor([[5, 6, 7, 0], [9, 6, 7, 0], [6, 7, 8, 0], [1, 2, 7, 0]], dtype=torch.int32).cuda()
+    fin = torch.tensor([0, 1, 0, 0], dtype=torch.int32).cuda()
+    left = torch.tensor([3], dtype=torch.int32).cuda()
+    seqs = torch.tensor([[6, 7], [8, -1]], dtype=torch.int32).cuda()
+    lens = torch.tensor([2, 1], dtype=torch.int32).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(L.load().opus_stop_sequences(out.data_ptr(), 4, 4, 2, None, seqs.data_ptr(), lens.data_ptr(), 2, 2,
+                                         fin.data_ptr(), left.data_ptr(), st))
+    assert fin.tolist() == [1, 1, 1, 0] and int(left) == 1      # row 1 was already finished: not counted twice
+    # generate: take a greedy run, then ask to stop at a 2-token sequence that row 0 emitted
+    cfg = SMALL
+    kw = {k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()}
+    lw = synth.llama_weights(seed=2, peaked=True, device="cuda", **kw)
+    model = B200Llama(lw, **cfg)
+    lens_p = [30, 21, 17]
+    cu = np.concatenate([[0], np.cumsum(lens_p)]).astype(np.int32)
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(3, cfg["vocab"], (sum(lens_p),), generator=g)
+    emb = lw["model.embed_tokens.weight"][ids.cuda()].to(torch.bfloat16)
+    pad = 0
+    base = model.generate_packed(emb, cu, 12, pad_id=pad)
+    stop = base[0, 3:5].tolist()
+    got = model.generate_packed(emb, cu, 12, pad_id=pad, stop_sequences=[stop])
+    want = base.clone()
+    for b in range(3):
+        row = base[b].tolist()
+        hits = [i for i in range(1, 12) if row[i - 1: i + 1] == stop]
+        if hits:
+            want[b, hits[0] + 1:] = pad
+    assert torch.equal(got, want)
+    assert (got[0, 5:] == pad).all() and torch.equal(got[0, :5], base[0, :5])
+    assert torch.equal(model.generate_packed(emb, cu, 12, pad_id=pad, stop_sequences=[stop], use_graph=False), got)
+    assert torch.equal(model.generate_packed(emb, cu, 12, pad_id=pad), base)       # and off again: state is rebuilt

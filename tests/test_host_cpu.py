@@ -23,7 +23,7 @@ def test_shared_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.opus_abi_version() == 2
+    assert lib.opus_abi_version() == 3
     assert isinstance(lib.opus_last_error(), bytes)
 
 
@@ -197,3 +197,19 @@ def test_streamk_tail_partition_covers_every_unit_once():
         for sk in (1, 2, 3, 53, 76, 114, g - 1):
             for kb in (1, 2, 5, 16, 20, 64, 80, 224):
                 sim(sk, kb, g)
+
+
+def test_keywords_stopping_criteria_host_half():
+    """mm_utils.py:43-61: keywords -> id sequences, a leading BOS dropped only when something follows it."""
+    from opus_pllm_b200.mm_utils import KeywordsStoppingCriteria
+
+    class Tok:
+        bos_token_id = 1
+
+        def __call__(self, text):
+            table = {"###": [1, 835], "</s>": [1], "Human:": [1, 12968, 29901]}
+            return type("E", (), {"input_ids": table[text]})()
+
+    crit = KeywordsStoppingCriteria(["###", "</s>", "Human:"], Tok(), torch.zeros(2, 7, dtype=torch.long))
+    assert [k.tolist() for k in crit.keyword_ids] == [[835], [1], [12968, 29901]]
+    assert crit.max_keyword_len == 2 and crit.start_len == 7
