@@ -327,6 +327,21 @@ def main():
     roofline_decode = {"bound": "hbm", "achieved": dec_bytes / dec_ms / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
                        "frac": dec_bytes / dec_ms / 1e6 / peaks["hbm"], "ms_per_decode_step": dec_ms,
                        "bytes_per_step": dec_bytes}
+    if new > 1 and world == 1:
+        # the same decode loop (graph replays against the last prefill's cache) timed ALONE after a pause: inside the step
+        # it inherits the power-capped SM clock of the prefill that precedes it, and ~35 % of a decode step is
+        # launch / latency bound, i.e. scales with that clock. Not part of `value`.
+        st_alone = model.llama.prefill(ops.splice_gather(src_d, model.llama.embed,
+                                                         model._soft_tokens(seqs, None).reshape(-1, lcfg["dim"])), plan=plan)
+        sync_all()
+        time.sleep(1.5)
+        for _ in range(2):
+            model.llama.generate_from_prefill(st_alone, new, use_graph=use_graph)
+        reps = 3
+        t_alone = timed(lambda: model.llama.generate_from_prefill(st_alone, new, use_graph=use_graph), reps) / reps / steps_dec
+        roofline_decode["alone"] = {"ms_per_decode_step": t_alone, "achieved": dec_bytes / t_alone / 1e6,
+                                    "frac": dec_bytes / t_alone / 1e6 / peaks["hbm"],
+                                    "note": "decode loop timed by itself (no prefill in front): SM clock not power-capped"}
     pre_flops = (2.0 * M * 6979321856 + 2.0 * B * 4096 * 128256 + 2.0 * 4096 * 32 * B * wl["prompt_len"] ** 2) if args.size == "full" else 0
     roofline_prefill = {"bound": "tensor", "achieved": pre_flops / phases["prefill_ms"] / 1e9, "peak": peaks["tf_sustained"],
                         "unit": "TFLOP/s", "frac": pre_flops / phases["prefill_ms"] / 1e9 / peaks["tf_sustained"]}
