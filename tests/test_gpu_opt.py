@@ -245,7 +245,12 @@ def test_opt_full_width_layers_vs_oracle_bf16():
     w32 = {k: v.float() for k, v in lw.items()}
     want_logits, _ = opt_ref.opt_forward(w32, ocfg, emb.float(), mask, opt_ref.positions_from_mask(mask))   # fp32 truth
     assert _cos(logits, want_logits) >= 0.999
-    assert float((logits.float() - want_logits).abs().max()) <= 0.06 * float(want_logits.std()) + 1e-3
+    # max-abs: 6 % of the logit std, and never worse than 2x the distance of the reference-style bf16 run from fp32
+    # (peaked logits reach |x| ~ 40, where one bf16 ulp is already 0.25)
+    bf_logits, _ = opt_ref.opt_forward(lw, ocfg, emb, mask, opt_ref.positions_from_mask(mask))
+    noise = float((bf_logits - want_logits).abs().max())
+    err = float((logits.float() - want_logits).abs().max())
+    assert err <= max(0.06 * float(want_logits.std()), 2.0 * noise) + 1e-3, (err, noise)
     want = opt_ref.greedy_generate(lw, ocfg, emb, mask, new)                                                  # bf16, HF order
     assert float((got == want).all(1).float().mean()) >= 0.8       # 5 prompts: at most one may differ (bar: 99 % at scale)
     assert torch.equal(got[:, 0], want[:, 0])
