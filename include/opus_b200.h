@@ -331,7 +331,8 @@ int opus_release_graphs(void);
  * runs o_proj -> norm -> gate/up -> down -> norm -> next qkv / lm_head of a decode step as one persistent chain kernel,
  * 0 (default) = one kernel per GEMM / norm; "chain_l2_depth" = k-blocks the chain kernel prefetches into L2 per phase;
  * "gemm_2cta" = 0 single-CTA GEMM everywhere, 1 CTA-pair (cta_group::2) form for every large plain GEMM, 2 (default) the
- * pair form except under the SwiGLU epilogue;
+ * pair form except under the SwiGLU epilogue; "gemm_2cta_tr" = 0 keeps swap-AB launches at batch 129..256 on the
+ * single-CTA kernel (default 1: CTA-pair kernel where its work items fill the pairs);
  * "decode_rope_fused" = 0 runs the decode step's split-K reduce + RoPE + KV append as its own kernel instead of inside
  * the paged-attention CTAs (default 1);
  * "tma_store" = 0 sends the plain bf16 / GELU GEMM epilogues back to direct row-per-thread stores (and the encoder's rotary

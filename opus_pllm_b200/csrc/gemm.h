@@ -142,6 +142,7 @@ size_t gemm_workspace_bytes(int M, int N, int split_k);
 void gemm_set_streamk_fill(int percent);  // 0 disables the stream-K tail
 void gemm_set_streamk_plain(int on);
 void gemm_set_tma_store(int on);
+void gemm_set_2cta_tr(int on);            // CTA-pair form for swap-AB launches at batch 129..256 (default on)
 void gemm_set_2cta(int on);               // CTA-pair (cta_group::2) form for large plain GEMMs          // TMA-store epilogue (and the rotary fusion that rides on it)     // stream-K tail in the plain (non swap-AB) form, off by default
 
 }  // namespace opus

@@ -856,6 +856,10 @@ struct Cfg2 {
   static constexpr int SMEM = BARS_OFF + 1024 + 256 + 1024;
 };
 
+// TR = swap-AB form (decode at batch 129..256: A = weights, the pair shares the 256-row activation tile, so a stage holds
+// 16 KB of weights + 16 KB of activations instead of 16 + 32 and six stages = 96 KB of weights are in flight per SM
+// instead of 64 KB). Work items are (256-row tile, k-split) pairs; the plain form always has split_k = 1.
+template <bool TR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
@@ -876,8 +880,15 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM);     // 256-row tiles
   const int n_tiles = p.num_n_tiles;
-  const int total = m_tiles * n_tiles;
+  const int total = m_tiles * n_tiles * p.split_k;
   const int group = max(1, p.group_m / 2);
+  // work item t -> (tile, k-split): k-block range [kb0, kb1) of the split
+  auto split_of = [&](int t, int& mn, int& split, int& kb0, int& kb1) {
+    mn = t / p.split_k;
+    split = t - mn * p.split_k;
+    kb0 = (int)(((long long)split * p.k_blocks) / p.split_k);
+    kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.split_k);
+  };
   auto tile_of = [&](int t, int& m, int& n) {             // grouped-M raster over 256-row tiles
     const int per_group = group * n_tiles;
     const int g = t / per_group, r = t - g * per_group;
@@ -916,10 +927,33 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int pre = 0;
+      if constexpr (TR) {
+        // PDL prologue (see the single-CTA kernel): the first ring pass of WEIGHT tiles is requested before waiting for
+        // the preceding kernel, the activation halves follow after the wait
+        if (pair < total) {
+          int mn, split, kb0, kb1, m, n;
+          split_of(pair, mn, split, kb0, kb1);
+          tile_of(mn, m, n);
+          pre = min(C::STAGES, kb1 - kb0);
+          for (int i = 0; i < pre; ++i) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[i], 2 * C::STAGE);
+            tma_load_2d_pair(smem + i * C::STAGE, &tmap_a, &full_bar[i], (kb0 + i) * BK, (2 * m + rank) * BM, p.hint_a);
+          }
+          grid_dep_wait();
+          for (int i = 0; i < pre; ++i)
+            tma_load_2d_pair(smem + i * C::STAGE + C::STAGE_A, &tmap_b, &full_bar[i], (kb0 + i) * BK,
+                             n * BN + rank * (BN / 2), p.hint_b);
+          if (pre == C::STAGES) { stage = 0; phase = 1; } else { stage = pre; }
+        } else {
+          grid_dep_wait();
+        }
+      }
       for (int t = pair; t < total; t += n_pairs) {
-        int m, n;
-        tile_of(t, m, n);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        int mn, split, kb0, kb1, m, n;
+        split_of(t, mn, split, kb0, kb1);
+        tile_of(mn, m, n);
+        for (int kb = kb0 + (t == pair ? pre : 0); kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE);   // bytes of both CTAs
@@ -928,6 +962,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if constexpr (TR) grid_dep_launch();   // late trigger: every load of this CTA is in flight
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -938,10 +973,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = pair; t < total; t += n_pairs) {
+        int mn, split, kb0, kb1;
+        split_of(t, mn, split, kb0, kb1);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE);
@@ -949,7 +986,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           const uint64_t db = umma_smem_desc_sw128(sa + C::STAGE_A);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage]);   // both CTAs' slots
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -962,17 +999,19 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int quad = warp & 3;
     const int chunk0 = (warp - 2) >> 2;
     const int epi_tid = threadIdx.x - 64;
+    if constexpr (TR) grid_dep_wait();   // output / partial buffers may still be in use by the preceding kernel
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < total; t += n_pairs) {
       TileCoord tc;
-      int m, n;
-      tile_of(t, m, n);
-      tc.m = 2 * m + rank; tc.n = n; tc.kb_begin = 0; tc.kb_end = p.k_blocks; tc.split = 0;
+      int mn, m, n;
+      split_of(t, mn, tc.split, tc.kb_begin, tc.kb_end);
+      tile_of(mn, m, n);
+      tc.m = 2 * m + rank; tc.n = n;
       tc.kind = WORK_TILE; tc.sk_tile = 0; tc.first_cta = 0;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_item<BN, false>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out, smem + C::STAGES * C::STAGE);
+      epilogue_item<BN, TR>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out, smem + C::STAGES * C::STAGE);
       tc_fence_before();
       mbar_arrive_leader(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -1571,10 +1610,11 @@ bool gemm_fuses_rope(const GemmArgs& a) {
 namespace {
 int g_2cta = -1;   // CTA-pair form for large plain GEMMs (tunable "gemm_2cta", env OPUS_GEMM_2CTA; default 2)
 
+template <bool TR>
 int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_2cta_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM) != cudaSuccess)
       return OPUS_ERR_CUDA;
     configured = true;
   }
@@ -1588,24 +1628,46 @@ int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
     rc = make_tmap_bf16(&to, p.out, p.M, p.epi == EPI_SWIGLU ? p.N / 2 : p.N, p.ldo, 32);
     if (rc) return rc;
   }
+  const int items = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles * p.split_k;
+  const int max_pairs = num_sms() / 2;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(num_sms() & ~1);
+  cfg.gridDim = dim3(2 * (TR && items < max_pairs ? items : max_pairs));
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg2::SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_2cta_kernel, ta, tb, to, p);
+  cfg.numAttrs = (TR && pdl_for(true)) ? 2 : 1;   // decode-sized launches chain through PDL like the single-CTA kernel
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_2cta_kernel<TR>, ta, tb, to, p);
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
+
+// swap-AB launches the pair kernel takes (tunable "gemm_2cta_tr", env OPUS_GEMM_2CTA_TR; default on): batch tile of 256
+// (129..256 rows) whose (256-feature tile, k-split) items fill the 74 pairs to >= 85 % of whole waves. The stream-K tail
+// stays with the single-CTA kernel (decode gate/up: 112 pair tiles would be 1.5 waves).
+int g_2cta_tr = -1;
+bool pair_takes_transposed(const GemmArgs& a, const GemmParams& p, int bn) {
+  if (g_2cta_tr < 0) {
+    const char* e = std::getenv("OPUS_GEMM_2CTA_TR");
+    g_2cta_tr = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (!g_2cta_tr || !a.transposed || bn != 256 || a.block_n != 0 || a.N <= 128 || a.N > 256 || a.epi == EPI_SWIGLU)
+    return false;
+  const int max_pairs = num_sms() / 2;
+  const int items = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles * p.split_k;
+  const int waves = (items + max_pairs - 1) / max_pairs;
+  return items * 100 >= 85 * waves * max_pairs;
+}
 }  // namespace
 
+void gemm_set_2cta_tr(int on) { g_2cta_tr = on ? 1 : 0; }
 void gemm_set_2cta(int on) { g_2cta = on < 0 ? 0 : (on > 2 ? 2 : on); }
 
 // D = epi(A * B^T). See gemm.h for the contract.
@@ -1621,7 +1683,12 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   // 1 = every eligible launch, 2 = every eligible launch except the SwiGLU epilogue (measured slower there)
   if (g_2cta && !a.transposed && bn == 256 && p.split_k == 1 && p.sk_tiles == 0 && a.M >= 1024 && a.block_n == 0 &&
       !(g_2cta == 2 && a.epi == EPI_SWIGLU))
-    return launch_2cta(p, a, stream);
+    return launch_2cta<false>(p, a, stream);
+  if (pair_takes_transposed(a, p, bn)) {
+    p.sk_tiles = 0;                                   // whole (tile, split) items only
+    p.dp_items = p.num_m_tiles * p.num_n_tiles * p.split_k;
+    return launch_2cta<true>(p, a, stream);
+  }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {

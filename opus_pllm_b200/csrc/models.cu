@@ -619,6 +619,10 @@ int set_tunable(const char* name, int value) {
     gemm_set_2cta(value);
     return release_graphs();
   }
+  if (std::strcmp(name, "gemm_2cta_tr") == 0) {
+    gemm_set_2cta_tr(value);
+    return release_graphs();
+  }
   if (std::strcmp(name, "tma_store") == 0) {
     gemm_set_tma_store(value);
     return release_graphs();

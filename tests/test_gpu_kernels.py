@@ -219,6 +219,37 @@ def test_gemm_cta_pair_form_is_bit_identical(ops, M, N, K):
     _close_bf16(out[1][0], R.linear_ref(x, w, b))
 
 
+@pytest.mark.parametrize("rows", [129, 200, 256])
+@pytest.mark.parametrize("N,K,split", [(4096, 4096, 4), (6144, 4096, 3), (4096, 14336, 4), (18816, 1024, 1), (8320, 512, 2)])
+def test_gemm_cta_pair_swap_ab_form_is_bit_identical(ops, rows, N, K, split):
+    """Swap-AB (weight-streaming) launches at batch 129..256 run on the CTA-pair kernel (each CTA holds half of the
+    256-row activation tile; (256-feature tile, k-split) work items): same k order per element as the single-CTA
+    kernel, so split-K partials and every fused epilogue must agree bit for bit (decode shapes of Llama-3-8B: o_proj,
+    qkv, down; a 74-tile single wave; an odd 128-feature tail)."""
+    from opus_pllm_b200 import _lib as L
+    x = _randn((rows, K), 54)
+    w = _randn((N, K), 55, scale=K ** -0.5)
+    b = _randn((N,), 56, dtype=torch.float32)
+    res = _randn((rows, N), 57)
+    lib = L.load()
+    out = {}
+    try:
+        for mode in (1, 0):
+            L.check(lib.opus_set_tunable(b"gemm_2cta_tr", mode))
+            h = res.clone()
+            ops.gemm(x, w, epilogue=L.EPI_RES_BF16, bias=b, residual=h, out=h, transposed=True)
+            out[mode] = (ops.gemm(x, w, epilogue=L.EPI_PARTIAL_F32, transposed=True, split_k=split),
+                         ops.gemm(x, w, epilogue=L.EPI_BF16, bias=b, transposed=True),
+                         ops.gemm(x, w, epilogue=L.EPI_BF16_GELU, bias=b, transposed=True), h)
+    finally:
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 1))
+    for a, c in zip(out[1], out[0]):
+        assert torch.equal(a, c)
+    assert out[1][0].shape == (split, rows, N)
+    _close_bf16(out[1][1], R.linear_ref(x, w, b))
+    assert torch.allclose(out[1][0].sum(0), R.linear_ref(x, w), rtol=1e-4, atol=2e-3)
+
+
 def test_gemm_linearity_full_size(ops):
     """size-independent property at a BASELINE-sized weight: f(x1 + x2) == f(x1) + f(x2) up to bf16 rounding."""
     from opus_pllm_b200._lib import EPI_F32

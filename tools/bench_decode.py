@@ -47,7 +47,7 @@ def setk(**kw):
 
 
 run("defaults (kernel per op, PDL chain)")
-if os.environ.get("AFTER_PREFILL"):
+def after_prefill(label):
     # the same decode loop timed right after a prefill, as inside bench.py (clock / power state carried over)
     tot = 0.0
     for _ in range(3):
@@ -59,8 +59,15 @@ if os.environ.get("AFTER_PREFILL"):
         torch.cuda.synchronize()
         tot += a.elapsed_time(b)
     ms = tot / 3 / (new - 1)
-    print(f"{'decode timed right after a prefill':40s} {ms:7.3f} ms/step  {bytes_step / ms / 1e6:7.0f} GB/s  frac {bytes_step / ms / 1e6 / 6551.4:.3f}", flush=True)
-if os.environ.get("FUSED"):
+    print(f"{label:40s} {ms:7.3f} ms/step  {bytes_step / ms / 1e6:7.0f} GB/s  frac {bytes_step / ms / 1e6 / 6551.4:.3f}", flush=True)
+
+
+if os.environ.get("AFTER_PREFILL"):
+    after_prefill("decode timed right after a prefill")
+    if os.environ.get("FUSED"):
+        setk(decode_fused=1); run("decode_fused=1 (chain kernel)"); after_prefill("chain kernel right after a prefill")
+        setk(decode_fused=0)
+if os.environ.get("FUSED") and not os.environ.get("AFTER_PREFILL"):
     setk(decode_fused=1); run("decode_fused=1 (chain kernel)"); setk(decode_fused=0)
 if os.environ.get("SWEEP"):
     setk(pf_qkv=0, pf_o=0, pf_gu=0, pf_down=0, pf_lm=0); base = run("all off")
