@@ -156,6 +156,47 @@ def read_esm2(path: str) -> tuple[dict, dict]:
     return sd, dict(n_layers=n_layers, dim=dim, n_heads=dim // 64, ffn_dim=ffn)
 
 
+# ------------------------------------------------------------------------------------------------ component seams
+FAIR_ESM_HUB = "~/.cache/torch/hub/checkpoints/esm2_t33_650M_UR50D.pt"   # what esm.pretrained.esm2_t33_650M_UR50D() caches
+
+
+def build_protein_encoder(ckpt=None, esm_path: str | None = None, device="cuda"):
+    """`protein_encoder/builder.py:3-6` -> `ProteinSeqEmbeddingExtractor(ckpt)` (cstp_v3/modelling.py:19-36): the ESM-2
+    t33 650M weights (fair-esm hub cache, or `esm_path`), optionally overridden by the `protein_model.model.*` tensors of
+    a CSTP training checkpoint (`torch.load(ckpt)['model']`, loaded non-strictly like the reference). Returns an object
+    with `get_protein_seq_embeddings(list[str]) -> float32[B, 1280]` on the GPU (used by opus_arch.py:53 and
+    scripts/generate_esm_*.py)."""
+    from .encoder import B200ProteinEncoder
+    sd, cfg = read_esm2(esm_path or os.path.expanduser(FAIR_ESM_HUB))
+    if ckpt is not None:
+        raw = _load_any(ckpt)["model"]
+        pref = "protein_model.model."
+        over = {k[len(pref):]: v for k, v in raw.items() if k.startswith(pref)}
+        sd.update({k: v for k, v in over.items() if k in sd})          # strict=False: unknown keys are ignored
+    return B200ProteinEncoder(sd, device=device, **cfg)
+
+
+def build_protein_projector(cstp_chackpoint_path: str, device="cuda"):
+    """`protein_projector/builder.py:15-29`: the CSTP Lightning checkpoint -> object with `.protein_forward(x[B,1280]) ->
+    [B,5120]`, `.to(device)`, `.parameters()`, `.eval()` (only the protein projection is on the generation path)."""
+    from .projector import B200ProteinProjector
+    sd = read_cstp_checkpoint(cstp_chackpoint_path)
+    return B200ProteinProjector(sd["protein_projection.linear.weight"], sd["protein_projection.linear.bias"], device=device)
+
+
+def build_switch_projector(model_args, n_tokens: int = 8, device="cuda"):
+    """`protein_mlp/builder.py:11-25`: `model_args.hidden_size`, `.switch_projector_type` ('linear' | 'mlp{N}x_gelu',
+    default 'mlp2x_gelu'), `.pretrain_protein_projector_ckpt` (None -> the projector reads the 1280-wide ESM embedding,
+    else the 5120-wide CSTP one) -> callable with `.load_state_dict({'0.weight', '0.bias', '2.weight', '2.bias'})`."""
+    from .projector import B200SwitchProjector
+    ptype = getattr(model_args, "switch_projector_type", "mlp2x_gelu")
+    in_dim = 5120 if getattr(model_args, "pretrain_protein_projector_ckpt", None) is not None else 1280
+    try:
+        return B200SwitchProjector(in_dim, model_args.hidden_size * n_tokens, ptype, device=device)
+    except NotImplementedError:
+        return None   # the reference falls off the end of the function for unknown types (builder.py:25)
+
+
 # ------------------------------------------------------------------------------------------------ reference entry point
 def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=False, load_4bit=False,
                           accelerator=None, switch_projector_type="mlp2x_gelu", cstp_path=True, esm_path=None,
@@ -195,7 +236,7 @@ def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=F
         print("No adapter path!")
     cstp_sd = read_cstp_checkpoint(cstp_path) if isinstance(cstp_path, str) else None
     if esm_path is None:
-        esm_path = os.path.expanduser("~/.cache/torch/hub/checkpoints/esm2_t33_650M_UR50D.pt")  # fair-esm hub cache
+        esm_path = os.path.expanduser(FAIR_ESM_HUB)
     esm_sd, esm_cfg = read_esm2(esm_path)
     model = build_from_state_dicts(llama_sd, llama_cfg, esm_sd, esm_cfg, cstp_sd, switch_sd,
                                    switch_type=switch_projector_type, lora_sd=lora_sd, lora_alpha=alpha, lora_r=r,

@@ -576,3 +576,43 @@ def test_stop_sequences_kernel_and_generate(tmp_path):
     assert (got[0, 5:] == pad).all() and torch.equal(got[0, :5], base[0, :5])
     assert torch.equal(model.generate_packed(emb, cu, 12, pad_id=pad, stop_sequences=[stop], use_graph=False), got)
     assert torch.equal(model.generate_packed(emb, cu, 12, pad_id=pad), base)       # and off again: state is rebuilt
+
+
+# ------------------------------------------------------------------------------------------------ builder seams
+def test_component_builder_seams_on_gpu(tmp_path):
+    """`build_protein_encoder(ckpt)` / `build_protein_projector(path)` / `build_switch_projector(model_args)`:
+    objects built from files behave like the ones assembled from the tensors; a CSTP checkpoint's
+    `protein_model.model.*` tensors override the base ESM-2 weights (cstp_v3/modelling.py:22-31); and the embedding
+    producer (scripts/generate_esm_embedding.py) returns the encoder's embeddings regardless of batching."""
+    from types import SimpleNamespace
+    from tests.test_loaders_cpu import CFG, ESM, write_fake_release
+    from opus_pllm_b200 import builder, generate_esm_embedding as G
+    from opus_pllm_b200.encoder import B200ProteinEncoder
+    rel = write_fake_release(str(tmp_path), CFG, ESM)
+    seqs = synth.proteins(6, 5, 70, seed=4)
+    enc = builder.build_protein_encoder(None, esm_path=rel["esm"])
+    direct = B200ProteinEncoder(rel["esm_sd"], **ESM)
+    want = direct.get_protein_seq_embeddings(seqs)
+    assert torch.equal(enc.get_protein_seq_embeddings(seqs), want)
+    # CSTP checkpoint override of one layer's fc1 (+ an unknown key that must be ignored)
+    over = {k: v.clone() for k, v in rel["esm_sd"].items()}
+    over["layers.0.fc1.weight"] = over["layers.0.fc1.weight"] * 0.5
+    ck = tmp_path / "cstp_train.ckpt"
+    torch.save({"model": {"protein_model.model.layers.0.fc1.weight": over["layers.0.fc1.weight"],
+                          "protein_model.model.contact_head.regression.weight": torch.zeros(1, 4),
+                          "text_model.whatever": torch.zeros(2)}}, ck)
+    enc2 = builder.build_protein_encoder(str(ck), esm_path=rel["esm"])
+    got2 = enc2.get_protein_seq_embeddings(seqs)
+    assert torch.equal(got2, B200ProteinEncoder(over, **ESM).get_protein_seq_embeddings(seqs))
+    assert not torch.equal(got2, want)
+    # projector seams
+    pp = builder.build_protein_projector(builder.return_cstp_path(rel["weights"], "modality_encoder/modality_encoding_adapter.ckpt"))
+    c = pp.to("cuda").protein_forward(want)
+    assert c.shape == (6, 256) and _cos(c, mm_ref.protein_forward(want, rel["proj"]["protein_projection.linear.weight"].cuda(),
+                                                                  rel["proj"]["protein_projection.linear.bias"].cuda())) >= 0.999
+    # producer: one protein per call (the reference's loop) == packed, length-sorted batches
+    emb = G.embed_all(enc, seqs + seqs[:2], max_tokens=100)
+    assert set(emb) == set(seqs)
+    for s in seqs:
+        one = enc.get_protein_seq_embeddings([s])[0].cpu()
+        assert _cos(torch.tensor(emb[s]), one) >= 0.99999 and float((torch.tensor(emb[s]) - one).abs().max()) <= 2e-2

@@ -131,3 +131,48 @@ def test_read_hf_opt_directory_and_family_dispatch(tmp_path):
         builder.read_hf_opt(d)
     with pytest.raises(NotImplementedError):                                              # builder.py:95-96
         builder.load_pretrained_model("/nonexistent/mistral-7b", None, "mistral-7b")   # (tmp_path itself contains "opt")
+
+
+def test_component_builder_seams_and_embedding_producer_host_logic(tmp_path):
+    """The reference's three builder seams keep their names / arguments, and the embedding producer keeps the
+    scripts' file formats (scripts/generate_esm_embedding.py, generate_esm_for_each_seq.py). Host logic only."""
+    import inspect
+    from types import SimpleNamespace
+    from opus_pllm_b200 import generate_esm_embedding as G
+    assert list(inspect.signature(builder.build_protein_encoder).parameters)[0] == "ckpt"
+    assert list(inspect.signature(builder.build_protein_projector).parameters)[0] == "cstp_chackpoint_path"
+    assert list(inspect.signature(builder.build_switch_projector).parameters)[:2] == ["model_args", "n_tokens"]
+    sw = builder.build_switch_projector(SimpleNamespace(hidden_size=64, pretrain_protein_projector_ckpt="x"), device="cpu")
+    assert (sw.in_dim, sw.hidden_dim, sw.depth) == (5120, 512, 2)
+    sw = builder.build_switch_projector(SimpleNamespace(hidden_size=64, pretrain_protein_projector_ckpt=None,
+                                                        switch_projector_type="linear"), n_tokens=4, device="cpu")
+    assert (sw.in_dim, sw.hidden_dim, sw.depth) == (1280, 256, 1)
+    assert builder.build_switch_projector(SimpleNamespace(hidden_size=64, pretrain_protein_projector_ckpt=None,
+                                                          switch_projector_type="conv"), device="cpu") is None
+    # batching: longest first, token budget respected, every index exactly once
+    seqs = ["A" * n for n in (5, 300, 12, 298, 7, 4000)]
+    bs = G.batches_by_length(seqs, 620)
+    assert sorted(i for b in bs for i in b) == list(range(6)) and bs[0] == [5]
+    assert all(sum(len(seqs[i]) + 2 for i in b) <= 620 or len(b) == 1 for b in bs)
+
+    class FakeEncoder:                                           # embedding = [len, #A, 0, ...] so results are checkable
+        calls = 0
+
+        def get_protein_seq_embeddings(self, data):
+            FakeEncoder.calls += 1
+            return torch.tensor([[float(len(s)), float(s.count("A"))] + [0.0] * 2 for s in data])
+
+    recs = [dict(instruction="i", input=s, output="o", extra=1) for s in ("MKA", "AAAA", "MKA", "G" * 4001, "K" * 4000)]
+    src, dct = tmp_path / "d.json", tmp_path / "known.json"
+    json.dump(recs, open(src, "w"))
+    json.dump({"AAAA": [9.0, 9.0, 9.0, 9.0]}, open(dct, "w"))
+    args = SimpleNamespace(file_path=str(src), save_path=str(tmp_path / "out.jsonl"), dict_path=str(dct), esm_path=None,
+                           ckpt=None, max_tokens=4096, dict_only=False)
+    assert G.generate_esm_embedding(args, FakeEncoder()) == 4   # the 4001-residue protein is skipped (> 4000)
+    lines = [json.loads(l) for l in open(args.save_path)]
+    assert [l["input"] for l in lines] == ["MKA", "AAAA", "MKA", "K" * 4000]
+    assert lines[0]["input_embed"] == [3.0, 1.0, 0.0, 0.0] and lines[1]["input_embed"] == [9.0] * 4   # dict entry reused
+    assert set(lines[0]) == {"instruction", "input", "output", "input_embed"}
+    args.dict_only, args.save_path = True, str(tmp_path / "seq2embed.json")
+    assert G.generate_esm_embedding(args, FakeEncoder()) == 2   # unique sequences shorter than 4000
+    assert set(json.load(open(args.save_path))) == {"MKA", "AAAA"}
