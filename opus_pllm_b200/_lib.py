@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libopus_b200.so")
+# OPUS_B200_LIB points at another build of the same ABI (A/B measurements of kernel variants); default = the in-tree build
+LIB_PATH = os.environ.get("OPUS_B200_LIB") or os.path.join(_HERE, "libopus_b200.so")
 
 OK = 0
 EPI_BF16, EPI_BF16_GELU, EPI_RES_F32, EPI_RES_BF16, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_F32, EPI_BF16_RELU = range(8)

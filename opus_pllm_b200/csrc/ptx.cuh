@@ -281,20 +281,33 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 // exact-erf GELU (fair-esm / nn.GELU()), branch-free: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the
-// bf16 rounding every caller applies) on the fast pipes: one rcp.approx, one ex2.approx, seven FMAs. erff() costs about
-// twice the instructions and a branch per element, which made the K = 1280 fc1 tiles of the encoder epilogue-bound
-// (868 TFLOP/s against 1177-1278 for its sibling GEMMs).
-__device__ __forceinline__ float erf_fast(float x) {
+// bf16 rounding every caller applies). erff() costs about twice the instructions and a branch per element, which made the
+// K = 1280 fc1 tiles of the encoder epilogue-bound. 15 instructions per element: the 1/sqrt(2) and log2(e) factors are
+// folded into the constants, rcp / ex2 are the raw MUFU forms (exp2f / __fdividef add range scaling: 2 FSETP + 3 FMUL +
+// FSEL + FMNMX per element in the SASS), and 0.5 x (1 + sign(x) erf|u|) is evaluated as h + |h| - |h| r, which also
+// removes the cancellation of 1 + erf(u) in the negative tail.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));   // rcp.approx: no slow-path branch
+  const float t = rcp_approx(fmaf(0.23164189f, ax, 1.0f));    // 1 / (1 + 0.3275911 |x| / sqrt(2))
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
-  return copysignf(fmaf(-p * t, e, 1.0f), x);
+  const float a2 = ax * 0.84932180f;                           // |x| sqrt(log2(e) / 2): exp(-x^2 / 2) = 2^-(a2^2)
+  const float r = (p * t) * ex2_approx(-(a2 * a2));            // r = 1 - erf(|x| / sqrt(2))
+  const float h = 0.5f * x, ah = fabsf(h);
+  return fmaf(-ah, r, h + ah);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 // silu on the fast pipes, branch-free: ex2.approx and rcp.approx (2 ulp each, no slow-path subroutine). Every caller
 // rounds the result to bf16, so it differs from x / (1 + expf(-x)) only next to bf16 rounding ties (~2^-14 of inputs).
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
