@@ -616,3 +616,34 @@ def test_component_builder_seams_on_gpu(tmp_path):
     for s in seqs:
         one = enc.get_protein_seq_embeddings([s])[0].cpu()
         assert _cos(torch.tensor(emb[s]), one) >= 0.99999 and float((torch.tensor(emb[s]) - one).abs().max()) <= 2e-2
+
+
+@pytest.mark.parametrize("batch", [160, 256])
+def test_decode_batch_above_128_pair_kernel_is_bit_identical(batch):
+    """Decode at batch 129..256: the q|k|v, o_proj and down split-K GEMMs run on the CTA-pair swap-AB kernel
+    (`gemm_2cta_tr`). With the pair kernel off the same launches go to the single-CTA kernel: tokens, logits and the KV
+    cache must not change by a bit (Llama-3-8B-wide layers, reduced depth, ragged prompts)."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    cfg = dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128, ffn_dim=14336, vocab=8192)
+    w = synth.llama_weights(seed=13, device="cuda", dtype=torch.bfloat16,
+                            **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [9 + (i * 7) % 40 for i in range(batch)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    emb = synth.weight((int(cu[-1]), cfg["dim"]), "pair_decode_prompt", 0.02).cuda().to(torch.bfloat16)
+    lib = L.load()
+    plan = model.make_plan(cu, 6)
+    try:
+        res = {}
+        for mode in (1, 0):
+            L.check(lib.opus_set_tunable(b"gemm_2cta_tr", mode))
+            model._k.zero_(); model._v.zero_()
+            st = model.prefill(emb, plan=plan)
+            toks = model.generate_from_prefill(st, 6)
+            res[mode] = (toks.clone(), model._ws_bufs["logits"][:batch].clone(), model._k.clone(), model._v.clone())
+    finally:
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 1))
+        model.release_plan(plan)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
