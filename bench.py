@@ -193,10 +193,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION / INFO
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("OPUS_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL writes its "NCCL version ..." banner to fd 1 when the first
+        # communicator is created, so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from opus_pllm_b200 import ops
     ops.device_check()
     peaks = _peaks()
