@@ -68,6 +68,8 @@ struct AttnParams {
   int ldq, ldk, ldv, ldo;  // row strides (elements)
   int n_q_heads, group;    // group = q heads per kv head
   float scale_log2;        // softmax scale * log2(e)
+  int tail_only;           // > 0 (grid.x = 1): only the LAST 256-row-aligned query block of a sequence, and only when it
+                           // holds <= tail_only rows (the rows the tcgen05 kernel was told to skip)
 };
 
 template <int D, int ROWS, int THREADS>
@@ -98,7 +100,12 @@ __global__ void __launch_bounds__(BM * 2, (D == 64) ? (BM == 64 ? 3 : 2) : 1) at
   const int seq_start = p.cu_seqlens[b];
   const int len = p.cu_seqlens[b + 1] - seq_start;
   const int mblk = CAUSAL ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy causal tiles first
-  const int q0 = mblk * BM;
+  int q0 = mblk * BM;
+  if (p.tail_only > 0) {
+    if (len <= 0) return;
+    q0 = ((len - 1) / 256) * 256;
+    if (len - q0 > p.tail_only) return;
+  }
   if (q0 >= len) return;
   const int kvh = h / p.group;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -522,7 +529,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
 }
 
 template <int D, bool CAUSAL, int BM>
-int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st) {
+int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st, bool tail = false) {
   constexpr int SMEM = BM * D * 2 + 4 * BN * D * 2;
   constexpr int ATT_THREADS = BM * 2;
   static bool configured = false;
@@ -532,7 +539,7 @@ int launch_varlen(const AttnParams& p, int n_seqs, int max_len, cudaStream_t st)
       return OPUS_ERR_CUDA;
     configured = true;
   }
-  dim3 grid((max_len + BM - 1) / BM, p.n_q_heads, n_seqs);
+  dim3 grid(tail ? 1 : (max_len + BM - 1) / BM, p.n_q_heads, n_seqs);
   launch_pdl(false, attn_varlen_kernel<D, CAUSAL, BM>, dim3(grid), dim3(ATT_THREADS), SMEM, st, p);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
@@ -559,9 +566,37 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
                          ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                            reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
     const bool want_tc = mode == 2 || (mode == 0 && max_len >= 192);
-    if (want_tc && aligned && (head_dim == 64 || head_dim == 128))
+    if (want_tc && aligned && (head_dim == 64 || head_dim == 128)) {
+      // Short tails: a sequence whose last 256-row work item holds <= 64 query rows (T = 258: two rows) would push a
+      // nearly empty 128-row tile through the whole tcgen05 pipeline (~6 us per (sequence, head), 40 % of the encoder's
+      // attention time at C1). Those rows run on one 64-row mma.sync tile instead, launched first (it is tiny); the two
+      // kernels write disjoint rows of `o`. Enabled when the longest sequence has such a tail (uniform batches) or for
+      // ragged encoder batches; OPUS_ATTN_TAIL=0 disables it.
+      static int tail_mode = -1;
+      if (tail_mode < 0) {
+        const char* e = std::getenv("OPUS_ATTN_TAIL");
+        tail_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+      }
+      constexpr int kTail = 64;
+      const int max_tail = max_len - ((max_len - 1) / 256) * 256;
+      const bool split_tail = tail_mode && (max_tail <= kTail || (!causal && n_seqs >= 8));
+      if (split_tail) {
+        AttnParams tp;
+        tp.q = q; tp.k = k; tp.v = v; tp.o = o;
+        tp.cu_seqlens = cu_seqlens;
+        tp.ldq = ldq; tp.ldk = ldk; tp.ldv = ldv; tp.ldo = ldo;
+        tp.n_q_heads = n_q_heads;
+        tp.group = n_q_heads / n_kv_heads;
+        tp.scale_log2 = scale * 1.4426950408889634f;
+        tp.tail_only = kTail;
+        int rc;
+        if (head_dim == 64) rc = causal ? launch_varlen<64, true, 64>(tp, n_seqs, max_len, st, true) : launch_varlen<64, false, 64>(tp, n_seqs, max_len, st, true);
+        else rc = causal ? launch_varlen<128, true, 64>(tp, n_seqs, max_len, st, true) : launch_varlen<128, false, 64>(tp, n_seqs, max_len, st, true);
+        if (rc != OPUS_OK) return rc;
+      }
       return attn_varlen_tc(q, ldq, k, ldk, v, ldv, o, ldo, cu_seqlens, n_seqs, n_tok, max_len, n_q_heads, n_kv_heads,
-                            head_dim, causal, scale, st);
+                            head_dim, causal, scale, st, split_tail ? kTail : 0);
+    }
   }
   if ((ldq | ldk | ldv) % 8 || ldo % 2) return OPUS_ERR_ARG;
   AttnParams p;
@@ -571,6 +606,7 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
   p.n_q_heads = n_q_heads;
   p.group = n_q_heads / n_kv_heads;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.tail_only = 0;
   // 64-row query tiles when they waste fewer padded rows than 128-row tiles (or the sequences are short)
   const bool bm64 = ((max_len + 63) / 64) * 64 < ((max_len + 127) / 128) * 128;
   if (head_dim == 64 && !causal) return bm64 ? launch_varlen<64, false, 64>(p, n_seqs, max_len, st) : launch_varlen<64, false, 128>(p, n_seqs, max_len, st);

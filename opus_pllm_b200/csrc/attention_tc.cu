@@ -40,6 +40,8 @@ struct AttnTcParams {
   int group;          // q heads per kv head
   float scale_log2;   // softmax scale * log2(e)
   int n_seqs, n_q_heads, n_mblk, n_items;  // work list: n_mblk tile pairs x n_seqs x n_q_heads
+  int skip_tail;      // > 0: a sequence's last work item is left out when it holds <= skip_tail query rows (the caller
+                      // runs those rows on the 64-row mma.sync kernel: a 2-row tail would cost a whole 128-row pipeline)
 };
 
 template <int D>
@@ -185,7 +187,7 @@ __device__ __forceinline__ Item get_item(const AttnTcParams& p, int w) {
   it.q0 = mblk * 2 * TBM;
   it.seq_start = p.cu_seqlens[b];
   it.len = p.cu_seqlens[b + 1] - it.seq_start;
-  it.valid = it.q0 < it.len;
+  it.valid = it.q0 < it.len && !(p.skip_tail > 0 && it.len - it.q0 <= p.skip_tail);
   it.n_a = ((CAUSAL ? min(it.len, it.q0 + TBM) : it.len) + TBN - 1) / TBN;
   it.n_b = (it.q0 + TBM < it.len) ? ((CAUSAL ? min(it.len, it.q0 + 2 * TBM) : it.len) + TBN - 1) / TBN : 0;
   it.n_max = it.n_b > 0 ? it.n_b : it.n_a;
@@ -482,7 +484,7 @@ int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
 // Same contract as attn_varlen (attention.cu). n_tok = total packed rows (for the tensor maps).
 int attn_varlen_tc(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                    __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int n_tok, int max_len, int n_q_heads,
-                   int n_kv_heads, int head_dim, int causal, float scale, cudaStream_t st) {
+                   int n_kv_heads, int head_dim, int causal, float scale, cudaStream_t st, int skip_tail) {
   if (n_seqs == 0 || max_len == 0) return OPUS_OK;
   if ((ldq | ldk | ldv | ldo) % 8) return OPUS_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
@@ -503,6 +505,7 @@ int attn_varlen_tc(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int 
   p.n_seqs = n_seqs; p.n_q_heads = n_q_heads;
   p.n_mblk = (max_len + 2 * TBM - 1) / (2 * TBM);
   p.n_items = p.n_mblk * n_seqs * n_q_heads;
+  p.skip_tail = skip_tail;
   const bool narrow = max_len <= 384;
 #define OPUS_TC_CASE(HD, C)                                                                                     \
   if (head_dim == HD && (causal != 0) == C)                                                                     \

@@ -72,7 +72,7 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
 // tcgen05 / TMEM / TMA implementation of the same contract (attention_tc.cu); attn_varlen dispatches to it.
 int attn_varlen_tc(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                    __nv_bfloat16* o, int ldo, const int* cu_seqlens, int n_seqs, int n_tok, int max_len, int n_q_heads,
-                   int n_kv_heads, int head_dim, int causal, float scale, cudaStream_t st);
+                   int n_kv_heads, int head_dim, int causal, float scale, cudaStream_t st, int skip_tail = 0);
 int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                       const int* block_table, int max_blocks, const int* ctx_len, __nv_bfloat16* o, int ldo,
                       int n_seqs, int n_q_heads, int n_kv_heads, int head_dim, int block_size, float scale,
