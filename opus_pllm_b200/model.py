@@ -101,6 +101,33 @@ class B200OpusLlama:
     def get_protein_encoder(self):
         return self.protein_encoder
 
+    def initialize_protein_modules(self, model_args, fsdp=None):
+        """opus_arch.py:46-90 (called by load_pretrained_model, builder.py:118-119): (re)build the protein encoder, the CSTP
+        projector and the switch projector from `model_args` -- `.esm_ckpt` (None = base ESM-2; `.esm_path` optionally
+        names the base weights file), `.pretrain_protein_projector_ckpt` (None = identity), `.has_switch_projector`,
+        `.switch_projector_type`, `.pretrain_switch_projector_ckpt` -- through the three builder seams."""
+        from . import builder as B
+        self.config.device = getattr(model_args, "device", self.device)
+        self.config.has_protein_encoder = getattr(model_args, "has_protein_encoder", True)
+        self.config.has_switch_projector = getattr(model_args, "has_switch_projector", False)
+        if self.protein_encoder is None:
+            self.protein_encoder = B.build_protein_encoder(getattr(model_args, "esm_ckpt", None),
+                                                           esm_path=getattr(model_args, "esm_path", None),
+                                                           device=self.device)
+        else:
+            self.protein_encoder.load_model()                                            # opus_arch.py:63
+        ckpt = getattr(model_args, "pretrain_protein_projector_ckpt", None)
+        self.protein_projector = (B.build_protein_projector(ckpt, device=self.device).to(self.device)
+                                  if ckpt is not None else IdentityProjector())
+        if self.config.has_switch_projector:
+            if not hasattr(model_args, "hidden_size"):
+                model_args.hidden_size = self.config.hidden_size
+            self.switch_projector = B.build_switch_projector(model_args, self.n_soft, device=self.device)
+            sw_ckpt = getattr(model_args, "pretrain_switch_projector_ckpt", None)
+            if sw_ckpt is not None:
+                self.switch_projector.load_state_dict(B.read_switch_projector(sw_ckpt))
+        self._fused = None
+
     def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
         flat = ids.reshape(-1).to(self.device, torch.int32)
         return ops.embed_gather(flat, self.llama.embed).reshape(*ids.shape, self.llama.dim)

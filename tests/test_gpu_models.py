@@ -647,3 +647,29 @@ def test_decode_batch_above_128_pair_kernel_is_bit_identical(batch):
         model.release_plan(plan)
     for a, b in zip(res[1], res[0]):
         assert torch.equal(a, b)
+
+
+def test_initialize_protein_modules_rebuilds_the_seams(tmp_path):
+    """opus_arch.py:46-90: the model's protein modules (re)built from `model_args` through the builder seams give the
+    same generation as the model assembled by load_pretrained_model from the same files."""
+    from types import SimpleNamespace
+    from tests.test_loaders_cpu import CFG, ESM, ToyTokenizer, write_fake_release
+    from opus_pllm_b200 import builder
+    from opus_pllm_b200.model import build_from_state_dicts
+    rel = write_fake_release(str(tmp_path), CFG, ESM)
+    cstp = builder.return_cstp_path(rel["weights"], "modality_encoder/modality_encoding_adapter.ckpt")
+    sw = builder.return_cstp_path(rel["weights"], "modality_refinement_projector/modality_refinement_projection.bin")
+    _, ref_model, _ = builder.load_pretrained_model(rel["base"], rel["weights"], "Meta-Llama-3-tiny", cstp_path=cstp,
+                                                    esm_path=rel["esm"], tokenizer=ToyTokenizer())
+    bare = build_from_state_dicts(rel["llama"], CFG, None, None, None, None, lora_sd=rel["lora"], lora_alpha=8.0, lora_r=4,
+                                  eos_token_id=[2, 3])
+    assert bare.get_protein_encoder() is None
+    bare.get_model().initialize_protein_modules(SimpleNamespace(
+        device="cuda", has_protein_encoder=True, has_switch_projector=True, esm_ckpt=None, esm_path=rel["esm"],
+        pretrain_protein_projector_ckpt=cstp, pretrain_switch_projector_ckpt=sw, switch_projector_type="mlp2x_gelu",
+        hidden_size=CFG["dim"]), fsdp=None)
+    seqs = synth.proteins(3, 10, 50, seed=2)
+    ids = torch.stack(synth.prompt_ids(3, 20, vocab=CFG["vocab"], sentinel_at=5)).cuda()
+    a = ref_model.generate(ids, seqs, do_sample=False, max_new_tokens=5, pad_token_id=2)
+    b = bare.generate(ids, seqs, do_sample=False, max_new_tokens=5, pad_token_id=2)
+    assert torch.equal(a, b)
