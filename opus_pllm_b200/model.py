@@ -123,6 +123,9 @@ class B200OpusLlama:
             if not hasattr(model_args, "hidden_size"):
                 model_args.hidden_size = self.config.hidden_size
             self.switch_projector = B.build_switch_projector(model_args, self.n_soft, device=self.device)
+            # the reference hard-codes 5120 / 1280 (protein_mlp/builder.py:14); take the width that is really there
+            self.switch_projector.in_dim = (self.protein_projector.out_dim if ckpt is not None
+                                            else getattr(self.protein_encoder, "dim", self.switch_projector.in_dim))
             sw_ckpt = getattr(model_args, "pretrain_switch_projector_ckpt", None)
             if sw_ckpt is not None:
                 self.switch_projector.load_state_dict(B.read_switch_projector(sw_ckpt))
