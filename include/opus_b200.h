@@ -142,7 +142,8 @@ int opus_stop_sequences(const int32_t* out_ids, int out_ld, int n_rows, int step
                         const int32_t* stop_seqs, const int32_t* stop_lens, int n_stop, int stop_ld, int32_t* finished,
                         int32_t* n_unfinished, void* stream);
 int opus_embed_gather_bf16(const int32_t* tok, const void* table, void* x, int n_rows, int dim, void* stream);
-/* OPT / Galactica family (language_model/opus_opt.py -> HF OPTDecoder). nn.LayerNorm over a bf16 residual stream with
+/* OPT / Galactica family (multi_modality_v1/model/language_model/opus_opt.py:82-93,127-132 hand the work to HF
+ * OPTForCausalLM; family chosen at model/builder.py:71-82). nn.LayerNorm over a bf16 residual stream with
  * the fusions of opus_rmsnorm_bf16 plus the bias of the linear whose split-K partials are reduced:
  *   h = x  or  bf16(sum_s partial[s] + red_bias)   (exactly one of x / partial non-null; red_bias fp32 [cols] nullable)
  *   h = bf16(h + residual) if residual;  h_out <- h if h_out;
