@@ -254,3 +254,33 @@ def test_opt_full_width_layers_vs_oracle_bf16():
     want = opt_ref.greedy_generate(lw, ocfg, emb, mask, new)                                                  # bf16, HF order
     assert float((got == want).all(1).float().mean()) >= 0.8       # 5 prompts: at most one may differ (bar: 99 % at scale)
     assert torch.equal(got[:, 0], want[:, 0])
+
+
+def test_opt_scoring_path_vs_oracle():
+    """Teacher-forced scoring (`forward(labels=...)`, opus_opt.py:82-93 -> HF loss) with an OPT decoder: per-row losses
+    from chunked final LayerNorm -> lm_head -> fp32 cross entropy against the oracle's all-position logits."""
+    c = dict(n_layers=2, dim=256, n_heads=2, ffn_dim=512, vocab=1024, max_pos=256)
+    lw, model = _build(c, 41, "gelu", True)
+    lens = [37, 5, 64]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    gen = torch.Generator().manual_seed(6)
+    ids = [torch.randint(3, c["vocab"], (n,), generator=gen) for n in lens]
+    emb_w = lw["model.decoder.embed_tokens.weight"]
+    packed = torch.cat([emb_w[i] for i in ids]).cuda().to(torch.bfloat16)
+    targets = torch.cat([torch.cat([i[1:], torch.tensor([-100])]) for i in ids]).to(torch.int32)   # next-token targets
+    losses, logits = model.score_packed(packed, cu, targets.cuda(), return_logits=True, chunk_rows=50)
+    ocfg = opt_ref.OptCfg(n_layers=c["n_layers"], dim=c["dim"], n_heads=c["n_heads"], ffn_dim=c["ffn_dim"],
+                          vocab=c["vocab"], max_pos=c["max_pos"], activation="gelu")
+    w32 = {k: v.to(torch.bfloat16).float() for k, v in lw.items()}
+    off = 0
+    for i in ids:
+        n = len(i)
+        e = w32["model.decoder.embed_tokens.weight"][i][None]
+        m = torch.ones(1, n, dtype=torch.bool)
+        want, _ = opt_ref.opt_forward(w32, ocfg, e, m, opt_ref.positions_from_mask(m), all_positions=True)
+        got = logits[off: off + n].float().cpu()
+        assert _cos(got, want[0]) >= 0.999
+        ce = torch.nn.functional.cross_entropy(want[0][:-1], i[1:], reduction="none")
+        assert float((losses[off: off + n - 1].cpu() - ce).abs().max()) <= 0.05
+        assert float(losses[off + n - 1]) == 0.0                  # ignore_index row
+        off += n
