@@ -79,8 +79,6 @@ def eval_model(args, tokenizer=None, model=None):
     seqs_all, instr_all, gt_all = [q["input"] for q in qs], [q["instruction"] for q in qs], [q["output"] for q in qs]
     seqs, instrs = split_between_processes(seqs_all, rank, world), split_between_processes(instr_all, rank, world)
     max_new = args.max_new_tokens if args.max_new_tokens_fixed else max_new_tokens_for(args.input_path, args.max_new_tokens)
-    if args.temperature > 0 and args.continuous_batching:
-        raise NotImplementedError("--continuous-batching decodes greedily; run it with --temperature 0")
     dev = model.device
     prompts = [build_prompt(i, system, args.input_path) for i in instrs]
     ids = [tokenizer_seq_token(p, tokenizer, DEFAULT_SEQ_TOKEN_INDEX, return_tensors="pt") for p in prompts]
@@ -93,7 +91,8 @@ def eval_model(args, tokenizer=None, model=None):
     if args.continuous_batching:
         from .scheduler import ContinuousBatcher
         outs = ContinuousBatcher(model, max_slots=args.batch_size).generate(
-            ids, seqs, max_new, eos_ids=model.config.eos_token_id, pad_id=tokenizer.eos_token_id)
+            ids, seqs, max_new, eos_ids=model.config.eos_token_id, pad_id=tokenizer.eos_token_id,
+            sampling=(args.temperature, args.top_p, args.seed + 1000003 * rank) if args.temperature > 0 else None)
         rows = [torch.nn.functional.pad(o, (0, max_new - o.numel()), value=tokenizer.eos_token_id) for o in outs]
     else:
         for i in range(0, len(ids), args.batch_size):

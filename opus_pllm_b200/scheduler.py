@@ -4,7 +4,9 @@ The reference has no scheduler: `run_opus_ddp.py` walks the prompt list in fixed
 its slowest row stops (`eval/run_opus_ddp.py:75,88-134`). Here a fixed number of decode *slots* is kept busy instead:
 whenever a sequence emits EOS (or reaches max_new_tokens) its pages go back to the allocator and the slot is refilled by
 prefilling the next waiting prompt, while the other slots keep decoding. Outputs are returned in input order, so the
-call stays a drop-in for the per-batch `generate` loop of the eval scripts. Greedy only.
+call stays a drop-in for the per-batch `generate` loop of the eval scripts. Greedy, or temperature / top-p sampling
+(`sampling=(temperature, top_p, seed)`, the eval scripts' default decode): sampled rounds are replayed without the CUDA
+graph because the per-round seed is a kernel argument (the draw is hash(seed, row, step) and steps restart every round).
 
 All device work reuses the C ABI entry points (`opus_llama_prefill`, `opus_llama_select`, `opus_llama_decode_loop`); the
 scheduler itself is host logic over the decode-state arrays.
@@ -36,7 +38,7 @@ class ContinuousBatcher:
             outs.append(self.model._soft_tokens(list(seqs[i: i + self.enc_chunk]), None))
         return torch.cat(outs, 0)  # [n, n_soft, H]
 
-    def _state(self, n: int, max_blocks: int, out_ld: int, eos_ids, pad_id: int):
+    def _state(self, n: int, max_blocks: int, out_ld: int, eos_ids, pad_id: int, sampling=None):
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=self.dev)  # noqa: E731
         bufs = dict(next_tok=i32(n), ctx_len=i32(n), pos=i32(n), slot=i32(n), block_table=i32(n, max_blocks),
                     finished=i32(n), n_unfinished=i32(1), step=i32(1), out_ids=i32(n, out_ld),
@@ -46,12 +48,22 @@ class ContinuousBatcher:
             setattr(s, k, bufs[k].data_ptr())
         s.max_blocks, s.out_ld = max_blocks, out_ld
         s.eos_ids, s.n_eos, s.pad_id = bufs["eos"].data_ptr(), len(eos_ids), pad_id
+        if sampling is not None:
+            s.do_sample, s.temperature, s.top_p, s.seed = 1, float(sampling[0]), float(sampling[1]), int(sampling[2])
         return s, bufs
+
+    @staticmethod
+    def _mix(seed: int, n: int) -> int:
+        """independent 64-bit stream per (seed, round / admission index): splitmix64 finaliser"""
+        x = (seed + 0x9E3779B97F4A7C15 * (n + 1)) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return x ^ (x >> 31)
 
     # ------------------------------------------------------------------------------------------ main entry
     @torch.no_grad()
     def generate(self, prompts: list[torch.Tensor], seqs: list[str], max_new_tokens: int, eos_ids=(), pad_id: int = 0,
-                 use_graph: bool = True) -> list[torch.Tensor]:
+                 use_graph: bool = True, sampling=None) -> list[torch.Tensor]:
         """prompts[i]: 1-D int64 ids with one -200 sentinel (no padding); seqs[i]: its protein. Returns, per prompt, the
         new tokens (int64, cut after the first EOS, at most max_new_tokens) — same content as generate() row by row."""
         lib, ll = L.load(), self.llama
@@ -80,7 +92,10 @@ class ContinuousBatcher:
         ll._ensure_ws(int(max(lens.max() * min(S, 8), S)), S)
         scratch = ll._alloc.alloc(1)[0]
 
-        st, bufs = self._state(S, max_blocks, self.R, eos_ids, pad_id)
+        st, bufs = self._state(S, max_blocks, self.R, eos_ids, pad_id, sampling)
+        if sampling is not None:
+            use_graph = False               # the seed changes every round and is baked into a captured graph
+        n_round = n_adm = 0
         bufs["block_table"].fill_(scratch)
         bufs["finished"].fill_(1)
         slot_req = [-1] * S                   # request id held by each slot
@@ -139,7 +154,9 @@ class ContinuousBatcher:
                                                embeds.data_ptr(), d_pos.data_ptr(), d_slot.data_ptr(), d_cu.data_ptr(),
                                                d_last.data_ptr(), len(adm), n_tok, int(np.diff(cu).max()), stream),
                         "opus_llama_prefill")
-                ast, ab = self._state(len(adm), max_blocks, 1, eos_ids, pad_id)
+                n_adm += 1
+                adm_sampling = None if sampling is None else (sampling[0], sampling[1], self._mix(int(sampling[2]) ^ 0x5DEECE66D, n_adm))
+                ast, ab = self._state(len(adm), max_blocks, 1, eos_ids, pad_id, adm_sampling)
                 ab["n_unfinished"].fill_(len(adm))
                 L.check(lib.opus_llama_select(C.byref(ll._model), C.byref(ll._ws), C.byref(ast), len(adm), stream),
                         "opus_llama_select")
@@ -162,6 +179,9 @@ class ContinuousBatcher:
                 bufs["ctx_len"][torch.tensor(idle, device=self.dev)] = 0
             bufs["step"].fill_(-1)
             bufs["n_unfinished"].fill_(active)
+            if sampling is not None:
+                n_round += 1
+                st.seed = self._mix(int(sampling[2]), n_round)
             rc = lib.opus_llama_decode_loop(C.byref(ll._model), C.byref(ll._cache), C.byref(ll._ws), C.byref(st), S,
                                             self.R, 0, int(use_graph), stream)
             L.check(rc, "opus_llama_decode_loop")

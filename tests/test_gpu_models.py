@@ -490,6 +490,18 @@ def test_continuous_batching_matches_plain_generate():
     assert same >= n - 0, [(g.tolist(), w.tolist()) for g, w in zip(got, want) if not torch.equal(g, w)][:2]
     # the allocator got every page back
     assert len(model.llama._alloc.free) == model.llama._alloc.num_blocks
+    # sampling through the scheduler (the eval scripts' default decode): a nucleus that only holds the top token must
+    # reproduce the greedy result; a real nucleus is reproducible per seed and moves with it
+    got_s = cb.generate(prompts, seqs, new, eos_ids=eos, pad_id=eos[0], sampling=(1.0, 1e-6, 11))
+    assert all(torch.equal(g, w) for g, w in zip(got_s, want))
+    hot = [cb.generate(prompts, seqs, new, eos_ids=eos, pad_id=eos[0], sampling=(3.0, 0.95, sd)) for sd in (5, 5, 6)]
+    assert all(torch.equal(a, b) for a, b in zip(hot[0], hot[1]))
+    assert any(not torch.equal(a, b) for a, b in zip(hot[0], hot[2]))
+    assert any(not torch.equal(a, w) for a, w in zip(hot[0], want))
+    # rounds of one request must not repeat the same draws: with a flat nucleus the tokens of consecutive rounds differ
+    long = max(hot[0], key=len).tolist()
+    assert long[1:6] != long[6:11] or len(long) < 11
+    assert len(model.llama._alloc.free) == model.llama._alloc.num_blocks
 
 
 # ------------------------------------------------------------------------------------------------ loaders + eval driver
