@@ -160,6 +160,38 @@ def read_esm2(path: str) -> tuple[dict, dict]:
 FAIR_ESM_HUB = "~/.cache/torch/hub/checkpoints/esm2_t33_650M_UR50D.pt"   # what esm.pretrained.esm2_t33_650M_UR50D() caches
 
 
+def default_esm_path() -> str:
+    """$OPUS_ESM_PATH, else the file fair-esm's `esm.pretrained.esm2_t33_650M_UR50D()` downloads into the torch hub cache
+    ($TORCH_HOME/hub/checkpoints, default ~/.cache/torch/hub/checkpoints)."""
+    env = os.environ.get("OPUS_ESM_PATH")
+    if env:
+        return env
+    home = os.environ.get("TORCH_HOME")
+    if home:
+        return os.path.join(home, "hub", "checkpoints", os.path.basename(FAIR_ESM_HUB))
+    return os.path.expanduser(FAIR_ESM_HUB)
+
+
+def _eos_ids(model_dir: str, config_eos) -> list[int]:
+    """EOS ids HF `generate()` stops on: `generation_config.json` (what the reference's `model.generate` reads;
+    Meta-Llama-3-8B-Instruct lists [128001, 128009] there) merged with `config.json`'s `eos_token_id`."""
+    ids: list[int] = []
+    sources = [config_eos]
+    gpath = os.path.join(model_dir, "generation_config.json")
+    if os.path.exists(gpath):
+        try:
+            sources.insert(0, json.load(open(gpath)).get("eos_token_id"))
+        except (OSError, ValueError):
+            pass
+    for src in sources:
+        if src is None:
+            continue
+        for e in (src if isinstance(src, (list, tuple)) else [src]):
+            if e is not None and int(e) not in ids:
+                ids.append(int(e))
+    return ids
+
+
 def build_protein_encoder(ckpt=None, esm_path: str | None = None, device="cuda"):
     """`protein_encoder/builder.py:3-6` -> `ProteinSeqEmbeddingExtractor(ckpt)` (cstp_v3/modelling.py:19-36): the ESM-2
     t33 650M weights (fair-esm hub cache, or `esm_path`), optionally overridden by the `protein_model.model.*` tensors of
@@ -167,7 +199,7 @@ def build_protein_encoder(ckpt=None, esm_path: str | None = None, device="cuda")
     with `get_protein_seq_embeddings(list[str]) -> float32[B, 1280]` on the GPU (used by opus_arch.py:53 and
     scripts/generate_esm_*.py)."""
     from .encoder import B200ProteinEncoder
-    sd, cfg = read_esm2(esm_path or os.path.expanduser(FAIR_ESM_HUB))
+    sd, cfg = read_esm2(esm_path or default_esm_path())
     if ckpt is not None:
         raw = _load_any(ckpt)["model"]
         pref = "protein_model.model."
@@ -222,9 +254,10 @@ def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=F
         tokenizer = transformers.AutoTokenizer.from_pretrained(model_base_path, use_fast=False)
         if family == "opt":
             tokenizer.pad_token, tokenizer.unk_token, tokenizer.eos_token = "<pad>", "<unk>", "</s>"   # builder.py:80-82
-        else:
+        elif "llama" in name:
             tokenizer.pad_token = tokenizer.unk_token = tokenizer.eos_token             # builder.py:69-70
             tokenizer.pad_token_id = tokenizer.unk_token_id = tokenizer.eos_token_id
+        # the Qwen branch (builder.py:83-94) leaves the tokenizer as loaded
     if accelerator is not None:
         accelerator.wait_for_everyone()                                                 # builder.py:102-103
     lora_sd, alpha, r, switch_sd = None, 32.0, 16, None
@@ -235,12 +268,10 @@ def load_pretrained_model(model_base_path, adapter_path, model_name, load_8bit=F
     else:
         print("No adapter path!")
     cstp_sd = read_cstp_checkpoint(cstp_path) if isinstance(cstp_path, str) else None
-    if esm_path is None:
-        esm_path = os.path.expanduser(FAIR_ESM_HUB)
-    esm_sd, esm_cfg = read_esm2(esm_path)
+    esm_sd, esm_cfg = read_esm2(esm_path or default_esm_path())
     model = build_from_state_dicts(llama_sd, llama_cfg, esm_sd, esm_cfg, cstp_sd, switch_sd,
                                    switch_type=switch_projector_type, lora_sd=lora_sd, lora_alpha=alpha, lora_r=r,
-                                   eos_token_id=extra["eos_token_id"] if extra["eos_token_id"] is not None else (),
+                                   eos_token_id=_eos_ids(model_base_path, extra["eos_token_id"]),
                                    device=device, family=family)
     context_len = extra["max_sequence_length"] or 512                                  # builder.py:126-131
     return tokenizer, model, context_len

@@ -3,7 +3,8 @@
 Same flags, same prompt construction, same data-parallel scheme (contiguous shards of the prompt list, one gather at the
 end; `--temperature 0.1 --top_p 0.7` sampling by default like the reference, `--temperature 0` = greedy). Differences:
 the collective is a tensor all-gather of token ids instead of `gather_object`, `--seed` pins the sampling stream, and
-`--continuous-batching` (greedy only) keeps a fixed number of decode slots busy instead of walking fixed batches of 8. Launch with torchrun (one process per GPU) or plain python (one GPU).
+`--continuous-batching` (greedy or sampled, `--stop-keyword` honoured) keeps a fixed number of decode slots busy instead
+of walking fixed batches of 8. Launch with torchrun (one process per GPU) or plain python (one GPU).
 
   torchrun --nproc-per-node 8 -m opus_pllm_b200.eval_ddp --model-base-path <llama3 dir> \
       --opus-pllm-weights-path <weights dir> --input_path data.json --save_path out.json
@@ -37,13 +38,26 @@ def default_system_prompt() -> str | None:
         return None
 
 
-def max_new_tokens_for(input_path: str, default: int) -> int:
-    """dataset-name heuristics of the reference (run_opus_ddp.py:93-101)"""
+def max_new_tokens_for(input_path: str, default: int | None = None) -> int:
+    """the value run_opus_ddp.py:92-101 FORCES (whatever --max_new_tokens says) once it meets an instruction that does
+    not carry `<seq>` itself: 32 for localization sets, 128 for keyword sets, 256 otherwise"""
     if "localization" in input_path:
         return 32
     if "keywords" in input_path:
         return 128
-    return default if default != 32 else 256
+    return 256
+
+
+def max_new_tokens_schedule(instructions, input_path: str, user_value: int, fixed: bool = False) -> list[int]:
+    """max_new_tokens in force after each instruction, as the reference's loop leaves it (run_opus_ddp.py:90-101 mutates
+    `args.max_new_tokens` while it builds the prompts, so the override is decided per instruction and sticks for the rest
+    of the run): the user's value until the first instruction without `<seq>`, the forced value from then on."""
+    cur, out = int(user_value), []
+    for ins in instructions:
+        if not fixed and DEFAULT_SEQ_TOKEN not in ins:
+            cur = max_new_tokens_for(input_path)
+        out.append(cur)
+    return out
 
 
 def build_prompt(instruct: str, system: str, input_path: str) -> str:
@@ -78,31 +92,38 @@ def eval_model(args, tokenizer=None, model=None):
     qs = [q for q in json.load(open(args.input_path)) if q["input"] is not None]
     seqs_all, instr_all, gt_all = [q["input"] for q in qs], [q["instruction"] for q in qs], [q["output"] for q in qs]
     seqs, instrs = split_between_processes(seqs_all, rank, world), split_between_processes(instr_all, rank, world)
-    max_new = args.max_new_tokens if args.max_new_tokens_fixed else max_new_tokens_for(args.input_path, args.max_new_tokens)
+    sched = max_new_tokens_schedule(instrs, args.input_path, args.max_new_tokens, args.max_new_tokens_fixed)
+    # every rank pads its rows to the same width for the gather: the largest value the schedule can reach anywhere
+    max_new = max([args.max_new_tokens] + max_new_tokens_schedule(instr_all, args.input_path, args.max_new_tokens,
+                                                                 args.max_new_tokens_fixed))
     dev = model.device
     prompts = [build_prompt(i, system, args.input_path) for i in instrs]
     ids = [tokenizer_seq_token(p, tokenizer, DEFAULT_SEQ_TOKEN_INDEX, return_tensors="pt") for p in prompts]
-    stop_kw = {}
+    stop_kw, stop_ids = {}, []
     if getattr(args, "stop_keyword", False):   # opt-in: stop a row once it has emitted the "###" separator (device-side)
         from .mm_utils import KeywordsStoppingCriteria
-        stop_kw = {"stopping_criteria": [KeywordsStoppingCriteria([SEP], tokenizer)]}
+        crit = KeywordsStoppingCriteria([SEP], tokenizer)
+        stop_kw = {"stopping_criteria": [crit]}
+        stop_ids = [[int(t) for t in torch.as_tensor(q).reshape(-1).tolist()] for q in crit.keyword_ids]
     t0 = time.time()
     rows = []
+    pad_row = lambda o: torch.nn.functional.pad(o, (0, max_new - o.numel()), value=tokenizer.eos_token_id)  # noqa: E731
     if args.continuous_batching:
         from .scheduler import ContinuousBatcher
         outs = ContinuousBatcher(model, max_slots=args.batch_size).generate(
-            ids, seqs, max_new, eos_ids=model.config.eos_token_id, pad_id=tokenizer.eos_token_id,
+            ids, seqs, sched, eos_ids=model.config.eos_token_id, pad_id=tokenizer.eos_token_id, stop_sequences=stop_ids,
             sampling=(args.temperature, args.top_p, args.seed + 1000003 * rank) if args.temperature > 0 else None)
-        rows = [torch.nn.functional.pad(o, (0, max_new - o.numel()), value=tokenizer.eos_token_id) for o in outs]
+        rows = [pad_row(o) for o in outs]
     else:
         for i in range(0, len(ids), args.batch_size):
             batch = left_pad_sequence(ids[i: i + args.batch_size], tokenizer.pad_token_id, batch_first=True)
+            batch_new = sched[min(i + args.batch_size, len(ids)) - 1]      # the value in force when this batch is generated
             out = model.generate(batch, seqs[i: i + args.batch_size], attention_mask=batch != tokenizer.pad_token_id,
                                  pad_token_id=tokenizer.eos_token_id, do_sample=args.temperature > 0,
                                  temperature=args.temperature, top_p=args.top_p, num_beams=args.num_beams,
-                                 max_new_tokens=max_new, use_cache=True, **stop_kw,
+                                 max_new_tokens=batch_new, use_cache=True, **stop_kw,
                                  **({"seed": args.seed + 1000003 * rank + i} if args.temperature > 0 else {}))
-            rows.extend(torch.nn.functional.pad(o, (0, max_new - o.numel()), value=tokenizer.eos_token_id) for o in out.cpu())
+            rows.extend(pad_row(o) for o in out.cpu())
     local = torch.stack(rows).to(dev) if rows else torch.zeros((0, max_new), dtype=torch.int64, device=dev)
     gathered = gather_token_ids(local, tokenizer.eos_token_id)
     if rank == 0:

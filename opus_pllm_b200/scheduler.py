@@ -62,14 +62,22 @@ class ContinuousBatcher:
 
     # ------------------------------------------------------------------------------------------ main entry
     @torch.no_grad()
-    def generate(self, prompts: list[torch.Tensor], seqs: list[str], max_new_tokens: int, eos_ids=(), pad_id: int = 0,
-                 use_graph: bool = True, sampling=None) -> list[torch.Tensor]:
+    def generate(self, prompts: list[torch.Tensor], seqs: list[str], max_new_tokens, eos_ids=(), pad_id: int = 0,
+                 use_graph: bool = True, sampling=None, stop_sequences=()) -> list[torch.Tensor]:
         """prompts[i]: 1-D int64 ids with one -200 sentinel (no padding); seqs[i]: its protein. Returns, per prompt, the
-        new tokens (int64, cut after the first EOS, at most max_new_tokens) — same content as generate() row by row."""
+        new tokens (int64, cut after the first EOS, at most max_new_tokens) — same content as generate() row by row.
+        max_new_tokens: one int, or one int per request. stop_sequences: token-id sequences after which a request is
+        complete (the `"###"` keyword of mm_utils.KeywordsStoppingCriteria), matched on the host when a round is read back."""
         lib, ll = L.load(), self.llama
-        lib.opus_release_graphs()  # decode graphs are keyed by buffer addresses; ours are private to this call
         n_req = len(prompts)
+        if n_req == 0:                     # e.g. a rank whose shard of the prompt list is empty
+            return []
+        lib.opus_release_graphs()  # decode graphs are keyed by buffer addresses; ours are private to this call
         eos_set = set(int(e) for e in eos_ids)
+        stops = [tuple(int(t) for t in q) for q in (stop_sequences or ()) if len(q)]
+        new_of = [int(max_new_tokens)] * n_req if np.isscalar(max_new_tokens) else [int(v) for v in max_new_tokens]
+        assert len(new_of) == n_req
+        max_new_tokens = max(new_of)
         soft = self._soft_tokens(seqs)
         soft2d = soft.reshape(-1, soft.shape[-1]).contiguous()
         n_soft = soft.shape[1]
@@ -87,6 +95,10 @@ class ContinuousBatcher:
         max_blocks = int((lens.max() + max_new_tokens + margin + BLOCK - 1) // BLOCK)
         need_pages = lambda ln: int((ln + max_new_tokens + margin + BLOCK - 1) // BLOCK)  # noqa: E731
         S = min(self.S, n_req)
+        # positions reach prompt + new tokens + the steps a finished slot keeps spinning until its round is read back
+        total = int(lens.max()) + max_new_tokens + margin
+        if total > ll.max_positions:
+            ll._build_rope(1 << (total - 1).bit_length())     # OPT: raises (its learned position table cannot grow)
         # worst case all slots hold the longest prompts, +1 scratch page for idle slots
         ll._ensure_cache(S * max_blocks + 1)
         ll._ensure_ws(int(max(lens.max() * min(S, 8), S)), S)
@@ -121,8 +133,11 @@ class ContinuousBatcher:
             """append tokens of request r; True when the request is complete"""
             for t in toks:
                 results[r].append(int(t))
-                if int(t) in eos_set or len(results[r]) >= max_new_tokens:
+                if int(t) in eos_set or len(results[r]) >= new_of[r]:
                     return True
+                for q in stops:
+                    if len(results[r]) >= len(q) and tuple(results[r][-len(q):]) == q:
+                        return True
             return False
 
         while waiting or active:

@@ -213,3 +213,57 @@ def test_keywords_stopping_criteria_host_half():
     crit = KeywordsStoppingCriteria(["###", "</s>", "Human:"], Tok(), torch.zeros(2, 7, dtype=torch.long))
     assert [k.tolist() for k in crit.keyword_ids] == [[835], [1], [12968, 29901]]
     assert crit.max_keyword_len == 2 and crit.start_len == 7
+
+
+def test_compat_shim_loads_the_unmodified_reference_scripts():
+    """opus_pllm_b200.compat registers the backend as `multi_modality_model.multi_modality_v1.model.builder`; the three
+    reference eval scripts then import (no GPU needed for that) and bind this backend's loader. Skipped when the
+    reference tree has not been staged under baseline/_ref (oracle/stage_reference.py)."""
+    import os
+    import sys
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = os.path.join(root, "baseline", "_ref")
+    ev = os.path.join(ref, "multi_modality_model", "multi_modality_v1", "eval")
+    if not os.path.isfile(os.path.join(ev, "run_opus_ddp.py")):
+        pytest.skip("baseline/_ref not staged")
+    saved = dict(sys.modules)
+    sys.path[:0] = [ref, ev]
+    try:
+        from opus_pllm_b200 import builder, compat
+        compat.install(force_stubs=True)
+        for name in ("run_opus_ddp.py", "eval_run_multichoice.py", "run_opus_online.py"):
+            mod = compat.load_script(os.path.join(ev, name), "ref_" + name[:-3])
+            assert mod.load_pretrained_model is builder.load_pretrained_model
+            assert mod.tokenizer_seq_token.__module__ == "multi_modality_model.multi_modality_v1.mm_utils"
+        import accelerate
+        acc = accelerate.Accelerator()
+        with acc.split_between_processes(list(range(5))) as part:
+            assert part == list(range(5)) and acc.is_main_process
+        assert accelerate.utils.gather_object([[1, 2]]) == [[1, 2]]
+    finally:
+        sys.path.remove(ref); sys.path.remove(ev)
+        for k in set(sys.modules) - set(saved):
+            if k.startswith(("multi_modality_model", "accelerate", "metrics_computing_opi", "ref_")):
+                del sys.modules[k]
+
+
+def test_eval_ddp_max_new_tokens_schedule_follows_the_reference_loop():
+    """run_opus_ddp.py:90-101: the override is decided per instruction (only when `<seq>` is absent), always forces
+    32 / 128 / 256, and sticks for the rest of the run because the script mutates args.max_new_tokens."""
+    from opus_pllm_b200 import eval_ddp
+    ins = ["<seq>\nq0", "<seq>\nq1", "q2", "<seq>\nq3"]
+    assert eval_ddp.max_new_tokens_schedule(ins, "d/keywords.json", 50) == [50, 50, 128, 128]
+    assert eval_ddp.max_new_tokens_schedule(ins, "d/localization.json", 50) == [50, 50, 32, 32]
+    assert eval_ddp.max_new_tokens_schedule(ins, "d/function.json", 32) == [32, 32, 256, 256]
+    assert eval_ddp.max_new_tokens_schedule(ins[:2], "d/function.json", 77) == [77, 77]
+    assert eval_ddp.max_new_tokens_schedule(ins, "d/function.json", 9, fixed=True) == [9] * 4
+
+
+def test_eos_ids_merge_generation_config(tmp_path):
+    import json
+    from opus_pllm_b200 import builder
+    assert builder._eos_ids(str(tmp_path), 2) == [2] and builder._eos_ids(str(tmp_path), None) == []
+    json.dump({"eos_token_id": [128001, 128009]}, open(tmp_path / "generation_config.json", "w"))
+    assert builder._eos_ids(str(tmp_path), 128001) == [128001, 128009]
+    assert builder._eos_ids(str(tmp_path), [5]) == [128001, 128009, 5]
