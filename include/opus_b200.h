@@ -8,8 +8,9 @@
  * Conventions
  *   - every function returns 0 (OPUS_OK) or a negative OPUS_ERR_* code; opus_last_error() gives a message;
  *   - pointers are raw DEVICE pointers unless a parameter is documented as host memory; the caller owns all buffers
- *     (no hidden allocation), `stream` is a cudaStream_t passed as void*; no entry point synchronises the stream
- *     except opus_llama_generate when early EOS stopping is requested (documented there);
+ *     (no hidden allocation except the per-context stream-K scratch described under "Contexts"), `stream` is a
+ *     cudaStream_t passed as void*; no entry point synchronises the stream except opus_llama_decode_loop when early EOS
+ *     stopping is requested (check_every > 0, documented there) and the two profiling aids;
  *   - bf16 tensors are passed as void*; matrices are row-major with explicit leading dimensions in ELEMENTS;
  *   - weights of every nn.Linear keep the torch layout [out_features, in_features] (K contiguous).
  *   - There is NO CPU fallback: on a machine without an sm_100a GPU every compute entry point fails.
@@ -24,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OPUS_B200_ABI_VERSION 3
+#define OPUS_B200_ABI_VERSION 4
 
 enum {
   OPUS_OK = 0,
@@ -48,7 +49,27 @@ enum {
 };
 
 int opus_abi_version(void);
+/* Message of the last failing call made BY THE CALLING THREAD (thread-local; valid until that thread's next failure). */
 const char* opus_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Contexts
+ *
+ * All mutable library state lives in a context: the run-time tunables (opus_set_tunable), the cache of captured decode
+ * graphs (opus_llama_decode_loop), and two lazily allocated device scratch areas (the stream-K fix-up workspace of the
+ * GEMM, 19.4 MB, and the chain-trace buffer). Entry points act on the calling thread's CURRENT context; threads that
+ * never call opus_ctx_set_current share the process-default context. A context serialises its work on one stream at a
+ * time; use one context per concurrently used stream / host thread. The OPUS_* environment variables (OPUS_PDL,
+ * OPUS_ATTN, OPUS_ATTN_TAIL, OPUS_GEMM_2CTA, OPUS_GEMM_2CTA_TR, OPUS_GEMM_GROUP_M, OPUS_GEMM_HINTS, OPUS_TMA_STORE,
+ * OPUS_STREAMK, OPUS_DECODE_FUSED, OPUS_PF, OPUS_PF_*) are read once, when a context is created: launch paths never
+ * consult the environment.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct opus_ctx opus_ctx;
+int opus_ctx_create(opus_ctx** out);
+/* Destroys the graphs and scratch of `ctx` (the caller makes sure no work of this context is still in flight). */
+int opus_ctx_destroy(opus_ctx* ctx);
+/* Makes `ctx` the calling thread's current context; NULL returns the thread to the process-default context. */
+int opus_ctx_set_current(opus_ctx* ctx);
 /* 0 when the current device is an sm_100 part this library was built for, OPUS_ERR_CUDA otherwise. */
 int opus_device_check(void);
 
@@ -300,6 +321,9 @@ typedef struct {
    * a row also finishes when its last stop_lens[j] emitted tokens equal stop_seqs[j][0 .. stop_lens[j]) for some j.
    * stop_seqs int32 [n_stop, stop_ld] (NULL / n_stop == 0 = none). Checked by one extra small kernel per step. */
   const int32_t* stop_seqs; const int32_t* stop_lens; int32_t n_stop; int32_t stop_ld;
+  /* optional: the sampling seed in DEVICE memory (uint64 [1]); when non-NULL it overrides `seed`, so the caller can
+   * change the seed between replays of one captured decode graph (per call, per scheduling round) */
+  const uint64_t* seed_ptr;
 } opus_decode_state;
 
 /* Prefill over packed prompt embeddings (already spliced): embeds bf16 [n_tok, dim] is copied into ws->h; K/V of every
@@ -316,13 +340,15 @@ int opus_llama_decode_step(const opus_llama_model* model, const opus_kv_cache* c
 int opus_llama_select(const opus_llama_model* model, const opus_llama_workspace* ws, const opus_decode_state* state,
                       int n_seqs, void* stream);
 /* Greedy decode loop: n_steps calls of opus_llama_decode_step replayed from a CUDA graph captured on `stream`
- * (the graph is cached per (model, state, n_seqs) inside the library). If check_every > 0 the loop reads
+ * (the graph is cached inside the current context, keyed by the contents of all four structs and n_seqs). If check_every > 0 the loop reads
  * *n_unfinished every check_every steps (this synchronises the stream) and stops early when it reaches 0.
  * Returns the number of steps executed (>= 0) or a negative error. */
 int opus_llama_decode_loop(const opus_llama_model* model, const opus_kv_cache* cache, const opus_llama_workspace* ws,
                            const opus_decode_state* state, int n_seqs, int n_steps, int check_every, int use_graph,
                            void* stream);
-/* Drop cached CUDA graphs (call before freeing buffers they reference). */
+/* Drop the current context's cached CUDA graphs (call before freeing buffers they reference). A graph is keyed by
+ * everything a captured step bakes in (model / cache / workspace / state structs by value, batch size), so changing a
+ * scalar such as pad_id or top_p can never replay a stale graph; at most 16 graphs are kept per context. */
 int opus_release_graphs(void);
 /* Run-time tunables of the composite forwards (measurement aid; defaults are the tuned values). Names: "pf_qkv",
  * "pf_o", "pf_gu", "pf_down", "pf_lm" = k-blocks (64 K-elements each) per work item that a decode GEMM prefetches into
@@ -338,7 +364,9 @@ int opus_release_graphs(void);
  * the paged-attention CTAs (default 1);
  * "tma_store" = 0 sends the plain bf16 / GELU GEMM epilogues back to direct row-per-thread stores (and the encoder's rotary
  * embedding back to its own kernel).
- * Drops cached graphs. */
+ * "attn_mode" = 0 automatic, 1 mma.sync attention, 2 tcgen05 attention; "attn_tail" = 0 keeps short query tails inside the
+ * tcgen05 attention kernel.
+ * Acts on the current context and drops its cached graphs. */
 int opus_set_tunable(const char* name, int value);
 /* Profiling aid: between opus_trace_begin(stream) and opus_trace_end the composite forwards record a CUDA event after
  * every kernel launch (not inside graph capture); opus_trace_end synchronises and writes "label<TAB>microseconds\n"

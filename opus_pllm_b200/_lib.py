@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("OPUS_B200_LIB") or os.path.join(_HERE, "libopus_b200.
 OK = 0
 EPI_BF16, EPI_BF16_GELU, EPI_RES_F32, EPI_RES_BF16, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_F32, EPI_BF16_RELU = range(8)
 ARCH_LLAMA, ARCH_OPT = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_float, c_size_t, c_longlong = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
@@ -77,7 +77,8 @@ class DecodeState(C.Structure):
                 ("eos_ids", c_void_p), ("n_eos", C.c_int32), ("pad_id", C.c_int32),
                 ("seed", C.c_uint64), ("temperature", c_float), ("top_p", c_float), ("do_sample", C.c_int32),
                 ("reserved_", C.c_int32),
-                ("stop_seqs", c_void_p), ("stop_lens", c_void_p), ("n_stop", C.c_int32), ("stop_ld", C.c_int32)]
+                ("stop_seqs", c_void_p), ("stop_lens", c_void_p), ("n_stop", C.c_int32), ("stop_ld", C.c_int32),
+                ("seed_ptr", c_void_p)]
 
 
 # ---------------------------------------------------------------------------------------------- signatures
@@ -86,6 +87,9 @@ _SIGNATURES = {
     "opus_abi_version": (c_int, []),
     "opus_last_error": (C.c_char_p, []),
     "opus_device_check": (c_int, []),
+    "opus_ctx_create": (c_int, [C.POINTER(c_void_p)]),
+    "opus_ctx_destroy": (c_int, [c_void_p]),
+    "opus_ctx_set_current": (c_int, [c_void_p]),
     "opus_gemm_bf16": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int,
                                c_int, c_int, _P]),
     "opus_gemm_suggest_split_k": (c_int, [c_int, c_int, c_int, c_int]),

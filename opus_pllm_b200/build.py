@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libopus_b200.so")
-SOURCES = ["gemm_tcgen05.cu", "bandwidth.cu", "bandwidth_opt.cu", "attention.cu", "attention_tc.cu", "models.cu", "capi.cu"]
+SOURCES = ["gemm_tcgen05.cu", "bandwidth.cu", "bandwidth_opt.cu", "attention.cu", "attention_tc.cu", "models.cu", "context.cu", "capi.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-shared",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 

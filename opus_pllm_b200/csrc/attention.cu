@@ -556,12 +556,8 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
     // implementation choice: the tcgen05 kernel (attention_tc.cu; two 128-row query tiles per work item) unless every
     // sequence is short, where the 64-row mma.sync tiles below waste fewer padded rows. Measured (tools/sweep_attn.py):
     // tcgen05 wins from T = 258 (153 vs 164 us, encoder C1) to T = 2048 (363 vs 1143 us, causal hd 128).
-    // OPUS_ATTN=mma|tc forces one of them (A/B measurements, tests).
-    static int mode = -1;
-    if (mode < 0) {
-      const char* e = std::getenv("OPUS_ATTN");
-      mode = (e == nullptr) ? 0 : (e[0] == 't' ? 2 : 1);
-    }
+    // OPUS_ATTN=mma|tc (read at context creation) forces one of them (A/B measurements, tests).
+    const int mode = ctx().tun.attn_mode;
     const bool aligned = ((ldq | ldk | ldv | ldo) % 8) == 0 &&
                          ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                            reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
@@ -572,11 +568,7 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
       // attention time at C1). Those rows run on one 64-row mma.sync tile instead, launched first (it is tiny); the two
       // kernels write disjoint rows of `o`. Enabled when the longest sequence has such a tail (uniform batches) or for
       // ragged encoder batches; OPUS_ATTN_TAIL=0 disables it.
-      static int tail_mode = -1;
-      if (tail_mode < 0) {
-        const char* e = std::getenv("OPUS_ATTN_TAIL");
-        tail_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
-      }
+      const int tail_mode = ctx().tun.attn_tail;
       constexpr int kTail = 64;
       const int max_tail = max_len - ((max_len - 1) / 256) * 256;
       const bool split_tail = tail_mode && (max_tail <= kTail || (!causal && n_seqs >= 8));

@@ -644,9 +644,11 @@ __global__ void __launch_bounds__(SAMPLE_THREADS)
 sample_top_p_kernel(const __nv_bfloat16* __restrict__ logits, int ld, int vocab, float inv_temp, float top_p,
                     unsigned long long seed, int* __restrict__ finished, const int* __restrict__ eos_ids, int n_eos,
                     int pad_id, int* __restrict__ next_tok, int* __restrict__ out_ids, int out_ld, int step_imm,
-                    const int* __restrict__ step_ptr, int* __restrict__ n_unfinished, int* __restrict__ kept_count) {
+                    const int* __restrict__ step_ptr, int* __restrict__ n_unfinished, int* __restrict__ kept_count,
+                    const unsigned long long* __restrict__ seed_ptr) {
   grid_dep_launch();
   grid_dep_wait();
+  if (seed_ptr != nullptr) seed = *seed_ptr;   // seed in device memory: one captured graph serves every seed
   __shared__ float red[33];
   __shared__ float scan_m[SAMPLE_THREADS];
   __shared__ int scan_c[SAMPLE_THREADS];
@@ -997,12 +999,12 @@ int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* 
 int sample_top_p(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, float temperature, float top_p,
                  unsigned long long seed, int* finished, const int* eos_ids, int n_eos, int pad_id, int* next_tok,
                  int* out_ids, int out_ld, int step, int* n_unfinished, cudaStream_t st, const int* step_ptr,
-                 int* kept_count) {
+                 int* kept_count, const unsigned long long* seed_ptr) {
   if (n_rows == 0) return OPUS_OK;
   if (!(temperature > 0.f) || !(top_p > 0.f) || vocab <= 0) return OPUS_ERR_ARG;
   launch_pdl(true, sample_top_p_kernel, dim3(n_rows), dim3(SAMPLE_THREADS), 0, st, logits, ld, vocab, 1.0f / temperature,
              top_p, seed, finished, eos_ids, n_eos, pad_id, next_tok, out_ids, out_ld, step, step_ptr, n_unfinished,
-             kept_count);
+             kept_count, seed_ptr);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? OPUS_OK : OPUS_ERR_CUDA;
 }

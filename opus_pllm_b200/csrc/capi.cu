@@ -2,10 +2,10 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
 #include <string>
 
 #include "common.h"
+#include "context.h"
 #include "gemm.h"
 #include "kernels.h"
 #include "models.h"
@@ -13,16 +13,14 @@
 namespace opus {
 
 namespace {
-std::mutex g_err_mu;
-std::string g_err = "";
+thread_local std::string t_err;   // per calling thread: concurrent callers never see each other's message
 std::atomic<long long> g_launches{0};
 }  // namespace
 
 int fail(int rc, const char* what) {
   const cudaError_t ce = cudaPeekAtLastError();
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  g_err = std::string(what ? what : "?") + " -> " + std::to_string(rc);
-  if (ce != cudaSuccess) g_err += std::string(" [cuda: ") + cudaGetErrorString(ce) + "]";
+  t_err = std::string(what ? what : "?") + " -> " + std::to_string(rc);
+  if (ce != cudaSuccess) t_err += std::string(" [cuda: ") + cudaGetErrorString(ce) + "]";
   return rc;
 }
 void note_launch(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -46,11 +44,20 @@ extern "C" {
 
 int opus_abi_version(void) { return OPUS_B200_ABI_VERSION; }
 
-const char* opus_last_error(void) {
-  static thread_local std::string copy;
-  std::lock_guard<std::mutex> lk(g_err_mu);
-  copy = g_err;
-  return copy.c_str();
+const char* opus_last_error(void) { return t_err.c_str(); }
+
+int opus_ctx_create(opus_ctx** out) {
+  if (out == nullptr) return fail(OPUS_ERR_ARG, "opus_ctx_create: null out");
+  *out = reinterpret_cast<opus_ctx*>(ctx_create());
+  return OPUS_OK;
+}
+int opus_ctx_destroy(opus_ctx* c) {
+  ctx_destroy(reinterpret_cast<Context*>(c));
+  return OPUS_OK;
+}
+int opus_ctx_set_current(opus_ctx* c) {
+  ctx_set_current(reinterpret_cast<Context*>(c));
+  return OPUS_OK;
 }
 
 int opus_device_check(void) {

@@ -16,6 +16,7 @@
 // (cstp_v3/modelling.py:48), CSTP projection (modelling.py:396-400), switch projector (protein_mlp/builder.py:21-24),
 // and HF Llama q/k/v/o/gate/up/down/lm_head (reached through language_model/opus_llama.py:82-93).
 #include "common.h"
+#include "context.h"
 #include "gemm.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -1428,43 +1429,33 @@ int num_sms() {
 }
 
 // Stream-K fix-up workspace: one fp32 accumulator tile (128 x 256 max) per CTA plus one counter per tail tile.
-// Allocated once per process on first use (19.4 MB); the library serialises its work on one stream per process, and
-// consecutive launches on that stream reuse it in stream order.
-struct SkWorkspace {
-  float* ws = nullptr;
-  int* cnt = nullptr;
-  int state = 0;  // 0 = not tried, 1 = ready, -1 = unavailable
-};
-SkWorkspace g_sk;
-std::mutex g_sk_mu;
-
+// Allocated once per context on first use (19.4 MB); a context serialises its work on one stream, and consecutive
+// launches on that stream reuse it in stream order.
 bool ensure_sk_workspace() {
-  std::lock_guard<std::mutex> lk(g_sk_mu);
-  if (g_sk.state != 0) return g_sk.state > 0;
-  const char* e = std::getenv("OPUS_STREAMK");
-  if (e != nullptr && e[0] == '0') { g_sk.state = -1; return false; }
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (c.sk.state != 0) return c.sk.state > 0;
+  if (!c.tun.streamk) { c.sk.state = -1; return false; }
   const size_t bytes = (size_t)num_sms() * BM * 256 * sizeof(float);
-  if (cudaMalloc(&g_sk.ws, bytes) != cudaSuccess || cudaMalloc(&g_sk.cnt, 1024 * sizeof(int)) != cudaSuccess ||
-      cudaMemset(g_sk.cnt, 0, 1024 * sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&c.sk.ws, bytes) != cudaSuccess || cudaMalloc(&c.sk.cnt, 1024 * sizeof(int)) != cudaSuccess ||
+      cudaMemset(c.sk.cnt, 0, 1024 * sizeof(int)) != cudaSuccess) {
     cudaGetLastError();  // e.g. first call inside a stream capture: stay on the plain schedule
+    if (c.sk.ws) { cudaFree(c.sk.ws); c.sk.ws = nullptr; }
+    if (c.sk.cnt) { cudaFree(c.sk.cnt); c.sk.cnt = nullptr; }
     return false;       // state stays 0: retried on the next eager call
   }
-  g_sk.state = 1;
+  c.sk.state = 1;
   return true;
 }
 
-int g_sk_max_fill = 90;  // use the stream-K tail when the partial wave fills <= this percentage of the SMs
-// The plain (activations = A) form keeps one summation order for every token row by default, so a token's result does
-// not depend on where it sits in the batch (bitwise batch invariance); the tail is opt-in there. In the swap-AB form the
-// tiles partition the FEATURES, every batch row is treated alike, and the tail is on by default.
-int g_sk_plain = 0;
-int g_tma_store_on = -1;  // plain bf16 / GELU epilogues through shared memory + TMA stores (OPUS_TMA_STORE=0 disables)
-
 }  // namespace
 
-void gemm_set_streamk_fill(int percent) { g_sk_max_fill = percent; }
-void gemm_set_tma_store(int on) { g_tma_store_on = on != 0; }
-void gemm_set_streamk_plain(int on) { g_sk_plain = on; }
+// The plain (activations = A) form keeps one summation order for every token row by default, so a token's result does
+// not depend on where it sits in the batch (bitwise batch invariance); the stream-K tail is opt-in there. In the swap-AB
+// form the tiles partition the FEATURES, every batch row is treated alike, and the tail is on by default.
+void gemm_set_streamk_fill(int percent) { ctx().tun.streamk_fill = percent; }
+void gemm_set_tma_store(int on) { ctx().tun.tma_store = on != 0; }
+void gemm_set_streamk_plain(int on) { ctx().tun.streamk_plain = on; }
 
 int gemm_pick_bn(int N, int transposed) {
   if (transposed) {
@@ -1517,11 +1508,8 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   p.out = a.out; p.ldo = a.ldo;
   p.bias = a.bias;
   p.residual = a.residual; p.ldr = a.ldr;
-  static int group_override = -1;
-  if (group_override < 0) {
-    const char* e = std::getenv("OPUS_GEMM_GROUP_M");
-    group_override = e ? atoi(e) : 0;
-  }
+  const Tunables& tun = ctx().tun;
+  const int group_override = tun.group_m;
   // grouped-M raster: the A rows of one group (group_m x 128 x K) must stay L2-resident while the group's n-tiles are
   // walked; measured DRAM traffic per launch at M = 32768 (ncu): gate/up (K 4096) 4.96 GB at 16 -> 3.09 GB at 32, but
   // down (K 14336) 4.99 GB at 16 -> 5.65 GB at 32
@@ -1535,11 +1523,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   p.hint_b = a.transposed ? kCacheEvictLast : kCacheEvictNormal;
   {
     // plain form: the A panel of a raster group is re-read by every n-tile of the group, B is streamed once per group
-    static int plain_hints = -1;
-    if (plain_hints < 0) {
-      const char* e = std::getenv("OPUS_GEMM_HINTS");
-      plain_hints = e ? atoi(e) : 0;
-    }
+    const int plain_hints = tun.plain_hints;
     if (!a.transposed && plain_hints == 1) { p.hint_a = kCacheEvictLast; p.hint_b = kCacheEvictFirst; }
     if (!a.transposed && plain_hints == 2) { p.hint_a = kCacheEvictLast; p.hint_b = kCacheEvictNormal; }
     if (!a.transposed && plain_hints == 3) { p.hint_a = kCacheEvictNormal; p.hint_b = kCacheEvictFirst; }
@@ -1554,11 +1538,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     p.pf_items = items < num_sms() ? items : num_sms();  // first wave of the next launch
   }
 
-  if (g_tma_store_on < 0) {
-    const char* e = std::getenv("OPUS_TMA_STORE");
-    g_tma_store_on = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  p.tma_store = g_tma_store_on && !a.transposed && (a.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+  p.tma_store = tun.tma_store && !a.transposed && (a.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
                 ((bn >= 64 && (a.epi == EPI_BF16 || a.epi == EPI_BF16_GELU || a.epi == EPI_BF16_RELU)) ||
                  (bn == 256 && a.epi == EPI_SWIGLU && (a.N % 128) == 0));
   if (a.rl_cos != nullptr) {
@@ -1583,12 +1563,12 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   // wave quantisation: a last wave that fills only part of the machine is cut along K over all CTAs instead
   const int rem = tiles % num_sms();
   const bool sk_ready = ensure_sk_workspace();  // also on launches that do not need it: never first inside a capture
-  if (p.split_k == 1 && (a.transposed || g_sk_plain) && tiles > num_sms() && rem != 0 &&
-      rem * 100 <= g_sk_max_fill * num_sms() && a.epi != EPI_PARTIAL_F32 && sk_ready) {
+  if (p.split_k == 1 && (a.transposed || tun.streamk_plain) && tiles > num_sms() && rem != 0 &&
+      rem * 100 <= tun.streamk_fill * num_sms() && a.epi != EPI_PARTIAL_F32 && sk_ready) {
     p.sk_tiles = rem;
     p.dp_items = tiles - rem;
-    p.sk_ws = g_sk.ws;
-    p.sk_cnt = g_sk.cnt;
+    p.sk_ws = ctx().sk.ws;
+    p.sk_cnt = ctx().sk.cnt;
   }
   return OPUS_OK;
 }
@@ -1608,7 +1588,6 @@ bool gemm_fuses_rope(const GemmArgs& a) {
 }
 
 namespace {
-int g_2cta = -1;   // CTA-pair form for large plain GEMMs (tunable "gemm_2cta", env OPUS_GEMM_2CTA; default 2)
 
 template <bool TR>
 int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
@@ -1652,12 +1631,8 @@ int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
 // swap-AB launches the pair kernel takes (tunable "gemm_2cta_tr", env OPUS_GEMM_2CTA_TR; default on): batch tile of 256
 // (129..256 rows) whose (256-feature tile, k-split) items fill the 74 pairs to >= 85 % of whole waves. The stream-K tail
 // stays with the single-CTA kernel (decode gate/up: 112 pair tiles would be 1.5 waves).
-int g_2cta_tr = -1;
 bool pair_takes_transposed(const GemmArgs& a, const GemmParams& p, int bn) {
-  if (g_2cta_tr < 0) {
-    const char* e = std::getenv("OPUS_GEMM_2CTA_TR");
-    g_2cta_tr = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+  const int g_2cta_tr = ctx().tun.gemm_2cta_tr;
   if (!g_2cta_tr || !a.transposed || bn != 256 || a.block_n != 0 || a.N <= 128 || a.N > 256 || a.epi == EPI_SWIGLU)
     return false;
   const int max_pairs = num_sms() / 2;
@@ -1667,8 +1642,8 @@ bool pair_takes_transposed(const GemmArgs& a, const GemmParams& p, int bn) {
 }
 }  // namespace
 
-void gemm_set_2cta_tr(int on) { g_2cta_tr = on ? 1 : 0; }
-void gemm_set_2cta(int on) { g_2cta = on < 0 ? 0 : (on > 2 ? 2 : on); }
+void gemm_set_2cta_tr(int on) { ctx().tun.gemm_2cta_tr = on ? 1 : 0; }
+void gemm_set_2cta(int on) { ctx().tun.gemm_2cta = on < 0 ? 0 : (on > 2 ? 2 : on); }
 
 // D = epi(A * B^T). See gemm.h for the contract.
 int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
@@ -1676,10 +1651,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   int bn = 0;
   const int rc = prepare_gemm(a, p, bn);
   if (rc != OPUS_OK) return rc;
-  if (g_2cta < 0) {
-    const char* e = std::getenv("OPUS_GEMM_2CTA");
-    g_2cta = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
-  }
+  const int g_2cta = ctx().tun.gemm_2cta;
   // 1 = every eligible launch, 2 = every eligible launch except the SwiGLU epilogue (measured slower there)
   if (g_2cta && !a.transposed && bn == 256 && p.split_k == 1 && p.sk_tiles == 0 && a.M >= 1024 && a.block_n == 0 &&
       !(g_2cta == 2 && a.epi == EPI_SWIGLU))
@@ -1719,13 +1691,13 @@ int launch_chain(const ChainTmaps& tm, const ChainProgram& prog, cudaStream_t st
 }
 }  // namespace
 
-int g_chain_l2_depth = 0;  // measured: prefetching beyond the ring only adds traffic (tools/bench_decode.py)
-void gemm_set_chain_l2_depth(int kblocks) { g_chain_l2_depth = kblocks < 0 ? 0 : kblocks; }
-unsigned long long* g_chain_trace = nullptr;
+// measured: prefetching beyond the ring only adds traffic (tools/bench_decode.py), so the default depth is 0
+void gemm_set_chain_l2_depth(int kblocks) { ctx().tun.chain_l2_depth = kblocks < 0 ? 0 : kblocks; }
 // enable != 0: allocate the stamp buffer (once) and record every following chain launch (the last one wins);
 // out != nullptr: copy [num_sms][kMaxChainPhases][4] stamps to the host (synchronises the device). Returns the SM count.
 int gemm_chain_trace(int enable, unsigned long long* out, int cap_words) {
   const int words = num_sms() * kMaxChainPhases * 4;
+  unsigned long long*& g_chain_trace = ctx().chain_trace;
   if (enable && g_chain_trace == nullptr) {
     if (cudaMalloc(&g_chain_trace, words * sizeof(unsigned long long)) != cudaSuccess) return OPUS_ERR_CUDA;
     cudaMemset(g_chain_trace, 0, words * sizeof(unsigned long long));
@@ -1746,9 +1718,9 @@ int gemm_chain(const ChainPhase* phases, int n_phases, cudaStream_t stream) {
   ChainTmaps tm;
   ChainProgram prog{};
   prog.n_phases = n_phases;
-  prog.bar = g_sk.cnt + 1000;
-  prog.trace = g_chain_trace;
-  prog.l2_depth = g_chain_l2_depth;
+  prog.bar = ctx().sk.cnt + 1000;
+  prog.trace = ctx().chain_trace;
+  prog.l2_depth = ctx().tun.chain_l2_depth;
   int bn_all = 0;
   for (int i = 0; i < n_phases; ++i) {
     prog.kind[i] = phases[i].kind;

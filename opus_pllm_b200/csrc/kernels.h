@@ -42,7 +42,8 @@ int argmax_eos(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, int* 
 int sample_top_p(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, float temperature, float top_p,
                  unsigned long long seed, int* finished, const int* eos_ids, int n_eos, int pad_id, int* next_tok,
                  int* out_ids, int out_ld, int step, int* n_unfinished, cudaStream_t st,
-                 const int* step_ptr = nullptr, int* kept_count = nullptr);
+                 const int* step_ptr = nullptr, int* kept_count = nullptr,
+                 const unsigned long long* seed_ptr = nullptr /* device; overrides `seed` when non-null */);
 // loss[r] = logsumexp(logits[r,:]) - logits[r, target[r]] in fp32 (0 where target[r] < 0)
 int cross_entropy_rows(const __nv_bfloat16* logits, int ld, int vocab, const int* target, float* loss, int n_rows,
                        cudaStream_t st);

@@ -1,23 +1,21 @@
 // Kernel launch helper: every kernel of the library is launched with the programmatic-dependent-launch attribute, so
 // kernel N+1 can be scheduled (and run its prologue / weight prefetch) while kernel N drains. Kernels call
 // grid_dep_launch() early and grid_dep_wait() before touching memory produced by their predecessor.
-// OPUS_PDL=0 in the environment falls back to plain stream order, OPUS_PDL=2 enables it everywhere (A/B measurements).
+// OPUS_PDL=0 in the environment (read when the context is created) falls back to plain stream order, OPUS_PDL=2 enables
+// it everywhere (A/B measurements).
 #pragma once
 #include <cuda_runtime.h>
-#include <cstdlib>
 #include <utility>
+
+#include "context.h"
 
 namespace opus {
 
 // `small` = decode-sized launch. Measured on B200: PDL shortens the (HBM-bound, launch-latency-sensitive) decode step
 // but slows the power-capped multi-wave prefill/encoder kernels by a few percent, so only small launches opt in
-// (OPUS_PDL=2 forces it for every launch).
+// (OPUS_PDL=2 at context creation forces it for every launch, OPUS_PDL=0 disables it).
 inline bool pdl_for(bool small) {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = std::getenv("OPUS_PDL");
-    mode = (e == nullptr) ? 1 : (e[0] - '0');
-  }
+  const int mode = ctx().tun.pdl;
   return mode == 2 || (mode == 1 && small);
 }
 

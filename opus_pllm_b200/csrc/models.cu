@@ -6,10 +6,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <tuple>
+#include <string>
 #include <vector>
 
 #include "common.h"
+#include "context.h"
 #include "gemm.h"
 #include "kernels.h"
 #include "models.h"
@@ -78,38 +79,13 @@ void apply_prefetch(GemmArgs& a, const Prefetch* pf) {
   if (pf == nullptr || pf->w == nullptr || pf->depth <= 0) return;
   a.pf_w = pf->w; a.pf_rows = pf->rows; a.pf_K = pf->K; a.pf_split_k = pf->split_k; a.pf_depth = pf->depth;
 }
-// k-blocks to prefetch per work item for the decode chain (default 0 = off); OPUS_PF_<QKV|O|GU|DOWN|LM>=n overrides,
-// opus_set_tunable("pf_qkv", n) etc. changes them at run time (tools/bench_decode.py sweeps them).
-int g_pf_depth[5] = {-1, -1, -1, -1, -1};
-void pf_init() {
-  if (g_pf_depth[0] >= 0) return;
-  static const char* names[5] = {"OPUS_PF_QKV", "OPUS_PF_O", "OPUS_PF_GU", "OPUS_PF_DOWN", "OPUS_PF_LM"};
-  static const int defaults[5] = {0, 0, 0, 0, 0};  // measured: no gain at batch 64 (the launches are not HBM-starved)
-  const char* off = std::getenv("OPUS_PF");
-  const bool enabled = !(off != nullptr && off[0] == '0');
-  for (int i = 0; i < 5; ++i) {
-    const char* e = std::getenv(names[i]);
-    g_pf_depth[i] = !enabled ? 0 : (e != nullptr ? atoi(e) : defaults[i]);
-  }
-}
-int pf_depth_for(int which) {
-  pf_init();
-  return g_pf_depth[which];
-}
+// k-blocks to prefetch per work item for the decode chain (default 0 = off; OPUS_PF_<QKV|O|GU|DOWN|LM>=n at context
+// creation, opus_set_tunable("pf_qkv", n) etc. at run time; tools/bench_decode.py sweeps them).
 enum { PF_QKV = 0, PF_O = 1, PF_GU = 2, PF_DOWN = 3, PF_LM = 4 };
+int pf_depth_for(int which) { return ctx().tun.pf_depth[which]; }
 
-// fused decode chain (gemm_chain): opt-in with OPUS_DECODE_FUSED=1 / opus_set_tunable("decode_fused", 1). Measured on
-// B200 at batch 64 it is not yet faster than one PDL-chained kernel per op (4.48 vs 4.40 ms per step: its device-wide
-// barriers and norm phases cost what the kernel boundaries did; tools/trace_chain.py prints the phase timeline).
-int g_decode_rope_fused = 1;  // RoPE + KV append inside the decode attention kernel (tunable "decode_rope_fused")
-int g_decode_fused = -1;
-bool decode_fused() {
-  if (g_decode_fused < 0) {
-    const char* e = std::getenv("OPUS_DECODE_FUSED");
-    g_decode_fused = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return g_decode_fused != 0;
-}
+// fused decode chain (gemm_chain): opt-in with OPUS_DECODE_FUSED=1 / opus_set_tunable("decode_fused", 1).
+bool decode_fused() { return ctx().tun.decode_fused != 0; }
 
 // activations [rows, K] x weight [N, K]^T -> out, choosing the weight-streaming (swap-AB) form for small `rows`.
 int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* out, int ldo, const float* bias,
@@ -324,7 +300,8 @@ int llama_select(const opus_llama_model* m, const opus_llama_workspace* ws, cons
   if (s->do_sample)
     OPUS_TRY(sample_top_p(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->temperature, s->top_p,
                           s->seed, s->finished, s->eos_ids, s->n_eos, s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1,
-                          s->n_unfinished, st, s->step));
+                          s->n_unfinished, st, s->step, nullptr,
+                          reinterpret_cast<const unsigned long long*>(s->seed_ptr)));
   else
     OPUS_TRY(argmax_eos(static_cast<const bf16*>(ws->logits), m->vocab, m->vocab, n_seqs, s->finished, s->eos_ids,
                         s->n_eos, s->pad_id, s->next_tok, s->out_ids, s->out_ld, -1, s->n_unfinished, st, s->step));
@@ -509,7 +486,7 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
       const opus_llama_layer& L = m->layers[l];
       bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
       bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
-      if (g_decode_rope_fused) {
+      if (ctx().tun.decode_rope_fused) {
         OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp_qkv, s->pos, s->slot,
                                          static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin),
                                          kc, vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv,
@@ -557,7 +534,7 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
       pf_next.w = m->lm_head; pf_next.rows = m->vocab; pf_next.K = d; pf_next.split_k = 1; pf_next.depth = pf_depth_for(PF_LM);
     }
     OPUS_TRY(linear_splitk(xn, B, L.wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st, &pf_o));
-    if (g_decode_rope_fused) {
+    if (ctx().tun.decode_rope_fused) {
       // split-K reduce + RoPE + KV append happen inside the attention CTAs (one launch less per layer)
       OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp, s->pos, s->slot,
                                        static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin), kc,
@@ -589,91 +566,78 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
 }
 
 // ------------------------------------------------------------------------------------------------ decode loop + graph
-namespace {
-struct GraphEntry {
-  cudaGraphExec_t exec = nullptr;
-  long long launches = 0;
-};
-using GraphKey = std::tuple<const void*, const void*, const void*, const void*, int>;
-std::map<GraphKey, GraphEntry> g_graphs;
-std::mutex g_graph_mu;
-}  // namespace
-
 int set_tunable(const char* name, int value) {
-  static const char* names[5] = {"pf_qkv", "pf_o", "pf_gu", "pf_down", "pf_lm"};
+  static const char* pf_names[5] = {"pf_qkv", "pf_o", "pf_gu", "pf_down", "pf_lm"};
   if (name == nullptr) return fail(OPUS_ERR_ARG, "set_tunable: null name");
-  pf_init();
-  if (std::strcmp(name, "chain_l2_depth") == 0) {
-    gemm_set_chain_l2_depth(value);
-    return release_graphs();
+  Tunables& t = ctx().tun;
+  bool known = true;
+  if (std::strcmp(name, "chain_l2_depth") == 0) gemm_set_chain_l2_depth(value);
+  else if (std::strcmp(name, "decode_rope_fused") == 0) t.decode_rope_fused = value != 0;
+  else if (std::strcmp(name, "decode_fused") == 0) t.decode_fused = value != 0;
+  else if (std::strcmp(name, "gemm_2cta") == 0) gemm_set_2cta(value);
+  else if (std::strcmp(name, "gemm_2cta_tr") == 0) gemm_set_2cta_tr(value);
+  else if (std::strcmp(name, "tma_store") == 0) gemm_set_tma_store(value);
+  else if (std::strcmp(name, "streamk_plain") == 0) gemm_set_streamk_plain(value);
+  else if (std::strcmp(name, "streamk_fill") == 0) gemm_set_streamk_fill(value);
+  else if (std::strcmp(name, "attn_mode") == 0) t.attn_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
+  else if (std::strcmp(name, "attn_tail") == 0) t.attn_tail = value != 0;
+  else {
+    known = false;
+    for (int i = 0; i < 5; ++i)
+      if (std::strcmp(name, pf_names[i]) == 0) { t.pf_depth[i] = value < 0 ? 0 : value; known = true; }
   }
-  if (std::strcmp(name, "decode_rope_fused") == 0) {
-    g_decode_rope_fused = value != 0;
-    return release_graphs();
-  }
-  if (std::strcmp(name, "decode_fused") == 0) {
-    g_decode_fused = value != 0;
-    return release_graphs();
-  }
-  if (std::strcmp(name, "gemm_2cta") == 0) {
-    gemm_set_2cta(value);
-    return release_graphs();
-  }
-  if (std::strcmp(name, "gemm_2cta_tr") == 0) {
-    gemm_set_2cta_tr(value);
-    return release_graphs();
-  }
-  if (std::strcmp(name, "tma_store") == 0) {
-    gemm_set_tma_store(value);
-    return release_graphs();
-  }
-  if (std::strcmp(name, "streamk_plain") == 0) {
-    gemm_set_streamk_plain(value);
-    return release_graphs();
-  }
-  if (std::strcmp(name, "streamk_fill") == 0) {
-    gemm_set_streamk_fill(value);
-    return release_graphs();
-  }
-  for (int i = 0; i < 5; ++i) {
-    if (std::strcmp(name, names[i]) == 0) {
-      g_pf_depth[i] = value < 0 ? 0 : value;
-      return release_graphs();  // captured decode graphs bake the old value in
-    }
-  }
-  return fail(OPUS_ERR_ARG, "set_tunable: unknown name");
+  if (!known) return fail(OPUS_ERR_ARG, "set_tunable: unknown name");
+  return release_graphs();   // captured decode graphs bake the old value in
 }
 
 int release_graphs() {
-  std::lock_guard<std::mutex> lk(g_graph_mu);
-  for (auto& kv : g_graphs)
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  for (auto& kv : c.graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  g_graphs.clear();
+  c.graphs.clear();
   return OPUS_OK;
 }
+
+namespace {
+// Everything a captured decode step bakes into its kernel arguments: the struct contents (pointers AND scalars such as
+// pad_id, temperature, top_p, the immediate seed, max_blocks, n_eos, the stop-sequence fields) plus the batch size and the
+// per-layer weight table. Two calls that differ in any of them get different graphs; the values that legitimately change
+// between replays (positions, step counter, and the seed when state->seed_ptr is used) live in device memory.
+template <typename T>
+void key_add(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+std::string graph_key(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
+                      const opus_decode_state* s, int B) {
+  std::string k;
+  k.reserve(sizeof(*m) + sizeof(*kv) + sizeof(*ws) + sizeof(*s) + 8);
+  key_add(k, *m); key_add(k, *kv); key_add(k, *ws); key_add(k, *s); key_add(k, B);
+  return k;
+}
+}  // namespace
 
 int llama_decode_loop(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws,
                       const opus_decode_state* s, int B, int n_steps, int check_every, int use_graph,
                       cudaStream_t st) {
+  if (!m || !kv || !ws || !s) return fail(OPUS_ERR_ARG, "llama_decode_loop: null argument");
   if (n_steps <= 0) return 0;
   GraphEntry entry;
   if (use_graph) {
-    std::lock_guard<std::mutex> lk(g_graph_mu);
-    const GraphKey key{m->lm_head, ws->h, s->out_ids, kv->k, B};
-    auto it = g_graphs.find(key);
-    if (it == g_graphs.end()) {
+    Context& c = ctx();
+    std::lock_guard<std::mutex> lk(c.mu);
+    const std::string key = graph_key(m, kv, ws, s, B);
+    auto it = c.graphs.find(key);
+    if (it == c.graphs.end()) {
       cudaGraph_t graph = nullptr;
       const long long before = launch_count(false);
       // The caller's stream may be the legacy default stream, which cannot be captured: record the step on a private
       // non-blocking stream (nothing executes during capture) and replay the instantiated graph on the caller's stream.
-      static cudaStream_t cap_stream = nullptr;
-      if (cap_stream == nullptr &&
-          cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+      if (c.cap_stream == nullptr &&
+          cudaStreamCreateWithFlags(&c.cap_stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(OPUS_ERR_CUDA, "decode_loop: create capture stream");
-      if (cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+      if (cudaStreamBeginCapture(c.cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
         return fail(OPUS_ERR_CUDA, "decode_loop: begin capture");
-      const int rc = llama_decode_step(m, kv, ws, s, B, cap_stream);
-      const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
+      const int rc = llama_decode_step(m, kv, ws, s, B, c.cap_stream);
+      const cudaError_t ce = cudaStreamEndCapture(c.cap_stream, &graph);
       if (rc != OPUS_OK) {
         if (graph) cudaGraphDestroy(graph);
         return rc;
@@ -687,7 +651,12 @@ int llama_decode_loop(const opus_llama_model* m, const opus_kv_cache* kv, const 
         return fail(OPUS_ERR_CUDA, "decode_loop: instantiate");
       }
       cudaGraphDestroy(graph);
-      it = g_graphs.emplace(key, e).first;
+      if (c.graphs.size() >= 16) {   // bounded cache: callers that churn states (new out_ids per call) do not leak graphs
+        for (auto& g : c.graphs)
+          if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+        c.graphs.clear();
+      }
+      it = c.graphs.emplace(key, e).first;
     }
     entry = it->second;
   }

@@ -110,8 +110,10 @@ def eval_model(args, tokenizer=None, model=None):
     pad_row = lambda o: torch.nn.functional.pad(o, (0, max_new - o.numel()), value=tokenizer.eos_token_id)  # noqa: E731
     if args.continuous_batching:
         from .scheduler import ContinuousBatcher
+        # per request: the value the reference's fixed batch holding it would have been generated with
+        per_req = [sched[min((i // args.batch_size + 1) * args.batch_size, len(ids)) - 1] for i in range(len(ids))]
         outs = ContinuousBatcher(model, max_slots=args.batch_size).generate(
-            ids, seqs, sched, eos_ids=model.config.eos_token_id, pad_id=tokenizer.eos_token_id, stop_sequences=stop_ids,
+            ids, seqs, per_req, eos_ids=model.config.eos_token_id, pad_id=tokenizer.eos_token_id, stop_sequences=stop_ids,
             sampling=(args.temperature, args.top_p, args.seed + 1000003 * rank) if args.temperature > 0 else None)
         rows = [pad_row(o) for o in outs]
     else:

@@ -234,13 +234,16 @@ class B200Llama:
         """sampling = None (greedy) or (temperature, top_p, seed); stop_sequences = token-id sequences that finish a row."""
         n, dev = st["n_seqs"], self.device
         stops = tuple(tuple(int(t) for t in q) for q in (stop_sequences or ()) if len(q))
-        key = (n, max_new_tokens, tuple(eos_ids), pad_id, sampling, stops)
+        # the seed travels through a device buffer (state.seed_ptr), so one state / one captured graph serves every
+        # sampled call: a fresh seed per generate() (the reference's default decode) re-captures nothing
+        key = (n, max_new_tokens, tuple(eos_ids), pad_id, None if sampling is None else tuple(sampling[:2]), stops)
         cached = getattr(self, "_state_cache", None)
         if cached is None or cached[0] != key:
             i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=dev)  # noqa: E731
             bufs = dict(next_tok=i32(n), ctx_len=i32(n), pos=i32(n), slot=i32(n), block_table=i32(n, st["max_blocks"]),
                         finished=i32(n), n_unfinished=i32(1), step=i32(1), out_ids=i32(n, max_new_tokens),
-                        eos=torch.tensor(list(eos_ids) or [-1], dtype=torch.int32, device=dev))
+                        eos=torch.tensor(list(eos_ids) or [-1], dtype=torch.int32, device=dev),
+                        seed=torch.zeros(1, dtype=torch.int64, device=dev))
             if stops:
                 ld = max(len(q) for q in stops)
                 bufs["stop_seqs"] = torch.tensor([list(q) + [-1] * (ld - len(q)) for q in stops], dtype=torch.int32,
@@ -264,7 +267,9 @@ class B200Llama:
         s.max_blocks, s.out_ld = st["max_blocks"], max_new_tokens
         s.eos_ids, s.n_eos, s.pad_id = bufs["eos"].data_ptr(), len(eos_ids), pad_id
         if sampling is not None:
-            s.do_sample, s.temperature, s.top_p, s.seed = 1, float(sampling[0]), float(sampling[1]), int(sampling[2])
+            s.do_sample, s.temperature, s.top_p, s.seed = 1, float(sampling[0]), float(sampling[1]), 0
+            bufs["seed"].fill_(u64_as_i64(int(sampling[2])))
+            s.seed_ptr = bufs["seed"].data_ptr()
         if stops:
             s.stop_seqs, s.stop_lens = bufs["stop_seqs"].data_ptr(), bufs["stop_lens"].data_ptr()
             s.n_stop, s.stop_ld = len(stops), bufs["stop_seqs"].shape[1]
@@ -308,6 +313,12 @@ class B200Llama:
         if len(eos_ids):
             out = _trim_like_hf(out, eos_ids)
         return out
+
+
+def u64_as_i64(v: int) -> int:
+    """the bit pattern of an unsigned 64-bit seed as the signed value a torch.int64 buffer holds"""
+    v &= 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
 
 
 def _trim_like_hf(out: torch.Tensor, eos_ids) -> torch.Tensor:

@@ -5,8 +5,9 @@ its slowest row stops (`eval/run_opus_ddp.py:75,88-134`). Here a fixed number of
 whenever a sequence emits EOS (or reaches max_new_tokens) its pages go back to the allocator and the slot is refilled by
 prefilling the next waiting prompt, while the other slots keep decoding. Outputs are returned in input order, so the
 call stays a drop-in for the per-batch `generate` loop of the eval scripts. Greedy, or temperature / top-p sampling
-(`sampling=(temperature, top_p, seed)`, the eval scripts' default decode): sampled rounds are replayed without the CUDA
-graph because the per-round seed is a kernel argument (the draw is hash(seed, row, step) and steps restart every round).
+(`sampling=(temperature, top_p, seed)`, the eval scripts' default decode): every round draws from its own seed stream
+(the draw is hash(seed, row, step) and steps restart every round); the seed is handed over in device memory
+(`opus_decode_state.seed_ptr`), so sampled rounds replay the same CUDA graph as greedy ones.
 
 All device work reuses the C ABI entry points (`opus_llama_prefill`, `opus_llama_select`, `opus_llama_decode_loop`); the
 scheduler itself is host logic over the decode-state arrays.
@@ -21,7 +22,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .llama import BLOCK
+from .llama import BLOCK, u64_as_i64
 from .model import B200OpusLlama, SplicePlan
 
 
@@ -42,14 +43,18 @@ class ContinuousBatcher:
         i32 = lambda *s: torch.zeros(s, dtype=torch.int32, device=self.dev)  # noqa: E731
         bufs = dict(next_tok=i32(n), ctx_len=i32(n), pos=i32(n), slot=i32(n), block_table=i32(n, max_blocks),
                     finished=i32(n), n_unfinished=i32(1), step=i32(1), out_ids=i32(n, out_ld),
-                    eos=torch.tensor(list(eos_ids) or [-1], dtype=torch.int32, device=self.dev))
+                    eos=torch.tensor(list(eos_ids) or [-1], dtype=torch.int32, device=self.dev),
+                    seed=torch.zeros(1, dtype=torch.int64, device=self.dev))
         s = L.DecodeState()
         for k in ("next_tok", "ctx_len", "pos", "slot", "block_table", "finished", "n_unfinished", "step", "out_ids"):
             setattr(s, k, bufs[k].data_ptr())
         s.max_blocks, s.out_ld = max_blocks, out_ld
         s.eos_ids, s.n_eos, s.pad_id = bufs["eos"].data_ptr(), len(eos_ids), pad_id
         if sampling is not None:
-            s.do_sample, s.temperature, s.top_p, s.seed = 1, float(sampling[0]), float(sampling[1]), int(sampling[2])
+            # the seed lives in device memory (seed_ptr): the per-round streams below do not invalidate the decode graph
+            s.do_sample, s.temperature, s.top_p, s.seed = 1, float(sampling[0]), float(sampling[1]), 0
+            bufs["seed"].fill_(u64_as_i64(int(sampling[2])))
+            s.seed_ptr = bufs["seed"].data_ptr()
         return s, bufs
 
     @staticmethod
@@ -105,8 +110,6 @@ class ContinuousBatcher:
         scratch = ll._alloc.alloc(1)[0]
 
         st, bufs = self._state(S, max_blocks, self.R, eos_ids, pad_id, sampling)
-        if sampling is not None:
-            use_graph = False               # the seed changes every round and is baked into a captured graph
         n_round = n_adm = 0
         bufs["block_table"].fill_(scratch)
         bufs["finished"].fill_(1)
@@ -196,7 +199,7 @@ class ContinuousBatcher:
             bufs["n_unfinished"].fill_(active)
             if sampling is not None:
                 n_round += 1
-                st.seed = self._mix(int(sampling[2]), n_round)
+                bufs["seed"].fill_(u64_as_i64(self._mix(int(sampling[2]), n_round)))
             rc = lib.opus_llama_decode_loop(C.byref(ll._model), C.byref(ll._cache), C.byref(ll._ws), C.byref(st), S,
                                             self.R, 0, int(use_graph), stream)
             L.check(rc, "opus_llama_decode_loop")

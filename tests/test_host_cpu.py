@@ -23,8 +23,33 @@ def test_shared_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.opus_abi_version() == 3
+    assert lib.opus_abi_version() == 4 == _lib.ABI_VERSION
     assert isinstance(lib.opus_last_error(), bytes)
+
+
+def test_contexts_and_thread_local_errors():
+    """re-entrant per context. Tunables belong to the calling thread's current context (unknown names fail
+    without touching it), and the error message of a failing call is visible to the thread that made it only."""
+    import ctypes as C
+    import threading
+    from opus_pllm_b200 import _lib
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    assert lib.opus_ctx_create(C.byref(ctx)) == 0 and ctx.value
+    assert lib.opus_ctx_set_current(ctx) == 0
+    assert lib.opus_set_tunable(b"decode_fused", 1) == 0          # this context only
+    assert lib.opus_set_tunable(b"no_such_knob", 1) < 0
+    assert b"unknown name" in lib.opus_last_error()
+    seen = {}
+
+    def other():
+        seen["msg"] = lib.opus_last_error()                       # another thread: its own (empty) message
+        seen["rc"] = lib.opus_set_tunable(None, 0)
+        seen["msg2"] = lib.opus_last_error()
+    t = threading.Thread(target=other); t.start(); t.join()
+    assert seen["msg"] == b"" and seen["rc"] < 0 and b"null name" in seen["msg2"]
+    assert b"unknown name" in lib.opus_last_error()              # untouched by the other thread's failure
+    assert lib.opus_ctx_set_current(None) == 0 and lib.opus_ctx_destroy(ctx) == 0
 
 
 def test_no_cpu_fallback_ops_fail_loudly_without_cuda():
