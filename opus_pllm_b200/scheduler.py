@@ -31,6 +31,7 @@ class ContinuousBatcher:
         self.model, self.llama = model, model.llama
         self.S, self.R, self.enc_chunk = max_slots, round_steps, encoder_chunk
         self.dev = model.device
+        self.stats = {}
 
     # ------------------------------------------------------------------------------------------ helpers
     def _soft_tokens(self, seqs):
@@ -111,6 +112,7 @@ class ContinuousBatcher:
 
         st, bufs = self._state(S, max_blocks, self.R, eos_ids, pad_id, sampling)
         n_round = n_adm = 0
+        round_events, n_rounds, prefill_tokens = [], 0, 0
         bufs["block_table"].fill_(scratch)
         bufs["finished"].fill_(1)
         slot_req = [-1] * S                   # request id held by each slot
@@ -173,6 +175,7 @@ class ContinuousBatcher:
                                                d_last.data_ptr(), len(adm), n_tok, int(np.diff(cu).max()), stream),
                         "opus_llama_prefill")
                 n_adm += 1
+                prefill_tokens += n_tok
                 adm_sampling = None if sampling is None else (sampling[0], sampling[1], self._mix(int(sampling[2]) ^ 0x5DEECE66D, n_adm))
                 ast, ab = self._state(len(adm), max_blocks, 1, eos_ids, pad_id, adm_sampling)
                 ab["n_unfinished"].fill_(len(adm))
@@ -200,9 +203,14 @@ class ContinuousBatcher:
             if sampling is not None:
                 n_round += 1
                 bufs["seed"].fill_(u64_as_i64(self._mix(int(sampling[2]), n_round)))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             rc = lib.opus_llama_decode_loop(C.byref(ll._model), C.byref(ll._cache), C.byref(ll._ws), C.byref(st), S,
                                             self.R, 0, int(use_graph), stream)
             L.check(rc, "opus_llama_decode_loop")
+            e1.record()
+            round_events.append((e0, e1))
+            n_rounds += 1
             toks = ops.d2h(bufs["out_ids"]).numpy()          # [S, R]; synchronises
             for s in range(S):
                 r = slot_req[s]
@@ -210,5 +218,8 @@ class ContinuousBatcher:
                     retire(s)
         ll._alloc.release([scratch])
         torch.cuda.current_stream().synchronize()
+        # bookkeeping of the last call (bench.py: HBM roofline of the decode rounds)
+        self.stats = dict(rounds=n_rounds, decode_steps=n_rounds * self.R, slots=S, admissions=n_adm,
+                          prefill_tokens=prefill_tokens, decode_ms=float(sum(a.elapsed_time(b) for a, b in round_events)))
         lib.opus_release_graphs()
         return [torch.tensor(r, dtype=torch.int64) for r in results]
