@@ -280,7 +280,9 @@ typedef struct {
   int32_t arch;
   int32_t opt_act;                /* OPT family: 0 = ReLU, 1 = erf-GELU */
   const void* pos_embed;          /* OPT family: bf16 [pos_rows, dim] (HF embed_positions.weight, offset 2 included) */
-  int32_t pos_rows; int32_t reserved_;
+  int32_t pos_rows;
+  int32_t head_dim_real;          /* 0 or the model's head width when heads are stored zero-padded to head_dim columns
+                                   * (the softmax scale is 1/sqrt(head_dim_real)); see llama.py / opt.py */
   const float* norm_g; const float* norm_b; /* OPT family: decoder.final_layer_norm fp32 [dim] */
 } opus_llama_model;
 enum { OPUS_ARCH_LLAMA = 0, OPUS_ARCH_OPT = 1 };

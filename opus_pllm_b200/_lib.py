@@ -58,7 +58,7 @@ class LlamaModel(C.Structure):
                 ("rms_eps", c_float), ("embed", c_void_p), ("layers", C.POINTER(LlamaLayer)),
                 ("norm_w", c_void_p), ("lm_head", c_void_p), ("rope_cos", c_void_p), ("rope_sin", c_void_p),
                 ("arch", C.c_int32), ("opt_act", C.c_int32), ("pos_embed", c_void_p), ("pos_rows", C.c_int32),
-                ("reserved_", C.c_int32), ("norm_g", c_void_p), ("norm_b", c_void_p)]
+                ("head_dim_real", C.c_int32), ("norm_g", c_void_p), ("norm_b", c_void_p)]
 
 
 class KvCache(C.Structure):

@@ -323,16 +323,31 @@ __device__ __forceinline__ void load_panel_async(uint32_t smem_base, const __nv_
 template <int GROUP>
 __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const DecodeParams p) {
   grid_dep_launch();
-  grid_dep_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   // per warp: 2 stages x (K panel + V panel) = 16 KB; then the merge area
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int kvh = blockIdx.x, b = blockIdx.y;
+  // ctx_len / block_table / pos / slot of this step were written by decode_advance, several kernels back: every kernel
+  // in front of the q|k|v GEMM has completed by the time this grid can start (the GEMM triggers its dependents only
+  // after its own griddepcontrol.wait), so they may be read before OUR wait; only the GEMM's output may not.
   const int ctx = p.ctx_len[b];
   const int n_blocks = (ctx + DEC_BS - 1) / DEC_BS;
   const uint32_t s_warp = smem_u32(smem) + warp * (4 * DEC_PANEL);
   float* s_merge = reinterpret_cast<float*>(smem + DEC_WARPS * 4 * DEC_PANEL);  // [warps][GROUP][128+2]
+  const int* bt = p.block_table + (size_t)b * p.max_blocks;
+  auto panel_ptr = [&](const __nv_bfloat16* cache, int blk_idx) {
+    return cache + ((size_t)bt[blk_idx] * p.n_kv_heads + kvh) * (DEC_BS * DEC_D);
+  };
+  // The first K/V panels of this warp are cached tokens of EARLIER steps unless the block holds the token appended by
+  // this step (the last block): request them before waiting for the preceding kernel, so the page fetch overlaps its
+  // tail, the split-K reduce and the RoPE below.
+  const bool early = p.partial != nullptr && warp < n_blocks - 1;
+  if (early) {
+    load_panel_async(s_warp, panel_ptr(p.kcache, warp), lane);
+    load_panel_async(s_warp + DEC_PANEL, panel_ptr(p.vcache, warp), lane);
+  }
+  grid_dep_wait();
 
   if (p.partial != nullptr) {
     // ---- fused split-K reduce + RoPE + KV append for the heads of this (sequence, kv head) ----
@@ -414,13 +429,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
   for (int i = 0; i < DEC_D / 8; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
   float m_run = -INFINITY, l_run = 0.f;
 
-  const int* bt = p.block_table + (size_t)b * p.max_blocks;
-  auto panel_ptr = [&](const __nv_bfloat16* cache, int blk_idx) {
-    return cache + ((size_t)bt[blk_idx] * p.n_kv_heads + kvh) * (DEC_BS * DEC_D);
-  };
-
   int it = 0;
-  if (warp < n_blocks) {
+  if (!early && warp < n_blocks) {
     load_panel_async(s_warp, panel_ptr(p.kcache, warp), lane);
     load_panel_async(s_warp + DEC_PANEL, panel_ptr(p.vcache, warp), lane);
   }

@@ -35,16 +35,22 @@ constexpr int UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
 constexpr int NUM_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
 constexpr int NUM_EPI_THREADS = 256;  // two warps per TMEM lane quadrant, each draining every other 32-column chunk
 
-template <int BN>
+// TR (swap-AB) launches have no TMA-store staging, so the ring takes that space too: at decode sizes the bytes in flight
+// per SM set the streaming rate (measured on lm_head: 64 KB of weight tiles in flight 4.99 TB/s, 96 KB 5.99, 128 KB 6.45).
+template <int BN, bool TR = false>
 struct Cfg {
   static constexpr int STAGE_A = BM * BK * 2;
   static constexpr int STAGE_B = BN * BK * 2;
   static constexpr int STAGE = STAGE_A + STAGE_B;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STORE_BYTES = TR ? 0 : 8 * 4096;  // epilogue staging: one [32 rows x 64 bf16] swizzled box per warp
+  static constexpr int TAIL = 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*epilogue bias slice*/;
+  static constexpr int STAGES_PLAIN = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGES_FIT = (232448 - TAIL - STORE_BYTES) / STAGE;   // 227 KB of dynamic shared memory per CTA
+  static constexpr int STAGES = TR ? (STAGES_FIT > 11 ? 11 : STAGES_FIT) : STAGES_PLAIN;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
-  static constexpr int STORE_BYTES = 8 * 4096;  // epilogue staging: one [32 rows x 64 bf16] swizzled box per warp
   static constexpr int BARS_OFF = STAGES * STAGE + STORE_BYTES;
-  static constexpr int SMEM = BARS_OFF + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*epilogue bias slice*/;
+  static constexpr int SMEM = BARS_OFF + TAIL;
+  static_assert((2 * STAGES + 4) * 8 + 8 + 32 <= 256, "barriers + TMEM slot + reduction scratch live in 256 bytes");
 };
 
 enum WorkKind : int { WORK_TILE = 0, WORK_SK_PARTIAL = 1, WORK_SK_OWNER = 2 };
@@ -577,7 +583,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
     }
     // the tile's bias slice goes through shared memory once (one float per epilogue thread, BN <= 256): per-group global
     // loads showed up as long-scoreboard stalls in front of every add (ncu source view)
-    float* s_bias = reinterpret_cast<float*>(stage + Cfg<BN>::STORE_BYTES) + 64;   // after the barriers (256 B)
+    float* s_bias = reinterpret_cast<float*>(stage + Cfg<BN, false>::STORE_BYTES) + 64;   // after the barriers (256 B)
     if (p.bias != nullptr) {
       named_bar_sync(2, NUM_EPI_THREADS);                       // the previous tile's readers are done
       const int bc = tc.n * BN + epi_tid;
@@ -688,7 +694,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_pf, const __grid_constant__ CUtensorMap tmap_out,
                          const GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TR>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1161,7 +1167,7 @@ __device__ __forceinline__ void chain_norm_row(const ChainNorm& n, int row, int 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_chain_tcgen05_kernel(const __grid_constant__ ChainTmaps tm, const __grid_constant__ ChainProgram prog) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, true>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BARS_OFF);
@@ -1384,13 +1390,12 @@ int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t col
 template <int BN>
 int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, const void* B, int ldb, int grid,
            cudaStream_t stream) {
-  using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=
-            cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg<BN, false>::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg<BN, true>::SMEM) != cudaSuccess)
       return OPUS_ERR_CUDA;
     configured = true;
   }
@@ -1411,8 +1416,8 @@ int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, cons
     if (rc) return rc;
   }
   const cudaError_t le =
-      p.transposed ? launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, to, p)
-                   : launch_pdl(false, gemm_bf16_tcgen05_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, ta, tb, tp, to, p);
+      p.transposed ? launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), Cfg<BN, true>::SMEM, stream, ta, tb, tp, to, p)
+                   : launch_pdl(false, gemm_bf16_tcgen05_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), Cfg<BN, false>::SMEM, stream, ta, tb, tp, to, p);
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -1675,7 +1680,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
 namespace {
 template <int BN>
 int launch_chain(const ChainTmaps& tm, const ChainProgram& prog, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, true>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_chain_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) !=

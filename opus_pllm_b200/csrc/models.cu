@@ -217,6 +217,12 @@ int projector_forward(const opus_projector_model* m, const void* x_l2, int n, vo
 }
 
 namespace {
+// softmax scale: 1/sqrt of the model's REAL head width. Models whose heads are narrower than the 128 columns the
+// attention / cache kernels work on (Qwen2-0.5B, OPT-125m ... 2.7B, Galactica-1.3B: 64 or 80) are loaded with every head
+// zero-padded to 128 columns (llama.py / opt.py); head_dim_real then carries the width the scores are scaled by.
+inline float attn_scale(const opus_llama_model* m) {
+  return 1.0f / sqrtf((float)(m->head_dim_real > 0 ? m->head_dim_real : m->head_dim));
+}
 // OPT / Galactica family (defined below, after llama_select)
 int opt_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_llama_workspace* ws, const void* embeds,
                 const int* pos, const int* slot, const int* cu_seqlens, const int* last_rows, int n_seqs, int n_tok,
@@ -247,7 +253,7 @@ int llama_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus
     note_launch();
   }
   const size_t layer_stride = (size_t)kv->num_blocks * Hkv * kv->block_size * hd;
-  const float scale = 1.0f / sqrtf((float)hd);
+  const float scale = attn_scale(m);
   for (int l = 0; l < m->n_layers; ++l) {
     const opus_llama_layer& L = m->layers[l];
     bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
@@ -331,7 +337,8 @@ int opt_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_l
                 int max_len, cudaStream_t st) {
   OPUS_TRY(opt_check(m));
   const int d = m->dim, hd = m->head_dim, H = m->n_q_heads, ffn = m->ffn_dim;
-  const int qkv_n = 3 * d;
+  const int aw = H * hd;          // width of the head space (> dim when narrow heads are padded to 128 columns)
+  const int qkv_n = 3 * aw;
   bf16* h = static_cast<bf16*>(ws->h);
   bf16* xn = static_cast<bf16*>(ws->xn);
   bf16* qkv = static_cast<bf16*>(ws->qkv);
@@ -344,7 +351,7 @@ int opt_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_l
   }
   OPUS_TRY(add_pos_embed(h, static_cast<const bf16*>(m->pos_embed), pos, 2, m->pos_rows, n_tok, d, st));
   const size_t layer_stride = (size_t)kv->num_blocks * H * kv->block_size * hd;
-  const float scale = 1.0f / sqrtf((float)hd);
+  const float scale = attn_scale(m);
   for (int l = 0; l < m->n_layers; ++l) {
     const opus_llama_layer& L = m->layers[l];
     bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
@@ -371,9 +378,9 @@ int opt_prefill(const opus_llama_model* m, const opus_kv_cache* kv, const opus_l
                                      kv->block_size, st));
       }
     }
-    OPUS_TRY(attn_varlen(qkv, qkv_n, qkv + d, qkv_n, qkv + 2 * d, qkv_n, attn, d, cu_seqlens, n_seqs, n_tok, max_len, H,
+    OPUS_TRY(attn_varlen(qkv, qkv_n, qkv + aw, qkv_n, qkv + 2 * aw, qkv_n, attn, aw, cu_seqlens, n_seqs, n_tok, max_len, H,
                          H, hd, 1, scale, st));
-    OPUS_TRY(linear(attn, n_tok, L.wo, d, d, EPI_RES_BF16, h, d, L.bo, h, d, nullptr, 0, st));
+    OPUS_TRY(linear(attn, n_tok, L.wo, d, aw, EPI_RES_BF16, h, d, L.bo, h, d, nullptr, 0, st));
     OPUS_TRY(layernorm_bf16(h, nullptr, 0, nullptr, nullptr, nullptr, L.ln2_g, L.ln2_b, xn, n_tok, d, m->rms_eps, st));
     OPUS_TRY(linear(xn, n_tok, L.wgu, ffn, d, opt_fc1_epi(m), act, ffn, L.b1, nullptr, 0, nullptr, 0, st));
     OPUS_TRY(linear(act, n_tok, L.wdown, d, ffn, EPI_RES_BF16, h, d, L.b2, h, d, nullptr, 0, st));
@@ -391,14 +398,15 @@ int opt_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const op
                     const opus_decode_state* s, int B, cudaStream_t st) {
   OPUS_TRY(opt_check(m));
   const int d = m->dim, hd = m->head_dim, H = m->n_q_heads, ffn = m->ffn_dim;
-  const int qkv_n = 3 * d;
+  const int aw = H * hd;          // width of the head space (> dim when narrow heads are padded to 128 columns)
+  const int qkv_n = 3 * aw;
   bf16* h = static_cast<bf16*>(ws->h);
   bf16* xn = static_cast<bf16*>(ws->xn);
   bf16* qkv = static_cast<bf16*>(ws->qkv);
   bf16* attn = static_cast<bf16*>(ws->attn);
   bf16* act = static_cast<bf16*>(ws->act);
   const size_t layer_stride = (size_t)kv->num_blocks * H * kv->block_size * hd;
-  const float scale = 1.0f / sqrtf((float)hd);
+  const float scale = attn_scale(m);
   OPUS_TRY(decode_advance(s->ctx_len, s->pos, s->slot, s->block_table, s->max_blocks, kv->block_size, B, st, s->step));
   OPUS_TRY(embed_gather(s->next_tok, static_cast<const bf16*>(m->embed), h, B, d, st));
   OPUS_TRY(add_pos_embed(h, static_cast<const bf16*>(m->pos_embed), s->pos, 2, m->pos_rows, B, d, st));
@@ -413,9 +421,9 @@ int opt_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const op
     OPUS_TRY(linear_splitk(xn, B, L.wqkv, qkv_n, d, ws->partial, ws->partial_bytes, &sp, st));
     OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp, s->pos, s->slot,
                                      static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin), kc,
-                                     vc, s->block_table, s->max_blocks, s->ctx_len, attn, d, B, H, H, hd,
+                                     vc, s->block_table, s->max_blocks, s->ctx_len, attn, aw, B, H, H, hd,
                                      kv->block_size, scale, st, L.bqkv));
-    OPUS_TRY(linear_splitk(attn, B, L.wo, d, d, ws->partial, ws->partial_bytes, &sp, st));
+    OPUS_TRY(linear_splitk(attn, B, L.wo, d, aw, ws->partial, ws->partial_bytes, &sp, st));
     OPUS_TRY(layernorm_bf16(nullptr, ws->partial, sp, L.bo, h, h, L.ln2_g, L.ln2_b, xn, B, d, m->rms_eps, st));
     OPUS_TRY(linear(xn, B, L.wgu, ffn, d, opt_fc1_epi(m), act, ffn, L.b1, nullptr, 0, nullptr, 0, st));
     OPUS_TRY(linear_splitk(act, B, L.wdown, d, ffn, ws->partial, ws->partial_bytes, &sp, st));
@@ -443,7 +451,7 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
   bf16* attn = static_cast<bf16*>(ws->attn);
   bf16* act = static_cast<bf16*>(ws->act);
   const size_t layer_stride = (size_t)kv->num_blocks * Hkv * kv->block_size * hd;
-  const float scale = 1.0f / sqrtf((float)hd);
+  const float scale = attn_scale(m);
 
   OPUS_TRY(decode_advance(s->ctx_len, s->pos, s->slot, s->block_table, s->max_blocks, kv->block_size, B, st, s->step));
   OPUS_TRY(embed_gather(s->next_tok, static_cast<const bf16*>(m->embed), h, B, d, st));

@@ -17,6 +17,25 @@ from . import _lib as L
 from . import ops
 
 BLOCK = 16  # tokens per KV-cache page
+KERNEL_HEAD_DIM = 128  # head width of the attention / paged-cache kernels
+
+
+def pad_heads(t: torch.Tensor, n_heads: int, hd_real: int, dim: int, rotary: bool) -> torch.Tensor:
+    """Re-lay the head axis (`dim` of `t`, length n_heads * hd_real) out as n_heads * 128 with zero padding.
+    rotary=True keeps HF's rotate_half pairing (j, j + hd/2) on the kernels' pairing (j, j + 64):
+    [first half | zeros | second half | zeros]; rotary=False (OPT) is [head | zeros]. No-op for 128-wide heads."""
+    if hd_real == KERNEL_HEAD_DIM:
+        return t
+    t = t.movedim(dim, 0)
+    v = t.reshape(n_heads, hd_real, *t.shape[1:])
+    out = v.new_zeros((n_heads, KERNEL_HEAD_DIM) + tuple(v.shape[2:]))
+    if rotary:
+        h = hd_real // 2
+        out[:, :h] = v[:, :h]
+        out[:, KERNEL_HEAD_DIM // 2: KERNEL_HEAD_DIM // 2 + h] = v[:, h:]
+    else:
+        out[:, :hd_real] = v
+    return out.reshape((n_heads * KERNEL_HEAD_DIM,) + tuple(v.shape[2:])).movedim(0, dim).contiguous()
 
 
 class BlockAllocator:
@@ -43,10 +62,21 @@ class B200Llama:
                  max_positions: int = 8192, lora: dict | None = None, lora_alpha: float = 32.0, lora_r: int = 16):
         L.load()
         self.device = torch.device(device)
+        # The attention / KV-cache kernels work on 128-column heads. Narrower heads (Qwen2-0.5B: 64) are stored zero-padded
+        # to 128 columns in the rotate_half layout [first half | 0 | second half | 0]: q.k^T, the rotary pairing (j, j+64)
+        # and P.V are unchanged by the zero columns, the softmax scale uses the real width (opus_llama_model.head_dim_real).
+        self.hd_real = head_dim
+        if head_dim != KERNEL_HEAD_DIM:
+            if head_dim > KERNEL_HEAD_DIM or head_dim % 2:
+                raise NotImplementedError(f"head_dim {head_dim} is not supported (even values up to {KERNEL_HEAD_DIM})")
+            head_dim = KERNEL_HEAD_DIM
         self.n_layers, self.dim, self.Hq, self.Hkv, self.hd = n_layers, dim, n_q_heads, n_kv_heads, head_dim
         self.ffn, self.vocab, self.rms_eps, self.rope_theta = ffn_dim, vocab, rms_eps, rope_theta
         self.qkv_n = (n_q_heads + 2 * n_kv_heads) * head_dim
         b16 = lambda t: t.detach().to(self.device, torch.bfloat16).contiguous()  # noqa: E731
+        hr = self.hd_real
+        pad_out = lambda W, nh: pad_heads(W, nh, hr, 0, rotary=True)        # noqa: E731  rows / entries = head outputs
+        pad_in = lambda W, nh: pad_heads(W, nh, hr, 1, rotary=True)         # noqa: E731  columns = head inputs (o_proj)
 
         def merged(key: str) -> torch.Tensor:
             W = b16(weights[key + ".weight"])
@@ -63,11 +93,12 @@ class B200Llama:
         for i in range(n_layers):
             p = f"model.layers.{i}."
             q, k, v = (merged(p + f"self_attn.{n}") for n in ("q_proj", "k_proj", "v_proj"))
+            q, k, v = pad_out(q, n_q_heads), pad_out(k, n_kv_heads), pad_out(v, n_kv_heads)
             g, u = merged(p + "mlp.gate_proj"), merged(p + "mlp.up_proj")
             bq = [weights.get(p + f"self_attn.{n}.bias") for n in ("q_proj", "k_proj", "v_proj")]
             t = dict(ln1_w=b16(weights[p + "input_layernorm.weight"]),
                      wqkv=torch.cat([q, k, v], 0).contiguous(),
-                     wo=merged(p + "self_attn.o_proj"),
+                     wo=pad_in(merged(p + "self_attn.o_proj"), n_q_heads),
                      ln2_w=b16(weights[p + "post_attention_layernorm.weight"]),
                      # rows interleaved (gate_0, up_0, gate_1, up_1, ...) so SwiGLU lives in the GEMM epilogue
                      wgu=torch.stack([g, u], 1).reshape(2 * ffn_dim, dim).contiguous(),
@@ -75,7 +106,8 @@ class B200Llama:
             if any(b is not None for b in bq):   # Qwen2 family: q/k/v projections carry a bias (o_proj does not)
                 if any(b is None for b in bq):
                     raise L.OpusError(f"layer {i}: q/k/v projection biases must be given together")
-                t["bqkv"] = torch.cat([b.detach().to(self.device, torch.float32) for b in bq]).contiguous()
+                t["bqkv"] = torch.cat([pad_out(b.detach().to(self.device, torch.float32), nh)
+                                       for b, nh in zip(bq, (n_q_heads, n_kv_heads, n_kv_heads))]).contiguous()
             del q, k, v, g, u
             self._keep.append(t)
             for kk, vv in t.items():
@@ -92,15 +124,18 @@ class B200Llama:
 
     # HF LlamaRotaryEmbedding (default rope): fp32 angles, cos/sin cast to the activation dtype (bf16)
     def _build_rope(self, max_pos: int):
-        hd = self.hd
+        hd = self.hd_real
         inv_freq = 1.0 / (self.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
         fr = torch.outer(torch.arange(max_pos, dtype=torch.float32), inv_freq)
+        if hd != self.hd:   # padded heads: angle 0 (cos 1, sin 0) on the zero columns
+            fr = torch.cat([fr, torch.zeros(max_pos, (self.hd - hd) // 2)], -1)
         emb = torch.cat([fr, fr], -1)
         self.rope_cos = emb.cos().to(torch.bfloat16).to(self.device).contiguous()
         self.rope_sin = emb.sin().to(torch.bfloat16).to(self.device).contiguous()
         self.max_positions = max_pos
         m = L.LlamaModel()
         m.n_layers, m.dim, m.n_q_heads, m.n_kv_heads, m.head_dim = self.n_layers, self.dim, self.Hq, self.Hkv, self.hd
+        m.head_dim_real = 0 if self.hd_real == self.hd else self.hd_real
         m.ffn_dim, m.vocab, m.rope_max_pos, m.rms_eps = self.ffn, self.vocab, max_pos, self.rms_eps
         m.embed = self.embed.data_ptr()
         m.layers = C.cast(self._layers, C.POINTER(L.LlamaLayer))

@@ -4,9 +4,9 @@ Sibling family of the reference: `OpusOPTForCausalLM` (multi_modality_v1/model/l
 `load_pretrained_model` for 'opt' / 'galactica' base paths (model/builder.py:71-81). What HF's `OPTDecoder` adds over the
 Llama blocks is handled inside libopus_b200.so (`csrc/models.cu::opt_prefill / opt_decode_step`): learned positions
 (`embed_positions`, offset 2), LayerNorm with bias, biased q/k/v/out/fc1/fc2, ReLU (OPT) or erf-GELU (Galactica) MLP.
-Only `do_layer_norm_before=True` models with `word_embed_proj_dim == hidden_size` and head_dim 128 are accepted (OPT-6.7B
-/ 13B / 30B / 66B, Galactica-6.7B / 30B / 120B): the 350m post-LN variant cannot be loaded by the reference either (its
-lm_head is built hidden_size wide, opus_opt.py:35).
+Only `do_layer_norm_before=True` models with `word_embed_proj_dim == hidden_size` are accepted; heads narrower than the
+kernels' 128 columns (OPT-125m / 1.3B / 2.7B, Galactica-1.3B: 64 or 80) are stored zero-padded to 128 (llama.pad_heads).
+The 350m post-LN variant cannot be loaded by the reference either (its lm_head is built hidden_size wide, opus_opt.py:35).
 Weights use the HF state-dict names (`model.decoder.*`, `lm_head.weight` optional = tied).
 """
 from __future__ import annotations
@@ -17,7 +17,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .llama import B200Llama
+from .llama import KERNEL_HEAD_DIM, B200Llama, pad_heads
 
 P0 = "model.decoder."
 
@@ -27,8 +27,13 @@ class B200Opt(B200Llama):
                  max_pos: int = 2048, activation: str = "relu", ln_eps: float = 1e-5, device="cuda",
                  lora: dict | None = None, lora_alpha: float = 32.0, lora_r: int = 16):
         L.load()
-        if dim % n_heads or dim // n_heads != 128:
-            raise NotImplementedError(f"OPT family: head_dim {dim / n_heads:g} is not supported (128 only)")
+        if dim % n_heads or dim // n_heads > KERNEL_HEAD_DIM or (dim // n_heads) % 2:
+            raise NotImplementedError(f"OPT family: head_dim {dim / n_heads:g} is not supported (even values up to 128)")
+        # narrower heads (OPT-125m / 1.3B, Galactica-1.3B: 64; OPT-2.7B: 80) are stored zero-padded to the kernels' 128
+        # columns ([head | zeros]; no rotary pairing to preserve); the scores are scaled by the real width
+        self.hd_real = hr = dim // n_heads
+        pad_out = lambda W: pad_heads(W, n_heads, hr, 0, rotary=False)   # noqa: E731
+        pad_in = lambda W: pad_heads(W, n_heads, hr, 1, rotary=False)    # noqa: E731
         if activation not in ("relu", "gelu"):
             raise NotImplementedError(f"OPT family: activation_function {activation!r} (relu | gelu)")
         # older facebook/opt-* checkpoints store the decoder without the `model.` prefix
@@ -37,7 +42,7 @@ class B200Opt(B200Llama):
         self.n_layers, self.dim, self.Hq, self.Hkv, self.hd = n_layers, dim, n_heads, n_heads, 128
         self.ffn, self.vocab, self.rms_eps, self.rope_theta = ffn_dim, vocab, ln_eps, None
         self.activation = activation
-        self.qkv_n = 3 * dim
+        self.qkv_n = 3 * n_heads * 128
         b16 = lambda t: t.detach().to(self.device, torch.bfloat16).contiguous()  # noqa: E731
         f32 = lambda t: None if t is None else t.detach().to(self.device, torch.float32).contiguous()  # noqa: E731
 
@@ -62,12 +67,13 @@ class B200Opt(B200Llama):
         layers = (L.LlamaLayer * n_layers)()
         for i in range(n_layers):
             p = f"{P0}layers.{i}."
-            q, k, v = (merged(p + f"self_attn.{n}") for n in ("q_proj", "k_proj", "v_proj"))
+            q, k, v = (pad_out(merged(p + f"self_attn.{n}")) for n in ("q_proj", "k_proj", "v_proj"))
             bq = [weights.get(p + f"self_attn.{n}.bias") for n in ("q_proj", "k_proj", "v_proj")]
             if any(b is not None for b in bq) and any(b is None for b in bq):
                 raise L.OpusError(f"layer {i}: q/k/v projection biases must be given together")
+            bq = [None if b is None else pad_out(f32(b)) for b in bq]
             t = dict(wqkv=torch.cat([q, k, v], 0).contiguous(),
-                     wo=merged(p + "self_attn.out_proj"),
+                     wo=pad_in(merged(p + "self_attn.out_proj")),
                      wgu=merged(p + "fc1"),                                     # plain fc1 rows (no gate)
                      wdown=merged(p + "fc2"),
                      ln1_g=f32(weights[p + "self_attn_layer_norm.weight"]),
@@ -105,6 +111,7 @@ class B200Opt(B200Llama):
         m = L.LlamaModel()
         m.n_layers, m.dim, m.n_q_heads, m.n_kv_heads, m.head_dim = self.n_layers, self.dim, self.Hq, self.Hkv, self.hd
         m.ffn_dim, m.vocab, m.rope_max_pos, m.rms_eps = self.ffn, self.vocab, max_pos, self.rms_eps
+        m.head_dim_real = 0 if self.hd_real == self.hd else self.hd_real
         m.embed = self.embed.data_ptr()
         m.layers = C.cast(self._layers, C.POINTER(L.LlamaLayer))
         m.lm_head = self.lm_head.data_ptr()

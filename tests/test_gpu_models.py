@@ -427,6 +427,33 @@ def test_lora_merge_at_load():
     assert _cos(got, want) >= 0.999 and _cos(got, want) > _cos(got, base)
 
 
+@pytest.mark.parametrize("qkv_bias", [True, False])
+def test_narrow_heads_llama_family_vs_oracle(qkv_bias):
+    """head_dim 64 (Qwen2-0.5B: 14 q heads / 2 kv heads x 64, biased q/k/v): heads are stored zero-padded to the kernels' 128
+    columns in the rotate_half layout; prefill logits and greedy tokens must match the oracle run at the real head width."""
+    from opus_pllm_b200.llama import B200Llama
+    cfg = dict(n_layers=3, dim=448, n_q_heads=7, n_kv_heads=1, head_dim=64, ffn_dim=1024, vocab=2048)
+    kw = {k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()}
+    w = synth.llama_weights(seed=12, peaked=True, device="cuda", qkv_bias=qkv_bias, **kw)
+    model = B200Llama(w, **cfg, rope_theta=1000000.0)
+    assert model.hd == 128 and model.hd_real == 64
+    ocfg = llama_ref.LlamaCfg(n_layers=3, dim=448, n_q_heads=7, n_kv_heads=1, head_dim=64, ffn_dim=1024, vocab=2048,
+                              rope_theta=1000000.0)
+    for lens, new in (([40, 7, 129, 64], 12), ([30 + (i * 7) % 50 for i in range(40)], 8)):
+        cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(5))
+        emb = w["model.embed_tokens.weight"][tok.cuda()].to(torch.bfloat16)
+        got, logits = model.generate_packed(emb, cu, new, return_prefill_logits=True)
+        assert torch.equal(got, model.generate_packed(emb, cu, new, use_graph=False))
+        e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+        pos = (m_pad.long().cumsum(-1) - 1).masked_fill(~m_pad, 1)
+        want32, _ = llama_ref.llama_forward(_dev(w, torch.float32), ocfg, e_pad.float(), m_pad, pos)
+        assert _cos(logits, want32) >= 0.999
+        want = llama_ref.greedy_generate(_dev(w, torch.bfloat16), ocfg, e_pad, m_pad, new)
+        same = (got.cpu() == want.cpu()).all(1).float().mean()
+        assert float(same) >= 0.99, float(same)
+
+
 # ------------------------------------------------------------------------------------------------ whole path
 def test_generate_end_to_end_vs_oracle_pipeline():
     """proteins + prompts with -200 sentinels -> tokens, through the reference-shaped generate() call."""

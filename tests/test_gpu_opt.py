@@ -170,7 +170,7 @@ def test_opt_greedy_tokens_match_oracle_peaked(act, bias, B, T, new):
 
 def test_opt_rejects_unsupported_variants():
     from opus_pllm_b200.opt import B200Opt
-    c = dict(n_layers=1, dim=256, n_heads=4, ffn_dim=512, vocab=512, max_pos=64)     # head_dim 64
+    c = dict(n_layers=1, dim=288, n_heads=2, ffn_dim=512, vocab=512, max_pos=64)     # head_dim 144 > 128
     lw = synth.opt_weights(c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], c["max_pos"])
     with pytest.raises(NotImplementedError):
         B200Opt(lw, c["n_layers"], c["dim"], c["n_heads"], c["ffn_dim"], c["vocab"], max_pos=c["max_pos"])
@@ -284,3 +284,35 @@ def test_opt_scoring_path_vs_oracle():
         assert float((losses[off: off + n - 1].cpu() - ce).abs().max()) <= 0.05
         assert float(losses[off + n - 1]) == 0.0                  # ignore_index row
         off += n
+
+
+@pytest.mark.parametrize("dim,n_heads,act,bias", [(256, 4, "relu", True),      # head_dim 64: OPT-125m / 1.3B shape family
+                                                 (320, 4, "relu", True),      # head_dim 80: OPT-2.7B
+                                                 (512, 8, "gelu", False)])    # head_dim 64: Galactica-1.3B
+def test_opt_narrow_heads_token_parity(dim, n_heads, act, bias):
+    """OPT / Galactica sizes whose heads are narrower than the kernels' 128 columns (opus_opt.py wraps any HF OPT size;
+    the reference zoo ships OPUS-PLLM-Galactica-1.3B, head_dim 64): heads are stored zero-padded, results must still match
+    the oracle token for token (prefill through both GEMM forms, graph and eager decode)."""
+    c = dict(n_layers=3, dim=dim, n_heads=n_heads, ffn_dim=1024, vocab=2048, max_pos=512)
+    lw, model = _build(c, 91, act, bias, peaked=True)
+    assert model.hd == 128 and model.hd_real == dim // n_heads
+    for B, T, new in ((6, 40, 10), (40, 24, 6)):
+        lens = [T - (i % 5) for i in range(B)]
+        cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        gen = torch.Generator().manual_seed(5)
+        ids = [torch.randint(3, c["vocab"], (n,), generator=gen) for n in lens]
+        packed = torch.cat([lw["model.decoder.embed_tokens.weight"][i] for i in ids]).cuda().to(torch.bfloat16)
+        got = model.generate_packed(packed, cu, new)
+        assert torch.equal(got, model.generate_packed(packed, cu, new, use_graph=False))
+        w32 = {k: v.to(torch.bfloat16).float() for k, v in lw.items()}
+        Lm = max(lens)
+        emb = torch.zeros(B, Lm, c["dim"])
+        mask = torch.zeros(B, Lm, dtype=torch.bool)
+        for b, i in enumerate(ids):
+            emb[b, Lm - len(i):] = w32["model.decoder.embed_tokens.weight"][i]
+            mask[b, Lm - len(i):] = True
+        ocfg = opt_ref.OptCfg(n_layers=c["n_layers"], dim=c["dim"], n_heads=c["n_heads"], ffn_dim=c["ffn_dim"],
+                              vocab=c["vocab"], max_pos=c["max_pos"], activation=act)
+        want = opt_ref.greedy_generate(w32, ocfg, emb, mask, new)
+        same_rows = (got.cpu() == want).all(1).float().mean()
+        assert float(same_rows) >= 0.99, (float(same_rows), got.cpu()[:4], want[:4])

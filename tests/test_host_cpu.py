@@ -292,3 +292,34 @@ def test_eos_ids_merge_generation_config(tmp_path):
     json.dump({"eos_token_id": [128001, 128009]}, open(tmp_path / "generation_config.json", "w"))
     assert builder._eos_ids(str(tmp_path), 128001) == [128001, 128009]
     assert builder._eos_ids(str(tmp_path), [5]) == [128001, 128009, 5]
+
+
+def test_pad_heads_layout_preserves_rotary_pairs_and_dot_products():
+    """llama.pad_heads: narrow heads stored in 128 columns. With rotary=True the halves land at columns [0, h) and
+    [64, 64 + h), so the kernels' rotate_half pairing (j, j + 64) acts on the original pairs (j, j + h); dot products over
+    the padded axis equal the originals; projecting back through the padded o_proj columns is the identity."""
+    from opus_pllm_b200.llama import pad_heads
+    g = torch.Generator().manual_seed(0)
+    H, hr, D = 3, 64, 40
+    W = torch.randn(H * hr, D, generator=g)
+    Wp = pad_heads(W, H, hr, 0, rotary=True)
+    assert Wp.shape == (H * 128, D)
+    v, vp = W.view(H, hr, D), Wp.view(H, 128, D)
+    assert torch.equal(vp[:, :32], v[:, :32]) and torch.equal(vp[:, 64:96], v[:, 32:])
+    assert float(vp[:, 32:64].abs().max()) == 0 and float(vp[:, 96:].abs().max()) == 0
+    x = torch.randn(5, D, generator=g)
+    q, qp = (x @ W.T).view(5, H, hr), (x @ Wp.T).view(5, H, 128)
+    assert torch.allclose((q * q.flip(0)).sum(-1), (qp * qp.flip(0)).sum(-1), atol=1e-4)
+    # rotate_half on the padded layout == padded rotate_half of the original
+    rot = torch.cat([-q[..., 32:], q[..., :32]], -1)
+    rot_p = torch.cat([-qp[..., 64:], qp[..., :64]], -1)
+    assert torch.allclose(pad_heads(rot.reshape(5, H * hr), H, hr, 1, rotary=True).view(5, H, 128), rot_p)
+    # o_proj columns: out = attn @ Wo^T is unchanged when both are padded the same way
+    Wo = torch.randn(D, H * hr, generator=g)
+    a = torch.randn(5, H * hr, generator=g)
+    for rotary in (True, False):
+        ap, Wop = pad_heads(a, H, hr, 1, rotary=rotary), pad_heads(Wo, H, hr, 1, rotary=rotary)
+        assert torch.allclose(a @ Wo.T, ap @ Wop.T, atol=1e-4)
+    assert pad_heads(W, H * hr // 128, 128, 0, rotary=True) is W
+    W80 = torch.randn(2 * 80, D, generator=g)
+    assert pad_heads(W80, 2, 80, 0, rotary=False).view(2, 128, D)[:, 80:].abs().max() == 0
