@@ -44,7 +44,8 @@ struct SkWorkspace {
 
 struct Context {
   Tunables tun = Tunables::from_env();
-  std::mutex mu;                             // guards graphs / sk / cap_stream
+  std::mutex mu;                             // guards graphs / cap_stream (held across a graph capture)
+  std::mutex sk_mu;                          // guards sk: taken by GEMM launches, also from inside a capture
   std::map<std::string, GraphEntry> graphs;  // decode graphs keyed by everything a captured step bakes in
   cudaStream_t cap_stream = nullptr;
   SkWorkspace sk;

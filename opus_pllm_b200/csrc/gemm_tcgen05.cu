@@ -1438,7 +1438,7 @@ int num_sms() {
 // launches on that stream reuse it in stream order.
 bool ensure_sk_workspace() {
   Context& c = ctx();
-  std::lock_guard<std::mutex> lk(c.mu);
+  std::lock_guard<std::mutex> lk(c.sk_mu);   // not c.mu: the decode loop holds that one while it captures a step
   if (c.sk.state != 0) return c.sk.state > 0;
   if (!c.tun.streamk) { c.sk.state = -1; return false; }
   const size_t bytes = (size_t)num_sms() * BM * 256 * sizeof(float);

@@ -84,18 +84,10 @@ class ContinuousBatcher:
         new_of = [int(max_new_tokens)] * n_req if np.isscalar(max_new_tokens) else [int(v) for v in max_new_tokens]
         assert len(new_of) == n_req
         max_new_tokens = max(new_of)
-        soft = self._soft_tokens(seqs)
-        soft2d = soft.reshape(-1, soft.shape[-1]).contiguous()
-        n_soft = soft.shape[1]
-        # per-request splice plans (request i uses protein slot i)
-        plans = []
-        for i, p in enumerate(prompts):
-            ids = p.detach().cpu().numpy()[None, :]
-            sp = SplicePlan(ids, None, n_soft, 1)
-            src = sp.src.copy()
-            neg = src < 0
-            src[neg] -= i * n_soft            # -(j+1) -> -(i*n_soft + j + 1)
-            plans.append(src)
+        n_soft = self.model.n_soft
+        # per-request splice plans against protein slot 0; the slot of a request inside its admission chunk is added when
+        # it is admitted (the encoder + projectors run per admission chunk, not for the whole queue up front)
+        plans = [SplicePlan(p.detach().cpu().numpy()[None, :], None, n_soft, 1).src for p in prompts]
         lens = np.array([len(s) for s in plans], dtype=np.int64)
         margin = self.R + 1
         max_blocks = int((lens.max() + max_new_tokens + margin + BLOCK - 1) // BLOCK)
@@ -107,7 +99,7 @@ class ContinuousBatcher:
             ll._build_rope(1 << (total - 1).bit_length())     # OPT: raises (its learned position table cannot grow)
         # worst case all slots hold the longest prompts, +1 scratch page for idle slots
         ll._ensure_cache(S * max_blocks + 1)
-        ll._ensure_ws(int(max(lens.max() * min(S, 8), S)), S)
+        ll._ensure_ws(int(max(lens.max() * min(S, self.enc_chunk), S)), S)
         scratch = ll._alloc.alloc(1)[0]
 
         st, bufs = self._state(S, max_blocks, self.R, eos_ids, pad_id, sampling)
@@ -145,53 +137,69 @@ class ContinuousBatcher:
                         return True
             return False
 
-        while waiting or active:
-            # ---- admit: prefill waiting prompts into free slots (bounded by workspace rows)
+        def admit_chunk() -> bool:
+            """prefill one chunk of waiting prompts into free slots (bounded by the workspace rows and the encoder chunk)"""
+            nonlocal n_adm, prefill_tokens, active
             free = [s for s in range(S) if slot_req[s] < 0]
             adm = []
             budget = ll._ws_rows
-            while free and waiting and lens[waiting[0]] <= budget:
+            while free and waiting and lens[waiting[0]] <= budget and len(adm) < self.enc_chunk:
                 r = waiting.popleft()
                 adm.append((free.pop(0), r))
                 budget -= int(lens[r])
-            if adm:
-                cu = np.zeros(len(adm) + 1, dtype=np.int32)
-                np.cumsum([lens[r] for _, r in adm], out=cu[1:])
-                n_tok = int(cu[-1])
-                bt = np.full((len(adm), max_blocks), scratch, dtype=np.int32)
-                for j, (s, r) in enumerate(adm):
-                    pages = ll._alloc.alloc(need_pages(int(lens[r])))
-                    slot_pages[s] = pages
-                    bt[j, : len(pages)] = pages
-                seq_of = np.repeat(np.arange(len(adm), dtype=np.int32), np.diff(cu))
-                pos = (np.arange(n_tok, dtype=np.int32) - cu[:-1][seq_of]).astype(np.int32)
-                slot_map = (bt[seq_of, pos // BLOCK] * BLOCK + pos % BLOCK).astype(np.int32)
-                src = np.concatenate([plans[r] for _, r in adm]).astype(np.int32)
-                embeds = ops.splice_gather(ops.h2d(src, self.dev), ll.embed, soft2d)
-                d_pos, d_slot, d_cu = (ops.h2d(a, self.dev) for a in (pos, slot_map, cu))
-                d_last = ops.h2d((cu[1:] - 1).astype(np.int32), self.dev)
-                L.check(lib.opus_llama_prefill(C.byref(ll._model), C.byref(ll._cache), C.byref(ll._ws),
-                                               embeds.data_ptr(), d_pos.data_ptr(), d_slot.data_ptr(), d_cu.data_ptr(),
-                                               d_last.data_ptr(), len(adm), n_tok, int(np.diff(cu).max()), stream),
-                        "opus_llama_prefill")
-                n_adm += 1
-                prefill_tokens += n_tok
-                adm_sampling = None if sampling is None else (sampling[0], sampling[1], self._mix(int(sampling[2]) ^ 0x5DEECE66D, n_adm))
-                ast, ab = self._state(len(adm), max_blocks, 1, eos_ids, pad_id, adm_sampling)
-                ab["n_unfinished"].fill_(len(adm))
-                L.check(lib.opus_llama_select(C.byref(ll._model), C.byref(ll._ws), C.byref(ast), len(adm), stream),
-                        "opus_llama_select")
-                first = ops.d2h(ab["next_tok"]).tolist()
-                idx = torch.tensor([s for s, _ in adm], dtype=torch.long, device=self.dev)
-                bufs["next_tok"][idx] = ab["next_tok"]
-                bufs["ctx_len"][idx] = torch.tensor([int(lens[r]) for _, r in adm], dtype=torch.int32, device=self.dev)
-                bufs["block_table"][idx] = ops.h2d(bt, self.dev)
-                bufs["finished"][idx] = 0
-                for j, (s, r) in enumerate(adm):
-                    slot_req[s] = r
-                    active += 1
-                    if absorb(r, [first[j]]):
-                        retire(s)
+            if not adm:
+                return False
+            cu = np.zeros(len(adm) + 1, dtype=np.int32)
+            np.cumsum([lens[r] for _, r in adm], out=cu[1:])
+            n_tok = int(cu[-1])
+            bt = np.full((len(adm), max_blocks), scratch, dtype=np.int32)
+            for j, (s, r) in enumerate(adm):
+                pages = ll._alloc.alloc(need_pages(int(lens[r])))
+                slot_pages[s] = pages
+                bt[j, : len(pages)] = pages
+            seq_of = np.repeat(np.arange(len(adm), dtype=np.int32), np.diff(cu))
+            pos = (np.arange(n_tok, dtype=np.int32) - cu[:-1][seq_of]).astype(np.int32)
+            slot_map = (bt[seq_of, pos // BLOCK] * BLOCK + pos % BLOCK).astype(np.int32)
+            soft = self.model._soft_tokens([seqs[r] for _, r in adm], None)          # [len(adm), n_soft, H]
+            soft2d = soft.reshape(-1, soft.shape[-1]).contiguous()
+            parts = []
+            for j, (_, r) in enumerate(adm):
+                src = plans[r].copy()
+                src[src < 0] -= j * n_soft                                           # -(k+1) -> -(j*n_soft + k + 1)
+                parts.append(src)
+            src = np.concatenate(parts).astype(np.int32)
+            embeds = ops.splice_gather(ops.h2d(src, self.dev), ll.embed, soft2d)
+            d_pos, d_slot, d_cu = (ops.h2d(a, self.dev) for a in (pos, slot_map, cu))
+            d_last = ops.h2d((cu[1:] - 1).astype(np.int32), self.dev)
+            L.check(lib.opus_llama_prefill(C.byref(ll._model), C.byref(ll._cache), C.byref(ll._ws),
+                                           embeds.data_ptr(), d_pos.data_ptr(), d_slot.data_ptr(), d_cu.data_ptr(),
+                                           d_last.data_ptr(), len(adm), n_tok, int(np.diff(cu).max()), stream),
+                    "opus_llama_prefill")
+            n_adm += 1
+            prefill_tokens += n_tok
+            adm_sampling = None if sampling is None else (sampling[0], sampling[1], self._mix(int(sampling[2]) ^ 0x5DEECE66D, n_adm))
+            ast, ab = self._state(len(adm), max_blocks, 1, eos_ids, pad_id, adm_sampling)
+            ab["n_unfinished"].fill_(len(adm))
+            L.check(lib.opus_llama_select(C.byref(ll._model), C.byref(ll._ws), C.byref(ast), len(adm), stream),
+                    "opus_llama_select")
+            first = ops.d2h(ab["next_tok"]).tolist()
+            idx = torch.tensor([s for s, _ in adm], dtype=torch.long, device=self.dev)
+            bufs["next_tok"][idx] = ab["next_tok"]
+            bufs["ctx_len"][idx] = torch.tensor([int(lens[r]) for _, r in adm], dtype=torch.int32, device=self.dev)
+            bufs["block_table"][idx] = ops.h2d(bt, self.dev)
+            bufs["finished"][idx] = 0
+            for j, (s, r) in enumerate(adm):
+                slot_req[s] = r
+                active += 1
+                if absorb(r, [first[j]]):
+                    retire(s)
+            return True
+
+        while waiting or active:
+            # ---- admit chunk after chunk until the slots are full or the queue is empty; only then decode a round
+            while waiting and any(r < 0 for r in slot_req):
+                if not admit_chunk():
+                    break
             if not active:
                 continue
             # ---- one round of R decode steps over all slots (idle slots spin on the scratch page)
