@@ -62,6 +62,23 @@ struct GemmParams {
   int sk_tiles;
   float* sk_ws;
   int* sk_cnt;
+  // In-kernel split-K reduction (swap-AB, one wave): the CTA holding a tile's LAST k-split waits for the CTAs holding the
+  // other splits (they dump their fp32 accumulators to sk_ws and bump sk_cnt[tile]), adds the partial sums in split order
+  // and runs the real epilogue, so no separate reduce kernel follows the GEMM.
+  int sk_fix;
+  int epi_warm;   // swap-AB: run the epilogue once "dry" during the main loop to warm the instruction cache (tunable)
+  // EPI_RES_BF16 (swap-AB) by-product for a following RMSNorm: sumsq_out[slab][batch row] = sum over the 32 features of
+  // slab (= feature / 32) of the squared bf16 values this launch stored. One writer per entry: deterministic.
+  float* sumsq_out;
+  int sumsq_ld;
+  // RMSNorm applied to the activation operand on its way to the tensor cores (swap-AB, batch <= 64): the B operand is
+  // the raw residual stream h; dedicated warps rewrite every landed [batch x 64] k-slice in shared memory as
+  // bf16(gamma[k] * bf16(h * rstd[row])) (the rounding points of rmsnorm_bf16_kernel / HF LlamaRMSNorm) before the MMA
+  // warp may read it. rstd[row] = rsqrt(sum over nl_slabs of nl_sumsq[slab][row] / K + eps).
+  const float* nl_sumsq;
+  int nl_slabs, nl_ld;
+  const void* nl_gamma;  // bf16 [K]
+  float nl_eps;
 };
 
 // D[M,N] = A[M,K] * B[N,K]^T, both operands bf16 row-major with K contiguous.
@@ -104,6 +121,16 @@ struct GemmArgs {
   void* rl_kcache;
   void* rl_vcache;
   int rl_hq, rl_hkv, rl_bs;
+  // Decode-chain fusions (swap-AB form; see GemmParams): reduce the split-K partial sums inside the kernel (any epilogue
+  // other than EPI_PARTIAL_F32 then works with split_k > 1; needs tiles * split_k <= SM count); emit per-slab sums of
+  // squares of an EPI_RES_BF16 result; apply RMSNorm (norm_sumsq / norm_gamma / norm_eps) to the activation operand.
+  int splitk_fixup;
+  float* sumsq_out;        // fp32 [ceil(M / 32)][sumsq_ld], sumsq_ld >= N (batch rows)
+  int sumsq_ld;
+  const float* norm_sumsq; // fp32 [norm_slabs][norm_ld]; non-null selects the normalising launch (batch <= 64)
+  int norm_slabs, norm_ld;
+  const void* norm_gamma;  // bf16 [K]
+  float norm_eps;
 };
 // true when gemm_bf16 will apply the rope_* / rl_* fields of `a` in its epilogue (plain form, EPI_BF16, TMA-store path)
 bool gemm_fuses_rope(const GemmArgs& a);

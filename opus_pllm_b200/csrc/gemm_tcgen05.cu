@@ -37,21 +37,25 @@ constexpr int NUM_EPI_THREADS = 256;  // two warps per TMEM lane quadrant, each 
 
 // TR (swap-AB) launches have no TMA-store staging, so the ring takes that space too: at decode sizes the bytes in flight
 // per SM set the streaming rate (measured on lm_head: 64 KB of weight tiles in flight 4.99 TB/s, 96 KB 5.99, 128 KB 6.45).
-template <int BN, bool TR = false>
+template <int BN, bool TR = false, bool NORM = false>
 struct Cfg {
   static constexpr int STAGE_A = BM * BK * 2;
   static constexpr int STAGE_B = BN * BK * 2;
   static constexpr int STAGE = STAGE_A + STAGE_B;
   static constexpr int STORE_BYTES = TR ? 0 : 8 * 4096;  // epilogue staging: one [32 rows x 64 bf16] swizzled box per warp
-  static constexpr int TAIL = 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*epilogue bias slice*/;
+  static constexpr int TAIL = 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*epilogue bias slice / RMSNorm row scales*/;
   static constexpr int STAGES_PLAIN = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int STAGES_FIT = (232448 - TAIL - STORE_BYTES) / STAGE;   // 227 KB of dynamic shared memory per CTA
-  static constexpr int STAGES = TR ? (STAGES_FIT > 11 ? 11 : STAGES_FIT) : STAGES_PLAIN;
+  static constexpr int STAGES_MAX = NORM ? 8 : 11;   // barrier block: (2 or 3) * STAGES + 4 mbarriers in 256 bytes
+  static constexpr int STAGES = TR ? (STAGES_FIT > STAGES_MAX ? STAGES_MAX : STAGES_FIT) : STAGES_PLAIN;
+  static constexpr int N_BARS = (NORM ? 3 : 2) * STAGES + 4;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // two accumulator buffers
   static constexpr int BARS_OFF = STAGES * STAGE + STORE_BYTES;
   static constexpr int SMEM = BARS_OFF + TAIL;
-  static_assert((2 * STAGES + 4) * 8 + 8 + 32 <= 256, "barriers + TMEM slot + reduction scratch live in 256 bytes");
+  // barriers + TMEM slot (+ the chain kernel's 32-byte reduction scratch, never used together with NORM) in 256 bytes
+  static_assert(N_BARS * 8 + 8 + (NORM ? 0 : 32) <= 256, "barrier block overflows its 256 bytes");
 };
+constexpr int NUM_THREADS_NORM = NUM_THREADS + 128;   // + warps 10-13: RMSNorm of the activation k-slices in shared memory
 
 enum WorkKind : int { WORK_TILE = 0, WORK_SK_PARTIAL = 1, WORK_SK_OWNER = 2 };
 
@@ -91,6 +95,12 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
     raster_mn(p, mn, c.m, c.n);
     c.kb_begin = (int)(((long long)c.split * p.k_blocks) / p.split_k);
     c.kb_end = (int)(((long long)(c.split + 1) * p.k_blocks) / p.split_k);
+    if (p.sk_fix && p.split_k > 1) {
+      // one wave (t == blockIdx.x): the CTAs of a tile are neighbours, the one with the last split finishes the tile
+      c.sk_tile = mn;
+      c.first_cta = t - c.split;
+      c.kind = (c.split == p.split_k - 1) ? WORK_SK_OWNER : WORK_SK_PARTIAL;
+    }
     return true;
   }
   if (p.sk_tiles == 0) return false;
@@ -273,12 +283,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 // ---- transposed (swap-AB) epilogue: accumulator row = output feature `row`, column = batch row n -> out[n*ldo + row].
 // NC columns per call. It is instantiated with NC = 8 and driven by a ROLLED loop: a decode-sized launch executes this
 // code exactly once per CTA with a cold instruction cache, and a 32-way unrolled body cost ~6-18 us per launch.
+// dry = instruction-cache warm-up pass (see the epilogue warps of gemm_bf16_tcgen05_kernel): same instructions, every
+// memory access masked off.
 template <int NC>
 __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const uint32_t (&r)[NC], int row, int col0,
-                                                    int split) {
+                                                    int split, bool dry = false) {
   float v[NC];
 #pragma unroll
   for (int i = 0; i < NC; ++i) v[i] = __uint_as_float(r[i]);
+  if (dry) row = p.M + 2;   // beyond the matrix: every load / store predicate below turns false
   const bool row_ok = row < p.M;
   if (p.epi == EPI_PARTIAL_F32) {
     float* base = reinterpret_cast<float*>(p.out) + ((size_t)split * p.N + col0) * p.ldo + row;
@@ -300,7 +313,7 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
     // even lanes hold out[row/2]; lanes l and l+2 pair up so that every store is 4 bytes (see the note above)
     const int lane = row & 31;
     const bool hi = lane & 2;
-    const int nv = (((lane & 1) == 0) && (row | 3) < p.M) ? min(NC, p.N - col0) : 0;
+    const int nv = (((lane & 1) == 0) && (row | 3) < p.M) ? min(NC, p.N - col0) : 0;   // dry: row >= M
 #pragma unroll
     for (int i = 0; i < NC; i += 2) {
       const float send = hi ? o[i] : o[i + 1];
@@ -345,6 +358,36 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
     for (int i = 0; i < NC; ++i) x[i] = rr[i] + bf16_round(v[i] + b);
     const int nv = (row | 1) < p.M ? min(NC, p.N - col0) : 0;
     store_bf16_transposed_paired(base, (size_t)p.ldo, x, nv, row & 31);
+    if constexpr (NC == 8) {
+      if (p.sumsq_out != nullptr) {
+        // sum of squares of the stored bf16 values over this warp's 32 features, per batch column: transpose-reduce (at
+        // every step a lane hands half of its columns to its partner), then two plain butterfly steps. Fixed order.
+        const int lane = row & 31;
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float hv = (i < n_valid) ? bf16_round(x[i]) : 0.f;
+          a[i] = hv * hv;
+        }
+        const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+        float bq[4], cq[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float recv = __shfl_xor_sync(0xffffffffu, u16 ? a[j] : a[j + 4], 16);
+          bq[j] = (u16 ? a[j + 4] : a[j]) + recv;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float recv = __shfl_xor_sync(0xffffffffu, u8 ? bq[j] : bq[j + 2], 8);
+          cq[j] = (u8 ? bq[j + 2] : bq[j]) + recv;
+        }
+        float d = (u4 ? cq[1] : cq[0]) + __shfl_xor_sync(0xffffffffu, u4 ? cq[0] : cq[1], 4);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        const int c = (u16 ? 4 : 0) + (u8 ? 2 : 0) + (u4 ? 1 : 0);
+        if (!dry && (lane & 3) == 0 && col0 + c < p.N) p.sumsq_out[(size_t)(row >> 5) * p.sumsq_ld + col0 + c] = d;
+      }
+    }
   } else if (p.epi == EPI_RES_F32) {
     const float* rbase = reinterpret_cast<const float*>(p.residual) + (size_t)col0 * p.ldr + row;
     float* base = reinterpret_cast<float*>(p.out) + (size_t)col0 * p.ldo + row;
@@ -362,14 +405,15 @@ __device__ __forceinline__ void epilogue_transposed(const GemmParams& p, const u
 template <int BN, bool TR>
 __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoord& tc, uint32_t tmem_base, int acc,
                                               int quad, int lane, int chunk0, int epi_tid,
-                                              const CUtensorMap* tm_out = nullptr, uint8_t* stage = nullptr) {
+                                              const CUtensorMap* tm_out = nullptr, uint8_t* stage = nullptr,
+                                              bool dry = false) {
   const int lrow = quad * 32 + lane;  // accumulator row inside the tile
   const int row = tc.m * BM + lrow;
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
   // stream-K partials of this tile: sk_ws[cta][column][row] fp32 (lanes = consecutive rows -> coalesced)
   float* my_part = p.sk_ws + (size_t)blockIdx.x * (BM * BN) + lrow;
   if (tc.kind == WORK_SK_OWNER) {
-    if (epi_tid == 0) {
+    if (epi_tid == 0 && !dry) {
       const int need = (int)blockIdx.x - tc.first_cta;
       const long long t0 = clock64();
       while (ld_acquire_gpu(p.sk_cnt + tc.sk_tile) < need) {
@@ -393,7 +437,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
       for (int q = 0; q < NG; ++q)
 #pragma unroll
         for (int i = 0; i < 8; ++i) fix[q][i] = 0.f;
-      for (int c = tc.first_cta; c < (int)blockIdx.x; ++c) {
+      for (int c = dry ? (int)blockIdx.x : tc.first_cta; c < (int)blockIdx.x; ++c) {
         const float* src = p.sk_ws + (size_t)c * (BM * BN) + lrow;
         float t[kPrefetchFix ? NG : 1][8];
 #pragma unroll
@@ -417,8 +461,10 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
       for (int q = 0; q < NG; ++q) {
         const int g = chunk0 + 2 * q;
         if (tc.kind == WORK_SK_PARTIAL) {
+          if (!dry) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(av[q][i]);
+            for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(av[q][i]);
+          }
           continue;
         }
         if (tc.kind == WORK_SK_OWNER) {
@@ -426,7 +472,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
           for (int i = 0; i < 8; ++i) av[q][i] = __float_as_uint(__uint_as_float(av[q][i]) + fix[q][i]);
         }
         const int col0 = tc.n * BN + g * 8;
-        if (col0 < p.N) epilogue_transposed<8>(p, av[q], row, col0, tc.split);
+        if (col0 < p.N) epilogue_transposed<8>(p, av[q], row, col0, tc.split, dry);
       }
     } else {
       // rolled loop over 8-column groups (batch > 64)
@@ -436,19 +482,21 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
         tmem_ld_32x8(taddr + g * 8, r8);
         tmem_ld_wait();
         if (tc.kind == WORK_SK_PARTIAL) {
+          if (!dry) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(r8[i]);
+            for (int i = 0; i < 8; ++i) my_part[(size_t)(g * 8 + i) * BM] = __uint_as_float(r8[i]);
+          }
           continue;
         }
         if (tc.kind == WORK_SK_OWNER) {
-          for (int c = tc.first_cta; c < (int)blockIdx.x; ++c) {
+          for (int c = dry ? (int)blockIdx.x : tc.first_cta; c < (int)blockIdx.x; ++c) {
             const float* src = p.sk_ws + (size_t)c * (BM * BN) + (size_t)(g * 8) * BM + lrow;
 #pragma unroll
             for (int i = 0; i < 8; ++i) r8[i] = __float_as_uint(__uint_as_float(r8[i]) + __ldcg(src + (size_t)i * BM));
           }
         }
         const int col0 = tc.n * BN + g * 8;
-        if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split);
+        if (col0 < p.N) epilogue_transposed<8>(p, r8, row, col0, tc.split, dry);
       }
     }
   } else {
@@ -680,7 +728,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
   }  // plain form
   if (tc.kind == WORK_SK_PARTIAL) {
     named_bar_sync(1, NUM_EPI_THREADS);   // every thread's partial stores happen-before thread 0's fence + release
-    if (epi_tid == 0) {
+    if (epi_tid == 0 && !dry) {
       __threadfence();
       red_release_gpu_add(p.sk_cnt + tc.sk_tile, 1);
     }
@@ -689,21 +737,25 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
 
 // TR = swap-AB ("transposed") form. The two forms are separate instantiations so that a decode-sized launch does not carry
 // the plain form's epilogues in its instruction stream (and vice versa).
-template <int BN, bool TR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// NORM (swap-AB, batch <= 64): four more warps apply RMSNorm to every landed activation k-slice in shared memory before
+// the MMA warp may read it (GemmParams::nl_*), so the GEMM consumes the raw residual stream and no norm kernel runs.
+template <int BN, bool TR, bool NORM = false>
+__global__ void __launch_bounds__(NORM ? NUM_THREADS_NORM : NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_pf, const __grid_constant__ CUtensorMap tmap_out,
                          const GemmParams p) {
-  using C = Cfg<BN, TR>;
+  static_assert(!NORM || (TR && BN <= 64), "norm-on-load: swap-AB form, batch tile <= 64");
+  using C = Cfg<BN, TR, NORM>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte aligned bases
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::BARS_OFF);
-  uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA
+  uint64_t* full_bar = bars;                     // [STAGES]  TMA -> MMA (NORM: TMA -> norm warps)
   uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * C::STAGES;     // [2]       MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * C::STAGES + 2;  // [2]     epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  uint64_t* xf_bar = bars + 2 * C::STAGES + 4;   // [STAGES]  norm warps -> MMA (NORM only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::N_BARS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -718,6 +770,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], NUM_EPI_THREADS);
     }
+    if constexpr (NORM)
+      for (int s = 0; s < C::STAGES; ++s) mbar_init(&xf_bar[s], 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -729,7 +783,64 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (NORM && warp >= 10) {
+    // ===================== RMSNorm warps (10..13): activation k-slices, in place =====================
+    const int tt = threadIdx.x - NUM_THREADS;                                 // 0..127
+    float* s_rstd = reinterpret_cast<float*>(smem + C::BARS_OFF + 256);       // [64] row scales, then [64] scratch
+    grid_dep_wait();                                                          // nl_sumsq comes from the preceding kernels
+    {
+      // rstd[row] from the per-slab sums of squares: two threads per row, each sums one half of the slabs in slab
+      // order, halves combined lower + upper (fixed order -> bit-reproducible)
+      const int row = tt & 63, half = tt >> 6;
+      float acc = 0.f;
+      if (row < p.N) {
+        const int mid = p.nl_slabs >> 1;
+        const int s0 = half ? mid : 0, s1 = half ? p.nl_slabs : mid;
+        const float* src = p.nl_sumsq + row;
+#pragma unroll 8
+        for (int sl = s0; sl < s1; ++sl) acc += __ldcg(src + (size_t)sl * p.nl_ld);
+      }
+      if (half) s_rstd[64 + row] = acc;
+      named_bar_sync(3, 128);
+      if (!half) s_rstd[row] = row < p.N ? rsqrtf((acc + s_rstd[64 + row]) / (float)p.K + p.nl_eps) : 0.f;
+      named_bar_sync(3, 128);
+    }
+    // thread -> 16-byte chunk position `cpos` of rows row0, row0 + 16, ...: (row & 7) is the same for all of them, so the
+    // logical k-chunk behind the 128-byte swizzle (cpos ^ (row & 7)) and with it the gamma slice is fixed per thread
+    const int cpos = tt & 7, row0 = tt >> 3;
+    const int kchunk = cpos ^ (row0 & 7);
+    const __nv_bfloat16* gam = static_cast<const __nv_bfloat16*>(p.nl_gamma) + kchunk * 8;
+    float rs[BN / 16];
+#pragma unroll
+    for (int i = 0; i < BN / 16; ++i) rs[i] = s_rstd[row0 + 16 * i];
+    int stage = 0;
+    uint32_t phase = 0;
+    TileCoord tc;
+    for (int it = 0; get_work(p, it, tc); ++it) {
+      for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
+        const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gam + (size_t)kb * BK));   // in flight across the wait
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* sb = smem + stage * C::STAGE + C::STAGE_A + row0 * 128 + cpos * 16;
+        float gf[8];
+        bf16x8_unpack(gq, gf);
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+          uint4* ptr = reinterpret_cast<uint4*>(sb + i * 16 * 128);
+          float x[8], o[8];
+          bf16x8_unpack(*ptr, x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = gf[j] * bf16_round(x[j] * rs[i]);
+          uint4 q;
+          q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+          q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+          *ptr = q;
+        }
+        fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+        mbar_arrive(&xf_bar[stage]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -795,7 +906,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(NORM ? &xf_bar[stage] : &full_bar[stage], phase);   // NORM: the slice has been normalised in place
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE);
           const uint64_t da = umma_smem_desc_sw128(sa);
@@ -816,19 +927,32 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== epilogue warps (2..9) =====================
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access (hardware rule: warp id % 4)
     const int chunk0 = (warp - 2) >> 2;  // 0 or 1: the pair of warps of a quadrant interleave the column chunks
-    grid_dep_wait();            // residual / output buffers may still be in use by the preceding kernel
     int acc = 0;
     uint32_t acc_phase = 0;
     const int epi_tid = threadIdx.x - 64;  // 0..255
     TileCoord tc;
-    for (int it = 0; get_work(p, it, tc); ++it) {
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
+    // Swap-AB (decode-sized) launches execute their epilogue once per CTA, i.e. with a cold instruction cache, on the
+    // critical path between two dependent kernels. Pass -1 runs the first item's epilogue "dry" (same instructions,
+    // every memory access masked, TMEM contents ignored) while the main loop is still streaming weights, so the real
+    // pass finds its code cached. The dry pass touches no global memory and therefore runs before griddepcontrol.wait.
+    for (int it = (TR && p.epi_warm) ? -1 : 0;; ++it) {
+      const bool dry = it < 0;
+      if (!dry && it == 0) grid_dep_wait();   // residual / output buffers may still be in use by the preceding kernel
+      if (!get_work(p, dry ? 0 : it, tc)) {
+        if (dry) continue;                     // no work at all for this CTA: fall through to it = 0, which breaks
+        break;
+      }
+      if (!dry) {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+      }
       epilogue_item<BN, TR>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out,
-                        smem + C::STAGES * C::STAGE);
-      tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                        smem + C::STAGES * C::STAGE, dry);
+      if (!dry) {
+        tc_fence_before();
+        mbar_arrive(&acc_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
     if (p.tma_store && lane == 0) tma_store_wait_all();   // the staging buffers die with the CTA
   }
@@ -1415,9 +1539,25 @@ int launch(const GemmParams& p, const GemmArgs& pf, const void* A, int lda, cons
     rc = make_tmap_bf16(&to, p.out, p.M, p.epi == EPI_SWIGLU ? p.N / 2 : p.N, p.ldo, 32);
     if (rc) return rc;
   }
-  const cudaError_t le =
-      p.transposed ? launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), Cfg<BN, true>::SMEM, stream, ta, tb, tp, to, p)
-                   : launch_pdl(false, gemm_bf16_tcgen05_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), Cfg<BN, false>::SMEM, stream, ta, tb, tp, to, p);
+  cudaError_t le;
+  if (p.nl_sumsq != nullptr) {
+    if constexpr (BN <= 64) {
+      static bool norm_configured = false;
+      if (!norm_configured) {
+        if (cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg<BN, true, true>::SMEM) != cudaSuccess)
+          return OPUS_ERR_CUDA;
+        norm_configured = true;
+      }
+      le = launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, true, true>, dim3(grid), dim3(NUM_THREADS_NORM),
+                      Cfg<BN, true, true>::SMEM, stream, ta, tb, tp, to, p);
+    } else {
+      return OPUS_ERR_ARG;   // prepare_gemm only admits batch tiles <= 64
+    }
+  } else {
+    le = p.transposed ? launch_pdl(true, gemm_bf16_tcgen05_kernel<BN, true>, dim3(grid), dim3(NUM_THREADS), Cfg<BN, true>::SMEM, stream, ta, tb, tp, to, p)
+                      : launch_pdl(false, gemm_bf16_tcgen05_kernel<BN, false>, dim3(grid), dim3(NUM_THREADS), Cfg<BN, false>::SMEM, stream, ta, tb, tp, to, p);
+  }
   note_launch();
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? OPUS_OK : OPUS_ERR_CUDA;
 }
@@ -1507,7 +1647,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   p.k_blocks = (a.K + BK - 1) / BK;
   p.split_k = a.split_k > 0 ? a.split_k : 1;
   if (p.split_k > p.k_blocks) p.split_k = p.k_blocks;
-  if (p.split_k > 1 && a.epi != EPI_PARTIAL_F32) return OPUS_ERR_ARG;
+  if (p.split_k > 1 && a.epi != EPI_PARTIAL_F32 && !a.splitk_fixup) return OPUS_ERR_ARG;
   p.transposed = a.transposed;
   p.epi = a.epi;
   p.out = a.out; p.ldo = a.ldo;
@@ -1562,9 +1702,30 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     p.rope_cols = a.rope_cols; p.rope_q_cols = a.rope_q_cols; p.rope_q_scale = a.rope_q_scale;
   }
 
+  if (a.sumsq_out != nullptr) {
+    if (!a.transposed || a.epi != EPI_RES_BF16 || a.sumsq_ld < a.N) return OPUS_ERR_ARG;
+    p.sumsq_out = a.sumsq_out; p.sumsq_ld = a.sumsq_ld;
+  }
+  if (a.norm_sumsq != nullptr) {
+    if (!a.transposed || bn > 64 || (a.K % BK) || a.norm_gamma == nullptr || a.norm_slabs <= 0 || a.norm_ld < a.N ||
+        (reinterpret_cast<uintptr_t>(a.norm_gamma) & 15))
+      return OPUS_ERR_ARG;
+    p.nl_sumsq = a.norm_sumsq; p.nl_slabs = a.norm_slabs; p.nl_ld = a.norm_ld;
+    p.nl_gamma = a.norm_gamma; p.nl_eps = a.norm_eps;
+  }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   p.dp_items = tiles;
   p.sk_tiles = 0;
+  p.epi_warm = a.transposed ? tun.epi_warm : 0;
+  if (a.splitk_fixup && p.split_k > 1) {
+    // the CTAs of one tile wait on each other: every work item needs its own resident CTA (one wave)
+    if (!a.transposed || tiles > num_sms() || p.num_m_tiles * p.num_n_tiles > 1000 || a.epi == EPI_PARTIAL_F32 ||
+        !ensure_sk_workspace())
+      return OPUS_ERR_ARG;
+    p.sk_fix = 1;
+    p.sk_ws = ctx().sk.ws;
+    p.sk_cnt = ctx().sk.cnt;
+  }
   // wave quantisation: a last wave that fills only part of the machine is cut along K over all CTAs instead
   const int rem = tiles % num_sms();
   const bool sk_ready = ensure_sk_workspace();  // also on launches that do not need it: never first inside a capture

@@ -589,6 +589,8 @@ int set_tunable(const char* name, int value) {
   else if (std::strcmp(name, "streamk_fill") == 0) gemm_set_streamk_fill(value);
   else if (std::strcmp(name, "attn_mode") == 0) t.attn_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (std::strcmp(name, "attn_tail") == 0) t.attn_tail = value != 0;
+  else if (std::strcmp(name, "epi_warm") == 0) t.epi_warm = value != 0;
+  else if (std::strcmp(name, "decode_norm_fused") == 0) t.decode_norm_fused = value != 0;
   else {
     known = false;
     for (int i = 0; i < 5; ++i)

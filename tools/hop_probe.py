@@ -51,8 +51,12 @@ def seq(steps):
     return a.elapsed_time(b) / 10 / NL * 1e3
 
 
-prev = {}
-for steps in (["o"], ["o", "norm"], ["gu"], ["o", "norm", "gu"], ["down"], ["gu", "down"], ["gu", "down", "norm"],
-              ["o", "norm", "gu", "down", "norm"], ["qkv"], ["o", "norm", "gu", "down", "norm", "qkv"]):
-    us = seq(steps)
-    print(f"{'+'.join(steps):36s} {us:7.1f} us per repetition", flush=True)
+lib = L.load()
+for warm in ((0, 1) if os.environ.get("WARM_AB") else (None,)):
+    if warm is not None:
+        L.check(lib.opus_set_tunable(b"epi_warm", warm))
+        print(f"-- epi_warm = {warm}")
+    for steps in (["o"], ["o", "norm"], ["gu"], ["o", "norm", "gu"], ["down"], ["gu", "down"], ["gu", "down", "norm"],
+                  ["o", "norm", "gu", "down", "norm"], ["qkv"], ["o", "norm", "gu", "down", "norm", "qkv"]):
+        us = seq(steps)
+        print(f"{'+'.join(steps):36s} {us:7.1f} us per repetition", flush=True)
