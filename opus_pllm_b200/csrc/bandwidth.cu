@@ -847,6 +847,35 @@ __global__ void embed_gather_kernel(const int* __restrict__ tok, const __nv_bflo
   for (int c = lane; c < dim / 8; c += 32) dst[c] = from[c];
 }
 
+// decode input for the norm-fused decode path: x[b,:] = table[tok[b],:] and, per 32-feature slab, the sum of squares
+// of the row (sumsq[slab][b]; the consuming GEMM derives the RMSNorm row scale from it). One CTA per row, one thread per
+// slab (64 bytes = 4 x 16-byte loads).
+__global__ void embed_gather_sumsq_kernel(const int* __restrict__ tok, const __nv_bfloat16* __restrict__ table,
+                                          __nv_bfloat16* __restrict__ x, float* __restrict__ sumsq, int sumsq_ld,
+                                          int dim) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int row = blockIdx.x;
+  const uint4* from = reinterpret_cast<const uint4*>(table + (size_t)tok[row] * dim);
+  uint4* dst = reinterpret_cast<uint4*>(x + (size_t)row * dim);
+  for (int slab = threadIdx.x; slab < dim / 32; slab += blockDim.x) {
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 q = from[slab * 4 + c];
+      dst[slab * 4 + c] = q;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        sq += f.x * f.x;
+        sq += f.y * f.y;
+      }
+    }
+    sumsq[(size_t)slab * sumsq_ld + row] = sq;
+  }
+}
+
 // per-step decode bookkeeping: pos[b] = ctx_len[b]; slot[b] = block_table[b][ctx/bs]*bs + ctx%bs; ctx_len[b]++.
 __global__ void decode_advance_kernel(int* __restrict__ ctx_len, int* __restrict__ pos, int* __restrict__ slot,
                                       const int* __restrict__ block_table, int max_blocks, int block_size, int n,
@@ -1022,6 +1051,14 @@ int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, i
   if (dim % 8) return OPUS_ERR_ARG;
   if (n_rows == 0) return OPUS_OK;
   launch_pdl(n_rows <= 1024, embed_gather_kernel, dim3(cdiv(n_rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, tok, table, x, n_rows, dim);
+  return ok();
+}
+
+int embed_gather_sumsq(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, float* sumsq, int sumsq_ld,
+                       int n_rows, int dim, cudaStream_t st) {
+  if (dim % 32 || sumsq_ld < n_rows) return OPUS_ERR_ARG;
+  if (n_rows == 0) return OPUS_OK;
+  launch_pdl(true, embed_gather_sumsq_kernel, dim3(n_rows), dim3(128), 0, st, tok, table, x, sumsq, sumsq_ld, dim);
   return ok();
 }
 

@@ -79,58 +79,74 @@ __device__ __forceinline__ void raster_mn(const GemmParams& p, int mn, int& m, i
 
 // Work item number `it` (0, 1, 2, ...) of this CTA; false when the CTA is done. The producer, the MMA issuer and the
 // epilogue warps all walk the same sequence:
-//   * round-robin items t = blockIdx.x + it * gridDim.x < dp_items: whole (m, n, k-split) tiles;
-//   * then the CTA's share of the stream-K tail: unit range [b*U/ge, (b+1)*U/ge) of U = sk_tiles * k_blocks k-block units
-//     (ge = min(g, U) CTAs take part).
-//     The range is shorter than one tile's K extent (sk_tiles < g), so it touches at most two tiles: the head of a tile
-//     it does not finish (partial dump, walked FIRST so that no CTA ever waits on a CTA that is itself waiting) and the
-//     tail of a tile it finishes (owner: fix-up + epilogue).
+//   * the CTA's share of the stream-K tail: unit range [b*U/ge, (b+1)*U/ge) of U = sk_tiles * k_blocks k-block units
+//     (ge = min(g, U) CTAs take part). The range is shorter than one tile's K extent (sk_tiles < g), so it touches at
+//     most two tiles: the head of a tile it does not finish (partial dump) and the tail of a tile it finishes (owner:
+//     fix-up + epilogue);
+//   * round-robin items t = blockIdx.x + i * gridDim.x < dp_items: whole (m, n, k-split) tiles.
+// Order: the PARTIAL piece FIRST, then the round-robin tiles, then the piece(s) this CTA finishes. A dump therefore
+// happens a whole tile before any owner asks for it (its store + fence + flag latency leaves the critical path, and no
+// CTA ever waits on a CTA that is itself waiting), and the fix-up is the last thing a CTA does.
 __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord& c) {
   const int b = blockIdx.x, g = gridDim.x;
-  const int t = b + it * g;
   c.kind = WORK_TILE; c.sk_tile = 0; c.first_cta = 0;
-  if (t < p.dp_items) {
-    const int mn = t / p.split_k;
-    c.split = t - mn * p.split_k;
-    raster_mn(p, mn, c.m, c.n);
-    c.kb_begin = (int)(((long long)c.split * p.k_blocks) / p.split_k);
-    c.kb_end = (int)(((long long)(c.split + 1) * p.k_blocks) / p.split_k);
-    if (p.sk_fix && p.split_k > 1) {
-      // one wave (t == blockIdx.x): the CTAs of a tile are neighbours, the one with the last split finishes the tile
-      c.sk_tile = mn;
-      c.first_cta = t - c.split;
-      c.kind = (c.split == p.split_k - 1) ? WORK_SK_OWNER : WORK_SK_PARTIAL;
-    }
-    return true;
-  }
-  if (p.sk_tiles == 0) return false;
   const int n_dp = b < p.dp_items ? (p.dp_items - b + g - 1) / g : 0;
-  const int j = it - n_dp;  // 0 or 1
+  // ---- tail pieces of this CTA
+  int n_pre = 0, n_post = 0;
+  int tile[2], k0[2], k1[2];        // [0] = piece walked before the tiles (partial), [1], [2] -> see below
+  int ptile[2], pk0[2], pk1[2];     // post pieces, in walking order
   const int kb = p.k_blocks;
-  const long long U = (long long)p.sk_tiles * kb;
-  const int ge = U < g ? (int)U : g;  // CTAs sharing the tail: every one of them gets at least one unit
-  if (b >= ge || j > 1) return false;
-  const int u0 = (int)((long long)b * U / ge), u1 = (int)((long long)(b + 1) * U / ge);
-  const int tA = u0 / kb, tB = (u1 - 1) / kb;
-  int tile, k0, k1;
-  if (tA == tB) {
-    if (j > 0) return false;
-    tile = tA; k0 = u0 - tA * kb; k1 = u1 - tA * kb;
-  } else if (j == 0) {
-    tile = tB; k0 = 0; k1 = u1 - tB * kb;          // head of the next tile: not finished here
-  } else {
-    tile = tA; k0 = u0 - tA * kb; k1 = kb;         // tail of the previous tile: finished here
+  if (p.sk_tiles > 0) {
+    const long long U = (long long)p.sk_tiles * kb;
+    const int ge = U < g ? (int)U : g;  // CTAs sharing the tail: every one of them gets at least one unit
+    if (b < ge) {
+      const int u0 = (int)((long long)b * U / ge), u1 = (int)((long long)(b + 1) * U / ge);
+      const int tA = u0 / kb, tB = (u1 - 1) / kb;
+      auto add = [&](int t, int a0, int a1) {
+        if (a1 < kb) { tile[0] = t; k0[0] = a0; k1[0] = a1; n_pre = 1; }           // not finished here: partial
+        else { ptile[n_post] = t; pk0[n_post] = a0; pk1[n_post] = a1; ++n_post; }  // finished here
+      };
+      if (tA == tB) {
+        add(tA, u0 - tA * kb, u1 - tA * kb);
+      } else {
+        add(tB, 0, u1 - tB * kb);        // head of the next tile
+        add(tA, u0 - tA * kb, kb);       // tail of the previous tile
+      }
+      if (it >= n_pre + n_dp) {
+        const int j = it - n_pre - n_dp;
+        if (j >= n_post) return false;
+        c.split = 0;
+        raster_mn(p, p.dp_items + ptile[j], c.m, c.n);       // stream-K is only used with split_k == 1
+        c.kb_begin = pk0[j]; c.kb_end = pk1[j];
+        c.sk_tile = ptile[j];
+        // CTA holding unit x is ((x + 1) * ge - 1) / U
+        c.first_cta = (int)((((long long)ptile[j] * kb + 1) * ge - 1) / U);
+        c.kind = (c.first_cta == b) ? WORK_TILE : WORK_SK_OWNER;  // whole tile in this CTA's range: nothing to fix up
+        return true;
+      }
+      if (it < n_pre) {
+        c.split = 0;
+        raster_mn(p, p.dp_items + tile[0], c.m, c.n);
+        c.kb_begin = k0[0]; c.kb_end = k1[0];
+        c.sk_tile = tile[0];
+        c.kind = WORK_SK_PARTIAL;
+        return true;
+      }
+    }
   }
-  c.split = 0;
-  raster_mn(p, p.dp_items + tile, c.m, c.n);       // stream-K is only used with split_k == 1
-  c.kb_begin = k0; c.kb_end = k1;
-  c.sk_tile = tile;
-  if (k1 == kb) {
-    // CTA holding unit x is ((x + 1) * g - 1) / U
-    c.first_cta = (int)((((long long)tile * kb + 1) * ge - 1) / U);
-    c.kind = (c.first_cta == b) ? WORK_TILE : WORK_SK_OWNER;  // whole tile in this CTA's range: nothing to fix up
-  } else {
-    c.kind = WORK_SK_PARTIAL;
+  const int i = it - n_pre;
+  if (i >= n_dp) return false;
+  const int t = b + i * g;
+  const int mn = t / p.split_k;
+  c.split = t - mn * p.split_k;
+  raster_mn(p, mn, c.m, c.n);
+  c.kb_begin = (int)(((long long)c.split * p.k_blocks) / p.split_k);
+  c.kb_end = (int)(((long long)(c.split + 1) * p.k_blocks) / p.split_k);
+  if (p.sk_fix && p.split_k > 1) {
+    // one wave (t == blockIdx.x): the CTAs of a tile are neighbours, the one with the last split finishes the tile
+    c.sk_tile = mn;
+    c.first_cta = t - c.split;
+    c.kind = (c.split == p.split_k - 1) ? WORK_SK_OWNER : WORK_SK_PARTIAL;
   }
   return true;
 }
@@ -937,10 +953,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // pass finds its code cached. The dry pass touches no global memory and therefore runs before griddepcontrol.wait.
     for (int it = (TR && p.epi_warm) ? -1 : 0;; ++it) {
       const bool dry = it < 0;
-      if (!dry && it == 0) grid_dep_wait();   // residual / output buffers may still be in use by the preceding kernel
-      if (!get_work(p, dry ? 0 : it, tc)) {
-        if (dry) continue;                     // no work at all for this CTA: fall through to it = 0, which breaks
-        break;
+      if (dry) {
+        // warm the path of the CTA's LAST item: that epilogue (plain tile or stream-K owner) is the one the next kernel
+        // waits for; earlier items overlap the main loop anyway
+        int n = 0;
+        while (get_work(p, n, tc)) ++n;
+        if (n == 0) continue;                  // no work at all for this CTA: it = 0 breaks
+        get_work(p, n - 1, tc);
+      } else {
+        if (it == 0) grid_dep_wait();          // residual / output buffers may still be in use by the preceding kernel
+        if (!get_work(p, it, tc)) break;
       }
       if (!dry) {
         mbar_wait(&acc_full[acc], acc_phase);

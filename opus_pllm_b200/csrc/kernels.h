@@ -48,6 +48,9 @@ int sample_top_p(const __nv_bfloat16* logits, int ld, int vocab, int n_rows, flo
 int cross_entropy_rows(const __nv_bfloat16* logits, int ld, int vocab, const int* target, float* loss, int n_rows,
                        cudaStream_t st);
 int embed_gather(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, int n_rows, int dim, cudaStream_t st);
+// embed_gather + per-32-feature-slab sums of squares of every gathered row: sumsq[slab][row] (norm-fused decode path)
+int embed_gather_sumsq(const int* tok, const __nv_bfloat16* table, __nv_bfloat16* x, float* sumsq, int sumsq_ld,
+                       int n_rows, int dim, cudaStream_t st);
 int decode_advance(int* ctx_len, int* pos, int* slot, const int* block_table, int max_blocks, int block_size, int n,
                    cudaStream_t st, int* step = nullptr);
 int lora_merge(__nv_bfloat16* W, const __nv_bfloat16* A, const __nv_bfloat16* B, int out_f, int in_f, int r, float scale,

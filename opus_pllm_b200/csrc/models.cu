@@ -454,6 +454,78 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
   const float scale = attn_scale(m);
 
   OPUS_TRY(decode_advance(s->ctx_len, s->pos, s->slot, s->block_table, s->max_blocks, kv->block_size, B, st, s->step));
+  if (B <= 64 && ctx().tun.decode_norm_fused && ctx().tun.decode_rope_fused && (d % 64) == 0) {
+    // Norm-fused form (5 launches per layer instead of 7): the RMSNorm kernels disappear.
+    //   * o_proj / down reduce their split-K partial sums INSIDE the GEMM (the CTA holding a tile's last k-split adds the
+    //     others' dumps in split order: same sums as the reduce kernel), apply the residual epilogue, write the residual
+    //     stream h and, per 32-feature slab and batch row, the sum of squares of what they stored;
+    //   * q|k|v and gate/up take the raw h as their activation operand: four extra warps rewrite every landed k-slice in
+    //     shared memory as bf16(gamma * bf16(h * rstd)) -- the rounding points of rmsnorm_bf16_kernel -- before the
+    //     tensor core reads it; rstd comes from the slab sums (fixed summation order).
+    // The only difference from the kernel-per-op path is the order in which the squares of a row are added up.
+    const int slabs = d / 32, sld = 64;
+    if (ws->partial_bytes < gemm_workspace_bytes(B, qkv_n, 1) + (size_t)slabs * sld * sizeof(float))
+      return fail(OPUS_ERR_ARG, "llama_decode_step: split-K workspace too small for the norm-fused path");
+    float* sumsq = ws->partial + ws->partial_bytes / sizeof(float) - (size_t)slabs * sld;
+    const size_t part_bytes = ws->partial_bytes - (size_t)slabs * sld * sizeof(float);
+    OPUS_TRY(embed_gather_sumsq(s->next_tok, static_cast<const bf16*>(m->embed), h, sumsq, sld, B, d, st));
+    auto normed = [&](GemmArgs& a, const void* gamma) {
+      a.norm_sumsq = sumsq; a.norm_slabs = slabs; a.norm_ld = sld; a.norm_gamma = gamma; a.norm_eps = m->rms_eps;
+    };
+    auto reduced_residual = [&](const void* x, const void* w, int K, int split) {
+      GemmArgs a{};
+      a.transposed = 1;
+      a.A = w; a.lda = K; a.M = d;
+      a.B = x; a.ldb = K; a.N = B;
+      a.K = K;
+      a.epi = EPI_RES_BF16;
+      a.out = h; a.ldo = d;
+      a.residual = h; a.ldr = d;
+      a.split_k = split; a.splitk_fixup = 1;
+      a.sumsq_out = sumsq; a.sumsq_ld = sld;
+      return gemm_bf16(a, st);
+    };
+    const int sp_o = splitk_for(B, d, Hq * hd, part_bytes), sp_down = splitk_for(B, d, ffn, part_bytes);
+    for (int l = 0; l < m->n_layers; ++l) {
+      const opus_llama_layer& L = m->layers[l];
+      bf16* kc = static_cast<bf16*>(kv->k) + (size_t)l * layer_stride;
+      bf16* vc = static_cast<bf16*>(kv->v) + (size_t)l * layer_stride;
+      const int sp = splitk_for(B, qkv_n, d, part_bytes);
+      {
+        GemmArgs a{};
+        a.transposed = 1;
+        a.A = L.wqkv; a.lda = d; a.M = qkv_n;
+        a.B = h; a.ldb = d; a.N = B;
+        a.K = d;
+        a.epi = EPI_PARTIAL_F32;
+        a.out = ws->partial; a.ldo = qkv_n;
+        a.split_k = sp;
+        normed(a, L.ln1_w);
+        OPUS_TRY(gemm_bf16(a, st));
+      }
+      OPUS_TRY(attn_decode_paged_fused(qkv, qkv_n, ws->partial, sp, s->pos, s->slot,
+                                       static_cast<const bf16*>(m->rope_cos), static_cast<const bf16*>(m->rope_sin), kc,
+                                       vc, s->block_table, s->max_blocks, s->ctx_len, attn, Hq * hd, B, Hq, Hkv, hd,
+                                       kv->block_size, scale, st, L.bqkv));
+      OPUS_TRY(reduced_residual(attn, L.wo, Hq * hd, sp_o));
+      {
+        GemmArgs a{};
+        a.transposed = 1;
+        a.A = L.wgu; a.lda = d; a.M = 2 * ffn;
+        a.B = h; a.ldb = d; a.N = B;
+        a.K = d;
+        a.epi = EPI_SWIGLU;
+        a.out = act; a.ldo = ffn;
+        normed(a, L.ln2_w);
+        OPUS_TRY(gemm_bf16(a, st));
+      }
+      OPUS_TRY(reduced_residual(act, L.wdown, ffn, sp_down));
+    }
+    OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(m->norm_w), xn, B, d, m->rms_eps, st));
+    OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(llama_select(m, ws, s, B, st));
+    return OPUS_OK;
+  }
   OPUS_TRY(embed_gather(s->next_tok, static_cast<const bf16*>(m->embed), h, B, d, st));
   OPUS_TRY(rmsnorm_bf16(h, nullptr, 0, nullptr, nullptr, static_cast<const bf16*>(m->layers[0].ln1_w), xn, B, d,
                         m->rms_eps, st));

@@ -174,7 +174,8 @@ class B200Llama:
             rows = max(rows, self._ws_rows, 256)
             n_seqs = max(n_seqs, self._ws_seqs, 8)
             dev, bf = self.device, torch.bfloat16
-            part_bytes = 16 * n_seqs * max(self.qkv_n, self.dim) * 4
+            # split-K partial sums (up to 16 slices) + the per-slab sums of squares of the norm-fused decode path
+            part_bytes = 16 * n_seqs * max(self.qkv_n, self.dim) * 4 + (self.dim // 32) * 64 * 4
             b = dict(h=torch.empty((rows, self.dim), dtype=bf, device=dev),
                      xn=torch.empty((rows, self.dim), dtype=bf, device=dev),
                      qkv=torch.empty((rows, self.qkv_n), dtype=bf, device=dev),

@@ -278,6 +278,43 @@ def test_decode_fused_chain_matches_kernel_per_op(cfg, batch):
     assert _cos(fused_logits, plain_logits) >= 0.995
 
 
+@pytest.mark.parametrize("cfg,batch,qkv_bias", [(SMALL, 32, False), (SMALL, 5, True), (SMALL, 50, False),
+                                                 (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
+                                                       ffn_dim=14336, vocab=32768), 64, False)])
+def test_decode_norm_fused_matches_kernel_per_op(cfg, batch, qkv_bias):
+    """Norm-fused decode (tunable decode_norm_fused): o_proj / down reduce their split-K sums inside the GEMM and emit the
+    per-slab sums of squares, q|k|v and gate/up normalise the raw residual stream on its way into the tensor cores. Same
+    rounding points as the kernel-per-op path except the order of the RMSNorm sum of squares: tokens equal (peaked
+    weights), last-step logits equal to bf16 noise; graph and eager launches bit-identical; and the oracle agrees."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    w = synth.llama_weights(seed=4, peaked=True, device="cuda", qkv_bias=qkv_bias,
+                            **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [17 + (i * 5) % 40 for i in range(batch)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(6))
+    emb = w["model.embed_tokens.weight"][tok.cuda()].to(torch.bfloat16)
+    lib = L.load()
+    try:
+        L.check(lib.opus_set_tunable(b"decode_norm_fused", 1))
+        fused = model.generate_packed(emb, cu, 12)
+        fused_logits = model._ws_bufs["logits"][:batch].float().clone()
+        fused_eager = model.generate_packed(emb, cu, 12, use_graph=False)
+        L.check(lib.opus_set_tunable(b"decode_norm_fused", 0))
+        plain = model.generate_packed(emb, cu, 12)
+        plain_logits = model._ws_bufs["logits"][:batch].float().clone()
+    finally:
+        L.check(lib.opus_set_tunable(b"decode_norm_fused", 0))
+    assert torch.equal(fused, fused_eager)
+    assert torch.equal(fused, plain), float((fused == plain).float().mean())
+    assert _cos(fused_logits, plain_logits) >= 0.995
+    if cfg is SMALL:
+        e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+        want = llama_ref.greedy_generate(_dev(w, torch.bfloat16), _oracle_cfg(cfg), e_pad, m_pad, 12)
+        assert float((fused.cpu() == want.cpu()).all(1).float().mean()) >= 0.99
+
+
 @pytest.mark.parametrize("cfg,batch", [(SMALL, 9), (dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128,
                                                         ffn_dim=14336, vocab=8192), 64)])
 def test_decode_rope_fused_into_attention_is_bit_identical(cfg, batch):

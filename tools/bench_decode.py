@@ -46,7 +46,6 @@ def setk(**kw):
         L.check(lib.opus_set_tunable(k.encode(), v), k)
 
 
-run("defaults (kernel per op, PDL chain)")
 def after_prefill(label):
     # the same decode loop timed right after a prefill, as inside bench.py (clock / power state carried over)
     tot = 0.0
@@ -62,8 +61,16 @@ def after_prefill(label):
     print(f"{label:40s} {ms:7.3f} ms/step  {bytes_step / ms / 1e6:7.0f} GB/s  frac {bytes_step / ms / 1e6 / 6551.4:.3f}", flush=True)
 
 
+run("defaults (kernel per op, PDL chain)")
 if os.environ.get("AFTER_PREFILL"):
     after_prefill("decode timed right after a prefill")
+if os.environ.get("NORMF"):
+    setk(decode_norm_fused=1); run("decode_norm_fused=1 (5 launches per layer)")
+    if os.environ.get("AFTER_PREFILL"):
+        after_prefill("norm-fused right after a prefill")
+    setk(decode_norm_fused=0)
+if os.environ.get("AFTER_PREFILL"):
+    pass
     if os.environ.get("FUSED"):
         setk(decode_fused=1); run("decode_fused=1 (chain kernel)"); after_prefill("chain kernel right after a prefill")
         setk(decode_fused=0)
