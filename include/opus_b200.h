@@ -90,6 +90,21 @@ int opus_device_check(void);
 int opus_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int transposed, int epilogue,
                    void* out, int ldo, const float* bias, const void* residual, int ldr, int split_k, int block_n,
                    void* stream);
+/* Swap-AB GEMM (transposed = 1 semantics of opus_gemm_bf16: A = weight [M = out_features, K], B = activations [N = batch
+ * rows <= 256, K]) with the fusions of the norm-fused decode step (HF LlamaDecoderLayer reached from opus_llama.py:127-132):
+ *   splitk_fixup != 0 : split_k > 1 is reduced INSIDE the kernel (the CTA holding a tile's last k-split adds the other
+ *                       splits' accumulators in split order), so any epilogue works with split_k > 1; needs
+ *                       ceil(M/128) * split_k <= SM count. Replaces the separate reduce (opus_rmsnorm_bf16 with partials).
+ *   sumsq_out != NULL : OPUS_EPI_RES_BF16 only. sumsq_out[slab * sumsq_ld + n] = sum over the 32 features of slab
+ *                       (= feature / 32) of the squares of the bf16 values stored for batch row n (fp32; one writer each).
+ *   norm_sumsq != NULL: batch <= 64, K % 64 == 0. The activation operand is the raw residual stream h; every k-slice is
+ *                       rewritten in shared memory as bf16(norm_gamma[k] * bf16(h[n,k] * rstd[n])) before the tensor core
+ *                       reads it, rstd[n] = rsqrt(sum_slab norm_sumsq[slab * norm_ld + n] / K + norm_eps): HF
+ *                       LlamaRMSNorm with its rounding points, without a norm kernel or a normalised copy in HBM. */
+int opus_gemm_bf16_fused(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, void* out,
+                         int ldo, const float* bias, const void* residual, int ldr, int split_k, int splitk_fixup,
+                         float* sumsq_out, int sumsq_ld, const float* norm_sumsq, int norm_slabs, int norm_ld,
+                         const void* norm_gamma, float norm_eps, void* stream);
 /* Suggested split-K factor for a (rows of A = M, rows of B = N, K) problem; 1 = none. */
 int opus_gemm_suggest_split_k(int M, int N, int K, int transposed);
 /* out bf16 [rows, cols] = sum_s partial[s][rows][cols] (+ bias[col]) (optionally erf-GELU). */

@@ -92,6 +92,8 @@ _SIGNATURES = {
     "opus_ctx_set_current": (c_int, [c_void_p]),
     "opus_gemm_bf16": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int,
                                c_int, c_int, _P]),
+    "opus_gemm_bf16_fused": (c_int, [_P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, _P, c_int, c_int,
+                                     c_int, _P, c_int, _P, c_int, c_int, _P, c_float, _P]),
     "opus_gemm_suggest_split_k": (c_int, [c_int, c_int, c_int, c_int]),
     "opus_splitk_reduce_bf16": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "opus_esm_embed": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),

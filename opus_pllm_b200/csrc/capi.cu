@@ -82,6 +82,23 @@ int opus_gemm_bf16(const void* A, int lda, const void* B, int ldb, int M, int N,
   RET(gemm_bf16(a, ST(stream)), "opus_gemm_bf16");
 }
 
+int opus_gemm_bf16_fused(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int epilogue, void* out,
+                         int ldo, const float* bias, const void* residual, int ldr, int split_k, int splitk_fixup,
+                         float* sumsq_out, int sumsq_ld, const float* norm_sumsq, int norm_slabs, int norm_ld,
+                         const void* norm_gamma, float norm_eps, void* stream) {
+  if (!A || !B || !out) return fail(OPUS_ERR_ARG, "opus_gemm_bf16_fused: null pointer");
+  GemmArgs a{};
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb;
+  a.M = M; a.N = N; a.K = K;
+  a.transposed = 1; a.epi = epilogue;
+  a.out = out; a.ldo = ldo; a.bias = bias; a.residual = residual; a.ldr = ldr;
+  a.split_k = split_k; a.splitk_fixup = splitk_fixup;
+  a.sumsq_out = sumsq_out; a.sumsq_ld = sumsq_ld;
+  a.norm_sumsq = norm_sumsq; a.norm_slabs = norm_slabs; a.norm_ld = norm_ld;
+  a.norm_gamma = norm_gamma; a.norm_eps = norm_eps;
+  RET(gemm_bf16(a, ST(stream)), "opus_gemm_bf16_fused");
+}
+
 int opus_gemm_suggest_split_k(int M, int N, int K, int transposed) {
   return gemm_pick_split_k(M, N, K, gemm_pick_bn(N, transposed));
 }

@@ -84,17 +84,16 @@ __device__ __forceinline__ void raster_mn(const GemmParams& p, int mn, int& m, i
 //     most two tiles: the head of a tile it does not finish (partial dump) and the tail of a tile it finishes (owner:
 //     fix-up + epilogue);
 //   * round-robin items t = blockIdx.x + i * gridDim.x < dp_items: whole (m, n, k-split) tiles.
-// Order: the PARTIAL piece FIRST, then the round-robin tiles, then the piece(s) this CTA finishes. A dump therefore
-// happens a whole tile before any owner asks for it (its store + fence + flag latency leaves the critical path, and no
-// CTA ever waits on a CTA that is itself waiting), and the fix-up is the last thing a CTA does.
+// Order: round-robin tiles first, then the partial piece, then the piece(s) this CTA finishes (no CTA ever waits on a CTA
+// that is itself waiting). Walking the partial piece before the tiles was measured slower (gate/up 42.4 -> 43.7 us).
 __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord& c) {
   const int b = blockIdx.x, g = gridDim.x;
   c.kind = WORK_TILE; c.sk_tile = 0; c.first_cta = 0;
   const int n_dp = b < p.dp_items ? (p.dp_items - b + g - 1) / g : 0;
   // ---- tail pieces of this CTA
   int n_pre = 0, n_post = 0;
-  int tile[2], k0[2], k1[2];        // [0] = piece walked before the tiles (partial), [1], [2] -> see below
-  int ptile[2], pk0[2], pk1[2];     // post pieces, in walking order
+  int tile[1], k0[1], k1[1];        // the piece this CTA does not finish (partial dump), if any
+  int ptile[2], pk0[2], pk1[2];     // the piece(s) it finishes, in walking order
   const int kb = p.k_blocks;
   if (p.sk_tiles > 0) {
     const long long U = (long long)p.sk_tiles * kb;
@@ -112,8 +111,8 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
         add(tB, 0, u1 - tB * kb);        // head of the next tile
         add(tA, u0 - tA * kb, kb);       // tail of the previous tile
       }
-      if (it >= n_pre + n_dp) {
-        const int j = it - n_pre - n_dp;
+      if (it >= n_dp + n_pre) {
+        const int j = it - n_dp - n_pre;
         if (j >= n_post) return false;
         c.split = 0;
         raster_mn(p, p.dp_items + ptile[j], c.m, c.n);       // stream-K is only used with split_k == 1
@@ -124,7 +123,7 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
         c.kind = (c.first_cta == b) ? WORK_TILE : WORK_SK_OWNER;  // whole tile in this CTA's range: nothing to fix up
         return true;
       }
-      if (it < n_pre) {
+      if (it >= n_dp) {
         c.split = 0;
         raster_mn(p, p.dp_items + tile[0], c.m, c.n);
         c.kb_begin = k0[0]; c.kb_end = k1[0];
@@ -134,9 +133,8 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
       }
     }
   }
-  const int i = it - n_pre;
-  if (i >= n_dp) return false;
-  const int t = b + i * g;
+  if (it >= n_dp) return false;
+  const int t = b + it * g;
   const int mn = t / p.split_k;
   c.split = t - mn * p.split_k;
   raster_mn(p, mn, c.m, c.n);
@@ -787,7 +785,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_init(&acc_empty[a], NUM_EPI_THREADS);
     }
     if constexpr (NORM)
-      for (int s = 0; s < C::STAGES; ++s) mbar_init(&xf_bar[s], 128);
+      for (int s = 0; s < C::STAGES; ++s) mbar_init(&xf_bar[s], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -802,58 +800,70 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (NORM && warp >= 10) {
     // ===================== RMSNorm warps (10..13): activation k-slices, in place =====================
     const int tt = threadIdx.x - NUM_THREADS;                                 // 0..127
+    const int nw = warp - 10;                                                 // this warp takes k-blocks nw, nw + 4, ...
     float* s_rstd = reinterpret_cast<float*>(smem + C::BARS_OFF + 256);       // [64] row scales, then [64] scratch
     grid_dep_wait();                                                          // nl_sumsq comes from the preceding kernels
     {
       // rstd[row] from the per-slab sums of squares: two threads per row, each sums one half of the slabs in slab
-      // order, halves combined lower + upper (fixed order -> bit-reproducible)
+      // order (loads issued sixteen at a time), halves combined lower + upper: fixed order -> bit-reproducible
       const int row = tt & 63, half = tt >> 6;
       float acc = 0.f;
       if (row < p.N) {
         const int mid = p.nl_slabs >> 1;
         const int s0 = half ? mid : 0, s1 = half ? p.nl_slabs : mid;
         const float* src = p.nl_sumsq + row;
-#pragma unroll 8
-        for (int sl = s0; sl < s1; ++sl) acc += __ldcg(src + (size_t)sl * p.nl_ld);
+        for (int sl = s0; sl < s1; sl += 16) {
+          float t[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) t[u] = (sl + u < s1) ? __ldcg(src + (size_t)(sl + u) * p.nl_ld) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) acc += t[u];
+        }
       }
       if (half) s_rstd[64 + row] = acc;
       named_bar_sync(3, 128);
       if (!half) s_rstd[row] = row < p.N ? rsqrtf((acc + s_rstd[64 + row]) / (float)p.K + p.nl_eps) : 0.f;
       named_bar_sync(3, 128);
     }
-    // thread -> 16-byte chunk position `cpos` of rows row0, row0 + 16, ...: (row & 7) is the same for all of them, so the
-    // logical k-chunk behind the 128-byte swizzle (cpos ^ (row & 7)) and with it the gamma slice is fixed per thread
-    const int cpos = tt & 7, row0 = tt >> 3;
-    const int kchunk = cpos ^ (row0 & 7);
-    const __nv_bfloat16* gam = static_cast<const __nv_bfloat16*>(p.nl_gamma) + kchunk * 8;
-    float rs[BN / 16];
+    // Each warp owns whole k-slices (every fourth one), so four slices are in flight and the wait / fence latency of one
+    // overlaps the arithmetic of the others. Lane -> 16-byte chunk position `cpos` of rows r0, r0 + 4, r0 + 8, ...:
+    // (row & 7) alternates between r0 and r0 + 4, so the logical k-chunk behind the 128-byte swizzle (cpos ^ (row & 7))
+    // and with it the gamma slice alternates between two values per lane.
+    const int cpos = lane & 7, r0 = lane >> 3;
+    const __nv_bfloat16* gam0 = static_cast<const __nv_bfloat16*>(p.nl_gamma) + (cpos ^ r0) * 8;
+    const __nv_bfloat16* gam1 = static_cast<const __nv_bfloat16*>(p.nl_gamma) + (cpos ^ (r0 + 4)) * 8;
+    float rs[BN / 4];
 #pragma unroll
-    for (int i = 0; i < BN / 16; ++i) rs[i] = s_rstd[row0 + 16 * i];
-    int stage = 0;
-    uint32_t phase = 0;
+    for (int i = 0; i < BN / 4; ++i) rs[i] = s_rstd[r0 + 4 * i];
+    int gidx = 0;                                                             // k-slices of this CTA, over all its items
     TileCoord tc;
     for (int it = 0; get_work(p, it, tc); ++it) {
-      for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb) {
-        const uint4 gq = __ldg(reinterpret_cast<const uint4*>(gam + (size_t)kb * BK));   // in flight across the wait
+      for (int kb = tc.kb_begin; kb < tc.kb_end; ++kb, ++gidx) {
+        if ((gidx & 3) != nw) continue;
+        const int stage = gidx % C::STAGES;
+        const uint32_t phase = (uint32_t)(gidx / C::STAGES) & 1u;
+        const uint4 gq0 = __ldg(reinterpret_cast<const uint4*>(gam0 + (size_t)kb * BK));   // in flight across the wait
+        const uint4 gq1 = __ldg(reinterpret_cast<const uint4*>(gam1 + (size_t)kb * BK));
         mbar_wait(&full_bar[stage], phase);
-        uint8_t* sb = smem + stage * C::STAGE + C::STAGE_A + row0 * 128 + cpos * 16;
-        float gf[8];
-        bf16x8_unpack(gq, gf);
+        uint8_t* sb = smem + stage * C::STAGE + C::STAGE_A + r0 * 128 + cpos * 16;
+        float g0[8], g1[8];
+        bf16x8_unpack(gq0, g0);
+        bf16x8_unpack(gq1, g1);
 #pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-          uint4* ptr = reinterpret_cast<uint4*>(sb + i * 16 * 128);
+        for (int i = 0; i < BN / 4; ++i) {
+          uint4* ptr = reinterpret_cast<uint4*>(sb + i * 4 * 128);
           float x[8], o[8];
           bf16x8_unpack(*ptr, x);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = gf[j] * bf16_round(x[j] * rs[i]);
+          for (int j = 0; j < 8; ++j) o[j] = ((i & 1) ? g1[j] : g0[j]) * bf16_round(x[j] * rs[i]);
           uint4 q;
           q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
           q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
           *ptr = q;
         }
         fence_proxy_async();               // generic-proxy writes -> visible to the tensor core's (async proxy) reads
-        mbar_arrive(&xf_bar[stage]);
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[stage]);
       }
     }
   } else if (warp == 0) {

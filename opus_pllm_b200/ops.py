@@ -57,6 +57,31 @@ def launch_count(reset: bool = False) -> int:
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
+def gemm_fused(x: torch.Tensor, w: torch.Tensor, *, epilogue: int = L.EPI_BF16, bias: torch.Tensor | None = None,
+               residual: torch.Tensor | None = None, out: torch.Tensor | None = None, split_k: int = 0,
+               splitk_fixup: bool = False, sumsq_out: torch.Tensor | None = None, norm_sumsq: torch.Tensor | None = None,
+               norm_gamma: torch.Tensor | None = None, norm_eps: float = 1e-5) -> torch.Tensor:
+    """Swap-AB y = epilogue(f(x) @ w.T) with the decode-step fusions of opus_gemm_bf16_fused: in-kernel split-K reduce,
+    per-slab sums of squares of an EPI_RES_BF16 result (sumsq_out fp32 [N_out/32, ld >= rows]), RMSNorm of the activation
+    operand on load (norm_sumsq fp32 [slabs, ld >= rows], norm_gamma bf16 [K]; x is then the raw residual stream)."""
+    _chk(x, BF16, "x"); _chk(w, BF16, "w")
+    rows, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if epilogue == L.EPI_SWIGLU else N
+    if out is None:
+        out = (torch.empty((max(split_k, 1), rows, N), dtype=F32, device=x.device) if epilogue == L.EPI_PARTIAL_F32
+               else torch.empty((rows, n_out), dtype=BF16, device=x.device))
+    rc = L.load().opus_gemm_bf16_fused(
+        _p(w), w.stride(0), _p(x), x.stride(0), N, rows, K, epilogue, _p(out), out.stride(-2), _p(bias), _p(residual),
+        0 if residual is None else residual.stride(0), split_k, int(splitk_fixup),
+        _p(sumsq_out), 0 if sumsq_out is None else sumsq_out.stride(0),
+        _p(norm_sumsq), 0 if norm_sumsq is None else norm_sumsq.shape[0], 0 if norm_sumsq is None else norm_sumsq.stride(0),
+        _p(norm_gamma), norm_eps, _stream())
+    L.check(rc, "opus_gemm_bf16_fused")
+    return out
+
+
+
 def gemm(x: torch.Tensor, w: torch.Tensor, *, epilogue: int = L.EPI_BF16, bias: torch.Tensor | None = None,
          residual: torch.Tensor | None = None, out: torch.Tensor | None = None, transposed: bool | None = None,
          split_k: int = 0, block_n: int = 0) -> torch.Tensor:

@@ -538,3 +538,51 @@ def test_attn_decode_paged(ops, ctxs, Hq, Hkv):
         vv = vc[blocks].permute(0, 2, 1, 3).reshape(-1, Hkv, D)[:n]
         want = R.attention_ref(q[b].view(1, Hq, D), kk, vv, False, sc)
         _close_bf16(got[b].view(1, Hq, D), want, ulps=2.0, atol=8e-3)
+
+
+# ------------------------------------------------------------------------------------------------ norm-fused decode GEMMs
+@pytest.mark.parametrize("rows,n_out,K,split", [(64, 4096, 4096, 4), (50, 4096, 14336, 4), (7, 512, 1024, 2), (32, 1024, 512, 2)])
+def test_gemm_inkernel_splitk_residual_and_sumsq(rows, n_out, K, split):
+    """o_proj / down of the norm-fused decode step: split-K reduced inside the kernel (same slice order as the reduce
+    kernel), h = bf16(residual + bf16(sum)) in place, plus the per-32-feature-slab sums of squares of the stored values."""
+    from opus_pllm_b200 import _lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(rows + K)
+    x = (torch.randn(rows, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(n_out, K, device="cuda", generator=g) * 0.05).bfloat16()
+    res = torch.randn(rows, n_out, device="cuda", generator=g).bfloat16()
+    # reference: the existing two-kernel path (split-K partials + fused reduce/residual)
+    part = ops.gemm(x, w, epilogue=L.EPI_PARTIAL_F32, transposed=True, split_k=split)
+    want_h = res.clone()
+    ops.rmsnorm(None, None, partial=part, residual=res, h_out=want_h, normalise=False)
+    h = res.clone()
+    sumsq = torch.full((n_out // 32, 64), -1.0, device="cuda")
+    ops.gemm_fused(x, w, epilogue=L.EPI_RES_BF16, residual=h, out=h, split_k=split, splitk_fixup=True, sumsq_out=sumsq)
+    assert torch.equal(h, want_h)                                     # bit-identical: same partial sums, same order
+    want_sq = want_h.float().pow(2).reshape(rows, n_out // 32, 32).sum(-1).T           # [slab, row]
+    assert torch.allclose(sumsq[:, :rows], want_sq, rtol=1e-5, atol=1e-6)
+    assert bool((sumsq[:, rows:] == -1.0).all())                      # rows beyond the batch are not touched
+
+
+@pytest.mark.parametrize("rows,n_out,K,epi", [(64, 6144, 4096, "partial"), (64, 28672, 4096, "swiglu"), (19, 1024, 512, "bf16"),
+                                              (40, 2048, 1024, "swiglu")])
+def test_gemm_rmsnorm_on_load(rows, n_out, K, epi):
+    """q|k|v / gate-up of the norm-fused decode step: the activation operand is the raw residual stream, normalised in
+    shared memory on its way to the tensor cores. Against rmsnorm kernel + plain GEMM: identical except where the
+    different order of the sum of squares moves rstd by an ulp."""
+    from opus_pllm_b200 import _lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(rows * 3 + K)
+    h = (torch.randn(rows, K, device="cuda", generator=g) * 1.5).bfloat16()
+    w = (torch.randn(n_out, K, device="cuda", generator=g) * 0.03).bfloat16()
+    gamma = (1.0 + 0.1 * torch.randn(K, device="cuda", generator=g)).bfloat16()
+    code = {"partial": L.EPI_PARTIAL_F32, "swiglu": L.EPI_SWIGLU, "bf16": L.EPI_BF16}[epi]
+    split = 3 if epi == "partial" else 0
+    xn = ops.rmsnorm(h, gamma, 1e-5)
+    want = ops.gemm(xn, w, epilogue=code, transposed=True, split_k=split)
+    sumsq = torch.zeros((K // 32, 64), device="cuda")
+    sumsq[:, :rows] = h.float().pow(2).reshape(rows, K // 32, 32).sum(-1).T
+    got = ops.gemm_fused(h, w, epilogue=code, split_k=split, norm_sumsq=sumsq, norm_gamma=gamma, norm_eps=1e-5)
+    assert got.shape == want.shape
+    a, b = got.float(), want.float()
+    assert float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)) >= 0.99999
+    assert float((a - b).abs().max()) <= 2.0 ** -6 * float(b.abs().max())
+    assert float((a != b).float().mean()) <= 0.02            # only rstd-ulp rows may differ at all

@@ -17,6 +17,7 @@ gam = torch.ones(D, device="cuda").bfloat16()
 x = rnd(B, D); attn = rnd(B, D); act = rnd(B, F)
 h = rnd(B, D); xn = rnd(B, D)
 part = torch.empty((4, B, QKV), dtype=torch.float32, device="cuda")
+sumsq = torch.rand((D // 32, 64), device="cuda") * 32
 P = L.EPI_PARTIAL_F32
 
 
@@ -36,6 +37,16 @@ def seq(steps):
                     cur[0] = ops.rmsnorm(None, gam, partial=part.view(-1)[: 4 * B * D].view(4, B, D), residual=h, h_out=h)
                 elif s == "gu":
                     ops.gemm(cur[0], wgu[i], epilogue=L.EPI_SWIGLU, transposed=True, out=act)
+                elif s == "o_fix":      # in-kernel split-K reduce + residual + sumsq
+                    ops.gemm_fused(attn, wo[i], epilogue=L.EPI_RES_BF16, residual=h, out=h, split_k=4, splitk_fixup=True,
+                                   sumsq_out=sumsq)
+                elif s == "down_fix":
+                    ops.gemm_fused(act, wd[i], epilogue=L.EPI_RES_BF16, residual=h, out=h, split_k=4, splitk_fixup=True,
+                                   sumsq_out=sumsq)
+                elif s == "gu_n":       # RMSNorm of the activation operand on load
+                    ops.gemm_fused(h, wgu[i], epilogue=L.EPI_SWIGLU, out=act, norm_sumsq=sumsq, norm_gamma=gam)
+                elif s == "qkv_n":
+                    ops.gemm_fused(h, wq[i], epilogue=P, split_k=3, out=part[:3, :, :QKV], norm_sumsq=sumsq, norm_gamma=gam)
                 elif s == "down":
                     ops.gemm(act, wd[i], epilogue=P, transposed=True, split_k=4, out=part.view(-1)[: 4 * B * D].view(4, B, D))
     body(); torch.cuda.synchronize()
@@ -57,6 +68,7 @@ for warm in ((0, 1) if os.environ.get("WARM_AB") else (None,)):
         L.check(lib.opus_set_tunable(b"epi_warm", warm))
         print(f"-- epi_warm = {warm}")
     for steps in (["o"], ["o", "norm"], ["gu"], ["o", "norm", "gu"], ["down"], ["gu", "down"], ["gu", "down", "norm"],
-                  ["o", "norm", "gu", "down", "norm"], ["qkv"], ["o", "norm", "gu", "down", "norm", "qkv"]):
+                  ["o", "norm", "gu", "down", "norm"], ["qkv"], ["o", "norm", "gu", "down", "norm", "qkv"],
+                  ["o_fix"], ["gu_n"], ["down_fix"], ["qkv_n"], ["o_fix", "gu_n"], ["o_fix", "gu_n", "down_fix", "qkv_n"]):
         us = seq(steps)
         print(f"{'+'.join(steps):36s} {us:7.1f} us per repetition", flush=True)
