@@ -16,6 +16,7 @@
 #include "ptx.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace opus {
 
@@ -309,6 +310,13 @@ struct DecodeParams {
   __nv_bfloat16* kcache_w;
   __nv_bfloat16* vcache_w;
   const float* bias;           // fp32 [ldq] q|k|v projection bias (Qwen2) or nullptr
+  // Split-KV: the context of one (sequence, kv head) is cut into n_split page ranges handled by n_split CTAs (gridDim.z),
+  // so the work units are fine enough to balance over the SMs (batch 64: 512 units on 148 SMs leave 68 SMs with four
+  // units and 80 with three; 1024 half-units are handed out as CTA slots free up). Each CTA writes its un-normalised
+  // (max, sum, acc) to split_ws; the CTA that arrives LAST at split_cnt[unit] merges all parts in part order.
+  int n_split;
+  float* split_ws;             // [units][n_split][GROUP][DEC_D + 2] fp32
+  int* split_cnt;              // [units], zero before the launch; the merging CTA re-arms its entry
 };
 
 __device__ __forceinline__ void load_panel_async(uint32_t smem_base, const __nv_bfloat16* panel, int lane) {
@@ -333,6 +341,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
   // after its own griddepcontrol.wait), so they may be read before OUR wait; only the GEMM's output may not.
   const int ctx = p.ctx_len[b];
   const int n_blocks = (ctx + DEC_BS - 1) / DEC_BS;
+  const int part = blockIdx.z, per_part = (n_blocks + p.n_split - 1) / p.n_split;
+  const int blk_begin = min(n_blocks, part * per_part), blk_end = min(n_blocks, blk_begin + per_part);
+  const bool owns_last = n_blocks == 0 ? part == 0 : (blk_begin <= n_blocks - 1 && n_blocks - 1 < blk_end);
   const uint32_t s_warp = smem_u32(smem) + warp * (4 * DEC_PANEL);
   float* s_merge = reinterpret_cast<float*>(smem + DEC_WARPS * 4 * DEC_PANEL);  // [warps][GROUP][128+2]
   const int* bt = p.block_table + (size_t)b * p.max_blocks;
@@ -342,10 +353,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
   // The first K/V panels of this warp are cached tokens of EARLIER steps unless the block holds the token appended by
   // this step (the last block): request them before waiting for the preceding kernel, so the page fetch overlaps its
   // tail, the split-K reduce and the RoPE below.
-  const bool early = p.partial != nullptr && warp < n_blocks - 1;
+  const bool early = p.partial != nullptr && blk_begin + warp < blk_end && blk_begin + warp < n_blocks - 1;
   if (early) {
-    load_panel_async(s_warp, panel_ptr(p.kcache, warp), lane);
-    load_panel_async(s_warp + DEC_PANEL, panel_ptr(p.vcache, warp), lane);
+    load_panel_async(s_warp, panel_ptr(p.kcache, blk_begin + warp), lane);
+    load_panel_async(s_warp + DEC_PANEL, panel_ptr(p.vcache, blk_begin + warp), lane);
   }
   grid_dep_wait();
 
@@ -353,7 +364,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
     // ---- fused split-K reduce + RoPE + KV append for the heads of this (sequence, kv head) ----
     const int B = gridDim.y, Hq = p.n_kv_heads * GROUP;
     const int pos = p.pos[b], sl = p.slot[b];
-    for (int t = threadIdx.x; t < (GROUP + 2) * 8; t += DEC_WARPS * 32) {
+    // every part needs the rotated query heads (identical values, written by all of them); the new key / value row is
+    // reduced, rotated and appended by the part whose page range holds it
+    for (int t = threadIdx.x; t < (owns_last ? GROUP + 2 : GROUP) * 8; t += DEC_WARPS * 32) {
       const int hh = t >> 3, j0 = (t & 7) * 8;          // head of this CTA, first of 8 rotation pairs
       const bool is_k = hh == GROUP, is_v = hh == GROUP + 1;
       const int hcol = (hh < GROUP ? kvh * GROUP + hh : (is_k ? Hq + kvh : Hq + p.n_kv_heads + kvh)) * DEC_D;
@@ -430,15 +443,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
   float m_run = -INFINITY, l_run = 0.f;
 
   int it = 0;
-  if (!early && warp < n_blocks) {
-    load_panel_async(s_warp, panel_ptr(p.kcache, warp), lane);
-    load_panel_async(s_warp + DEC_PANEL, panel_ptr(p.vcache, warp), lane);
+  if (!early && blk_begin + warp < blk_end) {
+    load_panel_async(s_warp, panel_ptr(p.kcache, blk_begin + warp), lane);
+    load_panel_async(s_warp + DEC_PANEL, panel_ptr(p.vcache, blk_begin + warp), lane);
   }
   cp_async_commit();
-  for (int blk = warp; blk < n_blocks; blk += DEC_WARPS, ++it) {
+  for (int blk = blk_begin + warp; blk < blk_end; blk += DEC_WARPS, ++it) {
     const int st = it & 1;
     const int nxt = blk + DEC_WARPS;
-    if (nxt < n_blocks) {
+    if (nxt < blk_end) {
       load_panel_async(s_warp + (st ^ 1) * 2 * DEC_PANEL, panel_ptr(p.kcache, nxt), lane);
       load_panel_async(s_warp + (st ^ 1) * 2 * DEC_PANEL + DEC_PANEL, panel_ptr(p.vcache, nxt), lane);
     }
@@ -520,19 +533,69 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) attn_decode_paged_kernel(const
     if (t4 == 0) { dst[DEC_D] = m_run; dst[DEC_D + 1] = l_run; }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < GROUP * DEC_D; idx += DEC_WARPS * 32) {
-    const int hh = idx / DEC_D, c = idx - hh * DEC_D;
+  if (p.n_split <= 1) {
+    for (int idx = threadIdx.x; idx < GROUP * DEC_D; idx += DEC_WARPS * 32) {
+      const int hh = idx / DEC_D, c = idx - hh * DEC_D;
+      float mmax = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < DEC_WARPS; ++w) mmax = fmaxf(mmax, s_merge[((size_t)w * GROUP + hh) * MS + DEC_D]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int w = 0; w < DEC_WARPS; ++w) {
+        const float* src = s_merge + ((size_t)w * GROUP + hh) * MS;
+        const float mw = src[DEC_D];
+        const float sc = (mw == -INFINITY) ? 0.f : exp2f(mw - mmax);
+        num += src[c] * sc;
+        den += src[DEC_D + 1] * sc;
+      }
+      p.o[(size_t)b * p.ldo + (size_t)(kvh * GROUP + hh) * DEC_D + c] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
+    }
+    return;
+  }
+  // ---- split-KV: publish this part's (acc, max, sum) per head, the last part to arrive merges them in part order
+  const int unit = b * p.n_kv_heads + kvh;
+  float* mine = p.split_ws + ((size_t)unit * p.n_split + part) * GROUP * MS;
+  for (int idx = threadIdx.x; idx < GROUP * MS; idx += DEC_WARPS * 32) {
+    const int hh = idx / MS, c = idx - hh * MS;
     float mmax = -INFINITY;
 #pragma unroll
     for (int w = 0; w < DEC_WARPS; ++w) mmax = fmaxf(mmax, s_merge[((size_t)w * GROUP + hh) * MS + DEC_D]);
-    float num = 0.f, den = 0.f;
+    float v = 0.f;
+    if (c == DEC_D) {
+      v = mmax;
+    } else {
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) {
-      const float* src = s_merge + ((size_t)w * GROUP + hh) * MS;
-      const float mw = src[DEC_D];
+      for (int w = 0; w < DEC_WARPS; ++w) {
+        const float* src = s_merge + ((size_t)w * GROUP + hh) * MS;
+        const float mw = src[DEC_D];
+        v += src[c] * ((mw == -INFINITY) ? 0.f : exp2f(mw - mmax));   // c == DEC_D + 1: the sum, else the accumulator
+      }
+    }
+    mine[idx] = v;
+  }
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(p.split_cnt + unit, 1);
+    s_last = prev == p.n_split - 1;
+    if (s_last) p.split_cnt[unit] = 0;       // re-armed for the next launch (stream order separates launches)
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* parts = p.split_ws + (size_t)unit * p.n_split * GROUP * MS;
+  for (int idx = threadIdx.x; idx < GROUP * DEC_D; idx += DEC_WARPS * 32) {
+    const int hh = idx / DEC_D, c = idx - hh * DEC_D;
+    float mmax = -INFINITY;
+    for (int s2 = 0; s2 < p.n_split; ++s2) mmax = fmaxf(mmax, __ldcg(parts + ((size_t)s2 * GROUP + hh) * MS + DEC_D));
+    float num = 0.f, den = 0.f;
+    for (int s2 = 0; s2 < p.n_split; ++s2) {
+      const float* src = parts + ((size_t)s2 * GROUP + hh) * MS;
+      const float mw = __ldcg(src + DEC_D);
       const float sc = (mw == -INFINITY) ? 0.f : exp2f(mw - mmax);
-      num += src[c] * sc;
-      den += src[DEC_D + 1] * sc;
+      num += __ldcg(src + c) * sc;
+      den += __ldcg(src + DEC_D + 1) * sc;
     }
     p.o[(size_t)b * p.ldo + (size_t)(kvh * GROUP + hh) * DEC_D + c] = __float2bfloat16_rn(den > 0.f ? num / den : 0.f);
   }
@@ -618,6 +681,44 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
   return OPUS_ERR_ARG;
 }
 
+namespace {
+int decode_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+// Context-owned scratch of the split-KV merge: partial results + one arrival counter per (sequence, kv head) unit.
+// Allocated on first use outside a stream capture (the decode loop touches it before it captures), grown never.
+bool decode_split_scratch(size_t need_bytes, int units, float** ws, int** cnt) {
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lk(c.sk_mu);
+  constexpr size_t kBytes = 16u << 20;
+  constexpr int kUnits = 16384;
+  if (c.attn_ws == nullptr) {
+    if (cudaMalloc(&c.attn_ws, kBytes) != cudaSuccess || cudaMalloc(&c.attn_cnt, kUnits * sizeof(int)) != cudaSuccess ||
+        cudaMemset(c.attn_cnt, 0, kUnits * sizeof(int)) != cudaSuccess) {
+      cudaGetLastError();      // e.g. first call inside a capture: this launch runs unsplit
+      if (c.attn_ws) { cudaFree(c.attn_ws); c.attn_ws = nullptr; }
+      if (c.attn_cnt) { cudaFree(c.attn_cnt); c.attn_cnt = nullptr; }
+      return false;
+    }
+  }
+  if (need_bytes > kBytes || units > kUnits) return false;
+  *ws = c.attn_ws; *cnt = c.attn_cnt;
+  return true;
+}
+}  // namespace
+
+int attn_decode_warmup() {
+  float* ws; int* cnt;
+  return decode_split_scratch(0, 0, &ws, &cnt) ? OPUS_OK : OPUS_ERR_CUDA;
+}
+
 int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcache, const __nv_bfloat16* vcache,
                       const int* block_table, int max_blocks, const int* ctx_len, __nv_bfloat16* o, int ldo,
                       int n_seqs, int n_q_heads, int n_kv_heads, int head_dim, int block_size, float scale,
@@ -651,7 +752,23 @@ int attn_decode_paged_fused(__nv_bfloat16* qkv, int ldq, const float* partial, i
   p.qkv = qkv; p.pos = pos; p.slot = slot; p.cos_t = cos_t; p.sin_t = sin_t;
   p.kcache_w = kcache; p.vcache_w = vcache;
   p.bias = partial != nullptr ? bias : nullptr;
-  dim3 grid(n_kv_heads, n_seqs);
+  // split-KV when the (sequence, kv head) units are too coarse to balance over the SMs (see DecodeParams)
+  p.n_split = 1; p.split_ws = nullptr; p.split_cnt = nullptr;
+  {
+    const int units = n_kv_heads * n_seqs, sms = decode_num_sms();
+    const int slots = sms * 6;                           // resident CTAs (36 KB each)
+    int want = 1;
+    if (ctx().tun.attn_split != 0 && units < 2 * slots) {
+      want = ctx().tun.attn_split > 0 ? ctx().tun.attn_split : (units * 2 <= slots ? 4 : 2);
+      while (want > 1 && max_blocks < 2 * want) want >>= 1;       // at least two pages per part
+    }
+    if (want > 1) {
+      float* ws = nullptr; int* cnt = nullptr;
+      const size_t need = (size_t)units * want * group * (DEC_D + 2) * sizeof(float);
+      if (decode_split_scratch(need, units, &ws, &cnt)) { p.n_split = want; p.split_ws = ws; p.split_cnt = cnt; }
+    }
+  }
+  dim3 grid(n_kv_heads, n_seqs, p.n_split);
   const int smem = DEC_WARPS * 4 * DEC_PANEL + DEC_WARPS * group * (DEC_D + 2) * 4;
   static bool configured = false;
   if (!configured) {

@@ -45,6 +45,7 @@ Tunables Tunables::from_env() {
     const char* e = std::getenv("OPUS_PDL");
     t.pdl = (e == nullptr) ? 1 : (e[0] - '0');
   }
+  t.attn_split = env_int("OPUS_ATTN_SPLIT", -1);
   t.epi_warm = env_int("OPUS_EPI_WARM", 0) == 1;   // measured: no gain (tools/hop_probe.py WARM_AB=1), off by default
   t.decode_norm_fused = env_int("OPUS_DECODE_NORM_FUSED", 0) == 1;
   return t;
@@ -57,6 +58,8 @@ Context::~Context() {
   if (sk.ws) cudaFree(sk.ws);
   if (sk.cnt) cudaFree(sk.cnt);
   if (chain_trace) cudaFree(chain_trace);
+  if (attn_ws) cudaFree(attn_ws);
+  if (attn_cnt) cudaFree(attn_cnt);
 }
 
 Context& ctx() {

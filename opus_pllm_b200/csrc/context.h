@@ -28,6 +28,7 @@ struct Tunables {
   int attn_mode;          // OPUS_ATTN: 0 automatic, 1 mma.sync kernel, 2 tcgen05 kernel
   int attn_tail;          // OPUS_ATTN_TAIL: short query tails leave the tcgen05 kernel
   int pdl;                // OPUS_PDL: 0 off, 1 decode-sized launches, 2 every launch
+  int attn_split;         // OPUS_ATTN_SPLIT: split-KV parts of the decode attention (-1 automatic, 0 / 1 off, 2, 4)
   int epi_warm;           // OPUS_EPI_WARM: swap-AB GEMMs run their epilogue once "dry" to warm the instruction cache
   int decode_norm_fused;  // decode: RMSNorm folded into the GEMMs (in-kernel split-K reduce + norm-on-load), batch <= 64
   static Tunables from_env();
@@ -52,6 +53,8 @@ struct Context {
   cudaStream_t cap_stream = nullptr;
   SkWorkspace sk;
   unsigned long long* chain_trace = nullptr;
+  float* attn_ws = nullptr;                  // split-KV decode attention: partial results (guarded by sk_mu)
+  int* attn_cnt = nullptr;                   //   and per-unit arrival counters
   ~Context();
 };
 

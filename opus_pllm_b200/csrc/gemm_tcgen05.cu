@@ -420,7 +420,10 @@ template <int BN, bool TR>
 __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoord& tc, uint32_t tmem_base, int acc,
                                               int quad, int lane, int chunk0, int epi_tid,
                                               const CUtensorMap* tm_out = nullptr, uint8_t* stage = nullptr,
-                                              bool dry = false) {
+                                              bool dry = false, uint64_t* acc_bar = nullptr, uint32_t acc_parity = 0) {
+  // acc_bar != nullptr: the accumulator-ready barrier has NOT been waited for yet; this function waits for it after the
+  // owner's fix-up operands (the other CTAs' partial sums) have been requested, so that L2 round trip overlaps the tail
+  // of the item's own main loop instead of following it.
   const int lrow = quad * 32 + lane;  // accumulator row inside the tile
   const int row = tc.m * BM + lrow;
   const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
@@ -463,6 +466,10 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
 #pragma unroll
           for (int i = 0; i < 8; ++i) fix[q][i] += t[q][i];
       }
+    }
+    if (acc_bar != nullptr && !dry) {
+      mbar_wait(acc_bar, acc_parity);
+      tc_fence_after();
     }
     if constexpr (kPrefetchFix) {
       // Decode-sized tiles: every TMEM load of this warp is issued before the first global store. (A tcgen05.ld issued
@@ -514,6 +521,10 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
       }
     }
   } else {
+  if (acc_bar != nullptr && !dry) {
+    mbar_wait(acc_bar, acc_parity);
+    tc_fence_after();
+  }
   if (p.tma_store && tm_out != nullptr && tc.kind == WORK_TILE) {
     // bf16 (+bias, +GELU) tiles leave through shared memory: a thread owns one accumulator ROW, so direct stores put 32
     // different 128-byte lines behind every store instruction (measured: the K = 1280 encoder GEMMs ran at the pace of
@@ -974,12 +985,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (it == 0) grid_dep_wait();          // residual / output buffers may still be in use by the preceding kernel
         if (!get_work(p, it, tc)) break;
       }
-      if (!dry) {
-        mbar_wait(&acc_full[acc], acc_phase);
-        tc_fence_after();
-      }
+      // the accumulator-ready wait happens inside (after a stream-K owner has requested its fix-up operands)
       epilogue_item<BN, TR>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out,
-                        smem + C::STAGES * C::STAGE, dry);
+                        smem + C::STAGES * C::STAGE, dry, &acc_full[acc], acc_phase);
       if (!dry) {
         tc_fence_before();
         mbar_arrive(&acc_empty[acc]);

@@ -82,6 +82,8 @@ int attn_decode_paged(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* kcac
                       int n_seqs, int n_q_heads, int n_kv_heads, int head_dim, int block_size, float scale,
                       cudaStream_t st);
 
+// allocates the context's split-KV scratch (call outside stream capture; the decode loop does before it captures)
+int attn_decode_warmup();
 // Same, with the decode step's split-K reduce + RoPE + KV append done by the attention CTAs themselves: `qkv` is written
 // (bf16 q|k|v row of every sequence) from `partial` ([n_partial][n_seqs][ldq] fp32) before the heads are attended.
 int attn_decode_paged_fused(__nv_bfloat16* qkv, int ldq, const float* partial, int n_partial, const int* pos,

@@ -662,6 +662,7 @@ int set_tunable(const char* name, int value) {
   else if (std::strcmp(name, "attn_mode") == 0) t.attn_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
   else if (std::strcmp(name, "attn_tail") == 0) t.attn_tail = value != 0;
   else if (std::strcmp(name, "epi_warm") == 0) t.epi_warm = value != 0;
+  else if (std::strcmp(name, "attn_split") == 0) t.attn_split = value;
   else if (std::strcmp(name, "decode_norm_fused") == 0) t.decode_norm_fused = value != 0;
   else {
     known = false;
@@ -702,6 +703,7 @@ int llama_decode_loop(const opus_llama_model* m, const opus_kv_cache* kv, const 
                       cudaStream_t st) {
   if (!m || !kv || !ws || !s) return fail(OPUS_ERR_ARG, "llama_decode_loop: null argument");
   if (n_steps <= 0) return 0;
+  attn_decode_warmup();   // context scratch of the split-KV attention: never allocated first inside the capture below
   GraphEntry entry;
   if (use_graph) {
     Context& c = ctx();
