@@ -18,7 +18,7 @@ struct Tunables {
   int decode_fused;       // OPUS_DECODE_FUSED: persistent chain kernel for the decode GEMMs
   int chain_l2_depth;     // k-blocks the chain kernel prefetches into L2 per phase
   int gemm_2cta;          // OPUS_GEMM_2CTA: 0 off, 1 every eligible plain GEMM, 2 all but the SwiGLU epilogue
-  int gemm_2cta_tr;       // OPUS_GEMM_2CTA_TR: CTA-pair form for swap-AB launches at batch 129..256
+  int gemm_2cta_tr;       // OPUS_GEMM_2CTA_TR: CTA-pair form for swap-AB launches at batch 129..256 (0 off, 1 all but SwiGLU, 2 all)
   int tma_store;          // OPUS_TMA_STORE: plain bf16 / GELU epilogues through shared memory + TMA stores
   int streamk;            // OPUS_STREAMK: 0 disables the stream-K tail
   int streamk_plain;      // stream-K tail in the plain (non swap-AB) form

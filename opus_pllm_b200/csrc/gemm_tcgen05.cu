@@ -62,8 +62,10 @@ enum WorkKind : int { WORK_TILE = 0, WORK_SK_PARTIAL = 1, WORK_SK_OWNER = 2 };
 struct TileCoord {
   int m, n, kb_begin, kb_end, split;
   int kind;       // WorkKind
-  int sk_tile;    // index of the stream-K tile (counter slot)
-  int first_cta;  // owner only: partials of CTAs [first_cta, blockIdx.x) belong to this tile
+  int sk_tile;    // index of the stream-K tile
+  int first_cta;  // owner only: partials of CTAs first_cta, first_cta + cta_stride, ... < blockIdx.x belong to this tile
+  int cta_stride; // 1; 2 in the CTA-pair kernel (the contributors are the same-rank CTAs of the preceding pairs)
+  int cnt_slot;   // arrival counter of the tile (pair kernel: one per rank)
 };
 
 // (m, n) of output tile `mn` in the grouped-M raster
@@ -86,9 +88,9 @@ __device__ __forceinline__ void raster_mn(const GemmParams& p, int mn, int& m, i
 //   * round-robin items t = blockIdx.x + i * gridDim.x < dp_items: whole (m, n, k-split) tiles.
 // Order: round-robin tiles first, then the partial piece, then the piece(s) this CTA finishes (no CTA ever waits on a CTA
 // that is itself waiting). Walking the partial piece before the tiles was measured slower (gate/up 42.4 -> 43.7 us).
-__device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord& c) {
-  const int b = blockIdx.x, g = gridDim.x;
-  c.kind = WORK_TILE; c.sk_tile = 0; c.first_cta = 0;
+// b = index of the unit walking the sequence (CTA, or CTA pair), g = number of such units
+__device__ __forceinline__ bool get_work_bg(const GemmParams& p, int it, TileCoord& c, const int b, const int g) {
+  c.kind = WORK_TILE; c.sk_tile = 0; c.first_cta = 0; c.cta_stride = 1; c.cnt_slot = 0;
   const int n_dp = b < p.dp_items ? (p.dp_items - b + g - 1) / g : 0;
   // ---- tail pieces of this CTA
   int n_pre = 0, n_post = 0;
@@ -117,7 +119,7 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
         c.split = 0;
         raster_mn(p, p.dp_items + ptile[j], c.m, c.n);       // stream-K is only used with split_k == 1
         c.kb_begin = pk0[j]; c.kb_end = pk1[j];
-        c.sk_tile = ptile[j];
+        c.sk_tile = c.cnt_slot = ptile[j];
         // CTA holding unit x is ((x + 1) * ge - 1) / U
         c.first_cta = (int)((((long long)ptile[j] * kb + 1) * ge - 1) / U);
         c.kind = (c.first_cta == b) ? WORK_TILE : WORK_SK_OWNER;  // whole tile in this CTA's range: nothing to fix up
@@ -127,7 +129,7 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
         c.split = 0;
         raster_mn(p, p.dp_items + tile[0], c.m, c.n);
         c.kb_begin = k0[0]; c.kb_end = k1[0];
-        c.sk_tile = tile[0];
+        c.sk_tile = c.cnt_slot = tile[0];
         c.kind = WORK_SK_PARTIAL;
         return true;
       }
@@ -142,11 +144,14 @@ __device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord&
   c.kb_end = (int)(((long long)(c.split + 1) * p.k_blocks) / p.split_k);
   if (p.sk_fix && p.split_k > 1) {
     // one wave (t == blockIdx.x): the CTAs of a tile are neighbours, the one with the last split finishes the tile
-    c.sk_tile = mn;
+    c.sk_tile = c.cnt_slot = mn;
     c.first_cta = t - c.split;
     c.kind = (c.split == p.split_k - 1) ? WORK_SK_OWNER : WORK_SK_PARTIAL;
   }
   return true;
+}
+__device__ __forceinline__ bool get_work(const GemmParams& p, int it, TileCoord& c) {
+  return get_work_bg(p, it, c, (int)blockIdx.x, (int)gridDim.x);
 }
 
 __device__ __forceinline__ void bf16x8_unpack(const uint4 q, float* f) {
@@ -431,15 +436,15 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
   float* my_part = p.sk_ws + (size_t)blockIdx.x * (BM * BN) + lrow;
   if (tc.kind == WORK_SK_OWNER) {
     if (epi_tid == 0 && !dry) {
-      const int need = (int)blockIdx.x - tc.first_cta;
+      const int need = ((int)blockIdx.x - tc.first_cta) / tc.cta_stride;
       const long long t0 = clock64();
-      while (ld_acquire_gpu(p.sk_cnt + tc.sk_tile) < need) {
+      while (ld_acquire_gpu(p.sk_cnt + tc.cnt_slot) < need) {
         if (clock64() - t0 > 20000000000LL) {
           printf("opus_b200: stream-K fix-up wait timed out (block %d, tile %d)\n", (int)blockIdx.x, tc.sk_tile);
           __trap();
         }
       }
-      p.sk_cnt[tc.sk_tile] = 0;  // re-armed for the next launch (stream order separates launches)
+      p.sk_cnt[tc.cnt_slot] = 0;  // re-armed for the next launch (stream order separates launches)
     }
     named_bar_sync(1, NUM_EPI_THREADS);
   }
@@ -454,7 +459,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
       for (int q = 0; q < NG; ++q)
 #pragma unroll
         for (int i = 0; i < 8; ++i) fix[q][i] = 0.f;
-      for (int c = dry ? (int)blockIdx.x : tc.first_cta; c < (int)blockIdx.x; ++c) {
+      for (int c = dry ? (int)blockIdx.x : tc.first_cta; c < (int)blockIdx.x; c += tc.cta_stride) {
         const float* src = p.sk_ws + (size_t)c * (BM * BN) + lrow;
         float t[kPrefetchFix ? NG : 1][8];
 #pragma unroll
@@ -510,7 +515,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
           continue;
         }
         if (tc.kind == WORK_SK_OWNER) {
-          for (int c = dry ? (int)blockIdx.x : tc.first_cta; c < (int)blockIdx.x; ++c) {
+          for (int c = dry ? (int)blockIdx.x : tc.first_cta; c < (int)blockIdx.x; c += tc.cta_stride) {
             const float* src = p.sk_ws + (size_t)c * (BM * BN) + (size_t)(g * 8) * BM + lrow;
 #pragma unroll
             for (int i = 0; i < 8; ++i) r8[i] = __float_as_uint(__uint_as_float(r8[i]) + __ldcg(src + (size_t)i * BM));
@@ -740,7 +745,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
         continue;
       }
       if (tc.kind == WORK_SK_OWNER) {
-        for (int cc = tc.first_cta; cc < (int)blockIdx.x; ++cc) {
+        for (int cc = tc.first_cta; cc < (int)blockIdx.x; cc += tc.cta_stride) {
           const float* src = p.sk_ws + (size_t)cc * (BM * BN) + (size_t)(c * 32) * BM + lrow;
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldcg(src + (size_t)i * BM));
@@ -755,7 +760,7 @@ __device__ __forceinline__ void epilogue_item(const GemmParams& p, const TileCoo
     named_bar_sync(1, NUM_EPI_THREADS);   // every thread's partial stores happen-before thread 0's fence + release
     if (epi_tid == 0 && !dry) {
       __threadfence();
-      red_release_gpu_add(p.sk_cnt + tc.sk_tile, 1);
+      red_release_gpu_add(p.sk_cnt + tc.cnt_slot, 1);
     }
   }
 }
@@ -1068,6 +1073,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     m = first_m + r % gsz;
     n = r / gsz;
   };
+  // Item `it` of this PAIR: tc.m is the 256-row tile. Swap-AB form: the generic sequence (whole tiles round-robin, then
+  // this pair's share of the stream-K tail; the host filled p.num_m_tiles / dp_items / sk_tiles in pair units).
+  auto pair_work = [&](int it, TileCoord& c) -> bool {
+    if constexpr (TR) {
+      return get_work_bg(p, it, c, pair, n_pairs);
+    } else {
+      const int t = pair + it * n_pairs;
+      if (t >= total) return false;
+      int mn;
+      split_of(t, mn, c.split, c.kb_begin, c.kb_end);
+      tile_of(mn, c.m, c.n);
+      c.kind = WORK_TILE; c.sk_tile = 0; c.first_cta = 0; c.cta_stride = 1; c.cnt_slot = 0;
+      return true;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -1102,10 +1122,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if constexpr (TR) {
         // PDL prologue (see the single-CTA kernel): the first ring pass of WEIGHT tiles is requested before waiting for
         // the preceding kernel, the activation halves follow after the wait
-        if (pair < total) {
-          int mn, split, kb0, kb1, m, n;
-          split_of(pair, mn, split, kb0, kb1);
-          tile_of(mn, m, n);
+        TileCoord t0;
+        if (pair_work(0, t0)) {
+          const int kb0 = t0.kb_begin, kb1 = t0.kb_end, m = t0.m, n = t0.n;
           pre = min(C::STAGES, kb1 - kb0);
           for (int i = 0; i < pre; ++i) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[i], 2 * C::STAGE);
@@ -1120,11 +1139,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           grid_dep_wait();
         }
       }
-      for (int t = pair; t < total; t += n_pairs) {
-        int mn, split, kb0, kb1, m, n;
-        split_of(t, mn, split, kb0, kb1);
-        tile_of(mn, m, n);
-        for (int kb = kb0 + (t == pair ? pre : 0); kb < kb1; ++kb) {
+      TileCoord tw;
+      for (int it = 0; pair_work(it, tw); ++it) {
+        const int kb0 = tw.kb_begin, kb1 = tw.kb_end, m = tw.m, n = tw.n;
+        for (int kb = kb0 + (it == 0 ? pre : 0); kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE);   // bytes of both CTAs
@@ -1143,9 +1161,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = pair; t < total; t += n_pairs) {
-        int mn, split, kb0, kb1;
-        split_of(t, mn, split, kb0, kb1);
+      TileCoord tw;
+      for (int it = 0; pair_work(it, tw); ++it) {
+        const int kb0 = tw.kb_begin, kb1 = tw.kb_end;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -1173,13 +1191,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if constexpr (TR) grid_dep_wait();   // output / partial buffers may still be in use by the preceding kernel
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = pair; t < total; t += n_pairs) {
-      TileCoord tc;
-      int mn, m, n;
-      split_of(t, mn, tc.split, tc.kb_begin, tc.kb_end);
-      tile_of(mn, m, n);
-      tc.m = 2 * m + rank; tc.n = n;
-      tc.kind = WORK_TILE; tc.sk_tile = 0; tc.first_cta = 0;
+    TileCoord tc;
+    for (int it = 0; pair_work(it, tc); ++it) {
+      // this CTA's half of the pair's tile; stream-K bookkeeping per rank: the contributors of a tile are the same-rank
+      // CTAs of the preceding pairs, and every rank has its own arrival counter
+      tc.m = 2 * tc.m + rank;
+      tc.first_cta = 2 * tc.first_cta + rank;
+      tc.cta_stride = 2;
+      tc.cnt_slot = 2 * tc.sk_tile + rank;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       epilogue_item<BN, TR>(p, tc, tmem_base, acc, quad, lane, chunk0, epi_tid, &tmap_out, smem + C::STAGES * C::STAGE);
@@ -1796,7 +1815,26 @@ bool gemm_fuses_rope(const GemmArgs& a) {
 namespace {
 
 template <bool TR>
-int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
+int launch_2cta(const GemmParams& p_in, const GemmArgs& a, cudaStream_t stream) {
+  GemmParams p = p_in;
+  if constexpr (TR) {
+    // work partition in PAIR units: 256-feature tiles, whole (tile, k-split) items round-robin over the pairs, and a
+    // partial last wave cut along K over all pairs (stream-K; same fix-up protocol as the single-CTA kernel, per rank)
+    const int max_pairs = num_sms() / 2;
+    p.num_m_tiles = (p.M + 2 * BM - 1) / (2 * BM);
+    p.group_m = p.num_n_tiles > 1 ? 1 : p.num_m_tiles;
+    const int items = p.num_m_tiles * p.num_n_tiles * p.split_k;
+    p.dp_items = items;
+    p.sk_tiles = 0;
+    const int rem = items % max_pairs;
+    if (p.split_k == 1 && items > max_pairs && rem != 0 && rem * 100 <= ctx().tun.streamk_fill * max_pairs &&
+        a.epi != EPI_PARTIAL_F32 && ensure_sk_workspace()) {
+      p.sk_tiles = rem;
+      p.dp_items = items - rem;
+      p.sk_ws = ctx().sk.ws;
+      p.sk_cnt = ctx().sk.cnt;
+    }
+  }
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(gemm_bf16_2cta_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM) != cudaSuccess)
@@ -1839,16 +1877,21 @@ int launch_2cta(const GemmParams& p, const GemmArgs& a, cudaStream_t stream) {
 // stays with the single-CTA kernel (decode gate/up: 112 pair tiles would be 1.5 waves).
 bool pair_takes_transposed(const GemmArgs& a, const GemmParams& p, int bn) {
   const int g_2cta_tr = ctx().tun.gemm_2cta_tr;
-  if (!g_2cta_tr || !a.transposed || bn != 256 || a.block_n != 0 || a.N <= 128 || a.N > 256 || a.epi == EPI_SWIGLU)
-    return false;
+  if (!g_2cta_tr || !a.transposed || bn != 256 || a.block_n != 0 || a.N <= 128 || a.N > 256) return false;
+  if (a.epi == EPI_SWIGLU && g_2cta_tr < 2) return false;     // tunable gemm_2cta_tr = 1: gate/up stays on the single-CTA kernel
+  if (a.splitk_fixup || a.sumsq_out != nullptr || a.norm_sumsq != nullptr || a.pf_w != nullptr) return false;
   const int max_pairs = num_sms() / 2;
   const int items = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles * p.split_k;
+  if (items < max_pairs) return items * 100 >= 85 * max_pairs;   // a single, well filled wave
+  // several waves: whole waves, or a partial last wave that the stream-K tail spreads over all pairs
+  const int rem = items % max_pairs;
+  const bool sk_ok = p.split_k == 1 && a.epi != EPI_PARTIAL_F32 && ctx().tun.streamk && rem * 100 <= ctx().tun.streamk_fill * max_pairs;
   const int waves = (items + max_pairs - 1) / max_pairs;
-  return items * 100 >= 85 * waves * max_pairs;
+  return rem == 0 || sk_ok || items * 100 >= 85 * waves * max_pairs;
 }
 }  // namespace
 
-void gemm_set_2cta_tr(int on) { ctx().tun.gemm_2cta_tr = on ? 1 : 0; }
+void gemm_set_2cta_tr(int on) { ctx().tun.gemm_2cta_tr = on < 0 ? 0 : (on > 2 ? 2 : on); }
 void gemm_set_2cta(int on) { ctx().tun.gemm_2cta = on < 0 ? 0 : (on > 2 ? 2 : on); }
 
 // D = epi(A * B^T). See gemm.h for the contract.
@@ -1862,11 +1905,7 @@ int gemm_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (g_2cta && !a.transposed && bn == 256 && p.split_k == 1 && p.sk_tiles == 0 && a.M >= 1024 && a.block_n == 0 &&
       !(g_2cta == 2 && a.epi == EPI_SWIGLU))
     return launch_2cta<false>(p, a, stream);
-  if (pair_takes_transposed(a, p, bn)) {
-    p.sk_tiles = 0;                                   // whole (tile, split) items only
-    p.dp_items = p.num_m_tiles * p.num_n_tiles * p.split_k;
-    return launch_2cta<true>(p, a, stream);
-  }
+  if (pair_takes_transposed(a, p, bn)) return launch_2cta<true>(p, a, stream);   // re-partitions the work in pair units
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   switch (bn) {

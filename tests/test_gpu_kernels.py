@@ -586,3 +586,34 @@ def test_gemm_rmsnorm_on_load(rows, n_out, K, epi):
     assert float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)) >= 0.99999
     assert float((a - b).abs().max()) <= 2.0 ** -6 * float(b.abs().max())
     assert float((a != b).float().mean()) <= 0.02            # only rstd-ulp rows may differ at all
+
+
+@pytest.mark.parametrize("rows,n_out,K,epi", [(256, 28672, 4096, "swiglu"), (200, 28672, 4096, "swiglu"), (256, 128256, 4096, "bf16"),
+                                              (130, 4096 * 5, 1024, "bf16")])
+def test_pair_kernel_streamk_tail_matches_single_cta(rows, n_out, K, epi):
+    """Batch 129..256 swap-AB launches run on the CTA-pair kernel; when their 256-feature tiles do not fill whole waves of
+    the 74 pairs the last partial wave is cut along K over all pairs (stream-K, per-rank fix-up). Against the single-CTA
+    kernel (tunable gemm_2cta_tr = 0): same values up to the fp32 summation order of the split tiles."""
+    from opus_pllm_b200 import _lib as L, ops
+    g = torch.Generator(device="cuda").manual_seed(n_out + rows)
+    x = (torch.randn(rows, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(n_out, K, device="cuda", generator=g) * 0.05).bfloat16()
+    code = {"swiglu": L.EPI_SWIGLU, "bf16": L.EPI_BF16}[epi]
+    lib = L.load()
+    try:
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 2))
+        got = ops.gemm(x, w, epilogue=code, transposed=True)
+        again = ops.gemm(x, w, epilogue=code, transposed=True)
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 0))
+        want = ops.gemm(x, w, epilogue=code, transposed=True)
+    finally:
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 2))
+    assert torch.equal(got, again)                                   # deterministic (fixed fix-up order)
+    a, b = got.float(), want.float()
+    assert float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)) >= 0.999999
+    assert float((a - b).abs().max()) <= 2.0 ** -7 * float(b.abs().max())
+    ref = (x.float() @ w.float().T)
+    if epi == "swiglu":
+        gte, up = ref[:, 0::2].bfloat16().float(), ref[:, 1::2].bfloat16().float()
+        ref = torch.nn.functional.silu(gte).bfloat16().float() * up
+    assert float(torch.nn.functional.cosine_similarity(a.flatten(), ref.flatten(), dim=0)) >= 0.9999

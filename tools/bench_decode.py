@@ -64,6 +64,8 @@ def after_prefill(label):
 run("defaults (kernel per op, PDL chain)")
 if os.environ.get("AFTER_PREFILL"):
     after_prefill("decode timed right after a prefill")
+if os.environ.get("PAIR_GU"):
+    setk(gemm_2cta_tr=2); run("gemm_2cta_tr=2 (gate/up on the CTA-pair kernel)"); setk(gemm_2cta_tr=1)
 if os.environ.get("NORMF"):
     setk(decode_norm_fused=1); run("decode_norm_fused=1 (5 launches per layer)")
     if os.environ.get("AFTER_PREFILL"):
