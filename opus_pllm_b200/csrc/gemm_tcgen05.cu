@@ -1827,8 +1827,11 @@ int launch_2cta(const GemmParams& p_in, const GemmArgs& a, cudaStream_t stream) 
     p.dp_items = items;
     p.sk_tiles = 0;
     const int rem = items % max_pairs;
-    if (p.split_k == 1 && items > max_pairs && rem != 0 && rem * 100 <= ctx().tun.streamk_fill * max_pairs &&
-        a.epi != EPI_PARTIAL_F32 && ensure_sk_workspace()) {
+    // opt-in (tunable pair_streamk): at a 256-wide batch tile a dumped accumulator is 128 KB per CTA, and the fix-up
+    // traffic costs more than the partial wave it removes (gate/up at batch 256: 6.17 ms per step with two uneven
+    // waves, 6.27 with the tail cut along K)
+    if (ctx().tun.pair_streamk && p.split_k == 1 && items > max_pairs && rem != 0 &&
+        rem * 100 <= ctx().tun.streamk_fill * max_pairs && a.epi != EPI_PARTIAL_F32 && ensure_sk_workspace()) {
       p.sk_tiles = rem;
       p.dp_items = items - rem;
       p.sk_ws = ctx().sk.ws;
@@ -1885,9 +1888,10 @@ bool pair_takes_transposed(const GemmArgs& a, const GemmParams& p, int bn) {
   if (items < max_pairs) return items * 100 >= 85 * max_pairs;   // a single, well filled wave
   // several waves: whole waves, or a partial last wave that the stream-K tail spreads over all pairs
   const int rem = items % max_pairs;
-  const bool sk_ok = p.split_k == 1 && a.epi != EPI_PARTIAL_F32 && ctx().tun.streamk && rem * 100 <= ctx().tun.streamk_fill * max_pairs;
+  const bool sk_ok = ctx().tun.pair_streamk && p.split_k == 1 && a.epi != EPI_PARTIAL_F32 && ctx().tun.streamk &&
+                     rem * 100 <= ctx().tun.streamk_fill * max_pairs;
   const int waves = (items + max_pairs - 1) / max_pairs;
-  return rem == 0 || sk_ok || items * 100 >= 85 * waves * max_pairs;
+  return rem == 0 || sk_ok || items * 100 >= (a.epi == EPI_SWIGLU ? 75 : 85) * waves * max_pairs;
 }
 }  // namespace
 
