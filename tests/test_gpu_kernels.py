@@ -608,10 +608,12 @@ def test_pair_kernel_streamk_tail_matches_single_cta(rows, n_out, K, epi):
         L.check(lib.opus_set_tunable(b"pair_streamk", 0))
         two_waves = ops.gemm(x, w, epilogue=code, transposed=True)      # the default: whole tiles only
         L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 0))
+        L.check(lib.opus_set_tunable(b"streamk_fill", 0))              # single-CTA kernel, whole tiles only
         want = ops.gemm(x, w, epilogue=code, transposed=True)
     finally:
         L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 2))
         L.check(lib.opus_set_tunable(b"pair_streamk", 0))
+        L.check(lib.opus_set_tunable(b"streamk_fill", 90))
     assert torch.equal(two_waves, want)                              # same k order per tile: bit-identical
     assert torch.equal(got, again)                                   # deterministic (fixed fix-up order)
     a, b = got.float(), want.float()
