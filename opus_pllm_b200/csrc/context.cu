@@ -48,6 +48,7 @@ Tunables Tunables::from_env() {
   // measured at batch 64 / ctx 512: 2 parts + last-arriver merge 4.70 ms per step against 4.25 unsplit (the merge is one more
   // dependent round trip through a saturated memory system), so the split is opt-in
   t.attn_split = env_int("OPUS_ATTN_SPLIT", 0);
+  t.l2_ahead = env_int("OPUS_L2_AHEAD", 0);
   t.pair_streamk = env_int("OPUS_PAIR_STREAMK", 0) == 1;
   t.epi_warm = env_int("OPUS_EPI_WARM", 0) == 1;   // measured: no gain (tools/hop_probe.py WARM_AB=1), off by default
   t.decode_norm_fused = env_int("OPUS_DECODE_NORM_FUSED", 0) == 1;

@@ -28,6 +28,7 @@ struct Tunables {
   int attn_mode;          // OPUS_ATTN: 0 automatic, 1 mma.sync kernel, 2 tcgen05 kernel
   int attn_tail;          // OPUS_ATTN_TAIL: short query tails leave the tcgen05 kernel
   int pdl;                // OPUS_PDL: 0 off, 1 decode-sized launches, 2 every launch
+  int l2_ahead;           // OPUS_L2_AHEAD: k-blocks a swap-AB GEMM requests into L2 ahead of its shared-memory ring
   int pair_streamk;       // OPUS_PAIR_STREAMK: stream-K tail in the CTA-pair swap-AB kernel (default off: measured slower)
   int attn_split;         // OPUS_ATTN_SPLIT: split-KV parts of the decode attention (0 / 1 off = default, -1 automatic, 2, 4)
   int epi_warm;           // OPUS_EPI_WARM: swap-AB GEMMs run their epilogue once "dry" to warm the instruction cache

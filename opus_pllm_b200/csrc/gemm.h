@@ -66,6 +66,7 @@ struct GemmParams {
   // other splits (they dump their fp32 accumulators to sk_ws and bump sk_cnt[tile]), adds the partial sums in split order
   // and runs the real epilogue, so no separate reduce kernel follows the GEMM.
   int sk_fix;
+  int l2_ahead;   // swap-AB: k-blocks of the weight stream requested into L2 ahead of the shared-memory ring (tunable)
   int epi_warm;   // swap-AB: run the epilogue once "dry" during the main loop to warm the instruction cache (tunable)
   // EPI_RES_BF16 (swap-AB) by-product for a following RMSNorm: sumsq_out[slab][batch row] = sum over the 32 features of
   // slab (= feature / 32) of the squared bf16 values this launch stored. One writer per entry: deterministic.

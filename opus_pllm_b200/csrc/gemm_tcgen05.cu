@@ -900,6 +900,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (TR) tma_load_2d_hint(sa, &tmap_a, &full_bar[i], (tc.kb_begin + i) * BK, tc.m * BM, p.hint_a);
           else tma_load_2d_hint(sa + C::STAGE_A, &tmap_b, &full_bar[i], (tc.kb_begin + i) * BK, tc.n * BN, p.hint_b);
         }
+        if constexpr (TR) {
+          // Weight streaming is latency x concurrency bound: the ring holds ~144 KB per SM, and at the power-capped clock
+          // the decode loop inherits from the prefill the L2 / crossbar part of the latency stretches (the same launch
+          // streams 18-24 % slower). Requesting the NEXT l2_ahead k-blocks into L2 keeps more HBM requests in flight than
+          // shared memory can hold; the ring then refills from L2.
+          for (int i = pre; i < min(pre + p.l2_ahead, tc.kb_end - tc.kb_begin); ++i)
+            tma_prefetch_l2_2d(&tmap_a, (tc.kb_begin + i) * BK, tc.m * BM);
+        }
         grid_dep_wait();
         for (int i = 0; i < pre; ++i) {
           uint8_t* sa = smem + i * C::STAGE;
@@ -912,6 +920,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       for (int it = 0; get_work(p, it, tc); ++it) {
         for (int kb = tc.kb_begin + (it == 0 ? pre : 0); kb < tc.kb_end; ++kb) {
+          if constexpr (TR) {
+            if (p.l2_ahead > 0 && kb + p.l2_ahead < tc.kb_end)       // keep the L2 lookahead window full
+              tma_prefetch_l2_2d(&tmap_a, (kb + p.l2_ahead) * BK, tc.m * BM);
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE;
           uint8_t* sb = sa + C::STAGE_A;
@@ -1776,6 +1788,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   p.dp_items = tiles;
   p.sk_tiles = 0;
   p.epi_warm = a.transposed ? tun.epi_warm : 0;
+  p.l2_ahead = a.transposed ? tun.l2_ahead : 0;
   if (a.splitk_fixup && p.split_k > 1) {
     // the CTAs of one tile wait on each other: every work item needs its own resident CTA (one wave)
     if (!a.transposed || tiles > num_sms() || p.num_m_tiles * p.num_n_tiles > 1000 || a.epi == EPI_PARTIAL_F32 ||

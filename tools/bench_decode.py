@@ -46,13 +46,19 @@ def setk(**kw):
         L.check(lib.opus_set_tunable(k.encode(), v), k)
 
 
-def after_prefill(label):
-    # the same decode loop timed right after a prefill, as inside bench.py (clock / power state carried over)
+def after_prefill(label, gap_ms=0.0):
+    # the same decode loop timed right after a prefill, as inside bench.py (clock / power state carried over);
+    # gap_ms > 0: the GPU idles that long between the two (is the power cap released faster when idle?) -- the gap is
+    # INSIDE the timed region
+    import time
     tot = 0.0
     for _ in range(3):
         st2 = ll.prefill(emb, plan=plan)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        if gap_ms > 0:
+            torch.cuda.synchronize()
+            time.sleep(gap_ms / 1e3)
         ll.generate_from_prefill(st2, new)
         b.record()
         torch.cuda.synchronize()
@@ -64,6 +70,15 @@ def after_prefill(label):
 run("defaults (kernel per op, PDL chain)")
 if os.environ.get("AFTER_PREFILL"):
     after_prefill("decode timed right after a prefill")
+if os.environ.get("L2AHEAD"):
+    for d in (4, 8, 16, 32):
+        setk(l2_ahead=d); run(f"l2_ahead={d}")
+        if os.environ.get("AFTER_PREFILL"):
+            after_prefill(f"l2_ahead={d} right after a prefill")
+    setk(l2_ahead=0)
+if os.environ.get("GAPS"):
+    for gms in (2, 5, 10, 20, 40):
+        after_prefill(f"after a prefill + {gms} ms idle gap (gap included)", gms)
 if os.environ.get("PAIR_GU"):
     setk(gemm_2cta_tr=2); run("gemm_2cta_tr=2 (gate/up on the CTA-pair kernel)"); setk(gemm_2cta_tr=1)
 if os.environ.get("NORMF"):
