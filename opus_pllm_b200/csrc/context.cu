@@ -36,6 +36,8 @@ Tunables Tunables::from_env() {
   t.streamk_fill = 90;
   t.group_m = env_int("OPUS_GEMM_GROUP_M", 0);
   t.plain_hints = env_int("OPUS_GEMM_HINTS", 0);
+  t.group_n = env_int("OPUS_GEMM_GROUP_N", 0);
+  t.group_n_hints = env_int("OPUS_GEMM_GROUP_N_HINTS", 1);
   {
     const char* e = std::getenv("OPUS_ATTN");
     t.attn_mode = (e == nullptr) ? 0 : (e[0] == 't' ? 2 : 1);

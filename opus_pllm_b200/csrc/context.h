@@ -24,6 +24,8 @@ struct Tunables {
   int streamk_plain;      // stream-K tail in the plain (non swap-AB) form
   int streamk_fill;       // largest partial-wave fill (percent) that takes the stream-K tail
   int group_m;            // OPUS_GEMM_GROUP_M: raster group override (0 = automatic)
+  int group_n;            // OPUS_GEMM_GROUP_N: weight-panel band of the grouped-N raster (CTA-pair kernel, K > 8192; 0 = off)
+  int group_n_hints;      // OPUS_GEMM_GROUP_N_HINTS: evict-first activations / evict-last weights under that raster
   int plain_hints;        // OPUS_GEMM_HINTS: L2 eviction hints of the plain form (0 = none)
   int attn_mode;          // OPUS_ATTN: 0 automatic, 1 mma.sync kernel, 2 tcgen05 kernel
   int attn_tail;          // OPUS_ATTN_TAIL: short query tails leave the tcgen05 kernel

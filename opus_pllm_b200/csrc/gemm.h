@@ -27,6 +27,7 @@ struct GemmParams {
   int transposed;
   int epi;
   int group_m;
+  int group_n;   // CTA-pair plain form: > 0 = grouped-N raster with bands of this many 256-wide weight panels
   void* out;
   int ldo;
   const float* bias;

@@ -1077,7 +1077,19 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     kb0 = (int)(((long long)split * p.k_blocks) / p.split_k);
     kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.split_k);
   };
-  auto tile_of = [&](int t, int& m, int& n) {             // grouped-M raster over 256-row tiles
+  auto tile_of = [&](int t, int& m, int& n) {             // grouped raster over 256-row tiles
+    if (p.group_n > 0) {
+      // grouped-N: a band of group_n weight panels stays L2-resident (evict-last) while ALL row tiles sweep past it, so
+      // the weights are read from HBM once and the activations once per band. For K = 14336 (down_proj) a panel is
+      // 7.3 MB: the grouped-M order touched the whole 117 MB weight matrix in every wave.
+      const int per_band = p.group_n * m_tiles;
+      const int g = t / per_band, r = t - g * per_band;
+      const int first_n = g * p.group_n;
+      const int gsz = min(n_tiles - first_n, p.group_n);
+      n = first_n + r % gsz;
+      m = r / gsz;
+      return;
+    }
     const int per_group = group * n_tiles;
     const int g = t / per_group, r = t - g * per_group;
     const int first_m = g * group;
@@ -1734,6 +1746,8 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   p.group_m = a.transposed ? (p.num_n_tiles > 1 ? 1 : p.num_m_tiles)
                            : (group_override > 0 ? group_override : (a.K > 8192 ? 16 : 32));
   if (p.group_m > p.num_m_tiles) p.group_m = p.num_m_tiles;
+  // CTA-pair kernel, long K: bands of weight panels instead of groups of row tiles (see tile_of); 0 = grouped-M
+  p.group_n = (!a.transposed && a.K > 8192) ? tun.group_n : 0;
   // weights are streamed once in the swap-AB form; activations are re-read by every tile
   p.hint_a = a.transposed ? kCacheEvictFirst : kCacheEvictNormal;
   p.hint_b = a.transposed ? kCacheEvictLast : kCacheEvictNormal;
@@ -1743,6 +1757,10 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
     if (!a.transposed && plain_hints == 1) { p.hint_a = kCacheEvictLast; p.hint_b = kCacheEvictFirst; }
     if (!a.transposed && plain_hints == 2) { p.hint_a = kCacheEvictLast; p.hint_b = kCacheEvictNormal; }
     if (!a.transposed && plain_hints == 3) { p.hint_a = kCacheEvictNormal; p.hint_b = kCacheEvictFirst; }
+    if (!a.transposed && plain_hints == 0 && p.group_n > 0 && tun.group_n_hints) {
+      p.hint_a = kCacheEvictFirst;   // a row panel is used by the tiles of one wave only
+      p.hint_b = kCacheEvictLast;    // the band's weight panels serve every wave of the band
+    }
   }
 
   if (a.pf_w != nullptr && a.pf_depth > 0 && a.pf_rows > 0 && a.pf_K > 0 && (a.pf_K % 8) == 0 &&

@@ -664,6 +664,9 @@ int set_tunable(const char* name, int value) {
   else if (std::strcmp(name, "epi_warm") == 0) t.epi_warm = value != 0;
   else if (std::strcmp(name, "attn_split") == 0) t.attn_split = value;
   else if (std::strcmp(name, "pair_streamk") == 0) t.pair_streamk = value != 0;
+  else if (std::strcmp(name, "group_n") == 0) t.group_n = value < 0 ? 0 : value;
+  else if (std::strcmp(name, "group_n_hints") == 0) t.group_n_hints = value != 0;
+  else if (std::strcmp(name, "group_m") == 0) t.group_m = value < 0 ? 0 : value;
   else if (std::strcmp(name, "l2_ahead") == 0) t.l2_ahead = value < 0 ? 0 : value;
   else if (std::strcmp(name, "decode_norm_fused") == 0) t.decode_norm_fused = value != 0;
   else {
