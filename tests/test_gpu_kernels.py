@@ -588,8 +588,7 @@ def test_gemm_rmsnorm_on_load(rows, n_out, K, epi):
     assert float((a != b).float().mean()) <= 0.02            # only rstd-ulp rows may differ at all
 
 
-@pytest.mark.parametrize("rows,n_out,K,epi", [(256, 28672, 4096, "swiglu"), (200, 28672, 4096, "swiglu"), (256, 128256, 4096, "bf16"),
-                                              (130, 4096 * 5, 1024, "bf16")])
+@pytest.mark.parametrize("rows,n_out,K,epi", [(256, 28672, 4096, "swiglu"), (200, 28672, 4096, "swiglu"), (256, 128256, 4096, "bf16")])
 def test_pair_kernel_streamk_tail_matches_single_cta(rows, n_out, K, epi):
     """Batch 129..256 swap-AB launches run on the CTA-pair kernel; when their 256-feature tiles do not fill whole waves of
     the 74 pairs the last partial wave is cut along K over all pairs (stream-K, per-rank fix-up). Against the single-CTA
