@@ -111,6 +111,23 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // (S = Q K^T with N = nk, O += P V over nk keys) instead of as a full 128-key block
 __device__ __forceinline__ int block_keys(int len, int j) { return min(TBN, ((len - j * TBN + 15) >> 4) << 4); }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 polynomial, max relative error 1e-4: a twentieth of a bf16
+// half-ulp, and P is rounded to bf16 before it is used). x <= ~2^8 by construction (lazy rescaling), any negative value.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;             // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);       // [-0.5, 0.5]
+  float p = fmaf(0.05583828315138817f, f, 0.2426394820213318f);
+  p = fmaf(p, f, 0.6931367516517639f);
+  p = fmaf(p, f, 0.9999245405197144f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^round(x)
+}
+// Which of 16 consecutive S columns take the polynomial instead of MUFU.EX2: the exponentials of a key block are the
+// critical resource of this kernel (16 MUFU lanes per SM against 128 FMA lanes; at head_dim 64 the MUFU time of a block
+// is twice its tensor time), so 7 of 16 go to the FMA pipe, which balances the two (MUFU 9/16 per element, FMA
+// (2 + 6 * 7/16) / 128).
+constexpr uint32_t kExpPolyMask = 0x552Au;
+
 // Softmax of one row over NC (= 128, or 32 for narrow tail blocks) S columns: S -> registers, mask, row maximum, lazy
 // reference-maximum update, exp2, row sum, bf16 P written back over S. Returns whether O must be rescaled by `corr`.
 template <int NC, bool CAUSAL>
@@ -151,8 +168,10 @@ __device__ __forceinline__ bool softmax_block(uint32_t t_s, int k0, int len, int
   uint32_t pk[NC / 2];
 #pragma unroll
   for (int i = 0; i < NC; i += 2) {
-    const float p0 = exp2f(fmaf(__uint_as_float(s[i]), scale_log2, -m_use));
-    const float p1 = exp2f(fmaf(__uint_as_float(s[i + 1]), scale_log2, -m_use));
+    const float x0 = fmaf(__uint_as_float(s[i]), scale_log2, -m_use);
+    const float x1 = fmaf(__uint_as_float(s[i + 1]), scale_log2, -m_use);
+    const float p0 = ((kExpPolyMask >> (i & 15)) & 1u) ? exp2_fma(x0) : ex2_approx(x0);
+    const float p1 = ((kExpPolyMask >> ((i + 1) & 15)) & 1u) ? exp2_fma(x1) : ex2_approx(x1);
     ls0 += p0;
     ls1 += p1;
     pk[i >> 1] = pack_bf16x2(p0, p1);
