@@ -195,11 +195,30 @@ class ContinuousBatcher:
                     retire(s)
             return True
 
+        # decode batch tiers of the kernels (batch tile 32 / 64 / 128 / 256): once the queue is empty the live requests are
+        # compacted into the smallest tier that holds them, so the ramp-down of a job does not pay full-batch steps
+        tiers = sorted({t for t in (32, 64, 128, 256) if t < S} | {S})
+        n_compact = 0
         while waiting or active:
             # ---- admit chunk after chunk until the slots are full or the queue is empty; only then decode a round
             while waiting and any(r < 0 for r in slot_req):
                 if not admit_chunk():
                     break
+            if not waiting and 0 < active and min(t for t in tiers if t >= active) < S:
+                tgt = min(t for t in tiers if t >= active)
+                live = [i for i in range(S) if slot_req[i] >= 0]
+                st2, bufs2 = self._state(tgt, max_blocks, self.R, eos_ids, pad_id, sampling)
+                idx = torch.tensor(live, dtype=torch.long, device=self.dev)
+                n_live = len(live)
+                bufs2["block_table"].fill_(scratch)
+                bufs2["finished"].fill_(1)
+                for k in ("next_tok", "ctx_len", "block_table"):
+                    bufs2[k][:n_live] = bufs[k][idx]
+                bufs2["finished"][:n_live] = 0
+                slot_req = [slot_req[i] for i in live] + [-1] * (tgt - n_live)
+                slot_pages = [slot_pages[i] for i in live] + [[] for _ in range(tgt - n_live)]
+                st, bufs, S = st2, bufs2, tgt
+                n_compact += 1
             if not active:
                 continue
             # ---- one round of R decode steps over all slots (idle slots spin on the scratch page)
@@ -227,7 +246,8 @@ class ContinuousBatcher:
         ll._alloc.release([scratch])
         torch.cuda.current_stream().synchronize()
         # bookkeeping of the last call (bench.py: HBM roofline of the decode rounds)
-        self.stats = dict(rounds=n_rounds, decode_steps=n_rounds * self.R, slots=S, admissions=n_adm,
+        self.stats = dict(rounds=n_rounds, decode_steps=n_rounds * self.R, slots=min(self.S, n_req), compactions=n_compact,
+                          admissions=n_adm,
                           prefill_tokens=prefill_tokens, decode_ms=float(sum(a.elapsed_time(b) for a, b in round_events)))
         lib.opus_release_graphs()
         return [torch.tensor(r, dtype=torch.int64) for r in results]

@@ -568,6 +568,30 @@ def test_continuous_batching_matches_plain_generate():
     assert len(model.llama._alloc.free) == model.llama._alloc.num_blocks
 
 
+def test_continuous_batching_compacts_into_smaller_batch_tiers():
+    """Once the queue is empty the live requests move into the smallest decode batch tier (32 / 64 / 128 / 256) that holds
+    them; results stay those of the per-prompt greedy call, in input order, and every page returns to the allocator."""
+    from opus_pllm_b200.model import build_from_state_dicts
+    from opus_pllm_b200.scheduler import ContinuousBatcher
+    cfg = SMALL
+    kw = {k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()}
+    lw = synth.llama_weights(seed=2, peaked=True, device="cuda", **kw)
+    esm_cfg = dict(n_layers=2, dim=128, n_heads=2, ffn_dim=512)
+    pw = synth.projector_weights(128, 256, 8 * cfg["dim"])
+    model = build_from_state_dicts(lw, cfg, synth.esm2_weights(2, 128, 512), esm_cfg, pw, pw)
+    n = 90
+    seqs = synth.proteins(n, 10, 40, seed=31)
+    prompts = synth.prompt_ids(n, 30, vocab=cfg["vocab"], ragged=7, sentinel_at=5, seed=78)
+    lens = [3 + (i * 7) % 30 for i in range(n)]                       # ragged per-request budgets: a long ramp-down
+    ids = torch.stack([torch.cat([torch.full((30 - p.numel(),), 1), p]) for p in prompts]).cuda()
+    full = model.generate(ids, seqs, attention_mask=ids != 1, pad_token_id=1, do_sample=False, max_new_tokens=max(lens)).cpu()
+    cb = ContinuousBatcher(model, max_slots=70, round_steps=4)
+    got = cb.generate(prompts, seqs, lens)
+    assert cb.stats["compactions"] >= 2 and cb.stats["slots"] == 70      # 70 -> 64 -> 32
+    assert all(torch.equal(g, full[i, : lens[i]]) for i, g in enumerate(got))
+    assert len(model.llama._alloc.free) == model.llama._alloc.num_blocks
+
+
 # ------------------------------------------------------------------------------------------------ loaders + eval driver
 def test_load_pretrained_model_and_eval_driver(tmp_path):
     """A fake OPUS-PLLM release on disk (HF safetensors dir, peft adapter, switch .bin, Lightning ckpt, fair-esm .pt)

@@ -323,3 +323,23 @@ def test_pad_heads_layout_preserves_rotary_pairs_and_dot_products():
     assert pad_heads(W, H * hr // 128, 128, 0, rotary=True) is W
     W80 = torch.randn(2 * 80, D, generator=g)
     assert pad_heads(W80, 2, 80, 0, rotary=False).view(2, 128, D)[:, 80:].abs().max() == 0
+
+
+def test_bench_reference_arm_runs_on_cpu_for_every_workload_kind():
+    """`bench.py --impl reference` (the driver's second arm) never touches the GPU: tiny size, one generate-type and one
+    encoder-type workload, one JSON line each with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    for wl, unit in (("c2", "tokens/s"), ("c1", "residues/s"), ("c5", "tokens/s")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "tiny",
+                            "--workload", wl, "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["unit"] == unit and d["value"] > 0 and d["gpu_launches"] == 0
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+        assert d["e2e"] == {"value": d["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert d["config"]["workload"].startswith(wl + ":")
