@@ -202,8 +202,8 @@ int opus_lora_merge_bf16(void* W, const void* A, const void* B, int out_features
 /* Flash-style attention over packed variable-length sequences: tokens of sequence b are rows
  * [cu_seqlens[b], cu_seqlens[b+1]). causal = 0: bidirectional (ESM encoder; padded batches pass their valid spans so
  * the key-padding mask is implicit); causal = 1: causal GQA (Llama prefill). head_dim in {64, 128}. n_tok = number of
- * packed rows of q/k/v (bounds of the TMA tensor maps). Sequences of >= 384 tokens run on the tcgen05/TMEM kernel,
- * shorter ones on the mma.sync kernel (OPUS_ATTN=tc|mma forces either). */
+ * packed rows of q/k/v (bounds of the TMA tensor maps). Batches whose longest sequence has >= 96 tokens run on the
+ * tcgen05/TMEM kernel, shorter ones on the mma.sync kernel (tunable "attn_mode" / OPUS_ATTN=tc|mma forces either). */
 int opus_attn_varlen_bf16(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                           const int32_t* cu_seqlens, int n_seqs, int n_tok, int max_len, int n_q_heads, int n_kv_heads,
                           int head_dim, int causal, float scale, void* stream);

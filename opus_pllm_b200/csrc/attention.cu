@@ -627,14 +627,16 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
   if (n_kv_heads <= 0 || n_q_heads % n_kv_heads) return OPUS_ERR_ARG;
   {
     // implementation choice: the tcgen05 kernel (attention_tc.cu; two 128-row query tiles per work item) unless every
-    // sequence is short, where the 64-row mma.sync tiles below waste fewer padded rows. Measured (tools/sweep_attn.py):
-    // tcgen05 wins from T = 258 (153 vs 164 us, encoder C1) to T = 2048 (363 vs 1143 us, causal hd 128).
+    // sequence is shorter than 96 tokens, where the 64-row mma.sync tiles below waste fewer padded rows. Measured
+    // (tools/sweep_attn.py): tcgen05 wins up to T = 2048 (363 vs 1143 us, causal hd 128).
     // OPUS_ATTN=mma|tc (read at context creation) forces one of them (A/B measurements, tests).
     const int mode = ctx().tun.attn_mode;
     const bool aligned = ((ldq | ldk | ldv | ldo) % 8) == 0 &&
                          ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
                            reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
-    const bool want_tc = mode == 2 || (mode == 0 && max_len >= 192);
+    // crossover measured with tools/sweep_attn_short.py (256 x T causal GQA hd 128 / 64 x T encoder hd 64): T = 64: 142 vs
+    // 165 us, T = 96: 349 vs 268, T = 128: 365 vs 310, T = 160: 527 vs 356; encoder T = 66: 31 vs 44, T = 130: 65 vs 57
+    const bool want_tc = mode == 2 || (mode == 0 && max_len >= 96);
     if (want_tc && aligned && (head_dim == 64 || head_dim == 128)) {
       // Short tails: a sequence whose last 256-row work item holds <= 64 query rows (T = 258: two rows) would push a
       // nearly empty 128-row tile through the whole tcgen05 pipeline (~6 us per (sequence, head), 40 % of the encoder's
