@@ -644,8 +644,10 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
       // kernels write disjoint rows of `o`. Enabled when the longest sequence has such a tail (uniform batches) or for
       // ragged encoder batches; OPUS_ATTN_TAIL=0 disables it.
       const int tail_mode = ctx().tun.attn_tail;
-      constexpr int kTail = 64;
       const int max_tail = max_len - ((max_len - 1) / 256) * 256;
+      // tails of at most 16 rows (T = 258: the last residue and <eos>) take a one-warp, 16-row tile per (sequence, head)
+      // instead of a 64-row tile whose other three warps only help to load K / V
+      const int kTail = max_tail <= 16 ? 16 : 64;
       const bool split_tail = tail_mode && (max_tail <= kTail || (!causal && n_seqs >= 8));
       if (split_tail) {
         AttnParams tp;
@@ -657,7 +659,10 @@ int attn_varlen(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk
         tp.scale_log2 = scale * 1.4426950408889634f;
         tp.tail_only = kTail;
         int rc;
-        if (head_dim == 64) rc = causal ? launch_varlen<64, true, 64>(tp, n_seqs, max_len, st, true) : launch_varlen<64, false, 64>(tp, n_seqs, max_len, st, true);
+        if (kTail == 16) {
+          if (head_dim == 64) rc = causal ? launch_varlen<64, true, 16>(tp, n_seqs, max_len, st, true) : launch_varlen<64, false, 16>(tp, n_seqs, max_len, st, true);
+          else rc = causal ? launch_varlen<128, true, 16>(tp, n_seqs, max_len, st, true) : launch_varlen<128, false, 16>(tp, n_seqs, max_len, st, true);
+        } else if (head_dim == 64) rc = causal ? launch_varlen<64, true, 64>(tp, n_seqs, max_len, st, true) : launch_varlen<64, false, 64>(tp, n_seqs, max_len, st, true);
         else rc = causal ? launch_varlen<128, true, 64>(tp, n_seqs, max_len, st, true) : launch_varlen<128, false, 64>(tp, n_seqs, max_len, st, true);
         if (rc != OPUS_OK) return rc;
       }
