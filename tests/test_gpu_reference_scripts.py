@@ -1,7 +1,8 @@
 """GPU: the reference's OWN eval scripts, unmodified, running on this backend (north star: "the eval scripts stay drop-in
 compatible").
 
-The scripts are executed from baseline/_ref/ — the unmodified reference tree staged there by oracle/stage_reference.py
+The scripts are executed from baseline/_ref/ — the three scripts and the helper modules they import, staged there
+unmodified by oracle/stage_reference.py
 (git-ignored, travels to the GPU box with the snapshot; /root/reference does not exist there). `opus_pllm_b200.compat`
 registers this package as `multi_modality_model.multi_modality_v1.model.builder`, so the scripts' own import statement
 yields this backend's `load_pretrained_model`; everything else they import from the reference (constants, conversation
