@@ -592,6 +592,56 @@ def test_continuous_batching_compacts_into_smaller_batch_tiers():
     assert len(model.llama._alloc.free) == model.llama._alloc.num_blocks
 
 
+def test_two_contexts_two_threads_generate_concurrently():
+    """the C ABI is re-entrant per context. Two host threads, each with its own opus_ctx, CUDA stream and model,
+    generate at the same time (decode graphs, stream-K scratch and tunables are per context; error strings per thread);
+    both reproduce what they produce alone, and a tunable set in one context does not leak into the other."""
+    import ctypes as C
+    import threading
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    lib = L.load()
+    cfg = SMALL
+    kw = {k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()}
+    models, inputs, alone = [], [], []
+    for i in range(2):
+        w = synth.llama_weights(seed=20 + i, peaked=True, device="cuda", **kw)
+        m = B200Llama(w, **cfg)
+        lens = [20 + (j * (3 + i)) % 30 for j in range(24 + 8 * i)]
+        cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(40 + i))
+        emb = w["model.embed_tokens.weight"][tok.cuda()].to(torch.bfloat16)
+        models.append(m); inputs.append((emb, cu))
+        alone.append(m.generate_packed(emb, cu, 16).cpu())
+    torch.cuda.synchronize()
+    out, err = [None, None], [None, None]
+
+    def worker(i):
+        try:
+            ctx = C.c_void_p()
+            L.check(lib.opus_ctx_create(C.byref(ctx)))
+            L.check(lib.opus_ctx_set_current(ctx))
+            if i == 1:
+                L.check(lib.opus_set_tunable(b"decode_rope_fused", 0))      # this context only
+            with torch.cuda.stream(torch.cuda.Stream()):
+                res = [models[i].generate_packed(*inputs[i], 16) for _ in range(3)]
+                torch.cuda.current_stream().synchronize()
+            out[i] = [r.cpu() for r in res]
+            L.check(lib.opus_release_graphs())
+            L.check(lib.opus_ctx_set_current(None))
+            L.check(lib.opus_ctx_destroy(ctx))
+        except Exception as e:  # noqa: BLE001
+            err[i] = e
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert err == [None, None], err
+    for i in range(2):
+        assert all(torch.equal(r, alone[i]) for r in out[i])
+    # the default context still has its own (default) tunables and works afterwards
+    assert torch.equal(models[0].generate_packed(*inputs[0], 16).cpu(), alone[0])
+
+
 # ------------------------------------------------------------------------------------------------ loaders + eval driver
 def test_load_pretrained_model_and_eval_driver(tmp_path):
     """A fake OPUS-PLLM release on disk (HF safetensors dir, peft adapter, switch .bin, Lightning ckpt, fair-esm .pt)
