@@ -1,21 +1,17 @@
 // Flash attention forward on tcgen05 tensor cores (variable-length packed sequences; bidirectional or causal GQA).
 //
 // One CTA = TWO 128-row query tiles (A, B) of one (sequence, head), processed ping-pong so that the tensor pipe works on
-// one tile while the softmax warps of the other tile are busy. Warp roles (576 threads):
+// one tile while the softmax warps of the other tile are busy. Warp roles (320 threads):
 //   warp 0      TMA producer: both Q tiles once, then K blocks and V blocks (128 keys) into two independent rings
 //               (SWIZZLE_128B panels of 64 columns);
 //   warp 1      MMA issuer (one thread) + TMEM owner:
 //                 S_X = Q_X K^T        UMMA 128x128x16, both operands K-major from shared memory
 //                 O_X (+)= P_X V       UMMA 128xDx16, A = P read from TENSOR MEMORY, B = V MN-major from shared memory
-//   warps 2-9   softmax of tile A, warps 10-17 softmax of tile B: TWO threads per query row (TMEM lane), each owning 64 of
-//               the 128 key columns of a block (the per-block chain S -> tcgen05.ld -> max -> exp2 -> tcgen05.st -> PV is
-//               latency bound, so halving the serial work per thread shortens it; the two halves exchange their row maximum
-//               through shared memory once per block and their row sums once per item). One pass: S (64 fp32) ->
-//               registers, max, exp2, row sum, bf16 P written back with tcgen05.st over the first 64 columns of S (P
-//               aliases S; every S value is in registers before the first P column is written). O stays in TMEM across
-//               key blocks; the softmax warps rescale it in place (half of the columns each) only when a row's running
-//               maximum grew by more than 2^8 (lazy rescaling: O and the row sum always share one reference maximum, so
-//               the result is exact).
+//   warps 2-5   softmax of tile A, warps 6-9 softmax of tile B: thread = query row (TMEM lane), so row max / row sum need
+//               no shuffles. One pass: S (128 fp32) -> registers, max, exp2, row sum, bf16 P written back with
+//               tcgen05.st over the first 64 columns of S (P aliases S). O stays in TMEM across key blocks; the softmax
+//               warps rescale it in place only when a row's running maximum grew by more than 2^8 (lazy rescaling:
+//               O and the row sum always share one reference maximum, so the result is exact).
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,256+D) O_B [256+D,256+2D).
 // Nothing T x T is materialised; K/V rows beyond the sequence end (next packed sequence / OOB zero fill) are masked in S.
 #include "common.h"
@@ -34,8 +30,7 @@ namespace {
 constexpr int TBM = 128;   // query rows per tile (two tiles per CTA)
 constexpr int TBN = 128;   // keys per block
 constexpr int PANEL = 128 * 128;  // bytes of one [128 rows x 64 bf16] swizzled panel
-constexpr int TC_THREADS = 576;   // 2 + 16 warps
-constexpr int SM_THREADS = 256;   // softmax threads per query tile (two per row)
+constexpr int TC_THREADS = 320;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnTcParams {
@@ -55,8 +50,7 @@ struct TcCfg {
   static constexpr int TILE_BYTES = NP * PANEL;           // one Q tile / one K block / one V block
   static constexpr int KS = (D == 128) ? 2 : 3;           // K ring stages
   static constexpr int VS = (D == 128) ? 2 : 3;           // V ring stages
-  static constexpr int XCHG_BYTES = 2 * 3 * 2 * 128 * 4;   // per tile: [block parity][half][row] row maxima + [half][row] row sums
-  static constexpr int SMEM = (2 + KS + VS) * TILE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + XCHG_BYTES;
+  static constexpr int SMEM = (2 + KS + VS) * TILE_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = 512;
   static constexpr int COL_S = 0, COL_O = 256;
 };
@@ -136,48 +130,31 @@ constexpr uint32_t kExpPolyMask = 0x552Au;
 
 // Softmax of one row over NC (= 128, or 32 for narrow tail blocks) S columns: S -> registers, mask, row maximum, lazy
 // reference-maximum update, exp2, row sum, bf16 P written back over S. Returns whether O must be rescaled by `corr`.
-// `half` selects this thread's columns: [half * NC/2, (half + 1) * NC/2) of the block (NC = 128), or, for narrow tail
-// blocks (NC = 32), all 32 columns for half 0 and none for half 1. xm = this tile's [2][128] exchange area for the row
-// maxima of THIS block (the caller alternates between two areas by block parity, so a thread that is one block ahead never
-// overwrites values its partner has not read yet); bar_id = the tile's named barrier (256 threads).
 template <int NC, bool CAUSAL>
 __device__ __forceinline__ bool softmax_block(uint32_t t_s, int k0, int len, int qrow, int qt0, float scale_log2,
-                                              bool first, float& m_run, float& l_run, float& corr, int half, int row,
-                                              float* xm, int bar_id) {
-  constexpr int W = NC == 128 ? 64 : 32;          // columns of this thread
-  const bool active = NC == 128 || half == 0;
-  const int c0 = NC == 128 ? half * 64 : 0;       // first column
-  uint32_t s[W];
-  if (active) {
+                                              bool first, float& m_run, float& l_run, float& corr) {
+  uint32_t s[NC];
 #pragma unroll
-    for (int c = 0; c < W / 32; ++c) tmem_ld_32x32(t_s + c0 + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
-    tmem_ld_wait();
-  } else {
-#pragma unroll
-    for (int i = 0; i < W; ++i) s[i] = 0xff800000u;
-  }
+  for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+  tmem_ld_wait();
   const bool need_mask = (k0 + NC > len) || (CAUSAL && k0 + NC - 1 > qt0);
-  if (need_mask && active) {
+  if (need_mask) {
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-      const int key = k0 + c0 + i;
+    for (int i = 0; i < NC; ++i) {
+      const int key = k0 + i;
       const bool ok = key < len && (!CAUSAL || key <= qrow);
       if (!ok) s[i] = 0xff800000u;  // -inf
     }
   }
   float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < W; i += 4) {
+  for (int i = 0; i < NC; i += 4) {
     mx0 = fmaxf(mx0, __uint_as_float(s[i]));
     mx1 = fmaxf(mx1, __uint_as_float(s[i + 1]));
     mx2 = fmaxf(mx2, __uint_as_float(s[i + 2]));
     mx3 = fmaxf(mx3, __uint_as_float(s[i + 3]));
   }
-  // the row maximum over both halves: every S value of the block is in registers by now (the barrier also orders the
-  // other half's tcgen05.ld before this thread's P store over the shared S / P columns)
-  xm[half * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-  named_bar_sync(bar_id, SM_THREADS);
-  const float m_blk = fmaxf(xm[row], xm[128 + row]) * scale_log2;
+  const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
   // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
   corr = 1.0f;
   bool rescale = false;
@@ -188,9 +165,9 @@ __device__ __forceinline__ bool softmax_block(uint32_t t_s, int k0, int len, int
   }
   const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
   float ls0 = 0.f, ls1 = 0.f;
-  uint32_t pk[W / 2];
+  uint32_t pk[NC / 2];
 #pragma unroll
-  for (int i = 0; i < W; i += 2) {
+  for (int i = 0; i < NC; i += 2) {
     const float x0 = fmaf(__uint_as_float(s[i]), scale_log2, -m_use);
     const float x1 = fmaf(__uint_as_float(s[i + 1]), scale_log2, -m_use);
     const float p0 = ((kExpPolyMask >> (i & 15)) & 1u) ? exp2_fma(x0) : ex2_approx(x0);
@@ -199,13 +176,12 @@ __device__ __forceinline__ bool softmax_block(uint32_t t_s, int k0, int len, int
     ls1 += p1;
     pk[i >> 1] = pack_bf16x2(p0, p1);
   }
-  l_run = l_run * corr + (ls0 + ls1);        // this half's share of the row sum
-  if (active) {
-    if constexpr (NC == 128) {
-      tmem_st_32x32(t_s + half * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-    } else {
-      tmem_st_32x16(t_s, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
-    }
+  l_run = l_run * corr + (ls0 + ls1);
+  if constexpr (NC == 128) {
+    tmem_st_32x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+    tmem_st_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+  } else {
+    tmem_st_32x16(t_s, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
   }
   return rescale;
 }
@@ -269,7 +245,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     mbar_init(q_empty, 1);
     for (int s = 0; s < C::KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < C::VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], SM_THREADS); mbar_init(&o_done[x], 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&o_done[x], 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -388,17 +364,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
     }
   } else {
-    // ===================== softmax warps: two threads per query row =====================
-    const int x = (warp - 2) >> 3;             // tile A (warps 2-9) or B (warps 10-17)
-    const int half = ((warp - 2) >> 2) & 1;    // which 64 of the 128 key columns of a block (and which half of O)
+    // ===================== softmax warps: thread = query row =====================
+    const int x = (warp - 2) >> 2;             // tile A (warps 2-5) or B (warps 6-9)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access (warp id % 4)
     const int row = quad * 32 + lane;          // row inside the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t t_s = tmem_base + lane_addr + C::COL_S + x * TBN;
     const uint32_t t_o = tmem_base + lane_addr + C::COL_O + x * D;
-    float* xchg = reinterpret_cast<float*>(smem + (2 + C::KS + C::VS) * C::TILE_BYTES + 1024) + x * (3 * 2 * 128);
-    float* xl = xchg + 2 * 2 * 128;            // [half][row] row sums (once per item)
-    const int bar_id = 1 + x;
     uint32_t g = 0;                            // key blocks processed by this warp group so far (barrier phases)
 
     for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
@@ -409,24 +381,23 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int len = it.len;
       const int qt0 = it.q0 + x * TBM;           // first query row of the tile (sequence-relative)
       const int qrow = qt0 + row;
-      float m_run = -INFINITY, l_run = 0.f;      // m_run in scaled log2 units; l_run = this half's share of the row sum
+      float m_run = -INFINITY, l_run = 0.f;      // m_run in scaled log2 units
 
       for (int j = 0; j < n_blocks; ++j, ++g) {
         const int k0 = j * TBN;
         mbar_wait(&s_full[x], g & 1);
         tc_fence_after();
         float corr;
-        float* xm = xchg + (g & 1) * (2 * 128);
         const bool rescale = (NARROW && block_keys(len, j) <= 32)
-                                 ? softmax_block<32, CAUSAL>(t_s, k0, len, qrow, qt0, p.scale_log2, j == 0, m_run, l_run, corr, half, row, xm, bar_id)
-                                 : softmax_block<128, CAUSAL>(t_s, k0, len, qrow, qt0, p.scale_log2, j == 0, m_run, l_run, corr, half, row, xm, bar_id);
+                                 ? softmax_block<32, CAUSAL>(t_s, k0, len, qrow, qt0, p.scale_log2, j == 0, m_run, l_run, corr)
+                                 : softmax_block<128, CAUSAL>(t_s, k0, len, qrow, qt0, p.scale_log2, j == 0, m_run, l_run, corr);
         if (j > 0) {
           // O_X must include block j-1 before it may be rescaled / before PV(j) accumulates on top of it
           mbar_wait(&o_done[x], (g - 1) & 1);
           tc_fence_after();
           if (__any_sync(0xffffffffu, rescale)) {
 #pragma unroll 1
-            for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {   // this half's share of the O columns
+            for (int c = 0; c < D / 32; ++c) {
               uint32_t r[32];
               tmem_ld_32x32(t_o + c * 32, r);
               tmem_ld_wait();
@@ -442,15 +413,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
       // O_X is complete once the PV MMA of the last block retires; the next item's PV_X(0) cannot start before this
       // warp group has produced that item's P_X(0), i.e. after this read-out.
-      xl[half * 128 + row] = l_run;
-      named_bar_sync(bar_id, SM_THREADS);
-      const float l_tot = xl[row] + xl[128 + row];
       mbar_wait(&o_done[x], (g - 1) & 1);
       tc_fence_after();
-      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
       __nv_bfloat16* dst = p.o + (size_t)(it.seq_start + qrow) * p.ldo + (size_t)it.h * D;
 #pragma unroll 1
-      for (int c = half * (D / 64); c < (half + 1) * (D / 64); ++c) {
+      for (int c = 0; c < D / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32(t_o + c * 32, r);
         tmem_ld_wait();
@@ -467,7 +435,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
       }
       tc_fence_before();
-      named_bar_sync(bar_id, SM_THREADS);      // xl is rewritten by the next item only after both halves have read it
     }
   }
 
