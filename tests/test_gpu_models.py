@@ -642,6 +642,45 @@ def test_two_contexts_two_threads_generate_concurrently():
     assert torch.equal(models[0].generate_packed(*inputs[0], 16).cpu(), alone[0])
 
 
+def test_opt_in_tunables_keep_the_results():
+    """Measured-and-parked alternatives stay correct: split-KV decode attention (2 / 4 parts, last-arriver merge), L2
+    lookahead and the epilogue warm-up pass in the swap-AB GEMM (bit-identical by construction), grouped-N raster of the
+    CTA-pair kernel (bit-identical: same k order per tile)."""
+    from opus_pllm_b200 import _lib as L, ops
+    from opus_pllm_b200.llama import B200Llama
+    lib = L.load()
+    cfg = dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128, ffn_dim=14336, vocab=8192)
+    w = synth.llama_weights(seed=4, peaked=True, device="cuda", **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [150 + (i * 37) % 200 for i in range(24)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(6))
+    emb = w["model.embed_tokens.weight"][tok.cuda()].to(torch.bfloat16)
+    base = model.generate_packed(emb, cu, 10)
+    base_logits = model._ws_bufs["logits"][:24].float().clone()
+    try:
+        for name, val, exact in (("attn_split", 2, False), ("attn_split", 4, False), ("attn_split", -1, False),
+                                 ("l2_ahead", 8, True), ("epi_warm", 1, True)):
+            L.check(lib.opus_set_tunable(name.encode(), val))
+            got = model.generate_packed(emb, cu, 10)
+            logits = model._ws_bufs["logits"][:24].float().clone()
+            L.check(lib.opus_set_tunable(name.encode(), 0))
+            assert torch.equal(got, base), (name, val)
+            if exact:
+                assert torch.equal(logits, base_logits), (name, val)
+            else:
+                assert _cos(logits, base_logits) >= 0.9999, (name, val)
+        x = (torch.randn(2048, 14336, device="cuda") * 0.05).bfloat16()
+        wd = (torch.randn(4096, 14336, device="cuda") * 0.02).bfloat16()
+        res = torch.randn(2048, 4096, device="cuda").bfloat16()
+        ref = ops.gemm(x, wd, epilogue=L.EPI_RES_BF16, residual=res, transposed=False)
+        L.check(lib.opus_set_tunable(b"group_n", 8))
+        assert torch.equal(ops.gemm(x, wd, epilogue=L.EPI_RES_BF16, residual=res, transposed=False), ref)
+    finally:
+        for name in ("attn_split", "l2_ahead", "epi_warm", "group_n"):
+            L.check(lib.opus_set_tunable(name.encode(), 0))
+
+
 # ------------------------------------------------------------------------------------------------ loaders + eval driver
 def test_load_pretrained_model_and_eval_driver(tmp_path):
     """A fake OPUS-PLLM release on disk (HF safetensors dir, peft adapter, switch .bin, Lightning ckpt, fair-esm .pt)
