@@ -182,3 +182,48 @@ def test_c5_continuous_batching_vs_oracle(full):
     same = sum(int(torch.equal(g.cpu(), w)) for g, w in zip(got, want))
     assert len(got) == n and same >= n - 0, (same, n)
     assert len(model.llama._alloc.free) == model.llama._alloc.num_blocks
+
+
+def test_c3_batch256_decode_full_depth(full):
+    """BASELINE config 3 regime at full width and depth: 256 prompts in one decode batch, i.e. the CTA-pair swap-AB kernels
+    (q|k|v, o_proj, gate/up, down, lm_head at a 256-wide batch tile) and the large-batch paged attention, against the
+    oracle's greedy loop. Short prompts keep the oracle cheap; >= 99 % of the prompts must agree token for token."""
+    model, sd = full["model"], full["sd"]
+    lc = sd["llama_cfg"]
+    ocfg = llama_ref.LlamaCfg(n_layers=lc["n_layers"], dim=lc["dim"], n_q_heads=lc["n_q_heads"],
+                              n_kv_heads=lc["n_kv_heads"], head_dim=lc["head_dim"], ffn_dim=lc["ffn_dim"], vocab=lc["vocab"])
+    n, new = 256, 16
+    lens = [40 + (i * 7) % 24 for i in range(n)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(1000, 120000, (int(cu[-1]),), generator=torch.Generator().manual_seed(77))
+    emb_w = sd["llama"]["model.embed_tokens.weight"]
+    emb = emb_w[tok.cuda()].to(torch.bfloat16)
+    got = model.llama.generate_packed(emb, cu, new)
+    assert got.shape == (n, new)
+    Lm = max(lens)
+    e = torch.zeros(n, Lm, lc["dim"], dtype=torch.bfloat16, device="cuda")
+    m = torch.zeros(n, Lm, dtype=torch.bool, device="cuda")
+    for b in range(n):
+        e[b, Lm - lens[b]:] = emb[cu[b]: cu[b + 1]]
+        m[b, Lm - lens[b]:] = True
+    want = []
+    with torch.no_grad():
+        for lo in range(0, n, 64):
+            want.append(llama_ref.greedy_generate(sd["llama"], ocfg, e[lo: lo + 64], m[lo: lo + 64], new))
+    want = torch.cat(want)
+    same = float((got == want).all(1).float().mean())
+    assert same >= 0.99, same
+
+
+def test_c4_long_proteins_full_depth(full):
+    """BASELINE config 4 at full depth: 33-layer ESM-2-650M on packed variable-length proteins of 1024-2048 residues
+    (positions beyond 1024, multi-block tcgen05 attention with ragged tails) against the fp32 oracle, one protein at a time."""
+    model, sd = full["model"], full["sd"]
+    ecfg = sd["esm_cfg"]
+    seqs = synth.proteins(4, 1024, 2048, seed=44)
+    got = model.protein_encoder.get_protein_seq_embeddings(seqs)
+    with torch.no_grad():
+        want = torch.cat([esm2_ref.get_protein_seq_embeddings(sd["esm"], [s], ecfg["n_layers"], ecfg["n_heads"]) for s in seqs])
+    cos = _cos_rows(got, want)
+    assert float(cos.min()) >= 0.9995, float(cos.min())
+    assert float((got - want).abs().max()) <= 3e-2, float((got - want).abs().max())
