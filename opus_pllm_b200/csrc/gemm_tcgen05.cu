@@ -1792,7 +1792,7 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   }
 
   if (a.sumsq_out != nullptr) {
-    if (!a.transposed || a.epi != EPI_RES_BF16 || a.sumsq_ld < a.N) return OPUS_ERR_ARG;
+    if (!a.transposed || a.epi != EPI_RES_BF16 || a.sumsq_ld < a.N || (a.M % 32)) return OPUS_ERR_ARG;
     p.sumsq_out = a.sumsq_out; p.sumsq_ld = a.sumsq_ld;
   }
   if (a.norm_sumsq != nullptr) {
