@@ -33,8 +33,9 @@ WORKLOADS = {
     # generate-type steps: encoder -> projectors -> splice -> prefill -> greedy decode of one batch
     "c2": dict(kind="generate", batch=64, protein_len=256, prompt_len=512, new_tokens=32,
                desc="OPUS-PLLM-Llama3-8B random-init, subcellular-localization prompts, bs 64, seq 512, 32 new tokens"),
-    "c3": dict(kind="generate", batch=256, protein_len=256, prompt_len=128, new_tokens=128,
-               desc="Llama3-8B+LoRA GO-term generation shard, bs 256/GPU, prompt 128, 128 new tokens"),
+    # BASELINE configs[2]: 4096 prompts over 8 GPUs = one shard of 512 prompts per GPU, decoded as ONE batch
+    "c3": dict(kind="generate", batch=512, protein_len=256, prompt_len=128, new_tokens=128,
+               desc="Llama3-8B+LoRA GO-term generation shard, 512 prompts/GPU in one batch, prompt 128, 128 new tokens"),
     "tiny": dict(kind="generate", batch=8, protein_len=64, prompt_len=64, new_tokens=8,
                  desc="tiny smoke workload (not a bench line)"),
     # BASELINE configs[0]: encoder + projector forward only (metric 2, residues/s)
@@ -44,9 +45,9 @@ WORKLOADS = {
     "c4": dict(kind="encode_prefill", batch=256, protein_len=(1024, 2048), prompt_len=128,
                desc="long-protein encoder stress: 256 seqs len U[1024,2048] varlen, encoder + projectors + prefill only"),
     # BASELINE configs[4]: long generations with ragged stops, continuous batching over the paged KV cache
-    "c5": dict(kind="continuous", requests=512, slots=256, protein_len=(64, 1024), prompt_len=128, new_tokens=512,
+    "c5": dict(kind="continuous", requests=1024, slots=512, protein_len=(64, 1024), prompt_len=128, new_tokens=512,
                stop_len=(64, 512),
-               desc="functional-description generation, up to 512 new tokens, continuous batching (256 slots) with paged KV; "
+               desc="functional-description generation, up to 512 new tokens, continuous batching (512 slots) with paged KV; "
                     "a random-init model has no meaningful EOS, so every request carries a synthetic stop length "
                     "U[64,512] (deterministic work)"),
 }
@@ -409,8 +410,19 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true",
                     help="skip the stock-transformers GPU leg (gpu_reference key of the default c2 line)")
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=INT",
+                    help="experiments only: override an integer field of the workload (e.g. --set batch=256); the "
+                         "override is recorded in config.overrides")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload] if args.size == "full" else _shrink(WORKLOADS[args.workload])
+    if args.set:
+        wl = dict(wl)
+        for kv in args.set:
+            k, v = kv.split("=")
+            if k not in wl or not isinstance(wl[k], int):
+                ap.error(f"--set {kv}: {k!r} is not an integer field of workload {args.workload}")
+            wl[k] = int(v)
+        wl["desc"] += " [overrides: " + ", ".join(args.set) + "]"
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -53,6 +53,7 @@ Tunables Tunables::from_env() {
   t.l2_ahead = env_int("OPUS_L2_AHEAD", 0);
   t.pair_streamk = env_int("OPUS_PAIR_STREAMK", 0) == 1;
   t.epi_warm = env_int("OPUS_EPI_WARM", 0) == 1;   // measured: no gain (tools/hop_probe.py WARM_AB=1), off by default
+  t.wide_overhead = env_int("OPUS_WIDE_OVERHEAD", 8);
   t.decode_norm_fused = env_int("OPUS_DECODE_NORM_FUSED", 0) == 1;
   return t;
 }

@@ -34,6 +34,7 @@ struct Tunables {
   int pair_streamk;       // OPUS_PAIR_STREAMK: stream-K tail in the CTA-pair swap-AB kernel (default off: measured slower)
   int attn_split;         // OPUS_ATTN_SPLIT: split-KV parts of the decode attention (0 / 1 off = default, -1 automatic, 2, 4)
   int epi_warm;           // OPUS_EPI_WARM: swap-AB GEMMs run their epilogue once "dry" to warm the instruction cache
+  int wide_overhead;      // OPUS_WIDE_OVERHEAD: per-item cost (in k-blocks) of the split-K choice at batch 257..512
   int decode_norm_fused;  // decode: RMSNorm folded into the GEMMs (in-kernel split-K reduce + norm-on-load), batch <= 64
   static Tunables from_env();
 };

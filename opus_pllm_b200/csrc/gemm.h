@@ -61,6 +61,7 @@ struct GemmParams {
   int rl_hq, rl_hkv, rl_bs;
   int dp_items;   // work items walked round-robin (full tiles x split_k) before the stream-K tail
   int sk_tiles;
+  int sk_share;   // CTAs (pairs) sharing the tail; 0 = all of them. A tail of a few tiles is cut into 8 pieces per tile only
   float* sk_ws;
   int* sk_cnt;
   // In-kernel split-K reduction (swap-AB, one wave): the CTA holding a tile's LAST k-split waits for the CTAs holding the
@@ -103,6 +104,7 @@ struct GemmArgs {
   int ldr;
   int split_k;  // 0/1 = none
   int block_n;  // 0 = auto
+  int streamk_tail;  // plain form: allow the stream-K tail for this launch (decode at batch 257..512; default: tunable streamk_plain)
   // Optional hint: the weight matrix [pf_rows, pf_K] (row stride pf_K) that the NEXT swap-AB launch on this stream will
   // stream with split factor pf_split_k. When pf_w != nullptr every CTA, after issuing its last own load, asks the TMA
   // unit to prefetch the first pf_depth k-blocks of "its" work item of that launch into L2, so HBM stays busy while
@@ -167,6 +169,7 @@ int gemm_chain_trace(int enable, unsigned long long* out, int cap_words);
 void gemm_set_chain_l2_depth(int kblocks);
 int gemm_pick_bn(int N, int transposed);
 int gemm_pick_split_k(int M, int N, int K, int bn);
+int gemm_pick_split_k_wide(int M, int N, int K);   // batch 257..512 on the CTA-pair swap-AB kernel
 size_t gemm_workspace_bytes(int M, int N, int split_k);
 void gemm_set_streamk_fill(int percent);  // 0 disables the stream-K tail
 void gemm_set_streamk_plain(int on);

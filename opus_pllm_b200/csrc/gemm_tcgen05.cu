@@ -99,7 +99,8 @@ __device__ __forceinline__ bool get_work_bg(const GemmParams& p, int it, TileCoo
   const int kb = p.k_blocks;
   if (p.sk_tiles > 0) {
     const long long U = (long long)p.sk_tiles * kb;
-    const int ge = U < g ? (int)U : g;  // CTAs sharing the tail: every one of them gets at least one unit
+    int ge = U < g ? (int)U : g;  // CTAs sharing the tail: every one of them gets at least one unit
+    if (p.sk_share > 0 && p.sk_share < ge) ge = p.sk_share;   // a small tail: few pieces per tile, short fix-ups
     if (b < ge) {
       const int u0 = (int)((long long)b * U / ge), u1 = (int)((long long)(b + 1) * U / ge);
       const int tA = u0 / kb, tB = (u1 - 1) / kb;
@@ -1706,6 +1707,24 @@ int gemm_pick_split_k(int M, int N, int K, int bn) {
   return s < 1 ? 1 : s;
 }
 
+// Swap-AB launches at batch 257..512 (two 256-wide batch tiles) run on the CTA-pair kernel; their work items are
+// (256-feature tile, batch tile, k-split). Pick the split with the shortest critical path: whole waves of pairs times the
+// k-blocks of one item plus a per-item cost (ring fill, accumulator drain, one more fp32 partial slice to reduce).
+int gemm_pick_split_k_wide(int M, int N, int K) {
+  const int items1 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+  const int kb = (K + BK - 1) / BK;
+  const int pairs = num_sms() / 2;
+  const int over = ctx().tun.wide_overhead;
+  int best = 1;
+  long best_cost = -1;
+  for (int s = 1; s <= 8 && kb / s >= 4; ++s) {
+    const int waves = (items1 * s + pairs - 1) / pairs;
+    const long cost = (long)waves * ((kb + s - 1) / s + over + 2 * s);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 size_t gemm_workspace_bytes(int M, int N, int split_k) { return (size_t)split_k * M * N * sizeof(float); }
 
 // Validates `a` and fills the device parameter block (tiling, split-K, stream-K tail, prefetch hint). bn = tile width.
@@ -1819,12 +1838,15 @@ static int prepare_gemm(const GemmArgs& a, GemmParams& p, int& bn) {
   // wave quantisation: a last wave that fills only part of the machine is cut along K over all CTAs instead
   const int rem = tiles % num_sms();
   const bool sk_ready = ensure_sk_workspace();  // also on launches that do not need it: never first inside a capture
-  if (p.split_k == 1 && (a.transposed || tun.streamk_plain) && tiles > num_sms() && rem != 0 &&
+  if (p.split_k == 1 && (a.transposed || tun.streamk_plain || a.streamk_tail) && tiles > num_sms() && rem != 0 &&
       rem * 100 <= tun.streamk_fill * num_sms() && a.epi != EPI_PARTIAL_F32 && sk_ready) {
     p.sk_tiles = rem;
     p.dp_items = tiles - rem;
     p.sk_ws = ctx().sk.ws;
     p.sk_cnt = ctx().sk.cnt;
+    // a tail of a few tiles (gate/up at batch 512: 448 tiles = 3 waves + 4): 8 pieces per tile on the first CTAs instead of
+    // a sliver on every CTA, so a tile's owner adds 7 accumulator dumps, not 36
+    if (!a.transposed && rem * 10 <= num_sms()) p.sk_share = rem * 8;
   }
   return OPUS_OK;
 }
@@ -1845,6 +1867,15 @@ bool gemm_fuses_rope(const GemmArgs& a) {
 
 namespace {
 
+// Stream-K tail of the CTA-pair swap-AB kernel: a tail of a few tiles (<= 10 % of the pairs, e.g. gate/up at batch 512:
+// 224 items = 3 waves + 2) is always cut along K, since its fix-up traffic is a couple of accumulators; larger tails only
+// with the tunable pair_streamk (a 256-wide accumulator dump is 128 KB per CTA, measured slower at batch 256).
+bool pair_streamk_takes(int rem, int max_pairs) {
+  if (rem == 0) return false;
+  if (rem * 10 <= max_pairs) return true;
+  return ctx().tun.pair_streamk && rem * 100 <= ctx().tun.streamk_fill * max_pairs;
+}
+
 template <bool TR>
 int launch_2cta(const GemmParams& p_in, const GemmArgs& a, cudaStream_t stream) {
   GemmParams p = p_in;
@@ -1861,12 +1892,15 @@ int launch_2cta(const GemmParams& p_in, const GemmArgs& a, cudaStream_t stream) 
     // opt-in (tunable pair_streamk): at a 256-wide batch tile a dumped accumulator is 128 KB per CTA, and the fix-up
     // traffic costs more than the partial wave it removes (gate/up at batch 256: 6.17 ms per step with two uneven
     // waves, 6.27 with the tail cut along K)
-    if (ctx().tun.pair_streamk && p.split_k == 1 && items > max_pairs && rem != 0 &&
-        rem * 100 <= ctx().tun.streamk_fill * max_pairs && a.epi != EPI_PARTIAL_F32 && ensure_sk_workspace()) {
+    if (pair_streamk_takes(rem, max_pairs) && p.split_k == 1 && items > max_pairs && rem != 0 && ctx().tun.streamk &&
+        a.epi != EPI_PARTIAL_F32 && ensure_sk_workspace()) {
       p.sk_tiles = rem;
       p.dp_items = items - rem;
       p.sk_ws = ctx().sk.ws;
       p.sk_cnt = ctx().sk.cnt;
+      // a tail of a few tiles: 8 pieces per tile on the first pairs instead of one sliver on every pair (the tile's owner
+      // adds the other pieces' 128 KB accumulator dumps one after the other)
+      if (rem * 10 <= max_pairs && !ctx().tun.pair_streamk) p.sk_share = rem * 8 < max_pairs ? rem * 8 : max_pairs;
     }
   }
   static bool configured = false;
@@ -1911,7 +1945,7 @@ int launch_2cta(const GemmParams& p_in, const GemmArgs& a, cudaStream_t stream) 
 // stays with the single-CTA kernel (decode gate/up: 112 pair tiles would be 1.5 waves).
 bool pair_takes_transposed(const GemmArgs& a, const GemmParams& p, int bn) {
   const int g_2cta_tr = ctx().tun.gemm_2cta_tr;
-  if (!g_2cta_tr || !a.transposed || bn != 256 || a.block_n != 0 || a.N <= 128 || a.N > 256) return false;
+  if (!g_2cta_tr || !a.transposed || bn != 256 || a.block_n != 0 || a.N <= 128 || a.N > 512) return false;
   if (a.epi == EPI_SWIGLU && g_2cta_tr < 2) return false;     // tunable gemm_2cta_tr = 1: gate/up stays on the single-CTA kernel
   if (a.splitk_fixup || a.sumsq_out != nullptr || a.norm_sumsq != nullptr || a.pf_w != nullptr) return false;
   const int max_pairs = num_sms() / 2;
@@ -1919,8 +1953,7 @@ bool pair_takes_transposed(const GemmArgs& a, const GemmParams& p, int bn) {
   if (items < max_pairs) return items * 100 >= 85 * max_pairs;   // a single, well filled wave
   // several waves: whole waves, or a partial last wave that the stream-K tail spreads over all pairs
   const int rem = items % max_pairs;
-  const bool sk_ok = ctx().tun.pair_streamk && p.split_k == 1 && a.epi != EPI_PARTIAL_F32 && ctx().tun.streamk &&
-                     rem * 100 <= ctx().tun.streamk_fill * max_pairs;
+  const bool sk_ok = pair_streamk_takes(rem, max_pairs) && p.split_k == 1 && a.epi != EPI_PARTIAL_F32 && ctx().tun.streamk;
   const int waves = (items + max_pairs - 1) / max_pairs;
   return rem == 0 || sk_ok || items * 100 >= (a.epi == EPI_SWIGLU ? 75 : 85) * waves * max_pairs;
 }

@@ -105,6 +105,9 @@ int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* 
     a.transposed = 0;
     a.A = x; a.lda = K; a.M = rows;
     a.B = w; a.ldb = K; a.N = N;
+    // decode at batch 257..512 (gate/up: 448 tiles = 3 waves + 4): the partial last wave is cut along K. Larger launches
+    // (prefill) keep one summation order for every token row.
+    a.streamk_tail = rows <= 512;
   }
   (void)ws; (void)ws_bytes;
   return gemm_bf16(a, st);
@@ -113,7 +116,8 @@ int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* 
 // swap-AB GEMM with split-K partials into `partial` ([s][rows][N] fp32). Returns the split count via *splits.
 int splitk_for(int rows, int N, int K, size_t partial_bytes) {
   const int bn = gemm_pick_bn(rows, 1);
-  int s = gemm_pick_split_k(N, rows, K, bn);
+  int s = (rows > 256 && rows <= 512 && ctx().tun.gemm_2cta_tr) ? gemm_pick_split_k_wide(N, rows, K)
+                                                                : gemm_pick_split_k(N, rows, K, bn);
   while (s > 1 && gemm_workspace_bytes(rows, N, s) > partial_bytes) --s;
   return s;
 }
@@ -668,6 +672,7 @@ int set_tunable(const char* name, int value) {
   else if (std::strcmp(name, "group_n_hints") == 0) t.group_n_hints = value != 0;
   else if (std::strcmp(name, "group_m") == 0) t.group_m = value < 0 ? 0 : value;
   else if (std::strcmp(name, "l2_ahead") == 0) t.l2_ahead = value < 0 ? 0 : value;
+  else if (std::strcmp(name, "wide_overhead") == 0) t.wide_overhead = value < 0 ? 0 : value;
   else if (std::strcmp(name, "decode_norm_fused") == 0) t.decode_norm_fused = value != 0;
   else {
     known = false;

@@ -195,9 +195,10 @@ class ContinuousBatcher:
                     retire(s)
             return True
 
-        # decode batch tiers of the kernels (batch tile 32 / 64 / 128 / 256): once the queue is empty the live requests are
-        # compacted into the smallest tier that holds them, so the ramp-down of a job does not pay full-batch steps
-        tiers = sorted({t for t in (32, 64, 128, 256) if t < S} | {S})
+        # decode batch tiers of the kernels (batch tile 32 / 64 / 128 / 256, two batch tiles above that): once the queue is
+        # empty the live requests are compacted into the smallest tier that holds them, so the ramp-down of a job does not
+        # pay full-batch steps
+        tiers = sorted({t for t in (32, 64, 128, 256, 384, 512) if t < S} | {S})
         n_compact = 0
         while waiting or active:
             # ---- admit chunk after chunk until the slots are full or the queue is empty; only then decode a round

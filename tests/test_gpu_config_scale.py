@@ -184,15 +184,18 @@ def test_c5_continuous_batching_vs_oracle(full):
     assert len(model.llama._alloc.free) == model.llama._alloc.num_blocks
 
 
-def test_c3_batch256_decode_full_depth(full):
-    """BASELINE config 3 regime at full width and depth: 256 prompts in one decode batch, i.e. the CTA-pair swap-AB kernels
-    (q|k|v, o_proj, gate/up, down, lm_head at a 256-wide batch tile) and the large-batch paged attention, against the
-    oracle's greedy loop. Short prompts keep the oracle cheap; >= 99 % of the prompts must agree token for token."""
+@pytest.mark.parametrize("n", [256, 512])
+def test_c3_wide_batch_decode_full_depth(full, n):
+    """BASELINE config 3 regime at full width and depth: 256 prompts in one decode batch (CTA-pair swap-AB kernels for
+    q|k|v, o_proj, gate/up, down, lm_head at a 256-wide batch tile) and the shard's 512 prompts in one batch (two batch tiles
+    per weight tile on the pair kernel, gate/up and lm_head in the plain form with a stream-K tail), with the large-batch
+    paged attention, against the oracle's greedy loop. Short prompts keep the oracle cheap; >= 99 % of the prompts must
+    agree token for token."""
     model, sd = full["model"], full["sd"]
     lc = sd["llama_cfg"]
     ocfg = llama_ref.LlamaCfg(n_layers=lc["n_layers"], dim=lc["dim"], n_q_heads=lc["n_q_heads"],
                               n_kv_heads=lc["n_kv_heads"], head_dim=lc["head_dim"], ffn_dim=lc["ffn_dim"], vocab=lc["vocab"])
-    n, new = 256, 16
+    new = 16
     lens = [40 + (i * 7) % 24 for i in range(n)]
     cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     tok = torch.randint(1000, 120000, (int(cu[-1]),), generator=torch.Generator().manual_seed(77))

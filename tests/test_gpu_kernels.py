@@ -191,6 +191,26 @@ def test_gemm_streamk_tail_plain(ops, rows, N, K, streamk_plain):
     _close_bf16(h, R.bf16r(res.float() + R.bf16r(R.linear_ref(x, w))), ulps=2.0, atol=2e-2)
 
 
+@pytest.mark.parametrize("rows,N,K", [(512, 28672, 4096), (384, 28672, 4096), (300, 128256, 1024)])
+def test_gemm_streamk_small_tail_plain_decode_shapes(ops, rows, N, K, streamk_plain):
+    """Decode at batch 257..512 runs gate/up and lm_head in the plain form with the stream-K tail on; a tail of a few tiles
+    (448 = 3 waves + 4) is shared by 8 CTAs per tile. Against whole tiles: same values up to the fp32 summation order of
+    the tail tiles, deterministic."""
+    from opus_pllm_b200 import _lib as L
+    x = _randn((rows, K), 47)
+    w = _randn((N, K), 48, scale=K ** -0.5)
+    got = ops.gemm(x, w, epilogue=L.EPI_SWIGLU, transposed=False)
+    assert torch.equal(got, ops.gemm(x, w, epilogue=L.EPI_SWIGLU, transposed=False))
+    got16 = ops.gemm(x, w, epilogue=L.EPI_BF16, transposed=False)
+    L.check(L.load().opus_set_tunable(b"streamk_plain", 0))
+    want = ops.gemm(x, w, epilogue=L.EPI_SWIGLU, transposed=False)
+    want16 = ops.gemm(x, w, epilogue=L.EPI_BF16, transposed=False)
+    for a, b in ((got, want), (got16, want16)):
+        assert float((a != b).float().mean()) <= 0.35          # only tail tiles may differ at all
+        assert float((a.float() - b.float()).abs().max()) <= 2.0 ** -6 * float(b.float().abs().max())
+    _close_bf16(got16, R.linear_ref(x, w))
+
+
 @pytest.mark.parametrize("M,N,K", [(1024, 256, 64), (1100, 768, 1280), (4096, 5120, 1280), (16512, 1280, 1280),
                                    (2500, 6272, 512)])
 def test_gemm_cta_pair_form_is_bit_identical(ops, M, N, K):
@@ -219,7 +239,7 @@ def test_gemm_cta_pair_form_is_bit_identical(ops, M, N, K):
     _close_bf16(out[1][0], R.linear_ref(x, w, b))
 
 
-@pytest.mark.parametrize("rows", [129, 200, 256])
+@pytest.mark.parametrize("rows", [129, 200, 256, 300, 512])          # above 256: two batch tiles per weight tile
 @pytest.mark.parametrize("N,K,split", [(4096, 4096, 4), (6144, 4096, 3), (4096, 14336, 4), (18816, 1024, 1), (8320, 512, 2)])
 def test_gemm_cta_pair_swap_ab_form_is_bit_identical(ops, rows, N, K, split):
     """Swap-AB (weight-streaming) launches at batch 129..256 run on the CTA-pair kernel (each CTA holds half of the
@@ -242,7 +262,7 @@ def test_gemm_cta_pair_swap_ab_form_is_bit_identical(ops, rows, N, K, split):
                          ops.gemm(x, w, epilogue=L.EPI_BF16, bias=b, transposed=True),
                          ops.gemm(x, w, epilogue=L.EPI_BF16_GELU, bias=b, transposed=True), h)
     finally:
-        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 1))
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 2))
     for a, c in zip(out[1], out[0]):
         assert torch.equal(a, c)
     assert out[1][0].shape == (split, rows, N)
@@ -588,7 +608,8 @@ def test_gemm_rmsnorm_on_load(rows, n_out, K, epi):
     assert float((a != b).float().mean()) <= 0.02            # only rstd-ulp rows may differ at all
 
 
-@pytest.mark.parametrize("rows,n_out,K,epi", [(256, 28672, 4096, "swiglu"), (200, 28672, 4096, "swiglu"), (256, 128256, 4096, "bf16")])
+@pytest.mark.parametrize("rows,n_out,K,epi", [(256, 28672, 4096, "swiglu"), (200, 28672, 4096, "swiglu"), (256, 128256, 4096, "bf16"),
+                                              (512, 28672, 4096, "swiglu"), (400, 128256, 4096, "bf16")])
 def test_pair_kernel_streamk_tail_matches_single_cta(rows, n_out, K, epi):
     """Batch 129..256 swap-AB launches run on the CTA-pair kernel; when their 256-feature tiles do not fill whole waves of
     the 74 pairs the last partial wave is cut along K over all pairs (stream-K, per-rank fix-up). Against the single-CTA
@@ -613,7 +634,12 @@ def test_pair_kernel_streamk_tail_matches_single_cta(rows, n_out, K, epi):
         L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 2))
         L.check(lib.opus_set_tunable(b"pair_streamk", 0))
         L.check(lib.opus_set_tunable(b"streamk_fill", 90))
-    assert torch.equal(two_waves, want)                              # same k order per tile: bit-identical
+    rem = (-(-n_out // 256) * -(-rows // 256)) % 74
+    if 0 < rem * 10 <= 74:      # a tail of a few tiles is always cut along K (gate/up at batch 512: 3 waves + 2 tiles)
+        assert float((two_waves != want).float().mean()) <= rem / (n_out // 256 * -(-rows // 256)) + 1e-6
+        assert float((two_waves.float() - want.float()).abs().max()) <= 2.0 ** -7 * float(want.float().abs().max())
+    else:
+        assert torch.equal(two_waves, want)                          # same k order per tile: bit-identical
     assert torch.equal(got, again)                                   # deterministic (fixed fix-up order)
     a, b = got.float(), want.float()
     assert float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)) >= 0.999999

@@ -832,10 +832,43 @@ def test_decode_batch_above_128_pair_kernel_is_bit_identical(batch):
             toks = model.generate_from_prefill(st, 6)
             res[mode] = (toks.clone(), model._ws_bufs["logits"][:batch].clone(), model._k.clone(), model._v.clone())
     finally:
-        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 1))
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 2))
         model.release_plan(plan)
     for a, b in zip(res[1], res[0]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("batch", [300, 512])
+def test_decode_batch_257_to_512_vs_oracle(batch):
+    """Decode at batch 257..512 (C3's 512 prompts per GPU as one batch): two 256-wide batch tiles per weight tile on the
+    CTA-pair swap-AB kernel, split-K chosen for whole waves of pairs (`gemm_pick_split_k_wide`), gate/up with a two-tile
+    stream-K tail. Llama-3-8B-wide layers at reduced depth, peaked logits, ragged prompts: tokens against the oracle, and
+    against the single-CTA kernels (pair kernel off)."""
+    from opus_pllm_b200 import _lib as L
+    from opus_pllm_b200.llama import B200Llama
+    cfg = dict(n_layers=2, dim=4096, n_q_heads=32, n_kv_heads=8, head_dim=128, ffn_dim=14336, vocab=8192)
+    w = synth.llama_weights(seed=17, peaked=True, device="cuda", dtype=torch.bfloat16,
+                            **{k if k != "ffn_dim" else "ffn": v for k, v in cfg.items()})
+    model = B200Llama(w, **cfg)
+    lens = [5 + (i * 11) % 28 for i in range(batch)]
+    cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    tok = torch.randint(0, cfg["vocab"], (int(cu[-1]),), generator=torch.Generator().manual_seed(6))
+    emb = w["model.embed_tokens.weight"][tok.cuda()].to(torch.bfloat16)
+    lib = L.load()
+    n_new = 8
+    try:
+        got = model.generate_packed(emb, cu, n_new)
+        assert torch.equal(got, model.generate_packed(emb, cu, n_new, use_graph=False))
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 0))
+        single = model.generate_packed(emb, cu, n_new)
+    finally:
+        L.check(lib.opus_set_tunable(b"gemm_2cta_tr", 2))
+    e_pad, m_pad = _padded(emb, cu, cfg["dim"])
+    want = llama_ref.greedy_generate(_dev(w, torch.bfloat16), _oracle_cfg(cfg), e_pad, m_pad, n_new)
+    assert got.shape == (batch, n_new)
+    assert float((got.cpu() == want.cpu()).all(1).float().mean()) >= 0.99
+    assert float((got == single).all(1).float().mean()) >= 0.99
+    assert len(torch.unique(got)) > 32
 
 
 def test_initialize_protein_modules_rebuilds_the_seams(tmp_path):

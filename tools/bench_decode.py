@@ -67,7 +67,9 @@ def after_prefill(label, gap_ms=0.0):
     print(f"{label:40s} {ms:7.3f} ms/step  {bytes_step / ms / 1e6:7.0f} GB/s  frac {bytes_step / ms / 1e6 / 6551.4:.3f}", flush=True)
 
 
-run("defaults (kernel per op, PDL chain)")
+if os.environ.get("SETK"):      # e.g. SETK="wide_overhead=4,gemm_2cta_tr=0"
+    setk(**{k: int(v) for k, v in (kv.split("=") for kv in os.environ["SETK"].split(","))})
+run("defaults (kernel per op, PDL chain)" if not os.environ.get("SETK") else os.environ["SETK"])
 if os.environ.get("AFTER_PREFILL"):
     after_prefill("decode timed right after a prefill")
 if os.environ.get("L2AHEAD"):
