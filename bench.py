@@ -381,6 +381,12 @@ def run_other_workload(args, wl, model, sd, lcfg, peaks, dev, rank, world, warmu
                               "time of the rounds of the last step", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
                     "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["source"],
                     "bytes": w_bytes + kv_bytes, "decode_ms": dec_ms}
+        # the tensor-pipe view of the same rounds (useful work only: one weight pass per generated token + its attention);
+        # with 512 slots the full-batch rounds are tensor-bound, the drained tiers HBM-bound
+        dec_flops = (2.0 * 7504658432 * n_tok + 4.0 * 4096 * 32 * kv_bytes / 131072.0) if full else 0.0
+        roofline["tensor"] = {"flops": dec_flops, "achieved": dec_flops / dec_ms / 1e9 if dec_ms > 0 else 0.0,
+                              "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                              "frac": dec_flops / dec_ms / 1e9 / peaks["tf_sustained"] if dec_ms > 0 else 0.0}
         extra["scheduler"] = stats
         cfg.update(requests_per_gpu=n_prot, slots=wl["slots"], prompt_len=wl["prompt_len"], max_new_tokens=wl["new_tokens"],
                    generated_tokens_per_step=n_tok, cuda_graph_decode=not args.no_graph)
@@ -635,6 +641,14 @@ def main():
     roofline_decode = {"bound": "hbm", "achieved": dec_bytes / dec_ms / 1e6, "peak": peaks["hbm"], "unit": "GB/s",
                        "frac": dec_bytes / dec_ms / 1e6 / peaks["hbm"], "ms_per_decode_step": dec_ms,
                        "bytes_per_step": dec_bytes}
+    # a decode step is 2 x 7.505 G FLOP per sequence (layer + lm_head weights) + the attention over the context: above
+    # ~batch 300 the tensor time at the sustained peak exceeds the HBM time of the same step, so both bounds are reported
+    dec_flops = (2.0 * 7504658432 * B + 4.0 * 4096 * 32 * B * ctx_mean) * (lcfg["n_layers"] / 32.0 if args.size == "full" else 0)
+    t_hbm, t_tensor = dec_bytes / peaks["hbm"] / 1e6, dec_flops / peaks["tf_sustained"] / 1e9      # ms
+    roofline_decode["tensor"] = {"flops_per_step": dec_flops, "achieved": dec_flops / dec_ms / 1e9, "peak": peaks["tf_sustained"],
+                                 "unit": "TFLOP/s", "frac": dec_flops / dec_ms / 1e9 / peaks["tf_sustained"]}
+    roofline_decode["tighter_bound"] = "tensor" if t_tensor > t_hbm else "hbm"
+    roofline_decode["frac_of_tighter_bound"] = max(t_hbm, t_tensor) / dec_ms
     if new > 1 and world == 1:
         # the same decode loop (graph replays against the last prefill's cache) timed ALONE after a pause: inside the step
         # it inherits the power-capped SM clock of the prefill that precedes it, and ~35 % of a decode step is
