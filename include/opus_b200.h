@@ -61,8 +61,9 @@ const char* opus_last_error(void);
  * never call opus_ctx_set_current share the process-default context. A context serialises its work on one stream at a
  * time; use one context per concurrently used stream / host thread. The OPUS_* environment variables (OPUS_PDL,
  * OPUS_ATTN, OPUS_ATTN_TAIL, OPUS_GEMM_2CTA, OPUS_GEMM_2CTA_TR, OPUS_GEMM_GROUP_M, OPUS_GEMM_HINTS, OPUS_TMA_STORE,
- * OPUS_STREAMK, OPUS_DECODE_FUSED, OPUS_PF, OPUS_PF_*) are read once, when a context is created: launch paths never
- * consult the environment.
+ * OPUS_STREAMK, OPUS_DECODE_FUSED, OPUS_PF, OPUS_PF_*, and the opt-in experiments OPUS_GEMM_GROUP_N,
+ * OPUS_GEMM_GROUP_N_HINTS, OPUS_ATTN_SPLIT, OPUS_L2_AHEAD, OPUS_PAIR_STREAMK, OPUS_EPI_WARM, OPUS_DECODE_NORM_FUSED,
+ * OPUS_WIDE_OVERHEAD) are read once, when a context is created: launch paths never consult the environment.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct opus_ctx opus_ctx;
 int opus_ctx_create(opus_ctx** out);
@@ -375,15 +376,22 @@ int opus_release_graphs(void);
  * runs o_proj -> norm -> gate/up -> down -> norm -> next qkv / lm_head of a decode step as one persistent chain kernel,
  * 0 (default) = one kernel per GEMM / norm; "chain_l2_depth" = k-blocks the chain kernel prefetches into L2 per phase;
  * "gemm_2cta" = 0 single-CTA GEMM everywhere, 1 CTA-pair (cta_group::2) form for every large plain GEMM, 2 (default) the
- * pair form except under the SwiGLU epilogue; "gemm_2cta_tr" = 0 keeps swap-AB launches at batch 129..256 on the
- * single-CTA kernel (default 1: CTA-pair kernel where its work items fill the pairs);
+ * pair form except under the SwiGLU epilogue; "gemm_2cta_tr" = 0 keeps swap-AB launches at batch 129..512 on the
+ * single-CTA kernel, 1 = CTA-pair kernel where its work items fill the pairs except under SwiGLU, 2 (default) = gate/up too
+ * (batch 129..256; at batch 257..512 gate/up and lm_head run in the plain form with a stream-K tail);
+ * "wide_overhead" = per-item cost, in k-blocks, of the split-K choice at batch 257..512 (default 8);
  * "decode_rope_fused" = 0 runs the decode step's split-K reduce + RoPE + KV append as its own kernel instead of inside
  * the paged-attention CTAs (default 1);
  * "tma_store" = 0 sends the plain bf16 / GELU GEMM epilogues back to direct row-per-thread stores (and the encoder's rotary
  * embedding back to its own kernel).
  * "attn_mode" = 0 automatic, 1 mma.sync attention, 2 tcgen05 attention; "attn_tail" = 0 keeps short query tails inside the
  * tcgen05 attention kernel.
- * Acts on the current context and drops its cached graphs. */
+ * Opt-in experiments, all measured slower or equal on B200 and off by default: "decode_norm_fused"
+ * (RMSNorm folded into the decode GEMMs, batch <= 64), "attn_split" (split-KV decode attention: -1 automatic, 2, 4),
+ * "pair_streamk" (stream-K tail of any size in the CTA-pair swap-AB kernel), "l2_ahead" (k-blocks requested into L2 ahead of
+ * the shared-memory ring), "epi_warm" (dry epilogue pass), "group_m" / "group_n" / "group_n_hints" (raster overrides of the
+ * plain GEMMs).
+ * Unknown names fail with OPUS_ERR_ARG. Acts on the current context and drops its cached graphs. */
 int opus_set_tunable(const char* name, int value);
 /* Profiling aid: between opus_trace_begin(stream) and opus_trace_end the composite forwards record a CUDA event after
  * every kernel launch (not inside graph capture); opus_trace_end synchronises and writes "label<TAB>microseconds\n"
