@@ -15,6 +15,7 @@ scheduler itself is host logic over the decode-state arrays.
 from __future__ import annotations
 
 import ctypes as C
+import time
 from collections import deque
 
 import numpy as np
@@ -24,6 +25,20 @@ from . import _lib as L
 from . import ops
 from .llama import BLOCK, u64_as_i64
 from .model import B200OpusLlama, SplicePlan
+
+
+def cut_round(toks: np.ndarray, room: np.ndarray, eos_ids) -> tuple[np.ndarray, np.ndarray]:
+    """Per slot of one round's tokens [S, R]: how many tokens the request keeps (up to and including its first EOS, at most
+    `room[s]` = what is left of its max_new_tokens) and whether that completes it. Stop keywords are matched separately."""
+    S, R = toks.shape
+    first = np.full(S, R + 1, dtype=np.int64)                # tokens up to and including the first EOS; R + 1 = none
+    if len(eos_ids) and S:
+        hit = np.isin(toks, np.asarray(list(eos_ids), dtype=toks.dtype))
+        any_hit = hit.any(1)
+        first[any_hit] = hit[any_hit].argmax(1) + 1
+    take = np.minimum(np.minimum(first, R), np.maximum(room, 0))
+    done = (take >= room) | (first <= take)
+    return take, done
 
 
 class ContinuousBatcher:
@@ -104,7 +119,8 @@ class ContinuousBatcher:
 
         st, bufs = self._state(S, max_blocks, self.R, eos_ids, pad_id, sampling)
         n_round = n_adm = 0
-        round_events, n_rounds, prefill_tokens = [], 0, 0
+        round_events, adm_events, n_rounds, prefill_tokens = [], [], 0, 0
+        t_wall0 = time.perf_counter()
         bufs["block_table"].fill_(scratch)
         bufs["finished"].fill_(1)
         slot_req = [-1] * S                   # request id held by each slot
@@ -115,16 +131,25 @@ class ContinuousBatcher:
         stream = torch.cuda.current_stream().cuda_stream
         active = 0
 
+        retired: list[int] = []               # slots freed since the last flush of the device-side state
+
         def retire(slot):
             nonlocal active
             r = slot_req[slot]
             done[r] = True
             ll._alloc.release(slot_pages[slot])
             slot_pages[slot], slot_req[slot] = [], -1
-            bufs["block_table"][slot].fill_(scratch)
-            bufs["finished"][slot] = 1
-            bufs["ctx_len"][slot] = 0
+            retired.append(slot)
             active -= 1
+
+        def flush_retired():
+            """one indexed update for all slots retired since the last call: scratch page, finished, empty context"""
+            if retired:
+                idx = torch.tensor(retired, dtype=torch.long, device=self.dev)
+                bufs["block_table"][idx] = scratch
+                bufs["finished"][idx] = 1
+                bufs["ctx_len"][idx] = 0
+                retired.clear()
 
         def absorb(r, toks) -> bool:
             """append tokens of request r; True when the request is complete"""
@@ -140,6 +165,7 @@ class ContinuousBatcher:
         def admit_chunk() -> bool:
             """prefill one chunk of waiting prompts into free slots (bounded by the workspace rows and the encoder chunk)"""
             nonlocal n_adm, prefill_tokens, active
+            flush_retired()
             free = [s for s in range(S) if slot_req[s] < 0]
             adm = []
             budget = ll._ws_rows
@@ -149,6 +175,9 @@ class ContinuousBatcher:
                 budget -= int(lens[r])
             if not adm:
                 return False
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            adm_events.append((a0, a1))
             cu = np.zeros(len(adm) + 1, dtype=np.int32)
             np.cumsum([lens[r] for _, r in adm], out=cu[1:])
             n_tok = int(cu[-1])
@@ -182,6 +211,7 @@ class ContinuousBatcher:
             ab["n_unfinished"].fill_(len(adm))
             L.check(lib.opus_llama_select(C.byref(ll._model), C.byref(ll._ws), C.byref(ast), len(adm), stream),
                     "opus_llama_select")
+            a1.record()
             first = ops.d2h(ab["next_tok"]).tolist()
             idx = torch.tensor([s for s, _ in adm], dtype=torch.long, device=self.dev)
             bufs["next_tok"][idx] = ab["next_tok"]
@@ -207,6 +237,7 @@ class ContinuousBatcher:
                     break
             if not waiting and 0 < active and min(t for t in tiers if t >= active) < S:
                 tgt = min(t for t in tiers if t >= active)
+                retired.clear()                     # the compacted state below is rebuilt from the live slots only
                 live = [i for i in range(S) if slot_req[i] >= 0]
                 st2, bufs2 = self._state(tgt, max_blocks, self.R, eos_ids, pad_id, sampling)
                 idx = torch.tensor(live, dtype=torch.long, device=self.dev)
@@ -223,8 +254,9 @@ class ContinuousBatcher:
             if not active:
                 continue
             # ---- one round of R decode steps over all slots (idle slots spin on the scratch page)
+            flush_retired()
             idle = [s for s in range(S) if slot_req[s] < 0]
-            if idle:
+            if idle:    # idle slots keep stepping on the scratch page: their context restarts every round
                 bufs["ctx_len"][torch.tensor(idle, device=self.dev)] = 0
             bufs["step"].fill_(-1)
             bufs["n_unfinished"].fill_(active)
@@ -240,15 +272,26 @@ class ContinuousBatcher:
             round_events.append((e0, e1))
             n_rounds += 1
             toks = ops.d2h(bufs["out_ids"]).numpy()          # [S, R]; synchronises
-            for s in range(S):
-                r = slot_req[s]
-                if r >= 0 and absorb(r, toks[s]):
-                    retire(s)
+            if stops:
+                for s in range(S):
+                    r = slot_req[s]
+                    if r >= 0 and absorb(r, toks[s]):
+                        retire(s)
+            else:       # no stop keywords: the cut positions of all slots at once
+                live = [s for s in range(S) if slot_req[s] >= 0]
+                room = np.array([new_of[slot_req[s]] - len(results[slot_req[s]]) for s in live], dtype=np.int64)
+                take, fin = cut_round(toks[live], room, eos_set)
+                for j, s in enumerate(live):
+                    results[slot_req[s]].extend(toks[s, : take[j]].tolist())
+                    if fin[j]:
+                        retire(s)
         ll._alloc.release([scratch])
         torch.cuda.current_stream().synchronize()
         # bookkeeping of the last call (bench.py: HBM roofline of the decode rounds)
         self.stats = dict(rounds=n_rounds, decode_steps=n_rounds * self.R, slots=min(self.S, n_req), compactions=n_compact,
-                          admissions=n_adm,
-                          prefill_tokens=prefill_tokens, decode_ms=float(sum(a.elapsed_time(b) for a, b in round_events)))
+                          admissions=n_adm, prefill_tokens=prefill_tokens,
+                          decode_ms=float(sum(a.elapsed_time(b) for a, b in round_events)),
+                          admission_ms=float(sum(a.elapsed_time(b) for a, b in adm_events)),
+                          wall_ms=(time.perf_counter() - t_wall0) * 1e3)
         lib.opus_release_graphs()
         return [torch.tensor(r, dtype=torch.int64) for r in results]

@@ -343,3 +343,25 @@ def test_bench_reference_arm_runs_on_cpu_for_every_workload_kind():
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
         assert d["e2e"] == {"value": d["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert d["config"]["workload"].startswith(wl + ":")
+
+
+def test_scheduler_cut_round_matches_the_token_by_token_rule():
+    """scheduler.cut_round (all slots of a round at once) against the scalar rule of the reference loop: keep tokens up to
+    and including the first EOS, never more than what is left of max_new_tokens; complete on EOS or on the limit."""
+    import numpy as np
+    from opus_pllm_b200.scheduler import cut_round
+    rng = np.random.default_rng(5)
+    for eos in ((), (7,), (7, 3)):
+        toks = rng.integers(0, 12, size=(200, 16)).astype(np.int32)
+        room = rng.integers(1, 40, size=200)
+        take, done = cut_round(toks, room, eos)
+        for s in range(200):
+            kept, fin = [], False
+            for t in toks[s]:
+                kept.append(int(t))
+                if int(t) in eos or len(kept) >= room[s]:
+                    fin = True
+                    break
+            assert take[s] == len(kept) and bool(done[s]) == fin, (s, eos)
+    take, done = cut_round(np.zeros((0, 16), dtype=np.int32), np.zeros(0, dtype=np.int64), (1,))
+    assert take.shape == (0,) and done.shape == (0,)
