@@ -89,7 +89,8 @@ bool decode_fused() { return ctx().tun.decode_fused != 0; }
 
 // activations [rows, K] x weight [N, K]^T -> out, choosing the weight-streaming (swap-AB) form for small `rows`.
 int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* out, int ldo, const float* bias,
-           const void* residual, int ldr, float* ws, size_t ws_bytes, cudaStream_t st, const Prefetch* pf = nullptr) {
+           const void* residual, int ldr, float* ws, size_t ws_bytes, cudaStream_t st, const Prefetch* pf = nullptr,
+           bool decode = false) {
   GemmArgs a{};
   apply_prefetch(a, pf);
   a.K = K;
@@ -105,9 +106,9 @@ int linear(const void* x, int rows, const void* w, int N, int K, int epi, void* 
     a.transposed = 0;
     a.A = x; a.lda = K; a.M = rows;
     a.B = w; a.ldb = K; a.N = N;
-    // decode at batch 257..512 (gate/up: 448 tiles = 3 waves + 4): the partial last wave is cut along K. Larger launches
-    // (prefill) keep one summation order for every token row.
-    a.streamk_tail = rows <= 512;
+    // decode at batch 257..512 (gate/up: 448 tiles = 3 waves + 4): the partial last wave is cut along K. The encoder and
+    // the prefill keep one summation order for every token row (a token's result does not depend on its batch).
+    a.streamk_tail = decode && rows <= 512;
   }
   (void)ws; (void)ws_bytes;
   return gemm_bf16(a, st);
@@ -429,13 +430,14 @@ int opt_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const op
                                      kv->block_size, scale, st, L.bqkv));
     OPUS_TRY(linear_splitk(attn, B, L.wo, d, aw, ws->partial, ws->partial_bytes, &sp, st));
     OPUS_TRY(layernorm_bf16(nullptr, ws->partial, sp, L.bo, h, h, L.ln2_g, L.ln2_b, xn, B, d, m->rms_eps, st));
-    OPUS_TRY(linear(xn, B, L.wgu, ffn, d, opt_fc1_epi(m), act, ffn, L.b1, nullptr, 0, nullptr, 0, st));
+    OPUS_TRY(linear(xn, B, L.wgu, ffn, d, opt_fc1_epi(m), act, ffn, L.b1, nullptr, 0, nullptr, 0, st, nullptr, true));
     OPUS_TRY(linear_splitk(act, B, L.wdown, d, ffn, ws->partial, ws->partial_bytes, &sp, st));
     const bool last = l + 1 == m->n_layers;
     OPUS_TRY(layernorm_bf16(nullptr, ws->partial, sp, L.b2, h, h, last ? m->norm_g : m->layers[l + 1].ln1_g,
                             last ? m->norm_b : m->layers[l + 1].ln1_b, xn, B, d, m->rms_eps, st));
   }
-  OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st));
+  OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st,
+                  nullptr, true));
   OPUS_TRY(llama_select(m, ws, s, B, st));
   return OPUS_OK;
 }
@@ -633,7 +635,7 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
     }
     OPUS_TRY(linear_splitk(attn, B, L.wo, d, Hq * hd, ws->partial, ws->partial_bytes, &sp, st, &pf_gu));
     OPUS_TRY(rmsnorm_bf16(nullptr, ws->partial, sp, h, h, static_cast<const bf16*>(L.ln2_w), xn, B, d, m->rms_eps, st));
-    OPUS_TRY(linear(xn, B, L.wgu, 2 * ffn, d, EPI_SWIGLU, act, ffn, nullptr, nullptr, 0, nullptr, 0, st, &pf_down));
+    OPUS_TRY(linear(xn, B, L.wgu, 2 * ffn, d, EPI_SWIGLU, act, ffn, nullptr, nullptr, 0, nullptr, 0, st, &pf_down, true));
     OPUS_TRY(linear_splitk(act, B, L.wdown, d, ffn, ws->partial, ws->partial_bytes, &sp, st, &pf_next));
     const bf16* next_w = static_cast<const bf16*>(l + 1 < m->n_layers ? m->layers[l + 1].ln1_w : m->norm_w);
     OPUS_TRY(rmsnorm_bf16(nullptr, ws->partial, sp, h, h, next_w, xn, B, d, m->rms_eps, st));
@@ -644,7 +646,7 @@ int llama_decode_step(const opus_llama_model* m, const opus_kv_cache* kv, const 
     pf_first.split_k = splitk_for(B, qkv_n, d, ws->partial_bytes); pf_first.depth = pf_depth_for(PF_QKV);
   }
   OPUS_TRY(linear(xn, B, m->lm_head, m->vocab, d, EPI_BF16, ws->logits, m->vocab, nullptr, nullptr, 0, nullptr, 0, st,
-                  &pf_first));
+                  &pf_first, true));
   OPUS_TRY(llama_select(m, ws, s, B, st));
   return OPUS_OK;
 }
