@@ -197,9 +197,11 @@ def test_streamk_tail_partition_covers_every_unit_once():
     """Python restatement of gemm_tcgen05.cu::get_work's stream-K tail partition: every k-block unit of the tail tiles is
     computed exactly once, a CTA touches at most two tiles, and the owner's [first_cta, owner) range is exactly the set
     of CTAs that dump a partial for that tile (so the counter it waits on reaches the expected value)."""
-    def sim(sk_tiles, kb, g):
+    def sim(sk_tiles, kb, g, share=0):
         U = sk_tiles * kb
         ge = min(g, U)
+        if 0 < share < ge:          # GemmParams::sk_share: a tail of a few tiles is cut into 8 pieces per tile only
+            ge = share
         cover, contrib, owners = [0] * U, {}, {}
         for b in range(ge):
             u0, u1 = b * U // ge, (b + 1) * U // ge
@@ -222,6 +224,9 @@ def test_streamk_tail_partition_covers_every_unit_once():
         for sk in (1, 2, 3, 53, 76, 114, g - 1):
             for kb in (1, 2, 5, 16, 20, 64, 80, 224):
                 sim(sk, kb, g)
+    for g, sk in ((148, 4), (148, 14), (74, 2), (74, 7), (74, 1)):      # small tails: rem * 10 <= g, share = 8 per tile
+        for kb in (5, 16, 64, 224):
+            sim(sk, kb, g, share=min(g, sk * 8))
 
 
 def test_keywords_stopping_criteria_host_half():
